@@ -1,0 +1,156 @@
+/*
+ * spq_b200.h -- C ABI of the B200 (sm_100a) switchable-precision fake-quant linear path.
+ *
+ * One shared library (libspq_b200.so), plain pointers and sizes, no torch types.  Every pointer
+ * is a DEVICE pointer unless its name ends in _host; tensors are borrowed (caller-owned,
+ * row-major, contiguous unless a leading dimension is given), nothing is allocated inside.
+ * Every entry point enqueues on `stream` (a cudaStream_t passed as void*) and returns
+ * SPQ_OK (0) or an error code; spq_last_error() gives the message.  There is no CPU fallback:
+ * on a machine without an sm_100 device the compute entry points return SPQ_ERR_CUDA.
+ *
+ * The reference (Laurence-Wu/LLM-QAT-on-gpt2) has no FFI; its boundary for this path is the
+ * Python class API of part1_switchable_precision.  Each entry point below names the reference
+ * code it replaces (file:line relative to the upstream repo root, p1 =
+ * part1_switchable_precision).  The Python classes of the same names in
+ * llm_qat_on_gpt2_b200/ bind these symbols with ctypes.
+ */
+#ifndef SPQ_B200_H
+#define SPQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPQ_ABI_VERSION 1
+#define SPQ_API __attribute__((visibility("default")))
+
+typedef void* spq_stream_t;          /* cudaStream_t */
+typedef uint16_t spq_half_t;         /* IEEE binary16 bit pattern */
+
+enum { SPQ_OK = 0, SPQ_ERR_INVALID = 1, SPQ_ERR_CUDA = 2, SPQ_ERR_UNSUPPORTED = 3 };
+/* how a per-channel parameter (scale, zero-point, statistic) broadcasts over a [rows, cols] view */
+enum { SPQ_PER_TENSOR = 0, SPQ_PER_ROW = 1, SPQ_PER_COL = 2 };
+enum { SPQ_MINMAX = 0, SPQ_LOG = 1 };
+/* what the GEMM-operand output of a quantise kernel holds */
+enum { SPQ_OPERAND_CODE = 0,     /* (q - zero_point): the integer code, exact in fp16 for <= 11 bits */
+       SPQ_OPERAND_DEQUANT = 1,  /* the dequantised value */
+       SPQ_OPERAND_RAW = 2 };    /* the unquantised input (32-bit path) */
+
+SPQ_API int spq_abi_version(void);
+SPQ_API const char* spq_last_error(void);
+/* sm count and compute capability of the current device */
+SPQ_API int spq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* device-side watchdog: nonzero if a GEMM pipeline wait ever timed out (synchronises) */
+SPQ_API int spq_debug_status(int* aborted_host);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+SPQ_API int64_t spq_launch_count(void);
+
+/* ---- (a) calibration statistics -------------------------------------------------------------
+ * Replaces LearnableFakeQuantize._collect_statistics_batch / _reduce_min_max
+ * (p1/quantization.py:152-162, 174-209).  x is viewed as [rows, cols]; the statistic is per
+ * column (input activations, LoRA A/B: channel_dim = -1 / 1), per row (weights: channel_dim = 0)
+ * or per tensor.  log_mode: statistics of log2(max(|x|, eps)), updated only if any(|x| > eps)
+ * (p1/quantization.py:177-197); when nothing exceeds eps and accumulate == 0 the statistics are
+ * filled with log2(eps).  accumulate: 0 = first batch (overwrite), 1 = running minimum/maximum.
+ * state[0] |= 1 when this batch had data above eps (always for min-max mode).
+ * NaN propagates as in torch.min/max.  Results are bit-exact (min/max are order independent;
+ * log2 is the correctly rounded float32 logarithm, taken after the reduction -- it is monotone).
+ */
+SPQ_API size_t spq_stats_workspace_bytes(int64_t rows, int64_t cols, int bcast);
+SPQ_API int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int bcast, int log_mode, float eps,
+                     float* stat_min, float* stat_max, int accumulate, int32_t* state,
+                     void* workspace, size_t workspace_bytes, spq_stream_t stream);
+
+/* Replaces LearnableFakeQuantize.finish_calibration (p1/quantization.py:104-139): scale and
+ * zero-point (min-max: symmetric or asymmetric; log: zero_point = log_min, scale = log_range)
+ * from n running statistics.  True IEEE division, as torch-CPU. */
+SPQ_API int spq_finish_calibration(const float* running_min, const float* running_max, int64_t n, int qtype,
+                           int symmetric, int bits, float eps, float* scale, float* zero_point,
+                           spq_stream_t stream);
+
+/* ---- (b) quantise ---------------------------------------------------------------------------
+ * Replaces MinMaxQuantizationFunction.forward / LogQuantizationFunction.forward
+ * (p1/quantization_methods.py:8-22, 33-79).  x is [rows, cols]; scale / zero_point broadcast per
+ * `bcast` (for log: zero_point = log_min, scale = log_range).  Outputs (each nullable):
+ *   dequant : the fake-quantised float32 tensor the reference returns
+ *   codes   : int32 -- min-max: the clamped rounded code q; log: the level index L
+ *   sign    : int8  -- log only: sign(x) in {-1,0,1}, 0 also where |x| < 1e-5 (zero mask)
+ *   operand : fp16 GEMM operand = fp16(v * row_mul[row] * col_mul[col] * mul), v chosen by
+ *             operand_kind (code - zero_point, dequantised value, or raw x); row_mul/col_mul nullable.
+ *             With operand_ld > 0 the operand is written with that leading dimension; with
+ *             operand_transposed != 0 it is written as [cols, rows].
+ * Codes are bit-exact w.r.t. the reference arithmetic (IEEE div, round-half-even, separate
+ * mul/add roundings; log2 correctly rounded via an exact slow path next to rounding ties).
+ */
+SPQ_API int spq_fake_quantize(const float* x, int64_t rows, int64_t cols,
+                      const float* scale, const float* zero_point, int bcast,
+                      int qtype, int bits, int symmetric,
+                      float* dequant, int32_t* codes, int8_t* sign,
+                      spq_half_t* operand, int operand_kind, const float* row_mul, const float* col_mul,
+                      float mul, int operand_transposed, spq_stream_t stream);
+
+/* Fused activation-side quantise for SPLinearWithLoRA.forward (p1/lora.py:141,149): one pass
+ * over x [M, K] (per-column or per-tensor scale) produces
+ *   a_q   [M, K] fp16 : the quantised GEMM operand (code or dequant * col_mul), and
+ *   a_raw [M, K] fp16 : the UNquantised x scaled per row by a power of two (the LoRA branch
+ *                       reads x, not q(x)), with raw_row_scale[m] the factor to multiply back.
+ * qtype < 0 skips a_q (32-bit / calibration pass: only the row-scaled raw operand). */
+SPQ_API int spq_quantize_act(const float* x, int64_t M, int64_t K,
+                     const float* scale, const float* zero_point, int bcast,
+                     int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
+                     spq_half_t* a_q, spq_half_t* a_raw, float* raw_row_scale, spq_stream_t stream);
+
+/* STE backward (p1/quantization_methods.py:25-28, 82-90): identity (min-max) or clamp to
+ * [-10, 10] (log).  out may alias grad. */
+SPQ_API int spq_ste_backward(const float* grad, int64_t n, int qtype, float* out, spq_stream_t stream);
+
+/* ---- (c) fused quant-GEMM -------------------------------------------------------------------
+ * Replaces F.linear(q(x), q(W), b) + LoRALayer.forward (p1/lora.py:45-54, 144-150):
+ *   D[m,n] = epi( sum_k A[m,k] B[n,k]  +  sum_j A2[m,j] B2[n,j] )
+ *   epi(v) = clamp(v * alpha * row_scale[m] * col_scale[n], +-clamp_abs) + bias[n] + C[m,n]
+ * A, B, A2, B2 are fp16, K-contiguous ("K-major"), leading dimensions in elements (multiples of
+ * 8); the second segment (the LoRA up-projection folded in as extra K) is optional (K2 = 0).
+ * row_scale, col_scale, bias, C are nullable; clamp_abs <= 0 disables the clamp.  D is float32,
+ * or fp16 (saturating) when d_is_half.  TMA-fed tcgen05.mma (kind::f16, fp32 accumulation in
+ * TMEM), persistent over the SMs.
+ */
+SPQ_API int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb,
+              int64_t M, int64_t N, int64_t K,
+              const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
+              float alpha, const float* row_scale, const float* col_scale, const float* bias,
+              float clamp_abs, const float* C, int64_t ldc,
+              void* D, int64_t ldd, int d_is_half, spq_stream_t stream);
+
+/* Transposed-operand GEMM for the weight-gradient shaped products of the STE backward
+ * (dA = x^T dT, dB = t^T dY, optional dW = dY^T q(x); torch autograd of p1/lora.py:51-52, 144):
+ *   D[i,j] = alpha * alpha_dev[0] * i_scale[i] * j_scale[j] * sum_m P[m,i] Q[m,j]
+ * P: [Mred, I] fp16, Q: [Mred, J] fp16, row-major (leading dimensions multiples of 8): both are
+ * MN-major tcgen05 operands loaded by TMA without a transpose.  D is a dense float32 matrix
+ * addressed D[i * d_stride_i + j * d_stride_j] (one of the strides is 1, so the result can be
+ * written transposed); it is zeroed here and accumulated with fp32 atomics because the reduction
+ * over Mred is split across CTAs.  alpha_dev (device scalar), i_scale, j_scale are nullable.
+ * Per-reduction-row scales cannot be applied here: fold them into P or Q. */
+SPQ_API int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq,
+                int64_t Mred, int64_t I, int64_t J, float alpha, const float* alpha_dev,
+                const float* i_scale, const float* j_scale,
+                float* D, int64_t d_stride_i, int64_t d_stride_j, spq_stream_t stream);
+
+/* ---- SwitchableLayerNorm (p1/switchable_batchnorm.py:102-109) ------------------------------ */
+SPQ_API int spq_layernorm_fwd(const float* x, int64_t rows, int64_t cols, const float* weight, const float* bias,
+                      float eps, float* y, float* mean, float* rstd, spq_stream_t stream);
+SPQ_API size_t spq_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cols);
+SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean,
+                      const float* rstd, int64_t rows, int64_t cols, float* dx, float* dweight,
+                      float* dbias, void* workspace, size_t workspace_bytes, spq_stream_t stream);
+
+/* ---- gradient-side operand: fp16(g[m,n] * 2^-e[m]) with e from the row's absmax ------------- */
+SPQ_API int spq_rowscale_f16(const float* g, int64_t M, int64_t N, float premul, spq_half_t* out,
+                     float* row_scale, spq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPQ_B200_H */

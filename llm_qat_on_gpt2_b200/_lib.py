@@ -1,0 +1,254 @@
+"""ctypes binding of libspq_b200.so (the C ABI declared in include/spq_b200.h).
+
+PyTorch is used for device memory and streams only: every wrapper takes torch CUDA tensors,
+passes raw device pointers plus the current CUDA stream, and raises on any non-zero status.
+There is no CPU path: calling a compute wrapper with the library missing, or with a tensor that
+is not on a CUDA device, raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspq_b200.so")
+
+PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
+MINMAX, LOG = 0, 1
+OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW = 0, 1, 2
+QTYPE = {"minmax": MINMAX, "log": LOG}
+
+# name -> (restype, argtypes); must list every SPQ_API symbol of include/spq_b200.h
+SIGNATURES = {
+    "spq_abi_version": (c_int, []),
+    "spq_last_error": (c_char_p, []),
+    "spq_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "spq_debug_status": (c_int, [POINTER(c_int)]),
+    "spq_launch_count": (c_int64, []),
+    "spq_stats_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "spq_minmax_stats": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spq_finish_calibration": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p,
+                                       c_void_p, c_void_p]),
+    "spq_fake_quantize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float,
+                                  c_int, c_void_p]),
+    "spq_quantize_act": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "spq_ste_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "spq_qgemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                          c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                          c_float, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,
+                          c_void_p, c_int64, c_int, c_void_p]),
+    "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "spq_layernorm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spq_rowscale_f16": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library and type every entry point.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -m llm_qat_on_gpt2_b200.build` "
+            "(there is no CPU fallback for the fake-quant linear path)")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.spq_abi_version() != 1:
+        raise RuntimeError(f"libspq_b200 ABI version {lib.spq_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().spq_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libspq_b200 operates on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
+    """Per (device, stream, tag) scratch buffer, grown on demand (stream-ordered reuse)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def launch_count() -> int:
+    return int(load_library().spq_launch_count())
+
+
+def debug_status() -> int:
+    v = c_int(0)
+    _check(load_library().spq_debug_status(ctypes.byref(v)), "spq_debug_status")
+    return v.value
+
+
+def device_info():
+    a, b, c = c_int(0), c_int(0), c_int(0)
+    _check(load_library().spq_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "spq_device_info")
+    return a.value, b.value, c.value
+
+
+# ------------------------------------------------------------------------------------------
+# thin typed wrappers (shapes are validated here; the kernels trust them)
+# ------------------------------------------------------------------------------------------
+
+def minmax_stats(x2d: torch.Tensor, bcast: int, log_mode: bool, eps: float, stat_min: torch.Tensor,
+                 stat_max: torch.Tensor, accumulate: bool, state: Optional[torch.Tensor]):
+    lib = load_library()
+    _req_cuda(x2d, stat_min, stat_max, state)
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    rows, cols = x2d.shape
+    n = {PER_TENSOR: 1, PER_ROW: rows, PER_COL: cols}[bcast]
+    assert stat_min.numel() == n and stat_max.numel() == n and stat_min.is_contiguous() and stat_max.is_contiguous()
+    nbytes = lib.spq_stats_workspace_bytes(rows, cols, bcast)
+    ws = _workspace(nbytes, x2d.device, "stats")
+    _check(lib.spq_minmax_stats(x2d.data_ptr(), rows, cols, bcast, int(log_mode), float(eps), stat_min.data_ptr(),
+                                stat_max.data_ptr(), int(accumulate), _ptr(state), ws.data_ptr(), ws.numel(),
+                                _stream()), "spq_minmax_stats")
+
+
+def finish_calibration(rmin, rmax, qtype: int, symmetric: bool, bits: int, eps: float, scale, zp):
+    _req_cuda(rmin, rmax, scale, zp)
+    n = rmin.numel()
+    assert rmax.numel() == n and scale.numel() == n and zp.numel() == n
+    _check(load_library().spq_finish_calibration(rmin.data_ptr(), rmax.data_ptr(), n, qtype, int(symmetric), bits,
+                                                 float(eps), scale.data_ptr(), zp.data_ptr(), _stream()),
+           "spq_finish_calibration")
+
+
+def fake_quantize(x2d, scale, zp, bcast, qtype, bits, symmetric, dequant=None, codes=None, sign=None,
+                  operand=None, operand_kind=OPERAND_DEQUANT, row_mul=None, col_mul=None, mul=1.0,
+                  operand_transposed=False):
+    _req_cuda(x2d, scale, zp, dequant, codes, sign, operand, row_mul, col_mul)
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    rows, cols = x2d.shape
+    need = {PER_TENSOR: 1, PER_ROW: rows, PER_COL: cols}[bcast]
+    assert scale.numel() == need and zp.numel() == need, (scale.shape, zp.shape, bcast, x2d.shape)
+    assert row_mul is None or row_mul.numel() == rows
+    assert col_mul is None or col_mul.numel() == cols
+    _check(load_library().spq_fake_quantize(x2d.data_ptr(), rows, cols, scale.data_ptr(), zp.data_ptr(), bcast, qtype,
+                                            bits, int(symmetric), _ptr(dequant), _ptr(codes), _ptr(sign),
+                                            _ptr(operand), operand_kind, _ptr(row_mul), _ptr(col_mul), float(mul),
+                                            int(operand_transposed), _stream()), "spq_fake_quantize")
+
+
+def quantize_act(x2d, scale, zp, bcast, qtype, bits, symmetric, operand_kind, col_mul, mul, a_q, a_raw, raw_row_scale):
+    _req_cuda(x2d, scale, zp, col_mul, a_q, a_raw, raw_row_scale)
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    M, K = x2d.shape
+    _check(load_library().spq_quantize_act(x2d.data_ptr(), M, K, _ptr(scale), _ptr(zp), bcast, qtype, bits,
+                                           int(symmetric), operand_kind, _ptr(col_mul), float(mul), _ptr(a_q),
+                                           _ptr(a_raw), _ptr(raw_row_scale), _stream()), "spq_quantize_act")
+
+
+def ste_backward(grad, qtype: int):
+    _req_cuda(grad)
+    g = grad.contiguous()
+    if g.dtype != torch.float32:
+        g = g.float()
+    out = torch.empty_like(g)
+    if g.numel():
+        _check(load_library().spq_ste_backward(g.data_ptr(), g.numel(), qtype, out.data_ptr(), _stream()),
+               "spq_ste_backward")
+    return out
+
+
+def qgemm(A, B, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None, col_scale=None, bias=None,
+          clamp_abs=0.0, C=None):
+    """out[M,N] = epi(A[M,K] B[N,K]^T + A2[M,K2] B2[N,K2]^T); A/B fp16 row-major, out fp32 or fp16."""
+    _req_cuda(A, B, out, A2, B2, row_scale, col_scale, bias, C)
+    assert A.dtype == torch.float16 and B.dtype == torch.float16
+    assert A.stride(-1) == 1 and B.stride(-1) == 1 and out.stride(-1) == 1
+    d_half = out.dtype == torch.float16
+    assert d_half or out.dtype == torch.float32
+    _check(load_library().spq_qgemm(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K,
+                                    _ptr(A2), 0 if A2 is None else A2.stride(0), _ptr(B2),
+                                    0 if B2 is None else B2.stride(0), K2, float(alpha), _ptr(row_scale),
+                                    _ptr(col_scale), _ptr(bias), float(clamp_abs), _ptr(C),
+                                    0 if C is None else C.stride(0), out.data_ptr(), out.stride(0), int(d_half),
+                                    _stream()), "spq_qgemm")
+    return out
+
+
+def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, transposed_out=False):
+    """out[I,J] (or out[J,I] when transposed_out) = alpha * P[Mred,I]^T Q[Mred,J]; fp16 in, fp32 out."""
+    _req_cuda(P, Q, out, alpha_dev, i_scale, j_scale)
+    assert P.dtype == torch.float16 and Q.dtype == torch.float16 and out.dtype == torch.float32
+    assert P.stride(-1) == 1 and Q.stride(-1) == 1 and out.is_contiguous()
+    Mred, I = P.shape
+    J = Q.shape[1]
+    assert Q.shape[0] == Mred
+    if transposed_out:
+        assert tuple(out.shape) == (J, I)
+        si, sj = 1, I
+    else:
+        assert tuple(out.shape) == (I, J)
+        si, sj = J, 1
+    _check(load_library().spq_gemm_tn(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), Mred, I, J, float(alpha),
+                                      _ptr(alpha_dev), _ptr(i_scale), _ptr(j_scale), out.data_ptr(), si, sj,
+                                      _stream()), "spq_gemm_tn")
+    return out
+
+
+def layernorm_fwd(x2d, weight, bias, eps, y, mean, rstd):
+    _req_cuda(x2d, weight, bias, y, mean, rstd)
+    rows, cols = x2d.shape
+    _check(load_library().spq_layernorm_fwd(x2d.data_ptr(), rows, cols, weight.data_ptr(), bias.data_ptr(), float(eps),
+                                            y.data_ptr(), _ptr(mean), _ptr(rstd), _stream()), "spq_layernorm_fwd")
+
+
+def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias):
+    lib = load_library()
+    _req_cuda(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias)
+    rows, cols = x2d.shape
+    nbytes = lib.spq_layernorm_bwd_workspace_bytes(rows, cols)
+    ws = _workspace(nbytes, x2d.device, "ln_bwd")
+    _check(lib.spq_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                 rows, cols, dx.data_ptr(), _ptr(dweight), _ptr(dbias), ws.data_ptr(), ws.numel(),
+                                 _stream()), "spq_layernorm_bwd")
+
+
+def rowscale_f16(g2d, out, row_scale):
+    _req_cuda(g2d, out, row_scale)
+    M, N = g2d.shape
+    _check(load_library().spq_rowscale_f16(g2d.data_ptr(), M, N, 1.0, out.data_ptr(), row_scale.data_ptr(), _stream()),
+           "spq_rowscale_f16")

@@ -1,0 +1,682 @@
+// Fused quant-GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma (kind::f16,
+// fp32 accumulation in TMEM) -> tcgen05.ld epilogue (scale / clamp / bias / residual).
+//
+// Replaces F.linear(q(x), q(W), b) + LoRALayer.forward of the reference (p1/lora.py:45-54,
+// 144-150): the operands are the fp16 code / dequant tensors produced by spq_quantize.cu, the
+// LoRA up-projection is folded in as one more K segment (A2, B2) of the same accumulator.
+//
+// Layout of one CTA (192 threads, persistent over output tiles):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5  epilogue: TMEM lane quadrant (warp_idx % 4) -> registers -> global
+// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), two TMEM accumulators with
+// tmem_full/tmem_empty mbarriers (MMA <-> epilogue) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include <cuda.h>
+
+#include "spq_common.cuh"
+
+namespace spq {
+namespace gemm {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 64;         // 64 fp16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+__device__ int g_abort = 0;    // watchdog: set when a pipeline wait timed out
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a broken pipeline must never hang the GPU.  On timeout the watchdog flag is set
+// and every later wait in the grid falls through, so the kernel terminates (with garbage output
+// and spq_debug_status() != 0).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t it = 0;; ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((it & 1023u) == 1023u) {
+            if (*reinterpret_cast<volatile int*>(&g_abort)) return;
+            if (it >= SPIN_LIMIT) {
+                atomicExch(&g_abort, 1);
+                return;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128B swizzle.
+//   K-major : rows of 128 B (64 fp16 along K), 8-row groups 1024 B apart (SBO); LBO unused (=1).
+//   MN-major: rows of 128 B (64 fp16 along M/N) indexed by k, 8-k groups 1024 B apart (SBO),
+//             consecutive 64-element M/N blocks `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;   // descriptor version (Blackwell)
+    d |= 2ull << 61;   // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor, kind::f16: fp16 x fp16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int umma_m, int umma_n, int a_mn_major, int b_mn_major) {
+    return (1u << 4)                                   // c_format = F32
+           | (0u << 7) | (0u << 10)                    // a_format = b_format = F16
+           | (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16)
+           | (static_cast<uint32_t>(umma_n >> 3) << 17) | (static_cast<uint32_t>(umma_m >> 4) << 24);
+}
+
+struct EpiParams {
+    const float* row_scale;   // [M] or null
+    const float* col_scale;   // [N] or null
+    const float* bias;        // [N] or null
+    const float* C;           // [M, ldc] or null (added after the clamp)
+    const float* alpha_dev;   // device scalar multiplied into alpha, or null
+    void* D;
+    long long ldc, ldd;
+    long long d_stride_n;     // 1 for row-major D; TN kernel may store transposed
+    float alpha;
+    float clamp_abs;          // <= 0: off
+};
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+    static constexpr int EPI_BYTES = 2 * BN * 4;      // col_scale + bias of the tile
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+// D[m,n] = epi( sum_k A[m,k] B[n,k] + sum_j A2[m,j] B2[n,j] ), all operands K-major fp16.
+template <int BN, bool OUT_HALF>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                int M, int N, int kb1, int kb2, EpiParams ep) {
+    using L = SmemLayout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    float* epi_cs = reinterpret_cast<float*>(smem + L::STAGES * L::STAGE_BYTES);
+    float* epi_bias = epi_cs + BN;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES + L::EPI_BYTES);
+    uint64_t* empty_bar = full_bar + L::STAGES;
+    uint64_t* tmem_full = empty_bar + L::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int num_tiles = n_tiles * m_tiles;
+    const int kb_total = kb1 + kb2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (kb2 > 0) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+        for (int s = 0; s < L::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);     // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "n"(L::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / n_tiles) * BM;
+                const int n0 = (t % n_tiles) * BN;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + A_TILE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if (kb < kb1) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+                        tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - kb1) * BK, m0);
+                        tma_load_2d(sb, &tmB2, &full_bar[stage], (kb - kb1) * BK, n0);
+                    }
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint64_t adesc = make_desc_sw128(sa, 16, 1024);
+                    const uint64_t bdesc = make_desc_sw128(sa + A_TILE_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // +32 B per UMMA_K inside the 128 B swizzle span: +2 in the (addr >> 4) field
+                        umma_f16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+                    if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5)
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int epi_tid = threadIdx.x - 64;         // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const float alpha = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m0 = (t / n_tiles) * BM;
+            const int n0 = (t % n_tiles) * BN;
+            // stage this tile's per-column parameters (previous tile's readers are done: barrier 1)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int j = epi_tid; j < BN; j += 128) {
+                const int n = n0 + j;
+                epi_cs[j] = (ep.col_scale && n < N) ? __ldg(ep.col_scale + n) : 1.0f;
+                epi_bias[j] = (ep.bias && n < N) ? __ldg(ep.bias + n) : 0.0f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < M;
+            const float rs = alpha * ((ep.row_scale && row_ok) ? __ldg(ep.row_scale + row) : 1.0f);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+                tmem_ld_wait();
+                const int nc = n0 + c * 32;
+                if (row_ok && nc < N) {
+                    float o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]) * (rs * epi_cs[c * 32 + j]);
+                        if (ep.clamp_abs > 0.f) x = fminf(fmaxf(x, -ep.clamp_abs), ep.clamp_abs);
+                        o[j] = x + epi_bias[c * 32 + j];
+                    }
+                    const bool full = (nc + 32 <= N);
+                    if (ep.C) {
+                        const float* crow = ep.C + static_cast<long long>(row) * ep.ldc + nc;
+                        if (full && ((ep.ldc & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 cv = *reinterpret_cast<const float4*>(crow + j);
+                                o[j] += cv.x; o[j + 1] += cv.y; o[j + 2] += cv.z; o[j + 3] += cv.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nc + j < N) o[j] += crow[j];
+                        }
+                    }
+                    if constexpr (OUT_HALF) {
+                        unsigned short* drow = reinterpret_cast<unsigned short*>(ep.D) + static_cast<long long>(row) * ep.ldd + nc;
+                        if (full && ((ep.ldd & 7) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 pk;
+                                pk.x = pack_h2(o[j], o[j + 1]); pk.y = pack_h2(o[j + 2], o[j + 3]);
+                                pk.z = pack_h2(o[j + 4], o[j + 5]); pk.w = pack_h2(o[j + 6], o[j + 7]);
+                                *reinterpret_cast<uint4*>(drow + j) = pk;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nc + j < N) drow[j] = f2h_sat(o[j]);
+                        }
+                    } else {
+                        float* drow = reinterpret_cast<float*>(ep.D) + static_cast<long long>(row) * ep.ldd + nc;
+                        if (full && ((ep.ldd & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(drow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nc + j < N) drow[j] = o[j];
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(L::TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp16 row-major [rows, cols] with leading dimension ld (elements); box = 64 columns x box_rows.
+static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SPQ_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld %lld box %d", static_cast<int>(r),
+                  static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld), box_rows);
+        return SPQ_ERR_CUDA;
+    }
+    return SPQ_OK;
+}
+
+template <int BN, bool OUT_HALF>
+static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2, int M,
+                     int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
+    using L = SmemLayout<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    qgemm_nt_kernel<BN, OUT_HALF><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, M, N, kb1, kb2, ep);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Transposed-operand GEMM (weight-gradient shape): D[i,j] += alpha * is[i] * js[j] * sum_m P[m,i] Q[m,j].
+// P [Mred, I] and Q [Mred, J] are row-major fp16, i.e. "MN-major" UMMA operands: a TMA box of
+// 64 reduction rows x 64 columns lands as 64 rows of 128 B (128B swizzle), consecutive 64-column
+// blocks 8 KB apart (LBO), 8-row groups 1 KB apart (SBO).  The reduction (over tokens) is split
+// across CTAs; partial tiles are combined with fp32 atomics (RED) into the pre-zeroed D.
+constexpr int TN_BOX_BYTES = 64 * 128;   // 64 reduction rows x 64 fp16
+
+template <int BJ>
+struct TnSmem {
+    static constexpr int P_BYTES = 2 * TN_BOX_BYTES;            // 128 output rows = 2 boxes
+    static constexpr int Q_BYTES = (BJ / 64) * TN_BOX_BYTES;
+    static constexpr int STAGE_BYTES = P_BYTES + Q_BYTES;
+    static constexpr int STAGES = (163840 / STAGE_BYTES) > 8 ? 8 : (163840 / STAGE_BYTES);
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 2) * 8 + 16 + 1024;
+    static constexpr int TMEM_COLS = BJ < 32 ? 32 : BJ;          // 64 / 128 / 256: powers of two
+};
+
+struct TnEpi {
+    const float* i_scale;
+    const float* j_scale;
+    const float* alpha_dev;
+    float* D;
+    long long stride_i, stride_j;
+    float alpha;
+};
+
+template <int BJ>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+qgemm_tn_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, int I, int J, int kb_total,
+                int kb_per_split, int j_tiles, TnEpi ep) {
+    using L = TnSmem<BJ>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + L::STAGES;
+    uint64_t* tmem_full = empty_bar + L::STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = (blockIdx.x / j_tiles) * BM;
+    const int j0 = (blockIdx.x % j_tiles) * BJ;
+    const int kb_begin = blockIdx.y * kb_per_split;
+    int kb_end = kb_begin + kb_per_split;
+    if (kb_end > kb_total) kb_end = kb_total;
+    const int nkb = kb_end - kb_begin;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmP);
+        tma_prefetch_desc(&tmQ);
+        for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "n"(L::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sp = smem + stage * L::STAGE_BYTES;
+                uint8_t* sq = sp + L::P_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                tma_load_2d(sp, &tmP, &full_bar[stage], i0, kb * 64);
+                tma_load_2d(sp + TN_BOX_BYTES, &tmP, &full_bar[stage], i0 + 64, kb * 64);
+#pragma unroll
+                for (int b = 0; b < BJ / 64; ++b) tma_load_2d(sq + b * TN_BOX_BYTES, &tmQ, &full_bar[stage], j0 + 64 * b, kb * 64);
+                if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BM, BJ, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sp = smem_u32(smem + stage * L::STAGE_BYTES);
+                const uint64_t pdesc = make_desc_sw128(sp, TN_BOX_BYTES, 1024);
+                const uint64_t qdesc = make_desc_sw128(sp + L::P_BYTES, TN_BOX_BYTES, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // 16 reduction rows = 2048 B per UMMA
+                    umma_f16(tmem_base, pdesc + static_cast<uint64_t>(128 * k), qdesc + static_cast<uint64_t>(128 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+                if (kb == nkb - 1) umma_commit(&tmem_full[0]);
+                if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (nkb > 0) {
+        const int quad = warp & 3;
+        mbar_wait(&tmem_full[0], 0);
+        tcgen05_fence_after();
+        const int i = i0 + quad * 32 + lane;
+        const bool i_ok = i < I;
+        const float a = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f) * ((ep.i_scale && i_ok) ? __ldg(ep.i_scale + i) : 1.0f);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BJ / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+            tmem_ld_wait();
+            if (i_ok) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                    const int j = j0 + c * 32 + jj;
+                    if (j < J) {
+                        const float js = ep.j_scale ? __ldg(ep.j_scale + j) : 1.0f;
+                        atomicAdd(ep.D + static_cast<long long>(i) * ep.stride_i + static_cast<long long>(j) * ep.stride_j,
+                                  __uint_as_float(v[jj]) * a * js);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(L::TMEM_COLS) : "memory");
+    }
+}
+
+template <int BJ>
+static int launch_tn(const CUtensorMap& tP, const CUtensorMap& tQ, int I, int J, int kb_total, const TnEpi& ep, cudaStream_t stream) {
+    using L = TnSmem<BJ>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_tn_kernel<BJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int i_tiles = (I + BM - 1) / BM, j_tiles = (J + BJ - 1) / BJ;
+    const int tiles = i_tiles * j_tiles;
+    int splits = (2 * sm_count() + tiles - 1) / tiles;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    const int per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;
+    dim3 grid(tiles, splits);
+    qgemm_tn_kernel<BJ><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tP, tQ, I, J, kb_total, per, j_tiles, ep);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+// fp16 row-major [rows, cols]: box = 64 columns x 64 rows (MN-major operand boxes)
+static int make_tmap_mn(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+    return make_tmap(tm, base, rows, cols, ld, 64);
+}
+
+}  // namespace gemm
+}  // namespace spq
+
+using namespace spq;
+using namespace spq::gemm;
+
+extern "C" int spq_debug_status(int* aborted_host) {
+    int v = 0;
+    SPQ_CUDA_OK(cudaDeviceSynchronize());
+    SPQ_CUDA_OK(cudaMemcpyFromSymbol(&v, g_abort, sizeof(int)));
+    if (aborted_host) *aborted_host = v;
+    if (v) {
+        int zero = 0;
+        SPQ_CUDA_OK(cudaMemcpyToSymbol(g_abort, &zero, sizeof(int)));
+    }
+    return SPQ_OK;
+}
+
+extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
+                         int64_t K, const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
+                         float alpha, const float* row_scale, const float* col_scale, const float* bias, float clamp_abs,
+                         const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, spq_stream_t stream) {
+    SPQ_REQUIRE(A && B && D, "spq_qgemm: null operand");
+    SPQ_REQUIRE(M > 0 && N > 0 && K > 0, "spq_qgemm: empty problem %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
+    SPQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "spq_qgemm: dimension overflow");
+    SPQ_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K, "spq_qgemm: lda/ldb must be multiples of 8 and >= K");
+    SPQ_REQUIRE(aligned16(A) && aligned16(B), "spq_qgemm: operands must be 16-byte aligned");
+    SPQ_REQUIRE(K2 == 0 || (A2 && B2 && (lda2 % 8) == 0 && (ldb2 % 8) == 0 && aligned16(A2) && aligned16(B2)),
+                "spq_qgemm: bad second K segment");
+    SPQ_REQUIRE(ldd >= N && (!C || ldc >= N), "spq_qgemm: ldd/ldc < N");
+
+    const int sms = sm_count();
+    if (sms <= 0) {
+        set_error("spq_qgemm: no CUDA device");
+        return SPQ_ERR_CUDA;
+    }
+    // tile width: the widest BN that still gives every SM a tile; otherwise the one with most tiles
+    int bn = 256;
+    {
+        const long long mt = (M + BM - 1) / BM;
+        auto tiles = [&](int b) { return mt * ((N + b - 1) / b); };
+        if (N <= 64) bn = 64;
+        else if (N <= 128) bn = 128;
+        else if (tiles(256) >= sms) bn = 256;
+        else if (tiles(128) >= sms) bn = 128;
+        else bn = 64;
+    }
+    CUtensorMap tA, tB, tA2, tB2;
+    int rc;
+    if ((rc = make_tmap(&tA, A, M, K, lda, BM)) != SPQ_OK) return rc;
+    if ((rc = make_tmap(&tB, B, N, K, ldb, bn)) != SPQ_OK) return rc;
+    if (K2 > 0) {
+        if ((rc = make_tmap(&tA2, A2, M, K2, lda2, BM)) != SPQ_OK) return rc;
+        if ((rc = make_tmap(&tB2, B2, N, K2, ldb2, bn)) != SPQ_OK) return rc;
+    } else {
+        tA2 = tA;
+        tB2 = tB;
+    }
+    EpiParams ep;
+    ep.row_scale = row_scale; ep.col_scale = col_scale; ep.bias = bias; ep.C = C; ep.alpha_dev = nullptr;
+    ep.D = D; ep.ldc = ldc; ep.ldd = ldd; ep.d_stride_n = 1; ep.alpha = alpha; ep.clamp_abs = clamp_abs;
+    const int kb1 = static_cast<int>((K + BK - 1) / BK);
+    const int kb2 = static_cast<int>((K2 + BK - 1) / BK);
+    cudaStream_t st = as_stream(stream);
+    const int m = static_cast<int>(M), n = static_cast<int>(N);
+    if (d_is_half) {
+        if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+        if (bn == 128) return launch_nt<128, true>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+        return launch_nt<64, true>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+    }
+    if (bn == 256) return launch_nt<256, false>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+    if (bn == 128) return launch_nt<128, false>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+    return launch_nt<64, false>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+}
+
+extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq, int64_t Mred, int64_t I, int64_t J,
+                           float alpha, const float* alpha_dev, const float* i_scale, const float* j_scale, float* D,
+                           int64_t d_stride_i, int64_t d_stride_j, spq_stream_t stream) {
+    SPQ_REQUIRE(P && Q && D, "spq_gemm_tn: null operand");
+    SPQ_REQUIRE(Mred > 0 && I > 0 && J > 0 && Mred < (1ll << 31) && I < (1ll << 31) && J < (1ll << 31), "spq_gemm_tn: bad shape");
+    SPQ_REQUIRE((ldp % 8) == 0 && (ldq % 8) == 0 && ldp >= I && ldq >= J && aligned16(P) && aligned16(Q),
+                "spq_gemm_tn: leading dimensions must be multiples of 8 and operands 16-byte aligned");
+    SPQ_REQUIRE((d_stride_i == 1) != (d_stride_j == 1) || (I == 1 || J == 1), "spq_gemm_tn: D must be contiguous along i or j");
+    if (sm_count() <= 0) {
+        set_error("spq_gemm_tn: no CUDA device");
+        return SPQ_ERR_CUDA;
+    }
+    cudaStream_t st = as_stream(stream);
+    // D is dense [I, J] (or [J, I] when stored transposed): zero it, the CTAs accumulate into it
+    SPQ_CUDA_OK(cudaMemsetAsync(D, 0, static_cast<size_t>(I) * static_cast<size_t>(J) * sizeof(float), st));
+    CUtensorMap tP, tQ;
+    int rc;
+    if ((rc = make_tmap_mn(&tP, P, Mred, I, ldp)) != SPQ_OK) return rc;
+    if ((rc = make_tmap_mn(&tQ, Q, Mred, J, ldq)) != SPQ_OK) return rc;
+    TnEpi ep;
+    ep.i_scale = i_scale; ep.j_scale = j_scale; ep.alpha_dev = alpha_dev; ep.D = D;
+    ep.stride_i = d_stride_i; ep.stride_j = d_stride_j; ep.alpha = alpha;
+    const int kb_total = static_cast<int>((Mred + 63) / 64);
+    const int i = static_cast<int>(I), j = static_cast<int>(J);
+    if (J <= 64) return launch_tn<64>(tP, tQ, i, j, kb_total, ep, st);
+    if (J <= 128) return launch_tn<128>(tP, tQ, i, j, kb_total, ep, st);
+    return launch_tn<256>(tP, tQ, i, j, kb_total, ep, st);
+}

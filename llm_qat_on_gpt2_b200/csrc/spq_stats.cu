@@ -1,0 +1,298 @@
+// Calibration statistics: per-channel / per-tensor min-max reduction (HBM-bound, one read of x).
+//
+// Replaces LearnableFakeQuantize._collect_statistics_batch, _reduce_min_max and
+// finish_calibration of the reference (p1/quantization.py:104-139, 152-162, 174-209), which
+// issue one min and one max pass per reduced dimension plus abs/gt/any/clamp/log2 temporaries.
+// Here: one streaming pass (float4, L1::no_allocate) produces partial min/max (of x, or of |x|
+// in log mode) and the any(|x| > eps) flag; a second tiny kernel folds the partials, applies
+// log2 (after the reduction -- log2 is monotone, so min(log2|x|) == log2(min|x|) bit for bit)
+// and merges into the running statistics.  No host synchronisation.
+#include "spq_common.cuh"
+
+namespace spq {
+namespace stats {
+
+constexpr int TX = 32, TY = 8;            // block = 32 x 8 threads
+constexpr int COLS_PER_BLOCK_V4 = TX * 4; // 128 columns per block (float4 per thread)
+
+struct Ws {
+    int32_t* flags;   // [0] any(|x|>eps)
+    float* pmin;      // [chunks, C]
+    float* pmax;
+};
+
+static inline int col_chunks(int64_t rows, int64_t cols) {
+    const int64_t col_tiles = (cols + COLS_PER_BLOCK_V4 - 1) / COLS_PER_BLOCK_V4;
+    int64_t want = (static_cast<int64_t>(148) * 8 + col_tiles - 1) / col_tiles;   // ~8 CTAs per SM
+    const int64_t max_chunks = (rows + 4 * TY - 1) / (4 * TY);                     // >= 32 rows per chunk
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
+// Partial reduction over rows for a tile of columns.  VEC = 4: float4 loads (cols % 4 == 0 and x
+// 16-byte aligned); VEC = 1: scalar fallback.
+template <int VEC, bool LOG>
+__global__ void __launch_bounds__(TX* TY)
+colstats_partial_kernel(const float* __restrict__ x, long long rows, long long cols, float eps, long long rows_per_chunk,
+                        float* __restrict__ pmin, float* __restrict__ pmax, int32_t* __restrict__ flags) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long c0 = (static_cast<long long>(blockIdx.x) * TX + tx) * VEC;
+    const long long r_begin = static_cast<long long>(blockIdx.y) * rows_per_chunk;
+    long long r_end = r_begin + rows_per_chunk;
+    if (r_end > rows) r_end = rows;
+
+    float mn[VEC], mx[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+    unsigned nan_cols = 0;   // bit j: column c0 + j saw a NaN (fminf/fmaxf drop NaN; torch keeps it)
+    bool any = false;
+
+    if (c0 < cols) {
+        const float* p = x + c0;
+        long long r = r_begin + ty;
+        if constexpr (VEC == 4) {
+            // 4 independent 16-byte loads in flight per thread
+            for (; r + 3 * TY < r_end; r += 4 * TY) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(p + (r + u * TY) * cols);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a = LOG ? fabsf(e[j]) : e[j];
+                        nan_cols |= (a != a) ? (1u << j) : 0u;
+                        if (LOG) any |= (a > eps);
+                        mn[j] = fminf(mn[j], a);
+                        mx[j] = fmaxf(mx[j], a);
+                    }
+                }
+            }
+        }
+        for (; r < r_end; r += TY) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (c0 + j < cols) {
+                    float a = __ldg(p + r * cols + j);
+                    if (LOG) a = fabsf(a);
+                    nan_cols |= (a != a) ? (1u << j) : 0u;
+                    if (LOG) any |= (a > eps);
+                    mn[j] = fminf(mn[j], a);
+                    mx[j] = fmaxf(mx[j], a);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+        if (nan_cols & (1u << j)) { mn[j] = NAN; mx[j] = NAN; }
+    __shared__ float s_mn[TY][TX * VEC + 1];
+    __shared__ float s_mx[TY][TX * VEC + 1];
+    __shared__ int s_any;
+    if (tx == 0 && ty == 0) s_any = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { s_mn[ty][tx * VEC + j] = mn[j]; s_mx[ty][tx * VEC + j] = mx[j]; }
+    __syncthreads();
+    if (LOG && any) s_any = 1;
+    __syncthreads();
+    const int lin = ty * TX + tx;
+    for (int c = lin; c < TX * VEC; c += TX * TY) {
+        float a = s_mn[0][c], b = s_mx[0][c];
+#pragma unroll
+        for (int y = 1; y < TY; ++y) { a = nan_min(a, s_mn[y][c]); b = nan_max(b, s_mx[y][c]); }
+        const long long col = static_cast<long long>(blockIdx.x) * TX * VEC + c;
+        if (col < cols) {
+            pmin[static_cast<long long>(blockIdx.y) * cols + col] = a;
+            pmax[static_cast<long long>(blockIdx.y) * cols + col] = b;
+        }
+    }
+    if (LOG && lin == 0 && s_any) atomicOr(flags, 1);
+}
+
+// One warp per row (weights: channel_dim = 0).
+template <bool LOG>
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const float* __restrict__ x, long long rows, long long cols, float eps, float* __restrict__ pmin,
+                float* __restrict__ pmax, int32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* p = x + row * cols;
+    float mn = INFINITY, mx = -INFINITY;
+    bool seen_nan = false, any = false;
+    auto upd = [&](float a) {
+        if (LOG) a = fabsf(a);
+        seen_nan |= (a != a);
+        if (LOG) any |= (a > eps);
+        mn = fminf(mn, a);
+        mx = fmaxf(mx, a);
+    };
+    if ((cols & 3) == 0 && aligned16_dev(p)) {
+        for (long long c = lane * 4; c < cols; c += 128) {
+            const float4 v = ld_stream_f4(p + c);
+            upd(v.x); upd(v.y); upd(v.z); upd(v.w);
+        }
+    } else {
+        for (long long c = lane; c < cols; c += 32) upd(__ldg(p + c));
+    }
+    if (seen_nan) { mn = NAN; mx = NAN; }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    const unsigned anyw = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) {
+        pmin[row] = mn;
+        pmax[row] = mx;
+        if (LOG && anyw) atomicOr(flags, 1);
+    }
+}
+
+// Fold `chunks` partials per channel, apply the log transform, merge into the running statistics.
+// collapse != 0: per-tensor -- all channels fold into stat[0] (single block).
+template <bool LOG>
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax, long long C, int chunks, int collapse,
+                      float eps, int accumulate, const int32_t* __restrict__ flags, float* __restrict__ stat_min,
+                      float* __restrict__ stat_max, int32_t* __restrict__ state) {
+    const bool any = LOG ? (flags[0] != 0) : true;
+    const float log_eps = LOG ? log2_cr(eps) : 0.f;
+    auto emit = [&](long long idx, float a, float b) {
+        if (LOG) {
+            if (any) {
+                a = log2_cr(a < eps ? eps : a);      // torch.clamp(min=eps) keeps NaN
+                b = log2_cr(b < eps ? eps : b);
+            } else {
+                if (accumulate) return;              // nothing above eps: statistics unchanged
+                a = log_eps; b = log_eps;            // first batch: filled with log2(eps)
+            }
+        }
+        if (accumulate) {
+            a = nan_min(stat_min[idx], a);
+            b = nan_max(stat_max[idx], b);
+        }
+        stat_min[idx] = a;
+        stat_max[idx] = b;
+    };
+    if (!collapse) {
+        const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (c < C) {
+            float a = pmin[c], b = pmax[c];
+            for (int k = 1; k < chunks; ++k) {
+                a = nan_min(a, pmin[static_cast<long long>(k) * C + c]);
+                b = nan_max(b, pmax[static_cast<long long>(k) * C + c]);
+            }
+            emit(c, a, b);
+        }
+    } else {
+        float a = INFINITY, b = -INFINITY;
+        const long long total = C * chunks;
+        for (long long i = threadIdx.x; i < total; i += blockDim.x) { a = nan_min(a, pmin[i]); b = nan_max(b, pmax[i]); }
+        a = warp_min(a); b = warp_max(b);
+        __shared__ float sa[8], sb[8];
+        if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (blockDim.x >> 5); ++w) { a = nan_min(a, sa[w]); b = nan_max(b, sb[w]); }
+            emit(0, a, b);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && state && any) atomicOr(state, 1);
+}
+
+__global__ void finish_calibration_kernel(const float* __restrict__ rmin, const float* __restrict__ rmax, long long n, int qtype,
+                                          int symmetric, float levels, float eps, float* __restrict__ scale,
+                                          float* __restrict__ zp) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lo = rmin[i], hi = rmax[i];
+    if (qtype == SPQ_LOG) {                       // p1/quantization.py:110-116
+        zp[i] = lo;
+        scale[i] = __fsub_rn(hi, lo);
+    } else if (symmetric) {                       // :118-122
+        float a = nan_max(fabsf(lo), fabsf(hi));
+        a = (a < eps) ? eps : a;
+        scale[i] = __fdiv_rn(a, levels);
+        zp[i] = 0.f;
+    } else {                                      // :123-127
+        float r = __fsub_rn(hi, lo);
+        r = (r < eps) ? eps : r;
+        const float s = __fdiv_rn(r, levels);
+        scale[i] = s;
+        zp[i] = rintf(__fdiv_rn(-lo, s));
+    }
+}
+
+}  // namespace stats
+}  // namespace spq
+
+using namespace spq;
+using namespace spq::stats;
+
+extern "C" size_t spq_stats_workspace_bytes(int64_t rows, int64_t cols, int bcast) {
+    if (rows <= 0 || cols <= 0) return 256;
+    size_t n;
+    if (bcast == SPQ_PER_ROW) n = static_cast<size_t>(rows);
+    else n = static_cast<size_t>(col_chunks(rows, cols)) * static_cast<size_t>(cols);
+    return 256 + 2 * n * sizeof(float);
+}
+
+extern "C" int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int bcast, int log_mode, float eps,
+                                float* stat_min, float* stat_max, int accumulate, int32_t* state, void* workspace,
+                                size_t workspace_bytes, spq_stream_t stream) {
+    SPQ_REQUIRE(x && stat_min && stat_max && workspace, "spq_minmax_stats: null pointer");
+    SPQ_REQUIRE(rows > 0 && cols > 0, "spq_minmax_stats: empty tensor [%lld, %lld]", (long long)rows, (long long)cols);
+    SPQ_REQUIRE(bcast == SPQ_PER_TENSOR || bcast == SPQ_PER_ROW || bcast == SPQ_PER_COL, "spq_minmax_stats: bad bcast %d", bcast);
+    SPQ_REQUIRE(workspace_bytes >= spq_stats_workspace_bytes(rows, cols, bcast), "spq_minmax_stats: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    Ws ws;
+    ws.flags = reinterpret_cast<int32_t*>(workspace);
+    ws.pmin = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+    SPQ_CUDA_OK(cudaMemsetAsync(ws.flags, 0, 16, st));
+    long long C;
+    int chunks;
+    if (bcast == SPQ_PER_ROW) {
+        C = rows; chunks = 1;
+        ws.pmax = ws.pmin + C;
+        const int warps = 8;
+        const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+        if (log_mode) rowstats_kernel<true><<<grid, warps * 32, 0, st>>>(x, rows, cols, eps, ws.pmin, ws.pmax, ws.flags);
+        else rowstats_kernel<false><<<grid, warps * 32, 0, st>>>(x, rows, cols, eps, ws.pmin, ws.pmax, ws.flags);
+        SPQ_LAUNCH_OK();
+    } else {
+        C = cols; chunks = col_chunks(rows, cols);
+        ws.pmax = ws.pmin + static_cast<size_t>(chunks) * C;
+        const long long rpc = (rows + chunks - 1) / chunks;
+        const bool vec = ((cols & 3) == 0) && aligned16(x);
+        dim3 block(TX, TY);
+        if (vec) {
+            dim3 grid(static_cast<unsigned>((cols + COLS_PER_BLOCK_V4 - 1) / COLS_PER_BLOCK_V4), chunks);
+            if (log_mode) colstats_partial_kernel<4, true><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+            else colstats_partial_kernel<4, false><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+        } else {
+            dim3 grid(static_cast<unsigned>((cols + TX - 1) / TX), chunks);
+            if (log_mode) colstats_partial_kernel<1, true><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+            else colstats_partial_kernel<1, false><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+        }
+        SPQ_LAUNCH_OK();
+    }
+    const int collapse = (bcast == SPQ_PER_TENSOR) ? 1 : 0;
+    const unsigned fgrid = collapse ? 1u : static_cast<unsigned>((C + 255) / 256);
+    if (log_mode)
+        stats_finalize_kernel<true><<<fgrid, 256, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
+    else
+        stats_finalize_kernel<false><<<fgrid, 256, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_finish_calibration(const float* running_min, const float* running_max, int64_t n, int qtype, int symmetric,
+                                      int bits, float eps, float* scale, float* zero_point, spq_stream_t stream) {
+    SPQ_REQUIRE(running_min && running_max && scale && zero_point && n > 0, "spq_finish_calibration: bad arguments");
+    SPQ_REQUIRE(bits >= 1 && bits <= 32, "spq_finish_calibration: bits %d", bits);
+    const double levels = symmetric ? (static_cast<double>(1ull << (bits - 1)) - 1.0) : (static_cast<double>(1ull << bits) - 1.0);
+    finish_calibration_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        running_min, running_max, n, qtype, symmetric, static_cast<float>(levels), eps, scale, zero_point);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}

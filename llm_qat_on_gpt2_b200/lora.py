@@ -1,0 +1,547 @@
+"""LoRALayer and SPLinearWithLoRA on the B200 kernels -- drop-ins for the reference classes of the
+same names (part1_switchable_precision/lora.py:13-150; byte-identical copy in part5_squad).
+
+Same constructors, attributes, ModuleDict keys ('{bits}bit'), state_dict keys and exceptions.
+What changes is where the arithmetic runs:
+
+  reference forward (p1/lora.py:127-150)          this module
+  -------------------------------------------     ------------------------------------------------
+  q_in(x)            ~4 / ~25 eager kernels   ->   spq_quantize_act: one pass over x writes the fp16
+  lora reads x again                               code/dequant operand AND the row-scaled raw operand
+  q_w(W) every call                           ->   cached fp16 operand, rebuilt only when W or a
+  q_A(A), q_B(B) every call                        calibration changes (input scale folded in per K)
+  F.linear + 2 matmuls + mul + add            ->   spq_qgemm (tcgen05): base and LoRA up-projection in
+                                                   one TMEM accumulator, scale + bias in the epilogue
+  autograd of the above (STE)                 ->   spq_qgemm / spq_gemm_tn on fp16 gradient operands
+
+Numerics: operands are fp16 (integer codes are exact; dequantised values carry 2^-11 relative
+rounding), accumulation is fp32; every power-of-two pre-scale is exact.  Outputs agree with the
+fp32 reference to rel ~3e-4 (tolerance 1e-3, BASELINE.json).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .quantization import LearnableFakeQuantize, pow2_ceil
+from .quantization_methods import _view2d
+
+
+# ----------------------------------------------------------------------------------------------
+# small helpers (device-side plumbing on tiny tensors; never a host sync)
+# ----------------------------------------------------------------------------------------------
+
+def _dummy_params(device):
+    key = (device.type, device.index)
+    p = _dummy_params.cache.get(key)
+    if p is None:
+        p = (torch.ones(1, device=device), torch.zeros(1, device=device))
+        _dummy_params.cache[key] = p
+    return p
+
+
+_dummy_params.cache = {}
+
+
+def _to_f16_operand(x2d, row_mul=None, col_mul=None, mul=1.0, transposed=False):
+    """fp16(x * row_mul[:,None] * col_mul[None,:] * mul) through the quantise kernel's raw mode."""
+    one, zero = _dummy_params(x2d.device)
+    rows, cols = x2d.shape
+    out = torch.empty((cols, rows) if transposed else (rows, cols), dtype=torch.float16, device=x2d.device)
+    _lib.fake_quantize(x2d, one, zero, _lib.PER_TENSOR, _lib.MINMAX, 8, True, operand=out,
+                       operand_kind=_lib.OPERAND_RAW, row_mul=row_mul, col_mul=col_mul, mul=mul,
+                       operand_transposed=transposed)
+    return out
+
+
+def _quantizer_params(q: LearnableFakeQuantize, x_like: torch.Tensor):
+    """(scale, zero_point) flattened + broadcast mode of quantiser q over a tensor shaped like x_like."""
+    sc = q.scale.detach().float().contiguous()
+    _, bcast = _view2d(x_like, sc)
+    zp = q.zero_point.detach().float()
+    if zp.numel() != sc.numel():
+        zp = zp.expand_as(sc)
+    return sc.reshape(-1).contiguous(), zp.reshape(-1).contiguous(), bcast
+
+
+def _dequant(q: LearnableFakeQuantize, w: torch.Tensor) -> torch.Tensor:
+    sc, zp, bcast = _quantizer_params(q, w)
+    w2 = w.detach().float().contiguous()
+    x2d = w2.reshape(-1, w2.shape[-1]) if bcast != _lib.PER_ROW else w2.reshape(w2.shape[0], -1)
+    out = torch.empty_like(x2d)
+    _lib.fake_quantize(x2d, sc, zp, bcast, _lib.QTYPE[q.quantizer_type], q.num_bits, q.symmetric, dequant=out)
+    return out.view(w.shape)
+
+
+def _quantized_operand(q, w, row_mul=None, col_mul=None, mul=1.0, transposed=False):
+    """fp16(q(w) * row_mul * col_mul * mul) for a 2-D parameter w, straight from the quantise kernel."""
+    sc, zp, bcast = _quantizer_params(q, w)
+    w2 = w.detach().float().contiguous()
+    rows, cols = w2.shape
+    out = torch.empty((cols, rows) if transposed else (rows, cols), dtype=torch.float16, device=w.device)
+    _lib.fake_quantize(w2, sc, zp, bcast, _lib.QTYPE[q.quantizer_type], q.num_bits, q.symmetric, operand=out,
+                       operand_kind=_lib.OPERAND_DEQUANT, row_mul=row_mul, col_mul=col_mul, mul=mul,
+                       operand_transposed=transposed)
+    return out
+
+
+def _norm_pow2(absmax: torch.Tensor, target_log2: int = 8) -> torch.Tensor:
+    """Power of two p with absmax / p in (2^(target-1), 2^target]; p = 1 for all-zero rows."""
+    return torch.where(absmax > 0, pow2_ceil(absmax) * (2.0 ** -target_log2), torch.ones_like(absmax))
+
+
+def _rowscaled_f16(x2d: torch.Tensor):
+    """Row-scaled fp16 copy of a float32 matrix: returns (x16, row_scale) with x = x16 * row_scale."""
+    M, K = x2d.shape
+    x16 = torch.empty((M, K), dtype=torch.float16, device=x2d.device)
+    rs = torch.empty(M, dtype=torch.float32, device=x2d.device)
+    _lib.quantize_act(x2d, None, None, _lib.PER_TENSOR, -1, 8, True, _lib.OPERAND_RAW, None, 1.0, None, x16, rs)
+    return x16, rs
+
+
+def _as_2d_f32(x: torch.Tensor, last: int) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("SPLinearWithLoRA runs on the CUDA kernels only (no CPU fallback); "
+                           f"got a tensor on {x.device}")
+    x2 = x.reshape(-1, last)
+    if x2.dtype != torch.float32:
+        x2 = x2.float()
+    return x2.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# plain (unquantised) linear on the tcgen05 GEMM: 32-bit teacher path, calibration pass, LM head
+# ----------------------------------------------------------------------------------------------
+
+class _FpWeightCache:
+    """fp16 operands of an unquantised weight, keyed on the tensor's storage and version."""
+
+    def __init__(self):
+        self.key = None
+        self.fwd = None     # (W16 [N,K], pw [N])
+        self.bwd = None     # (WT16 [K,N], pk [K])
+
+    def get(self, w: torch.Tensor, transposed: bool):
+        key = (w.data_ptr(), w._version, tuple(w.shape))
+        if key != self.key:
+            self.key, self.fwd, self.bwd = key, None, None
+        w2 = w.detach()
+        if not transposed:
+            if self.fwd is None:
+                wf = w2.float().contiguous()
+                pw = _norm_pow2(wf.abs().amax(dim=1))
+                self.fwd = (_to_f16_operand(wf, row_mul=1.0 / pw), pw)
+            return self.fwd
+        if self.bwd is None:
+            wf = w2.float().contiguous()
+            pk = _norm_pow2(wf.abs().amax(dim=0))
+            self.bwd = (_to_f16_operand(wf, col_mul=1.0 / pk, transposed=True), pk)
+        return self.bwd
+
+
+class _LinearFpFn(torch.autograd.Function):
+    """y = x W^T + b with fp16 operands / fp32 accumulation on spq_qgemm."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache):
+        N, K = weight.shape
+        x2d = _as_2d_f32(x, K)
+        M = x2d.shape[0]
+        x16, rs = _rowscaled_f16(x2d)
+        w16, pw = cache.get(weight, transposed=False)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        _lib.qgemm(x16, w16, M, N, K, y, row_scale=rs, col_scale=pw,
+                   bias=None if bias is None else bias.detach().float().contiguous())
+        ctx.cache = cache
+        ctx.x_shape = x.shape
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x16, rs, weight)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x16, rs, weight = ctx.saved_tensors
+        N, K = weight.shape
+        g2d = _as_2d_f32(gy, N)
+        M = g2d.shape[0]
+        g16, eg = _rowscaled_f16(g2d)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt16, pk = ctx.cache.get(weight, transposed=True)
+            gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
+            _lib.qgemm(g16, wt16, M, K, N, gx, row_scale=eg, col_scale=pk)
+            gx = gx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            # dW[n,k] = sum_m dY[m,n] x[m,k]: the per-token scales sit inside the reduction, so they
+            # are folded into one operand: x2 = x16 * (rs*eg / (max rs * max eg))
+            gmax, xmax = eg.max(), rs.max()
+            fold = (rs / xmax) * (eg / gmax)
+            x2 = _to_f16_operand(x16.float(), row_mul=fold)
+            gw = torch.empty((N, K), dtype=torch.float32, device=gy.device)
+            _lib.gemm_tn(g16, x2, gw, alpha=1.0, alpha_dev=(gmax * xmax).reshape(1).contiguous())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2d.sum(dim=0)
+        return gx, gw, gb, None
+
+
+def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None):
+    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache())
+
+
+# ----------------------------------------------------------------------------------------------
+# LoRA adapter
+# ----------------------------------------------------------------------------------------------
+
+class LoRALayer(nn.Module):
+    def __init__(self, in_features, out_features, rank, alpha, bits, quantizer_type, eps=1e-5, per_channel=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.rank = rank
+        self.alpha = alpha
+        self.bits = bits
+
+        if bits >= 32 or rank <= 0:
+            # reference :23-29 -- a disabled adapter keeps [1,1] buffers so the state_dict keys exist
+            self.enabled = False
+            self.scaling = 0
+            self.register_buffer('lora_A', torch.zeros(1, 1))
+            self.register_buffer('lora_B', torch.zeros(1, 1))
+            self.quantize_A = None
+            self.quantize_B = None
+        else:
+            self.enabled = True
+            self.scaling = alpha / rank
+            self.lora_A = nn.Parameter(torch.zeros(in_features, rank))
+            self.lora_B = nn.Parameter(torch.zeros(rank, out_features))
+            nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_B)
+            self.quantize_A = LearnableFakeQuantize(num_bits=bits, quantizer_type=quantizer_type, channel_dim=1,
+                                                    eps=eps, per_channel=per_channel)
+            self.quantize_B = LearnableFakeQuantize(num_bits=bits, quantizer_type=quantizer_type, channel_dim=1,
+                                                    eps=eps, per_channel=per_channel)
+            # unused by the reference's forward too, but part of its state_dict (:42-43)
+            self.register_buffer('lora_A_quantized', torch.empty(in_features, rank))
+            self.register_buffer('lora_B_quantized', torch.empty(rank, out_features))
+
+    def forward(self, x):
+        """Stand-alone adapter output ((x q(A)) q(B)) * alpha/rank (reference :45-54).  Inside
+        SPLinearWithLoRA the fused kernels are used instead of this composition."""
+        if not self.enabled or self.scaling == 0:
+            batch_shape = x.shape[:-1]
+            return torch.zeros(*batch_shape, self.out_features, device=x.device, dtype=x.dtype)
+        a_q = self.quantize_A(self.lora_A)
+        b_q = self.quantize_B(self.lora_B)
+        t = linear_fp(x, a_q.t())
+        return linear_fp(t, b_q.t()) * self.scaling
+
+
+# ----------------------------------------------------------------------------------------------
+# the fused quantised linear
+# ----------------------------------------------------------------------------------------------
+
+def _act_config(qi: LearnableFakeQuantize, K: int):
+    """How the activation operand is formed, and the per-K factor the weight operand must absorb.
+
+    min-max: operand = integer code (exact in fp16 up to 11 bits), weights absorb scale[k].
+    log    : operand = dequantised value * 2^-e[k] with e from the calibrated log-range,
+             weights absorb 2^e[k]."""
+    sc = qi.scale.detach().float().reshape(-1).contiguous()
+    zp = qi.zero_point.detach().float().reshape(-1)
+    if zp.numel() != sc.numel():
+        zp = zp.expand_as(sc)
+    zp = zp.contiguous()
+    if sc.numel() not in (1, K):
+        raise NotImplementedError(f"input quantiser scale of {sc.numel()} elements for in_features={K}")
+    bcast = _lib.PER_TENSOR if sc.numel() == 1 else _lib.PER_COL
+    if qi.quantizer_type == 'minmax':
+        code_mul = 2.0 ** -max(0, qi.num_bits - 11)
+        kind, col_mul, mul = _lib.OPERAND_CODE, None, code_mul
+        absorb = (sc / code_mul).expand(K).contiguous()
+    else:
+        lmax = (zp + sc.clamp(min=0)).clamp(-100.0, 100.0)
+        amul = torch.exp2(8.0 - torch.ceil(lmax)).expand(K).contiguous()
+        kind, col_mul, mul = _lib.OPERAND_DEQUANT, amul, 1.0
+        absorb = (1.0 / amul).contiguous()
+    return dict(scale=sc, zp=zp, bcast=bcast, kind=kind, col_mul=col_mul, mul=mul, absorb=absorb,
+                qtype=_lib.QTYPE[qi.quantizer_type], bits=qi.num_bits, symmetric=qi.symmetric,
+                input_qtype=qi.quantizer_type)
+
+
+class _SPLinearFn(torch.autograd.Function):
+    """Fused forward / STE backward of SPLinearWithLoRA at a quantised precision."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits):
+        use_lora = lora_A is not None
+        base, lo = mod._operands_for(bits, use_lora)
+        act = base['act']
+        N, K = weight.shape
+        x2d = _as_2d_f32(x, K)
+        M = x2d.shape[0]
+        a_q = torch.empty((M, K), dtype=torch.float16, device=x.device)
+        a_raw = torch.empty((M, K), dtype=torch.float16, device=x.device) if use_lora else None
+        rs = torch.empty(M, dtype=torch.float32, device=x.device) if use_lora else None
+        _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
+                          act['kind'], act['col_mul'], act['mul'], a_q, a_raw, rs)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        t = None
+        if use_lora:
+            r = lo['rank']
+            t = torch.empty((M, r), dtype=torch.float32, device=x.device)
+            _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, row_scale=rs, col_scale=lo['pa'])
+            t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f)
+        else:
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f)
+        ctx.use_lora = use_lora
+        ctx.x_shape = x.shape
+        ctx.has_bias = bias is not None
+        ctx.dims = (M, N, K)
+        ctx.base, ctx.lo = base, lo
+        need = ctx.needs_input_grad
+        ctx.bw = mod._backward_operands_for(bits, use_lora) if any(need[:5]) else None
+        ctx.weight_qtype = mod.quantizers_weight[f'{bits}bit'].quantizer_type
+        ctx.save_for_backward(a_q if need[1] else None, a_raw, rs, t)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        a_q, a_raw, rs, t = ctx.saved_tensors
+        base, lo, bw = ctx.base, ctx.lo, ctx.bw
+        M, N, K = ctx.dims
+        g2d = _as_2d_f32(gy, N)
+        dev = gy.device
+        act = base['act']
+        g16, eg = _rowscaled_f16(g2d)                 # dY = g16 * eg[:,None]
+        gx = gw = gb = gA = gB = None
+        need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
+        clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
+        gmax = eg.max() if (need_w or (ctx.use_lora and (need_A or need_B))) else None
+
+        dt16 = None
+        if ctx.use_lora and (need_x or need_A or need_B):
+            lb = bw['lora']
+            r = lo['rank']
+            if need_x or need_A:
+                # dtn[m,r] = dt[m,r] / eg[m],  dt = scaling * dY q(B)^T
+                dtn = torch.empty((M, r), dtype=torch.float32, device=dev)
+                _lib.qgemm(g16, lb['B_rn_op'], M, r, N, dtn, col_scale=lb['pb'])
+                if need_x:
+                    dt16 = _to_f16_operand(dtn, mul=lb['dt_mul'])
+                if need_A:
+                    # dA[k,r] = sum_m x[m,k] dt[m,r]; token scales rs*eg folded into dt
+                    xmax = rs.max()
+                    fold = (rs / xmax) * (eg / gmax)
+                    dt2 = _to_f16_operand(dtn, row_mul=fold, mul=lb['dt_mul'])
+                    gA = torch.empty((K, r), dtype=torch.float32, device=dev)
+                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=(gmax * xmax).reshape(1).contiguous())
+                    if lo['qtype_A'] == 'log':
+                        gA = _lib.ste_backward(gA, _lib.LOG)
+            if need_B:
+                # dB[r,n] = scaling * sum_m t[m,r] dY[m,n]; token scales folded into t
+                t2 = _to_f16_operand(t, row_mul=(eg / gmax).contiguous(), col_mul=lo['tmul_vec'])
+                gB = torch.empty((r, N), dtype=torch.float32, device=dev)
+                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax.reshape(1).contiguous(),
+                             j_scale=lo['inv_tmul_vec'], transposed_out=True)
+                if lo['qtype_B'] == 'log':
+                    gB = _lib.ste_backward(gB, _lib.LOG)
+
+        if need_x:
+            gx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            if dt16 is not None and clamp_in == 0.0:
+                # identity STE: base and LoRA input-gradients share one accumulator
+                _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, A2=dt16, B2=bw['lora']['A_kr_op'], K2=lo['rank'],
+                           row_scale=eg, col_scale=bw['pk'])
+            elif dt16 is not None:
+                # log STE clamps only the gradient that flows through q_in(x)
+                gl = torch.empty((M, K), dtype=torch.float32, device=dev)
+                _lib.qgemm(dt16, bw['lora']['A_kr_op'], M, K, lo['rank'], gl, row_scale=eg, col_scale=bw['pk'])
+                _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in, C=gl)
+            else:
+                _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in)
+            gx = gx.view(ctx.x_shape)
+        if need_w:
+            # dW[n,k] = sum_m dY[m,n] q(x)[m,k];  q(x)[m,k] = a_q[m,k] * absorb[k]
+            gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax).expand(M).contiguous())
+            gw = torch.empty((N, K), dtype=torch.float32, device=dev)
+            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax.reshape(1).contiguous(), j_scale=act['absorb'])
+            if ctx.weight_qtype == 'log':
+                gw = _lib.ste_backward(gw, _lib.LOG)
+        if ctx.has_bias and need_b:
+            gb = g2d.sum(dim=0)
+        return gx, gw, gb, gA, gB, None, None
+
+
+class SPLinearWithLoRA(nn.Module):
+    def __init__(self, in_features, out_features, bit_widths, lora_rank_per_bit, lora_alpha_per_bit,
+                 quantizer_per_bit, eps=1e-5, per_channel=True):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.bit_widths = bit_widths
+        self.lora_rank_per_bit = lora_rank_per_bit
+        student_bits = [b for b in bit_widths if b < 32]
+        # reference :71 -- starts at the second-largest configured width
+        self.current_bits = sorted(bit_widths, reverse=True)[1]
+
+        self.linear = nn.Linear(in_features, out_features, bias=True)
+        self.quantizers_weight = nn.ModuleDict({
+            f'{bits}bit': LearnableFakeQuantize(num_bits=bits, quantizer_type=quantizer_per_bit[bits],
+                                                channel_dim=0, eps=eps, per_channel=per_channel)
+            for bits in student_bits})
+        self.quantizers_input = nn.ModuleDict({
+            f'{bits}bit': LearnableFakeQuantize(num_bits=bits, quantizer_type=quantizer_per_bit[bits],
+                                                channel_dim=-1, eps=eps, per_channel=per_channel, is_input=True)
+            for bits in student_bits})
+        self.lora_adapters = nn.ModuleDict({
+            f'{bits}bit': LoRALayer(in_features, out_features, rank=lora_rank_per_bit[bits],
+                                    alpha=lora_alpha_per_bit[bits], bits=bits,
+                                    quantizer_type=quantizer_per_bit[bits], eps=eps, per_channel=per_channel)
+            for bits in student_bits})
+
+        self.register_buffer('weight_quantized', torch.empty(out_features, in_features))
+        self.register_buffer('input_quantized', None)
+        self.calibration_mode = False
+
+        # operand caches (not module state): bits -> {'base': {...}, 'lora': {...}, 'bwd': {...}}.
+        # Entries are replaced, never mutated, so an autograd node can keep the ones it used.
+        self._op_cache = {}
+        self._fp_cache = _FpWeightCache()   # 32-bit path
+        self._calib_cache = {}              # bits -> (key, dequantised weight, _FpWeightCache)
+
+    # ---------------------------------------------------------------- host state (reference :105-125)
+    def set_precision(self, bits) -> int:
+        if bits >= 32:
+            self.current_bits = 32
+            return bits
+        self.current_bits = bits
+        bits_key = f'{bits}bit'
+        self.quantizers_weight[bits_key].set_num_bits(bits)
+        self.quantizers_input[bits_key].set_num_bits(bits)
+        lora = self.lora_adapters[bits_key]
+        if lora.quantize_A is not None:
+            lora.quantize_A.set_num_bits(bits)
+        if lora.quantize_B is not None:
+            lora.quantize_B.set_num_bits(bits)
+        return self.current_bits
+
+    def get_active_lora(self):
+        return self.lora_adapters[f'{self.current_bits}bit']
+
+    # ---------------------------------------------------------------- operand caches
+    def _operands_for(self, bits, want_lora):
+        key = f'{bits}bit'
+        qi, qw, lo = self.quantizers_input[key], self.quantizers_weight[key], self.lora_adapters[key]
+        W = self.linear.weight
+        ent = self._op_cache.setdefault(bits, {'base': None, 'lora': None, 'bwd': None})
+        base_key = (W.data_ptr(), W._version, qw.generation, qi.generation)
+        base = ent['base']
+        if base is None or base['key'] != base_key:
+            with torch.no_grad():
+                act = _act_config(qi, self.in_features)
+                wq = _dequant(qw, W)
+                pw = _norm_pow2((wq.abs() * act['absorb']).amax(dim=1))
+                B_op = _quantized_operand(qw, W, row_mul=1.0 / pw, col_mul=act['absorb'])
+            base = ent['base'] = dict(key=base_key, act=act, wq=wq, pw=pw, B_op=B_op)
+            ent['lora'] = None
+            ent['bwd'] = None
+        if not want_lora:
+            return base, None
+        lkey = (base_key, lo.lora_A.data_ptr(), lo.lora_A._version, lo.lora_B.data_ptr(), lo.lora_B._version,
+                lo.quantize_A.generation, lo.quantize_B.generation)
+        lora = ent['lora']
+        if lora is None or lora['key'] != lkey:
+            for qq in (lo.quantize_A, lo.quantize_B):
+                if not qq.ready():
+                    # same exception the reference raises from quantize_A/B (p1/lora.py:49-50)
+                    raise RuntimeError(
+                        f"Quantizer not calibrated. Please run calibration first for {qq.quantizer_type} quantizer.")
+            with torch.no_grad():
+                K, r = lo.lora_A.shape
+                aq = _dequant(lo.quantize_A, lo.lora_A)            # [K, r]
+                pa = _norm_pow2(aq.abs().amax(dim=0), 0)            # |A'| <= 1
+                A_op = _quantized_operand(lo.quantize_A, lo.lora_A, col_mul=1.0 / pa, transposed=True)   # [r, K]
+                # |t| <= sum_k xbound[k] |Aq[k,r]| for inputs inside the calibrated range: static pre-scale of t
+                xb = qi.abs_bound().detach().float().reshape(-1).expand(K)
+                tmax = (xb[:, None] * aq.abs()).sum(dim=0).max()
+                tmul = torch.where(tmax > 0, (2.0 ** 14) / pow2_ceil(tmax), torch.ones_like(tmax))
+                tmul_vec = tmul.expand(r).contiguous()
+                Bl_op = _quantized_operand(lo.quantize_B, lo.lora_B,
+                                           row_mul=(lo.scaling / tmul).expand(r).contiguous(),
+                                           col_mul=1.0 / base['pw'], transposed=True)                    # [N, r]
+            lora = ent['lora'] = dict(key=lkey, rank=r, A_op=A_op, pa=pa, Bl_op=Bl_op, tmul_vec=tmul_vec,
+                                      inv_tmul_vec=(1.0 / tmul_vec).contiguous(), scaling=float(lo.scaling),
+                                      qtype_A=lo.quantize_A.quantizer_type, qtype_B=lo.quantize_B.quantizer_type)
+            ent['bwd'] = None
+        return base, lora
+
+    def _backward_operands_for(self, bits, want_lora):
+        base, lora = self._operands_for(bits, want_lora)
+        ent = self._op_cache[bits]
+        bkey = (base['key'], None if lora is None else lora['key'])
+        bw = ent['bwd']
+        if bw is not None and bw['key'] == bkey:
+            return bw
+        key = f'{bits}bit'
+        qw, lo = self.quantizers_weight[key], self.lora_adapters[key]
+        W = self.linear.weight
+        with torch.no_grad():
+            pk = _norm_pow2(base['wq'].abs().amax(dim=0))                                   # [K]
+            bw = dict(key=bkey, pk=pk, WT_op=_quantized_operand(qw, W, col_mul=1.0 / pk, transposed=True), lora=None)
+            if lora is not None:
+                N = self.out_features
+                dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
+                bq = _dequant(lo.quantize_B, lo.lora_B)                                     # [r, N]
+                pb = _norm_pow2(bq.abs().amax(dim=1) * abs(lo.scaling), 0)                  # [r]
+                bw['lora'] = dict(
+                    pb=pb, dt_mul=dt_mul,
+                    B_rn_op=_quantized_operand(lo.quantize_B, lo.lora_B, row_mul=1.0 / pb, mul=lo.scaling),      # [r, N]
+                    A_kr_op=_quantized_operand(lo.quantize_A, lo.lora_A, row_mul=1.0 / pk, mul=1.0 / dt_mul))    # [K, r]
+        ent['bwd'] = bw
+        return bw
+
+    def _calibration_weight(self, bits, weight_quantizer):
+        """q_w(W) and its fp16 operand cache for the calibration pass (inputs not quantised yet)."""
+        W = self.linear.weight
+        key = (W.data_ptr(), W._version, weight_quantizer.generation, weight_quantizer.collecting_stats)
+        ent = self._calib_cache.get(bits)
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                ent = (key, weight_quantizer(W), _FpWeightCache())
+            self._calib_cache[bits] = ent
+        return ent[1], ent[2]
+
+    # ---------------------------------------------------------------- forward (reference :127-150)
+    def forward(self, x):
+        if self.current_bits >= 32:
+            return linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache)
+
+        bits_key = f'{self.current_bits}bit'
+        if bits_key not in self.quantizers_weight or bits_key not in self.quantizers_input:
+            raise KeyError(f"No weight quantizer for {bits_key}")
+        weight_quantizer = self.quantizers_weight[bits_key]
+        input_quantizer = self.quantizers_input[bits_key]
+        active_lora = self.lora_adapters[bits_key]
+
+        if input_quantizer.ready() and weight_quantizer.ready():
+            lora_on = active_lora.enabled and active_lora.scaling != 0 and not self.calibration_mode
+            return _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
+                                     active_lora.lora_A if lora_on else None,
+                                     active_lora.lora_B if lora_on else None, self, self.current_bits)
+
+        # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
+        # reference, module by module (this is the calibration pass; errors surface as upstream).
+        x_quantized = input_quantizer(x)                       # collecting: records stats, returns x
+        if torch.is_grad_enabled() and self.linear.weight.requires_grad and not weight_quantizer.collecting_stats:
+            weight_quantized, cache = weight_quantizer(self.linear.weight), None
+        else:
+            weight_quantized, cache = self._calibration_weight(self.current_bits, weight_quantizer)
+        base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache)
+        if self.calibration_mode:
+            return base_output
+        return base_output + active_lora(x)

@@ -1,0 +1,310 @@
+"""GPU parity tests of the CUDA kernels, called through the C ABI (ctypes), against the numpy
+oracle and the reference-generated golden fixtures.  Run on the B200 box: pytest -m gpu.
+
+Bars (BASELINE.json): min/max statistics, scale / zero-point and integer codes bit-exact;
+dequantised values, GEMM outputs and gradients within rel 1e-3 of float32 (tolerances are
+written next to each assertion and are usually much tighter).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import (QuantizerState, collect_statistics, finish_calibration, log_quantize, minmax_quantize,
+                    switchable_layernorm_backward, switchable_layernorm_forward)
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from llm_qat_on_gpt2_b200 import _lib
+    _lib.load_library()
+    return _lib
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=dtype)
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def heavy_tailed(shape, seed, zeros=True):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(shape) * np.exp(1.5 * rng.standard_normal(shape))
+    if shape[-1] >= 8:
+        x[..., 3] *= 20.0
+        x[..., -2] *= 0.01
+    if zeros:
+        flat = x.reshape(-1)
+        idx = rng.permutation(flat.size)[: max(2, flat.size // 50)]
+        flat[idx[: len(idx) // 2]] = 0.0
+        flat[idx[len(idx) // 2:]] = 3e-6
+    return x.astype(np.float32)
+
+
+def test_device_is_blackwell(lib):
+    sms, major, minor = lib.device_info()
+    assert major == 10, f"expected an sm_100 device, got sm_{major}{minor}"
+    assert sms >= 100
+
+
+# --------------------------------------------------------------------------- statistics
+@pytest.mark.parametrize("shape,channel_dim,per_channel", [
+    ((4, 96, 768), -1, True), ((2304, 768), 0, True), ((768, 64), 1, True), ((64, 2304), 1, True),
+    ((3, 50, 40), -1, False), ((37, 13), 0, True), ((5, 7, 33), -1, True), ((1, 1, 8), -1, True),
+])
+@pytest.mark.parametrize("qtype", ["minmax", "log"])
+def test_calibration_statistics_bit_exact(lib, shape, channel_dim, per_channel, qtype):
+    from llm_qat_on_gpt2_b200 import LearnableFakeQuantize
+    q = LearnableFakeQuantize(8, channel_dim=channel_dim, quantizer_type=qtype, per_channel=per_channel).cuda()
+    o = QuantizerState(8, channel_dim=channel_dim, quantizer_type=qtype, per_channel=per_channel)
+    q.start_calibration(); o.start_calibration()
+    for b in range(3):
+        x = heavy_tailed(shape, 10 + b)
+        if b == 1 and qtype == "log":
+            x[:] = 1e-7                      # a batch with nothing above eps leaves the statistics alone
+        xd = dev(x)
+        assert q(xd) is xd                   # collecting mode passes x through
+        collect_statistics(o, x)
+    q.finish_calibration(); finish_calibration(o)
+    assert q.calibrated and q.num_batches_collected == 3
+    for name in ("running_min", "running_max", "scale", "zero_point"):
+        got = getattr(q, name).cpu().numpy()
+        want = getattr(o, name)
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        assert np.array_equal(got, want), f"{name} not bit-exact (max |d| {np.abs(got - want).max()})"
+
+
+def test_statistics_nan_and_allzero(lib):
+    from llm_qat_on_gpt2_b200 import LearnableFakeQuantize
+    # NaN propagates per channel, like torch.min/max
+    x = heavy_tailed((64, 40), 3, zeros=False)
+    x[5, 7] = np.nan
+    q = LearnableFakeQuantize(8, channel_dim=-1, quantizer_type="minmax").cuda()
+    q.start_calibration(); q(dev(x)); q.finish_calibration()
+    rmin = q.running_min.cpu().numpy().reshape(-1)
+    assert np.isnan(rmin[7]) and np.isfinite(np.delete(rmin, 7)).all()
+    # all-zero tensor through a log quantiser: the reference's default-shape quirk
+    g = np.load(os.path.join(GOLDEN, "quant_log_allzero.npz"))
+    q = LearnableFakeQuantize(8, channel_dim=1, quantizer_type="log").cuda()
+    q.start_calibration(); q(dev(g["x"])); q.finish_calibration()
+    for name in ("running_min", "running_max", "scale", "zero_point"):
+        got = getattr(q, name).cpu().numpy()
+        assert got.shape == g[name].shape and np.array_equal(got, g[name]), name
+    assert np.array_equal(q(dev(g["x"])).cpu().numpy(), g["out"])
+    with pytest.raises(RuntimeError):
+        LearnableFakeQuantize(8).cuda()(dev(x))          # uncalibrated
+    with pytest.raises(RuntimeError):
+        LearnableFakeQuantize(8)(torch.zeros(4, 4))      # CPU tensor: no fallback
+
+
+# --------------------------------------------------------------------------- quantise
+QUANT_CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "quant_*.npz"))
+                     if "allzero" not in p)
+
+
+@pytest.mark.parametrize("name", QUANT_CASES)
+def test_quantize_against_golden(lib, name):
+    """Reference-generated vectors: calibrate on the GPU, then quantise with the reference's own
+    calibrated parameters; codes must match the reference bit for bit."""
+    from llm_qat_on_gpt2_b200 import LearnableFakeQuantize, quantize_codes
+    g = np.load(os.path.join(GOLDEN, f"quant_{name}.npz"))
+    bits, cd, sym, pc, is_in, qt = [int(v) for v in g["meta"]]
+    qtype = "minmax" if qt == 0 else "log"
+    q = LearnableFakeQuantize(bits, channel_dim=None if cd == -99 else cd, quantizer_type=qtype,
+                              symmetric=bool(sym), per_channel=bool(pc), is_input=bool(is_in)).cuda()
+    q.start_calibration()
+    for xb in g["x_calib"]:
+        q(dev(xb))
+    q.finish_calibration()
+    for key in ("running_min", "running_max", "scale", "zero_point"):
+        got = getattr(q, key).cpu().numpy()
+        assert got.shape == g[key].shape, key
+        if qtype == "minmax":
+            assert np.array_equal(got, g[key]), key
+        else:   # torch-CPU's SLEEF log2 is 1 ulp off the correctly rounded value on 0.013 % of inputs
+            d = np.abs(got.view(np.int32).astype(np.int64) - g[key].view(np.int32).astype(np.int64))
+            assert d.max() <= (4 if key == "scale" else 1), (key, d.max())
+    out, codes, sign = quantize_codes(dev(g["x_test"]), dev(g["scale"]), dev(g["zero_point"]), bits, bool(sym), qtype)
+    assert np.array_equal(codes.cpu().numpy(), g["codes"]), f"{(codes.cpu().numpy() != g['codes']).sum()} code mismatches"
+    out = out.cpu().numpy()
+    if qtype == "minmax":
+        assert np.array_equal(out, g["out"])
+    else:
+        assert np.array_equal(out == 0, g["out"] == 0)
+        nz = g["out"] != 0
+        assert np.max(np.abs(out[nz] - g["out"][nz]) / np.abs(g["out"][nz])) <= 4e-6
+        assert np.array_equal(sign.cpu().numpy(), np.sign(g["out"]).astype(np.int8))
+
+
+@pytest.mark.parametrize("qtype,bits,symmetric", [("minmax", 4, True), ("minmax", 8, True), ("minmax", 8, False),
+                                                  ("minmax", 3, True), ("log", 8, True), ("log", 4, True),
+                                                  ("log", 8, False), ("log", 11, True)])
+@pytest.mark.parametrize("layout", ["per_col", "per_row", "per_tensor"])
+def test_quantize_codes_bit_exact_large(lib, qtype, bits, symmetric, layout):
+    """4 Mi elements per case against the oracle: every code identical."""
+    from llm_qat_on_gpt2_b200 import quantize_codes
+    rows, cols = 4096, 1024
+    x = heavy_tailed((rows, cols), 100 + bits)
+    cd, pc = {"per_col": (-1, True), "per_row": (0, True), "per_tensor": (0, False)}[layout]
+    o = QuantizerState(bits, channel_dim=cd, quantizer_type=qtype, symmetric=symmetric, per_channel=pc)
+    o.start_calibration(); collect_statistics(o, x[: rows // 2]); finish_calibration(o)   # half: the rest clips
+    if layout == "per_row":
+        o.scale = np.resize(o.scale, (rows, 1)).astype(np.float32); o.zero_point = np.resize(o.zero_point, (rows, 1)).astype(np.float32)
+    out, codes, sign = quantize_codes(dev(x), dev(o.scale), dev(o.zero_point), bits, symmetric, qtype)
+    if qtype == "minmax":
+        ref_out, ref_codes = minmax_quantize(x, o.scale, o.zero_point, bits, symmetric)
+        assert np.array_equal(codes.cpu().numpy(), ref_codes)
+        assert np.array_equal(out.cpu().numpy(), ref_out)
+    else:
+        ref_out, ref_level, ref_sign, ref_zero = log_quantize(x, o.zero_point, o.scale, bits, symmetric)
+        got = codes.cpu().numpy()
+        assert np.array_equal(got, ref_level), f"{(got != ref_level).sum()} level mismatches of {got.size}"
+        assert np.array_equal(sign.cpu().numpy() == 0, ref_zero | (x == 0))
+        o_ = out.cpu().numpy(); nz = ref_out != 0
+        assert np.max(np.abs(o_[nz] - ref_out[nz]) / np.abs(ref_out[nz])) <= 4e-6
+
+
+def test_quantize_act_operands(lib):
+    """Fused activation kernel: code operand exact, raw operand = x up to fp16 rounding."""
+    M, K = 777, 768
+    x = heavy_tailed((M, K), 5)
+    for qtype, bits in (("minmax", 4), ("minmax", 8), ("log", 8)):
+        o = QuantizerState(bits, channel_dim=-1, quantizer_type=qtype, is_input=True)
+        o.start_calibration(); collect_statistics(o, x); finish_calibration(o)
+        a_q = torch.empty((M, K), dtype=torch.float16, device="cuda")
+        a_raw = torch.empty((M, K), dtype=torch.float16, device="cuda")
+        rs = torch.empty(M, dtype=torch.float32, device="cuda")
+        lib.quantize_act(dev(x), dev(o.scale.reshape(-1)), dev(o.zero_point.reshape(-1)), lib.PER_COL,
+                         lib.QTYPE[qtype], bits, True, lib.OPERAND_CODE, None, 1.0, a_q, a_raw, rs)
+        if qtype == "minmax":
+            _, codes = minmax_quantize(x, o.scale.reshape(1, -1), o.zero_point.reshape(1, -1), bits, True)
+        else:
+            _, codes, _, _ = log_quantize(x, o.zero_point.reshape(1, -1), o.scale.reshape(1, -1), bits, True)
+        assert np.array_equal(a_q.float().cpu().numpy(), codes.astype(np.float32))
+        back = a_raw.float().cpu().numpy() * rs.cpu().numpy()[:, None]
+        amax = np.abs(x).max(axis=1, keepdims=True)
+        assert np.max(np.abs(back - x) / amax) <= 2.0 ** -10
+        r = rs.cpu().numpy()
+        assert np.array_equal(np.log2(r), np.round(np.log2(r)))          # powers of two
+
+
+# --------------------------------------------------------------------------- GEMM
+def _ref_gemm(A, B, A2=None, B2=None):
+    y = A.double() @ B.double().t()
+    if A2 is not None:
+        y = y + A2.double() @ B2.double().t()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 64, 64), (256, 512, 192), (300, 200, 72), (1, 8, 8),
+                                   (2048, 2304, 768), (2048, 768, 3072), (4096, 4800, 1600), (129, 257, 3080)])
+def test_qgemm_matches_fp64(lib, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda")).half()
+    B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    lib.qgemm(A, B, M, N, K, out)
+    assert lib.debug_status() == 0, "GEMM pipeline watchdog fired"
+    ref = _ref_gemm(A, B)
+    err = (out.double() - ref).norm() / ref.norm()
+    assert err <= 2e-6, f"rel err {err:.3e}"
+
+
+def test_qgemm_epilogue_and_second_segment(lib):
+    torch.manual_seed(1)
+    M, N, K, K2 = 515, 776, 320, 64
+    A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    A2 = torch.randn(M, K2, device="cuda").half(); B2 = (torch.randn(N, K2, device="cuda") * 0.1).half()
+    rs = torch.rand(M, device="cuda") + 0.5; cs = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda"); C = torch.randn(M, N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    lib.qgemm(A, B, M, N, K, out, A2=A2, B2=B2, K2=K2, alpha=0.5, row_scale=rs, col_scale=cs, bias=bias, clamp_abs=3.0, C=C)
+    ref = (_ref_gemm(A, B, A2, B2) * 0.5 * rs.double()[:, None] * cs.double()[None, :]).clamp(-3.0, 3.0) + bias.double() + C.double()
+    assert ((out.double() - ref).norm() / ref.norm()) <= 2e-6
+    # fp16 output, K2 = 16 (CPT rank), strided operands
+    K2 = 16
+    A2 = torch.randn(M, 32, device="cuda").half()[:, :K2]; B2 = (torch.randn(N, 32, device="cuda") * 0.1).half()[:, :K2]
+    outh = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    lib.qgemm(A, B, M, N, K, outh, A2=A2, B2=B2, K2=K2)
+    ref = _ref_gemm(A, B, A2, B2)
+    assert ((outh.double() - ref).norm() / ref.norm()) <= 1e-3     # fp16 storage rounding
+    assert lib.debug_status() == 0
+
+
+@pytest.mark.parametrize("Mred,I,J,transposed", [(64, 128, 64, False), (1000, 768, 64, False), (4096, 2304, 64, True),
+                                                 (333, 200, 130, False), (2048, 768, 768, False)])
+def test_gemm_tn_matches_fp64(lib, Mred, I, J, transposed):
+    torch.manual_seed(Mred + I)
+    P = torch.randn(Mred, I, device="cuda").half(); Q = (torch.randn(Mred, J, device="cuda") * 0.1).half()
+    isc = torch.rand(I, device="cuda") + 0.5; jsc = torch.rand(J, device="cuda") + 0.5
+    adev = torch.tensor([0.25], device="cuda")
+    out = torch.empty((J, I) if transposed else (I, J), device="cuda")
+    lib.gemm_tn(P, Q, out, alpha=2.0, alpha_dev=adev, i_scale=isc, j_scale=jsc, transposed_out=transposed)
+    assert lib.debug_status() == 0
+    ref = (P.double().t() @ Q.double()) * 0.5 * isc.double()[:, None] * jsc.double()[None, :]
+    if transposed:
+        ref = ref.t()
+    assert ((out.double() - ref).norm() / ref.norm()) <= 5e-6
+
+
+# --------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,C", [(51, 96), (4096, 768), (300, 1024), (64, 1600), (7, 3072)])
+def test_layernorm_against_oracle(lib, rows, C):
+    from llm_qat_on_gpt2_b200 import SwitchableLayerNorm
+    rng = np.random.default_rng(C)
+    x = heavy_tailed((rows, C), 1, zeros=False)
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32); b = (0.2 * rng.standard_normal(C)).astype(np.float32)
+    gy = rng.standard_normal((rows, C)).astype(np.float32)
+    ln = SwitchableLayerNorm(C, precision_levels=[4, 8, 32]).cuda()
+    ln.set_precision(8)
+    with torch.no_grad():
+        ln.weights["8"].copy_(dev(w)); ln.biases["8"].copy_(dev(b))
+    xd = dev(x).requires_grad_(True)
+    y = ln(xd)
+    y.backward(dev(gy))
+    y_ref, mean, rstd = switchable_layernorm_forward(x, w, b, 1e-5)
+    dx, dw, db = switchable_layernorm_backward(gy, x, w, mean, rstd)
+    assert rel_fro(y.detach().cpu().numpy(), y_ref) <= 2e-6
+    assert rel_fro(xd.grad.cpu().numpy(), dx) <= 1e-5
+    assert rel_fro(ln.weights["8"].grad.cpu().numpy(), dw) <= 1e-5
+    assert rel_fro(ln.biases["8"].grad.cpu().numpy(), db) <= 1e-5
+    assert ln.weights["4"].grad is None
+    with pytest.raises(ValueError):
+        ln.set_precision(5)
+
+
+def test_layernorm_golden(lib):
+    from llm_qat_on_gpt2_b200 import SwitchableLayerNorm
+    g = np.load(os.path.join(GOLDEN, "layernorm.npz"))
+    ln = SwitchableLayerNorm(96, precision_levels=[4, 8, 32]).cuda()
+    for p in (4, 8, 32):
+        with torch.no_grad():
+            ln.weights[str(p)].copy_(dev(g[f"w{p}"])); ln.biases[str(p)].copy_(dev(g[f"b{p}"]))
+    for p in (4, 8, 32):
+        ln.set_precision(p); ln.zero_grad()
+        x = dev(g["x"]).requires_grad_(True)
+        y = ln(x); y.backward(dev(g["grad_y"]))
+        assert rel_fro(y.detach().cpu().numpy(), g[f"y{p}"]) <= 2e-6
+        assert rel_fro(x.grad.cpu().numpy(), g[f"gx{p}"]) <= 1e-5
+        assert rel_fro(ln.weights[str(p)].grad.cpu().numpy(), g[f"gw{p}"]) <= 1e-5
+        assert rel_fro(ln.biases[str(p)].grad.cpu().numpy(), g[f"gb{p}"]) <= 1e-5
+
+
+def test_ste_backward(lib):
+    from llm_qat_on_gpt2_b200 import apply_log_quantization, apply_minmax_quantization
+    x = dev(heavy_tailed((33, 40), 2)).requires_grad_(True)
+    g = torch.randn(33, 40, device="cuda") * 8
+    s = torch.full((1, 40), 0.1, device="cuda"); z = torch.zeros(1, 40, device="cuda")
+    apply_minmax_quantization(x, s, z, 4, True).backward(g)
+    assert torch.equal(x.grad, g)
+    x.grad = None
+    apply_log_quantization(x, torch.full((1, 40), -10.0, device="cuda"), torch.full((1, 40), 15.0, device="cuda"), 8, True).backward(g)
+    assert torch.equal(x.grad, g.clamp(-10, 10))
