@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the switchable-precision fake-quant linear path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): GPT-2 small SPLMHeadModel, random-init weights, synthetic
+tokens, 8-bit log quantisation, per-GPU batch 32 x seq 1024.  One step = the calibration pass of
+the 48 input quantisers (start_calibration -> forward in collecting mode with LoRA off ->
+[MIN/MAX all-reduce across ranks] -> finish_calibration) followed by one quantised forward with
+the LoRA branch on and the next-token cross-entropy.  Tokens are counted once per step.
+
+Prints ONE JSON line (rank 0).  `value` = tokens/s with the token ids resident in HBM; `e2e` =
+the same through the public module API with the ids in pinned host memory and the loss read back
+to the host every step.  `--impl reference` times the CPU oracle (numpy restatement of the
+reference's PyTorch path, oracle/) on a bounded sample of the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GPT-2 SP tokens/s at 8-bit (calibration pass + quantised forward)"
+UNIT = "tokens/s"
+BITS = 8
+MODEL = dict(vocab_size=50257, n_positions=1024, n_embd=768, n_layer=12, n_head=12, layer_norm_epsilon=1e-5)
+BIT_WIDTHS = [4, 8, 32]
+QUANTIZER_PER_BIT = {4: "minmax", 8: "log", 32: None}          # p1/config_sp.py:14-30
+LORA_RANK = {4: 64, 8: 64, 32: 0}                              # p1/config_sp.py:36-37
+LORA_ALPHA = {4: 64, 8: 64, 32: 0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--seq", type=int, default=1024)
+    ap.add_argument("--cpu-sample-batch", type=int, default=1, help="sequences in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the numpy oracle on a bounded sample
+# ------------------------------------------------------------------------------------------
+
+def oracle_cfg():
+    return dict(n_layer=MODEL["n_layer"], n_head=MODEL["n_head"], n_embd=MODEL["n_embd"],
+                layer_norm_epsilon=MODEL["layer_norm_epsilon"], bit_widths=BIT_WIDTHS,
+                quantizer_per_bit=QUANTIZER_PER_BIT, lora_rank_per_bit=LORA_RANK, lora_alpha_per_bit=LORA_ALPHA,
+                per_channel=True)
+
+
+class CpuWorkload:
+    """Same step as the GPU arm, restated on the CPU oracle."""
+
+    def __init__(self, sample_batch, seq):
+        import numpy as np
+        from oracle.model_oracle import SPModelOracle, random_state_dict
+        self.np = np
+        cfg = oracle_cfg()
+        self.model = SPModelOracle(cfg, random_state_dict(cfg, MODEL["vocab_size"], MODEL["n_positions"], seed=0))
+        self.model.set_precision(BITS)
+        self.model.calibrate_weights(BITS)
+        self.model.calibrate_lora(BITS)
+        self.rng = np.random.default_rng(1)
+        self.B, self.T = sample_batch, seq
+
+    def step(self):
+        from oracle.model_oracle import cross_entropy_shifted
+        ids = self.rng.integers(0, MODEL["vocab_size"], (self.B, self.T))
+        self.model.calibrate_inputs(BITS, [ids])
+        logits = self.model.forward(ids)
+        return cross_entropy_shifted(logits, ids)
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_baseline(sample_batch, seq, steps=1, warmup=0):
+    w = CpuWorkload(sample_batch, seq)
+    for _ in range(warmup):
+        w.step()
+    t0 = time.perf_counter()
+    loss = None
+    for _ in range(steps):
+        loss = w.step()
+    dt = time.perf_counter() - t0
+    return {"value": sample_batch * seq * steps / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+            "sample": f"{steps} step(s) of calibration pass + forward on {sample_batch} x {seq} tokens "
+                      f"(numpy oracle, BLAS threads = host cores), {dt:.1f} s"}, dt / max(steps, 1), loss
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, sec_per_step, _ = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": base["sample"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"GPT-2 small (124M) SPLMHeadModel, 8-bit log per-channel: calibration pass + quantised forward + CE, "
+            f"batch {args.batch} x seq {args.seq} per GPU, LoRA rank 64, random-init weights")
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from transformers import GPT2Config
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel, _lib
+    from llm_qat_on_gpt2_b200 import dp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path for the product)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load_library()
+
+    cfg = GPT2Config(**MODEL, embd_pdrop=0.0)
+    cfg.bit_widths = BIT_WIDTHS
+    cfg.lora_rank_per_bit = LORA_RANK
+    cfg.lora_alpha_per_bit = LORA_ALPHA
+    cfg.quantizer_per_bit = QUANTIZER_PER_BIT
+    cfg.per_channel_quantization = True
+    cfg.attention_dtype = "fp16"       # stock torch SDPA (flash) between the hot-path linears
+    torch.manual_seed(0)               # identical replicas on every rank
+    model = SPLMHeadModel(cfg).to(dev).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("lora_B"):
+                p.normal_(0, 0.02)     # non-trivial LoRA branch
+    model.set_precision(BITS)
+    key = f"{BITS}bit"
+    linears = [m for m in model.modules() if m.__class__.__name__ == "SPLinearWithLoRA"]
+    # static calibration (untimed): weight and LoRA quantisers, as p1/train_sp.py:58-83, 125-163
+    with torch.no_grad():
+        for m in linears:
+            qw = m.quantizers_weight[key]
+            qw.start_calibration(); qw(m.linear.weight.data); qw.finish_calibration()
+            lo = m.lora_adapters[key]
+            for qq, w in ((lo.quantize_A, lo.lora_A), (lo.quantize_B, lo.lora_B)):
+                qq.start_calibration(); qq(w.data); qq.finish_calibration()
+    input_q = [m.quantizers_input[key] for m in linears]
+    group = dist.group.WORLD if world > 1 else None
+
+    B, T = args.batch, args.seq
+    gen = torch.Generator().manual_seed(1234 + rank)
+    n_batches = args.steps + args.warmup
+    host_ids = [torch.randint(0, MODEL["vocab_size"], (B, T), generator=gen).pin_memory() for _ in range(n_batches)]
+    dev_ids = [h.to(dev) for h in host_ids]
+
+    def step(ids):
+        with torch.no_grad():
+            for q in input_q:
+                q.start_calibration()
+            model.disable_lora_for_calibration()
+            model.transformer(ids)                       # statistics only need the transformer body
+            model.enable_lora_after_calibration()
+            dp.finish_calibration_many(input_q, group)   # one MIN/MAX exchange + one flag read
+            out = model(ids, labels=ids)
+        return out["loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- instrument the dominant kernel (spq_qgemm) with CUDA events on the launching stream
+    gemm_events = []
+    orig_qgemm = _lib.qgemm
+
+    def timed_qgemm(A, Bm, M, N, K, out, A2=None, B2=None, K2=0, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_qgemm(A, Bm, M, N, K, out, A2=A2, B2=B2, K2=K2, **kw)
+        e1.record()
+        gemm_events.append((e0, e1, 2.0 * M * N * (K + K2)))
+        return r
+
+    def patch(fn):
+        import llm_qat_on_gpt2_b200.lora as lora_mod
+        lora_mod._lib.qgemm = fn
+
+    for i in range(args.warmup):
+        step(dev_ids[i])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ("value")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    patch(timed_qgemm)
+    launches0 = _lib.launch_count()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        loss = step(dev_ids[args.warmup + i])
+    t1.record()
+    barrier()
+    ms_value = t0.elapsed_time(t1)
+    launches = _lib.launch_count() - launches0
+    patch(orig_qgemm)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    n_gemm = len(gemm_events)
+
+    # ---- timed region 2: end to end through the module API, ids from pinned host memory, loss to host
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        ids = host_ids[args.warmup + i].to(dev, non_blocking=True)
+        loss_host = float(step(ids).item())
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms_value, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_value, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        tokens = B * T * world * args.steps
+        value = tokens / (ms_value / 1e3)
+        e2e = tokens / (ms_e2e / 1e3)
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        peak = peaks["tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands (exact integer codes / dequantised values), f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "per_gpu_batch": B, "seq_len": T, "bits": BITS,
+                       "parallelism": f"dp{world} (replicas, batch-sharded; MIN/MAX all-reduce of calibration statistics)",
+                       "l2": "per-step working set (~10 GB of activations + 6.6 GB of logits) >> 126 MB L2; fresh token ids every step",
+                       "attention": "torch SDPA fp16 (outside the hot path)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * T * 8, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "loss": loss_host},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "spq::gemm::qgemm_nt_kernel (all launches in the timed region)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                         "peak_source": peaks["source"] + ", bf16 dense sustained",
+                         "launches": n_gemm, "share_of_step": gemm_ms / ms_value if ms_value else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _, _ = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=1, warmup=0)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
+constexpr int STG_LD = 36;      // floats per staged row: 32 + 4 pad (keeps 16 B alignment, conflict-free v4 access)
 
 __device__ int g_abort = 0;    // watchdog: set when a pipeline wait timed out
 
@@ -149,8 +150,9 @@ struct SmemLayout {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
     static constexpr int EPI_BYTES = 2 * BN * 4;      // col_scale + bias of the tile
+    static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;   // per-epilogue-warp 32 x 32 fp32 transpose buffer (padded rows)
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -165,7 +167,8 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     float* epi_cs = reinterpret_cast<float*>(smem + L::STAGES * L::STAGE_BYTES);
     float* epi_bias = epi_cs + BN;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES + L::EPI_BYTES);
+    float* stg_all = epi_bias + BN;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES + L::EPI_BYTES + L::STG_BYTES);
     uint64_t* empty_bar = full_bar + L::STAGES;
     uint64_t* tmem_full = empty_bar + L::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -287,63 +290,72 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool row_ok = row < M;
             const float rs = alpha * ((ep.row_scale && row_ok) ? __ldg(ep.row_scale + row) : 1.0f);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            float* stg = stg_all + (warp - 2) * 32 * STG_LD;       // this warp's transpose buffer
+            const int rbase = m0 + quad * 32;                      // first global row of this warp's 32 x BN strip
+            const bool d_vec = OUT_HALF ? (((ep.ldd & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.D) & 15u) == 0))
+                                        : (((ep.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.D) & 15u) == 0));
+            const bool c_vec = ep.C && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
                 tmem_ld_wait();
                 const int nc = n0 + c * 32;
-                if (row_ok && nc < N) {
-                    float o[32];
+                if (nc >= N) continue;                              // warp-uniform
+                // TMEM gives each lane one output ROW (32 consecutive columns).  Writing rows straight to
+                // global memory makes every store instruction touch 32 cache lines; instead the 32 x 32
+                // block is transposed through padded shared memory and written out coalesced.
+                float* srow = stg + lane * STG_LD;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]) * (rs * epi_cs[c * 32 + j]);
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float x = __uint_as_float(v[j + u]) * (rs * epi_cs[c * 32 + j + u]);
                         if (ep.clamp_abs > 0.f) x = fminf(fmaxf(x, -ep.clamp_abs), ep.clamp_abs);
-                        o[j] = x + epi_bias[c * 32 + j];
+                        op[u] = x + epi_bias[c * 32 + j + u];
                     }
-                    const bool full = (nc + 32 <= N);
-                    if (ep.C) {
-                        const float* crow = ep.C + static_cast<long long>(row) * ep.ldc + nc;
-                        if (full && ((ep.ldc & 3) == 0)) {
+                    *reinterpret_cast<float4*>(srow + j) = o;
+                }
+                __syncwarp();
+                const bool full = (nc + 32 <= N);
+                if (full && d_vec && (!ep.C || c_vec)) {
+                    // 8 lanes cover one 128 B row segment; one instruction writes 4 rows
+                    const int rsub = lane >> 3, cq = (lane & 7) * 4;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 cv = *reinterpret_cast<const float4*>(crow + j);
-                                o[j] += cv.x; o[j + 1] += cv.y; o[j + 2] += cv.z; o[j + 3] += cv.w;
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = i * 4 + rsub;
+                        const long long gr = rbase + rl;
+                        if (gr < M) {
+                            float4 o = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cq);
+                            if (ep.C) {
+                                const float4 cv = *reinterpret_cast<const float4*>(ep.C + gr * ep.ldc + nc + cq);
+                                o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (nc + j < N) o[j] += crow[j];
+                            if constexpr (OUT_HALF) {
+                                *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(ep.D) + gr * ep.ldd + nc + cq) =
+                                    make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                            } else {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.D) + gr * ep.ldd + nc + cq) = o;
+                            }
                         }
                     }
-                    if constexpr (OUT_HALF) {
-                        unsigned short* drow = reinterpret_cast<unsigned short*>(ep.D) + static_cast<long long>(row) * ep.ldd + nc;
-                        if (full && ((ep.ldd & 7) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint4 pk;
-                                pk.x = pack_h2(o[j], o[j + 1]); pk.y = pack_h2(o[j + 2], o[j + 3]);
-                                pk.z = pack_h2(o[j + 4], o[j + 5]); pk.w = pack_h2(o[j + 6], o[j + 7]);
-                                *reinterpret_cast<uint4*>(drow + j) = pk;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (nc + j < N) drow[j] = f2h_sat(o[j]);
-                        }
-                    } else {
-                        float* drow = reinterpret_cast<float*>(ep.D) + static_cast<long long>(row) * ep.ldd + nc;
-                        if (full && ((ep.ldd & 3) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(drow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (nc + j < N) drow[j] = o[j];
+                } else {
+                    // unaligned / ragged: one row per instruction, lane = column (still coalesced)
+                    const bool col_ok = nc + lane < N;
+#pragma unroll 4
+                    for (int rl = 0; rl < 32; ++rl) {
+                        const long long gr = rbase + rl;
+                        if (gr < M && col_ok) {
+                            float o = stg[rl * STG_LD + lane];
+                            if (ep.C) o += ep.C[gr * ep.ldc + nc + lane];
+                            if constexpr (OUT_HALF) reinterpret_cast<unsigned short*>(ep.D)[gr * ep.ldd + nc + lane] = f2h_sat(o);
+                            else reinterpret_cast<float*>(ep.D)[gr * ep.ldd + nc + lane] = o;
                         }
                     }
                 }
+                __syncwarp();                                        // staging buffer is reused by the next chunk
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -52,6 +53,7 @@ class LearnableFakeQuantize(nn.Module):
         # optional hook: called with (temp_min, temp_max) before the scale is computed, so a
         # data-parallel driver can MIN/MAX all-reduce the statistics (see dp.py)
         self.stats_sync_hook = None
+        self._stat_flag_host = None    # set by dp.finish_calibration_many to avoid a per-quantiser host read
 
     # ---------------------------------------------------------------- checkpoint loading
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
@@ -159,11 +161,15 @@ class LearnableFakeQuantize(nn.Module):
             tmin, tmax = self.temp_min, self.temp_max
             if self.stats_sync_hook is not None:
                 self.stats_sync_hook(self, tmin, tmax)
-            if self.quantizer_type == 'log' and int(self._stat_state.item()) == 0:
+            if self.quantizer_type == 'log':
+                had_data = self._stat_flag_host if self._stat_flag_host is not None else int(self._stat_state.item())
+            else:
+                had_data = 1
+            if not had_data:
                 # no batch exceeded eps: the reference's statistics are log2(eps) in the
                 # "default shape" (e.g. [r, 1] for a fresh all-zero lora_B of shape [r, N])
                 shape = self._log_default_shape()
-                log_eps = float(tmin.reshape(-1)[0].item())
+                log_eps = float(np.log2(np.float64(np.float32(self.eps))).astype(np.float32))
                 tmin = torch.full(shape, log_eps, dtype=torch.float32, device=tmin.device)
                 tmax = tmin.clone()
             with torch.no_grad():

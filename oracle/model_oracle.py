@@ -94,7 +94,7 @@ class SPModelOracle:
         return switchable_layernorm_forward(x, w, b, self.eps)[0]
 
     # -- forward (p1/models_sp.py:58-76, 124-128, 160-171, 300-336, 421-439) -----
-    def forward(self, input_ids: np.ndarray, return_hidden: bool = False):
+    def forward(self, input_ids: np.ndarray, return_hidden: bool = False, lm_head: bool = True):
         B, T = input_ids.shape
         C, H = self.n_embd, self.n_head
         hd = C // H
@@ -125,6 +125,8 @@ class SPModelOracle:
         h = self._ln(h, "transformer.ln_f")
         if return_hidden:
             hidden.append(h.copy())
+        if not lm_head:
+            return h
         logits = _mm(h, self.wte.T)          # tied, unquantised LM head (p1/models_sp.py:396-398)
         return (logits, hidden) if return_hidden else logits
 
@@ -151,7 +153,7 @@ class SPModelOracle:
             lin.q_in[bits].start_calibration()
             lin.calibration_mode = True
         for ids in batches:
-            self.forward(ids)
+            self.forward(ids, lm_head=False)     # statistics only need the transformer body
         for lin in self.all_linears():
             lin.calibration_mode = False
             finish_calibration(lin.q_in[bits])
@@ -161,3 +163,46 @@ class SPModelOracle:
         self.calibrate_weights(bits)
         self.calibrate_lora(bits)
         self.calibrate_inputs(bits, batches)
+
+
+def random_state_dict(cfg: dict, vocab_size: int, n_positions: int, seed: int = 0) -> Dict[str, np.ndarray]:
+    """Random-init parameters with the reference's state_dict key names and init scales
+    (nn.Linear-like N(0, 0.02) weights, LoRA A ~ U(-1/sqrt(K), 1/sqrt(K)), LoRA B ~ N(0, 0.02) so the
+    LoRA branch is non-trivial, LayerNorm weight 1 / bias 0).  Used by bench.py's CPU baseline."""
+    rng = np.random.default_rng(seed)
+    C = cfg["n_embd"]
+    sd = {"transformer.wte.weight": (0.02 * rng.standard_normal((vocab_size, C))).astype(F32),
+          "transformer.wpe.weight": (0.01 * rng.standard_normal((n_positions, C))).astype(F32)}
+
+    def ln(prefix):
+        for b in cfg["bit_widths"]:
+            sd[f"{prefix}.weights.{b}"] = np.ones(C, F32)
+            sd[f"{prefix}.biases.{b}"] = np.zeros(C, F32)
+
+    def lin(prefix, k, n):
+        sd[prefix + "linear.weight"] = (0.02 * rng.standard_normal((n, k))).astype(F32)
+        sd[prefix + "linear.bias"] = np.zeros(n, F32)
+        for b in cfg["bit_widths"]:
+            r = cfg["lora_rank_per_bit"].get(b, 0)
+            if b < 32 and r > 0:
+                lim = 1.0 / np.sqrt(k)
+                sd[f"{prefix}lora_adapters.{b}bit.lora_A"] = rng.uniform(-lim, lim, (k, r)).astype(F32)
+                sd[f"{prefix}lora_adapters.{b}bit.lora_B"] = (0.02 * rng.standard_normal((r, n))).astype(F32)
+
+    for i in range(cfg["n_layer"]):
+        p = f"transformer.h.{i}."
+        ln(p + "ln_1"); ln(p + "ln_2")
+        lin(p + "attn.c_attn.", C, 3 * C); lin(p + "attn.c_proj.", C, C)
+        lin(p + "mlp.c_fc.", C, 4 * C); lin(p + "mlp.c_proj.", 4 * C, C)
+    ln("transformer.ln_f")
+    return sd
+
+
+def cross_entropy_shifted(logits: np.ndarray, labels: np.ndarray) -> float:
+    """Mean next-token cross entropy, as SPLMHeadModel.forward with labels (p1/models_sp.py:441-449)."""
+    lg = logits[:, :-1, :].astype(np.float64)
+    tgt = labels[:, 1:]
+    lg = lg - lg.max(axis=-1, keepdims=True)
+    lse = np.log(np.exp(lg).sum(axis=-1))
+    picked = np.take_along_axis(lg, tgt[..., None], axis=-1)[..., 0]
+    return float((lse - picked).mean())

@@ -216,6 +216,43 @@ def log_quantize(x, log_min, log_range, num_bits: int, symmetric: bool = True,
     return out, level.astype(np.int32), sgn.astype(np.int8), zero_mask
 
 
+def _chunked(fn, x, params, threads):
+    """Evaluate the elementwise fn(x, *params) over row chunks on a thread pool (numpy ufuncs
+    release the GIL).  Bit-identical to the single call; only used to make the CPU baseline use
+    the host cores the way the reference's torch-CPU kernels do."""
+    shape = x.shape
+    last = shape[-1]
+    per_last = all(p.size == 1 or (p.size == last and p.shape[-1] == last) for p in params)
+    per_first = all(p.size == 1 or (p.ndim == x.ndim and p.shape[0] == shape[0] and p.size == shape[0]) for p in params)
+    if per_last:
+        x2 = x.reshape(-1, last)
+        ps = [p.reshape(1, -1) if p.size > 1 else p.reshape(1, 1) for p in params]
+        slicer = lambda p, a, b: p
+    elif per_first:
+        x2 = x.reshape(shape[0], -1)
+        ps = [p.reshape(-1, 1) if p.size > 1 else p.reshape(1, 1) for p in params]
+        slicer = lambda p, a, b: p[a:b] if p.shape[0] > 1 else p
+    else:
+        return fn(x, *params)
+    n = x2.shape[0]
+    k = min(threads, n)
+    if k <= 1:
+        return fn(x, *params)
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=threads)
+    bounds = [(i * n // k, (i + 1) * n // k) for i in range(k)]
+    parts = list(_POOL.map(lambda ab: fn(x2[ab[0]:ab[1]], *[slicer(p, ab[0], ab[1]) for p in ps]), bounds))
+    return np.concatenate(parts, axis=0).reshape(shape)
+
+
+_POOL = None
+
+
+ORACLE_THREADS = int(__import__("os").environ.get("SPQ_ORACLE_THREADS", "0")) or (__import__("os").cpu_count() or 1)
+
+
 def fake_quantize(q: QuantizerState, x: np.ndarray, **kw) -> np.ndarray:
     """LearnableFakeQuantize.forward (p1/quantization.py:211-226)."""
     if q.num_bits >= 32:
@@ -226,9 +263,16 @@ def fake_quantize(q: QuantizerState, x: np.ndarray, **kw) -> np.ndarray:
     if not q.calibrated:
         raise RuntimeError(
             f"Quantizer not calibrated. Please run calibration first for {q.quantizer_type} quantizer.")
+    big = np.size(x) >= (1 << 20) and ORACLE_THREADS > 1 and not kw
     if q.quantizer_type == "minmax":
+        if big:
+            return _chunked(lambda a, s, z: minmax_quantize(a, s, z, q.num_bits, q.symmetric)[0],
+                            np.asarray(x, F32), [np.asarray(q.scale, F32), np.asarray(q.zero_point, F32)], ORACLE_THREADS)
         return minmax_quantize(x, q.scale, q.zero_point, q.num_bits, q.symmetric)[0]
     if q.quantizer_type == "log":
+        if big:
+            return _chunked(lambda a, lmin, lrng: log_quantize(a, lmin, lrng, q.num_bits, q.symmetric)[0],
+                            np.asarray(x, F32), [np.asarray(q.zero_point, F32), np.asarray(q.scale, F32)], ORACLE_THREADS)
         return log_quantize(x, q.zero_point, q.scale, q.num_bits, q.symmetric, **kw)[0]
     raise ValueError(f"Unknown quantizer type: {q.quantizer_type}. Supported types: 'minmax', 'log'")
 

@@ -1,0 +1,22 @@
+"""Time / profile one spq_qgemm shape:  python tools/gemm_bench.py M N K [reps] [half]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from llm_qat_on_gpt2_b200 import _lib
+M, N, K = (int(v) for v in sys.argv[1:4])
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+half = len(sys.argv) > 5 and sys.argv[5] == "half"
+torch.manual_seed(0)
+A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
+out = torch.empty(M, N, device="cuda", dtype=torch.float16 if half else torch.float32)
+bias = torch.randn(N, device="cuda"); cs = torch.rand(N, device="cuda")
+for _ in range(3):
+    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")

@@ -26,7 +26,7 @@ def main():
                 print("   out[0,:8]", out[0, :8].tolist()); print("   ref[0,:8]", ref[0, :8].tolist())
         except Exception:
             traceback.print_exc()
-    for (Mred, I, J) in [(64, 128, 64), (256, 128, 64), (1000, 768, 64), (333, 200, 130), (2048, 768, 768)]:
+    for (Mred, I, J) in [(64, 128, 64), (256, 128, 64), (1000, 768, 64), (333, 200, 136), (2048, 768, 768)]:
         try:
             P = torch.randn(Mred, I, device="cuda").half(); Q = (torch.randn(Mred, J, device="cuda") * 0.1).half()
             out = torch.empty(I, J, device="cuda")
