@@ -164,7 +164,9 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 int M, int N, int kb1, int kb2, EpiParams ep) {
     using L = SmemLayout<BN>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024 B alignment for the 128B swizzle.  Offset arithmetic on the __shared__ symbol (not an integer
+    // round trip) so that the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* epi_cs = reinterpret_cast<float*>(smem + L::STAGES * L::STAGE_BYTES);
     float* epi_bias = epi_cs + BN;
     float* stg_all = epi_bias + BN;
@@ -304,31 +306,34 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (nc >= N) continue;                              // warp-uniform
                 // TMEM gives each lane one output ROW (32 consecutive columns).  Writing rows straight to
                 // global memory makes every store instruction touch 32 cache lines; instead the 32 x 32
-                // block is transposed through padded shared memory and written out coalesced.
+                // block is transposed through padded shared memory and written out coalesced.  The row
+                // scale is applied before the transpose (one value per lane), column scale / clamp / bias /
+                // residual after it (each lane then owns fixed columns).
                 float* srow = stg + lane * STG_LD;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float x = __uint_as_float(v[j + u]) * (rs * epi_cs[c * 32 + j + u]);
-                        if (ep.clamp_abs > 0.f) x = fminf(fmaxf(x, -ep.clamp_abs), ep.clamp_abs);
-                        op[u] = x + epi_bias[c * 32 + j + u];
-                    }
-                    *reinterpret_cast<float4*>(srow + j) = o;
-                }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(srow + j) =
+                        make_float4(__uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
+                                    __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
                 __syncwarp();
                 const bool full = (nc + 32 <= N);
                 if (full && d_vec && (!ep.C || c_vec)) {
                     // 8 lanes cover one 128 B row segment; one instruction writes 4 rows
                     const int rsub = lane >> 3, cq = (lane & 7) * 4;
+                    const float4 cs4 = *reinterpret_cast<const float4*>(epi_cs + c * 32 + cq);
+                    const float4 bi4 = *reinterpret_cast<const float4*>(epi_bias + c * 32 + cq);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rl = i * 4 + rsub;
                         const long long gr = rbase + rl;
                         if (gr < M) {
                             float4 o = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cq);
+                            o.x *= cs4.x; o.y *= cs4.y; o.z *= cs4.z; o.w *= cs4.w;
+                            if (ep.clamp_abs > 0.f) {
+                                o.x = fminf(fmaxf(o.x, -ep.clamp_abs), ep.clamp_abs); o.y = fminf(fmaxf(o.y, -ep.clamp_abs), ep.clamp_abs);
+                                o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
+                            }
+                            o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
                             if (ep.C) {
                                 const float4 cv = *reinterpret_cast<const float4*>(ep.C + gr * ep.ldc + nc + cq);
                                 o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
@@ -344,11 +349,14 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 } else {
                     // unaligned / ragged: one row per instruction, lane = column (still coalesced)
                     const bool col_ok = nc + lane < N;
+                    const float cs1 = epi_cs[c * 32 + lane], bi1 = epi_bias[c * 32 + lane];
 #pragma unroll 4
                     for (int rl = 0; rl < 32; ++rl) {
                         const long long gr = rbase + rl;
                         if (gr < M && col_ok) {
-                            float o = stg[rl * STG_LD + lane];
+                            float o = stg[rl * STG_LD + lane] * cs1;
+                            if (ep.clamp_abs > 0.f) o = fminf(fmaxf(o, -ep.clamp_abs), ep.clamp_abs);
+                            o += bi1;
                             if (ep.C) o += ep.C[gr * ep.ldc + nc + lane];
                             if constexpr (OUT_HALF) reinterpret_cast<unsigned short*>(ep.D)[gr * ep.ldd + nc + lane] = f2h_sat(o);
                             else reinterpret_cast<float*>(ep.D)[gr * ep.ldd + nc + lane] = o;
@@ -463,7 +471,9 @@ qgemm_tn_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
                 int kb_per_split, int j_tiles, TnEpi ep) {
     using L = TnSmem<BJ>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024 B alignment for the 128B swizzle.  Offset arithmetic on the __shared__ symbol (not an integer
+    // round trip) so that the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + L::STAGES;
     uint64_t* tmem_full = empty_bar + L::STAGES;
