@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--cpu-sample-batch", type=int, default=1, help="sequences in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="for ncu launch lists: warm up, run exactly one un-instrumented step, print nothing else")
     return ap.parse_args()
 
 
@@ -277,6 +279,14 @@ def gpu_arm(args):
     for i in range(args.warmup):
         step(dev_ids[i])
     barrier()
+    if args.profile_one_step:
+        n0 = _lib.launch_count()
+        torch.cuda.nvtx.range_push("spq_step")
+        step(dev_ids[args.warmup])
+        torch.cuda.nvtx.range_pop()
+        barrier()
+        print(json.dumps({"profile_one_step": True, "spq_launches_in_step": _lib.launch_count() - n0}), flush=True)
+        return
 
     # ---- timed region 1: inputs resident in HBM ("value")
     sampler = ClockSampler(local)

@@ -80,8 +80,8 @@ SPQ_API int spq_finish_calibration(const float* running_min, const float* runnin
  *   sign    : int8  -- log only: sign(x) in {-1,0,1}, 0 also where |x| < 1e-5 (zero mask)
  *   operand : fp16 GEMM operand = fp16(v * row_mul[row] * col_mul[col] * mul), v chosen by
  *             operand_kind (code - zero_point, dequantised value, or raw x); row_mul/col_mul nullable.
- *             With operand_ld > 0 the operand is written with that leading dimension; with
- *             operand_transposed != 0 it is written as [cols, rows].
+ *             operand_transposed != 0 writes it as [cols, rows]; operand_ld > 0 is its leading
+ *             dimension in elements (0 = dense), so odd widths can be padded to TMA's 16-byte strides.
  * Codes are bit-exact w.r.t. the reference arithmetic (IEEE div, round-half-even, separate
  * mul/add roundings; log2 correctly rounded via an exact slow path next to rounding ties).
  */
@@ -90,7 +90,7 @@ SPQ_API int spq_fake_quantize(const float* x, int64_t rows, int64_t cols,
                       int qtype, int bits, int symmetric,
                       float* dequant, int32_t* codes, int8_t* sign,
                       spq_half_t* operand, int operand_kind, const float* row_mul, const float* col_mul,
-                      float mul, int operand_transposed, spq_stream_t stream);
+                      float mul, int operand_transposed, int64_t operand_ld, spq_stream_t stream);
 
 /* Fused activation-side quantise for SPLinearWithLoRA.forward (p1/lora.py:141,149): one pass
  * over x [M, K] (per-column or per-tensor scale) produces
@@ -146,8 +146,10 @@ SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weig
                       const float* rstd, int64_t rows, int64_t cols, float* dx, float* dweight,
                       float* dbias, void* workspace, size_t workspace_bytes, spq_stream_t stream);
 
-/* ---- gradient-side operand: fp16(g[m,n] * 2^-e[m]) with e from the row's absmax ------------- */
-SPQ_API int spq_rowscale_f16(const float* g, int64_t M, int64_t N, float premul, spq_half_t* out,
+/* ---- gradient-side operand: out[m, 0:N] = fp16(g[m,n] * 2^-e[m]), e from the row's absmax,
+ * row_scale[m] = 2^e[m]; rows of `out` are ld_out elements apart (0 = N).  Any N (a two-pass
+ * kernel takes over when the row does not fit the register-resident one or is unaligned). */
+SPQ_API int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                      float* row_scale, spq_stream_t stream);
 
 #ifdef __cplusplus

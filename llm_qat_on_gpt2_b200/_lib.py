@@ -36,7 +36,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "spq_fake_quantize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float,
-                                  c_int, c_void_p]),
+                                  c_int, c_int64, c_void_p]),
     "spq_quantize_act": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "spq_ste_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
@@ -51,7 +51,7 @@ SIGNATURES = {
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "spq_rowscale_f16": (c_int, [c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "spq_rowscale_f16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -158,6 +158,7 @@ def finish_calibration(rmin, rmax, qtype: int, symmetric: bool, bits: int, eps: 
 def fake_quantize(x2d, scale, zp, bcast, qtype, bits, symmetric, dequant=None, codes=None, sign=None,
                   operand=None, operand_kind=OPERAND_DEQUANT, row_mul=None, col_mul=None, mul=1.0,
                   operand_transposed=False):
+    """`operand` may be a column-sliced view of a wider buffer (padded leading dimension)."""
     _req_cuda(x2d, scale, zp, dequant, codes, sign, operand, row_mul, col_mul)
     assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
     rows, cols = x2d.shape
@@ -168,7 +169,8 @@ def fake_quantize(x2d, scale, zp, bcast, qtype, bits, symmetric, dequant=None, c
     _check(load_library().spq_fake_quantize(x2d.data_ptr(), rows, cols, scale.data_ptr(), zp.data_ptr(), bcast, qtype,
                                             bits, int(symmetric), _ptr(dequant), _ptr(codes), _ptr(sign),
                                             _ptr(operand), operand_kind, _ptr(row_mul), _ptr(col_mul), float(mul),
-                                            int(operand_transposed), _stream()), "spq_fake_quantize")
+                                            int(operand_transposed), 0 if operand is None else operand.stride(0),
+                                            _stream()), "spq_fake_quantize")
 
 
 def quantize_act(x2d, scale, zp, bcast, qtype, bits, symmetric, operand_kind, col_mul, mul, a_q, a_raw, raw_row_scale):
@@ -250,5 +252,13 @@ def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias):
 def rowscale_f16(g2d, out, row_scale):
     _req_cuda(g2d, out, row_scale)
     M, N = g2d.shape
-    _check(load_library().spq_rowscale_f16(g2d.data_ptr(), M, N, 1.0, out.data_ptr(), row_scale.data_ptr(), _stream()),
-           "spq_rowscale_f16")
+    assert out.stride(-1) == 1
+    _check(load_library().spq_rowscale_f16(g2d.data_ptr(), M, N, out.data_ptr(), out.stride(0), row_scale.data_ptr(),
+                                           _stream()), "spq_rowscale_f16")
+
+
+def empty_f16_padded(rows: int, cols: int, device) -> torch.Tensor:
+    """[rows, cols] fp16 view whose row stride is a multiple of 8 elements (TMA needs 16-byte strides)."""
+    ld = (cols + 7) // 8 * 8
+    buf = torch.empty((rows, ld), dtype=torch.float16, device=device)
+    return buf if ld == cols else buf[:, :cols]

@@ -1,0 +1,426 @@
+"""CPTLinear and the CPT GPT-2 wrapper on the B200 kernels -- drop-ins for
+part2_cyclic_precision_training/cpt_model.py (LoRAAdapter :11, CPTLinear :37, CPTSelfAttention :116,
+CPTBlock :170, CPTModel :206).
+
+CPTLinear differs from part1's SPLinearWithLoRA in four ways, all kept: ONE shared LoRA adapter for
+every width (`shared_lora`, B stored [out, rank]); the adapter reads the QUANTISED input
+(`x_quant @ q(A) @ q(B).T`, :108-113); one `lora_weight_quantizers['{b}bit']` quantiser object is used
+for both A and B; and the LoRA gradients pass through `GradientQuantizer` (8-bit min-max fake
+quantisation of dA / dB once calibrated, p2/quantization.py:14-26).  The LM head is a CPTLinear
+(768 -> 50257, no bias), LayerNorm is stock nn.LayerNorm.
+
+Fused path: as in lora.py -- one pass over x produces the fp16 code/dequant operand, which here
+also feeds the LoRA down-projection (its per-K factor is absorbed into the A operand), the
+up-projection rides in the same TMEM accumulator as the base GEMM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from ..lora import (_FpWeightCache, _act_config, _as_2d_f32, _dequant, _norm_pow2, _quantized_operand, _rowscaled_f16,
+                    _to_f16_operand, linear_fp)
+from ..quantization import pow2_ceil
+from .quantization import GradientQuantizer, LearnableFakeQuantize
+
+
+class LoRAAdapter(nn.Module):
+    def __init__(self, in_features: int, out_features: int, rank: int = 16, alpha: float = 32,
+                 num_bits: int = 8, quantizer_type: str = 'log', gradient_bits: int = 8):
+        super().__init__()
+        self.rank = rank
+        self.alpha = alpha
+        self.scaling = alpha / rank if rank > 0 else 1.0
+        if rank > 0:
+            self.lora_A = nn.Parameter(torch.empty(in_features, rank))
+            nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
+            self.lora_B = nn.Parameter(torch.zeros(out_features, rank))
+            self.grad_quantizer_A = LearnableFakeQuantize(num_bits=gradient_bits, quantizer_type='minmax',
+                                                          channel_dim=0, per_channel=True)
+            self.grad_quantizer_B = LearnableFakeQuantize(num_bits=gradient_bits, quantizer_type='minmax',
+                                                          channel_dim=0, per_channel=True)
+        else:
+            self.lora_A = None
+            self.lora_B = None
+            self.grad_quantizer_A = None
+            self.grad_quantizer_B = None
+        self.calibration_mode = False
+
+
+def _grad_quantize(q: Optional[LearnableFakeQuantize], g: torch.Tensor) -> torch.Tensor:
+    """GradientQuantizer.backward (p2/quantization.py:19-26) on an already computed gradient."""
+    if q is not None and (q.collecting_stats or q.num_bits in q.calibrated_bits):
+        with torch.no_grad():
+            return q(g)
+    return g
+
+
+class _CPTLinearFn(torch.autograd.Function):
+    """Fused forward / backward of CPTLinear at a quantised width."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits):
+        use_lora = lora_A is not None
+        base, lo = mod._operands_for(bits, use_lora)
+        act = base['act']
+        N, K = weight.shape
+        x2d = _as_2d_f32(x, K)
+        M = x2d.shape[0]
+        a_q = torch.empty((M, K), dtype=torch.float16, device=x.device)
+        _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
+                          act['kind'], act['col_mul'], act['mul'], a_q, None, None)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        t = None
+        if use_lora:
+            r = lo['rank']
+            t = torch.empty((M, r), dtype=torch.float32, device=x.device)
+            _lib.qgemm(a_q, lo['A_op'], M, r, K, t, col_scale=lo['pa'])            # t = q(x) q(A)
+            t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f)
+        else:
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f)
+        need = ctx.needs_input_grad
+        ctx.use_lora, ctx.x_shape, ctx.has_bias, ctx.dims = use_lora, x.shape, bias is not None, (M, N, K)
+        ctx.base, ctx.lo, ctx.mod = base, lo, mod
+        ctx.bw = mod._backward_operands_for(bits, use_lora) if any(need[:5]) else None
+        ctx.weight_qtype = mod.quantizer_weight.quantizer_type
+        keep_aq = need[1] or (use_lora and need[3])
+        ctx.save_for_backward(a_q if keep_aq else None, t)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        a_q, t = ctx.saved_tensors
+        base, lo, bw, mod = ctx.base, ctx.lo, ctx.bw, ctx.mod
+        M, N, K = ctx.dims
+        g2d = _as_2d_f32(gy, N)
+        dev = gy.device
+        act = base['act']
+        g16, eg = _rowscaled_f16(g2d)
+        gx = gw = gb = gA = gB = None
+        need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
+        clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
+        gmax = eg.max() if (need_w or (ctx.use_lora and (need_A or need_B))) else None
+        dt16 = None
+        if ctx.use_lora and (need_x or need_A or need_B):
+            lb = bw['lora']
+            r = lo['rank']
+            if need_x or need_A:
+                dtn = torch.empty((M, r), dtype=torch.float32, device=dev)       # dt / eg,  dt = scaling * dY q(B)
+                _lib.qgemm(g16, lb['B_rn_op'], M, r, N, dtn, col_scale=lb['pb'])
+                if need_x:
+                    dt16 = _to_f16_operand(dtn, mul=lb['dt_mul'])
+                if need_A:
+                    # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
+                    dt2 = _to_f16_operand(dtn, row_mul=(eg / gmax).contiguous(), mul=lb['dt_mul'])
+                    gA = torch.empty((K, r), dtype=torch.float32, device=dev)
+                    _lib.gemm_tn(a_q, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax.reshape(1).contiguous(),
+                                 i_scale=act['absorb'])
+                    gA = _grad_quantize(mod.shared_lora.grad_quantizer_A, gA)
+                    if lo['qtype'] == 'log':
+                        gA = _lib.ste_backward(gA, _lib.LOG)
+            if need_B:
+                # dB[n,j] = scaling * sum_m dY[m,n] t[m,j]
+                t2 = _to_f16_operand(t, row_mul=(eg / gmax).contiguous(), col_mul=lo['tmul_vec'])
+                gB = torch.empty((N, r), dtype=torch.float32, device=dev)
+                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax.reshape(1).contiguous(),
+                             j_scale=lo['inv_tmul_vec'])
+                gB = _grad_quantize(mod.shared_lora.grad_quantizer_B, gB)
+                if lo['qtype'] == 'log':
+                    gB = _lib.ste_backward(gB, _lib.LOG)
+        if need_x:
+            # both terms flow through q_in(x) here, so the STE clamp applies to their sum
+            gx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            if dt16 is not None:
+                _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, A2=dt16, B2=bw['lora']['A_kr_op'], K2=lo['rank'],
+                           row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in)
+            else:
+                _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in)
+            gx = gx.view(ctx.x_shape)
+        if need_w:
+            gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax).expand(M).contiguous())
+            gw = torch.empty((N, K), dtype=torch.float32, device=dev)
+            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax.reshape(1).contiguous(), j_scale=act['absorb'])
+            if ctx.weight_qtype == 'log':
+                gw = _lib.ste_backward(gw, _lib.LOG)
+        if ctx.has_bias and need_b:
+            gb = g2d.sum(dim=0)
+        return gx, gw, gb, gA, gB, None, None
+
+
+class CPTLinear(nn.Module):
+    def __init__(self, in_features: int, out_features: int, bit_widths: list = [4, 6, 8],
+                 quantizer_per_bit: dict = None, gradient_bits: int = 8, bias: bool = True,
+                 shared_lora_rank: int = 16, shared_lora_alpha: int = 32):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.bit_widths = bit_widths
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+        self.shared_lora = LoRAAdapter(in_features, out_features, rank=shared_lora_rank, alpha=shared_lora_alpha,
+                                       num_bits=8, quantizer_type='log', gradient_bits=gradient_bits)
+        if quantizer_per_bit is None:
+            quantizer_per_bit = {bits: 'log' for bits in bit_widths}
+        self.lora_weight_quantizers = nn.ModuleDict({
+            f'{bits}bit': LearnableFakeQuantize(num_bits=bits, quantizer_type=quantizer_per_bit.get(bits, 'log'),
+                                                channel_dim=1, per_channel=True)
+            for bits in bit_widths})
+        max_bits = max([b for b in bit_widths if b < 32]) if any(b < 32 for b in bit_widths) else 8
+        max_quant_type = quantizer_per_bit.get(max_bits, 'log')
+        self.quantizer_weight = LearnableFakeQuantize(num_bits=max_bits, quantizer_type=max_quant_type,
+                                                      channel_dim=0, per_channel=True)
+        self.quantizer_input = LearnableFakeQuantize(num_bits=max_bits, quantizer_type=max_quant_type,
+                                                     channel_dim=-1, per_channel=True, is_input=True)
+        self.current_bits = max(bit_widths)
+        self.calibration_mode = False
+        self._op_cache = {}
+        self._fp_cache = _FpWeightCache()
+
+    def set_precision(self, num_bits: int):
+        if num_bits not in self.bit_widths:
+            raise ValueError(f"Precision {num_bits} not in widths {self.bit_widths}")
+        self.current_bits = num_bits
+        if num_bits < 32:
+            self.quantizer_weight.set_num_bits(num_bits)
+            self.quantizer_input.set_num_bits(num_bits)
+
+    # ---------------------------------------------------------------- operand caches (see lora.py)
+    def _operands_for(self, bits, want_lora):
+        qi, qw = self.quantizer_input, self.quantizer_weight
+        W = self.linear.weight
+        ent = self._op_cache.setdefault(bits, {'base': None, 'lora': None, 'bwd': None})
+        base_key = (W.data_ptr(), W._version, qw.generation, qi.generation, bits)
+        base = ent['base']
+        if base is None or base['key'] != base_key:
+            with torch.no_grad():
+                act = _act_config(qi, self.in_features)
+                wq = _dequant(qw, W)
+                pw = _norm_pow2((wq.abs() * act['absorb']).amax(dim=1))
+                B_op = _quantized_operand(qw, W, row_mul=1.0 / pw, col_mul=act['absorb'])
+            base = ent['base'] = dict(key=base_key, act=act, wq=wq, pw=pw, B_op=B_op)
+            ent['lora'] = ent['bwd'] = None
+        if not want_lora:
+            return base, None
+        sl = self.shared_lora
+        lq = self.lora_weight_quantizers[f'{bits}bit']
+        lkey = (base_key, sl.lora_A.data_ptr(), sl.lora_A._version, sl.lora_B.data_ptr(), sl.lora_B._version, lq.generation)
+        lora = ent['lora']
+        if lora is None or lora['key'] != lkey:
+            with torch.no_grad():
+                K, r = sl.lora_A.shape
+                act = base['act']
+                aq = _dequant(lq, sl.lora_A)                                   # [K, r]
+                pa = _norm_pow2((aq.abs() * act['absorb'][:, None]).amax(dim=0), 0)
+                A_op = _quantized_operand(lq, sl.lora_A, row_mul=act['absorb'], col_mul=1.0 / pa, transposed=True)   # [r, K]
+                xb = qi.abs_bound().detach().float().reshape(-1).expand(K)
+                tmax = (xb[:, None] * aq.abs()).sum(dim=0).max()
+                tmul = torch.where(tmax > 0, (2.0 ** 14) / pow2_ceil(tmax), torch.ones_like(tmax))
+                tmul_vec = tmul.expand(r).contiguous()
+                Bl_op = _quantized_operand(lq, sl.lora_B, row_mul=1.0 / base['pw'],
+                                           col_mul=(sl.scaling / tmul).expand(r).contiguous())                      # [N, r]
+            lora = ent['lora'] = dict(key=lkey, rank=r, A_op=A_op, pa=pa, Bl_op=Bl_op, tmul_vec=tmul_vec,
+                                      inv_tmul_vec=(1.0 / tmul_vec).contiguous(), scaling=float(sl.scaling),
+                                      qtype=lq.quantizer_type)
+            ent['bwd'] = None
+        return base, lora
+
+    def _backward_operands_for(self, bits, want_lora):
+        base, lora = self._operands_for(bits, want_lora)
+        ent = self._op_cache[bits]
+        bkey = (base['key'], None if lora is None else lora['key'])
+        bw = ent['bwd']
+        if bw is not None and bw['key'] == bkey:
+            return bw
+        qw, sl = self.quantizer_weight, self.shared_lora
+        W = self.linear.weight
+        with torch.no_grad():
+            pk = _norm_pow2(base['wq'].abs().amax(dim=0))
+            bw = dict(key=bkey, pk=pk, WT_op=_quantized_operand(qw, W, col_mul=1.0 / pk, transposed=True), lora=None)
+            if lora is not None:
+                lq = self.lora_weight_quantizers[f'{bits}bit']
+                N = self.out_features
+                dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
+                bq = _dequant(lq, sl.lora_B)                                    # [N, r]
+                pb = _norm_pow2(bq.abs().amax(dim=0) * abs(sl.scaling), 0)      # [r]
+                bw['lora'] = dict(
+                    pb=pb, dt_mul=dt_mul,
+                    B_rn_op=_quantized_operand(lq, sl.lora_B, col_mul=1.0 / pb, mul=sl.scaling, transposed=True),  # [r, N]
+                    A_kr_op=_quantized_operand(lq, sl.lora_A, row_mul=1.0 / pk, mul=1.0 / dt_mul))                  # [K, r]
+        ent['bwd'] = bw
+        return bw
+
+    # ---------------------------------------------------------------- forward (p2/cpt_model.py:92-114)
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.current_bits == 32:
+            return linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache)
+        qi, qw = self.quantizer_input, self.quantizer_weight
+        lora_on = not self.calibration_mode and self.shared_lora.rank > 0
+        lq = self.lora_weight_quantizers[f'{self.current_bits}bit'] if lora_on else None
+        if qi.ready() and qw.ready() and (lq is None or lq.ready()):
+            return _CPTLinearFn.apply(x, self.linear.weight, self.linear.bias,
+                                      self.shared_lora.lora_A if lora_on else None,
+                                      self.shared_lora.lora_B if lora_on else None, self, self.current_bits)
+        # calibration pass / uncalibrated width: the reference's composition, module by module
+        x_quant = qi(x)
+        weight_quant = qw(self.linear.weight)
+        out = linear_fp(x_quant, weight_quant, self.linear.bias)
+        if self.calibration_mode:
+            return out
+        lq = self.lora_weight_quantizers[f'{self.current_bits}bit']
+        a_q = GradientQuantizer.apply(lq(self.shared_lora.lora_A), self.shared_lora.grad_quantizer_A)
+        b_q = GradientQuantizer.apply(lq(self.shared_lora.lora_B), self.shared_lora.grad_quantizer_B)
+        lora_output = linear_fp(linear_fp(x_quant, a_q.t()), b_q)
+        return out + lora_output * self.shared_lora.scaling
+
+
+class CPTSelfAttention(nn.Module):
+    def __init__(self, config, bit_widths: list, quantizer_per_bit: dict = None, gradient_bits: int = 8,
+                 shared_lora_rank: int = 16, shared_lora_alpha: int = 32):
+        super().__init__()
+        self.n_head = config.n_head
+        self.n_embd = config.n_embd
+        self.head_dim = self.n_embd // self.n_head
+        kw = dict(shared_lora_rank=shared_lora_rank, shared_lora_alpha=shared_lora_alpha)
+        self.c_attn = CPTLinear(self.n_embd, 3 * self.n_embd, bit_widths, quantizer_per_bit, gradient_bits, **kw)
+        self.c_proj = CPTLinear(self.n_embd, self.n_embd, bit_widths, quantizer_per_bit, gradient_bits, **kw)
+        self.attn_dropout = nn.Dropout(config.embd_pdrop)
+        self.resid_dropout = nn.Dropout(config.embd_pdrop)
+
+    def set_precision(self, num_bits: int):
+        self.c_attn.set_precision(num_bits)
+        self.c_proj.set_precision(num_bits)
+
+    def forward(self, hidden_states, attention_mask=None, past_key_value=None):
+        B, T, _ = hidden_states.shape
+        q, k, v = self.c_attn(hidden_states).split(self.n_embd, dim=-1)
+        q = q.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
+        k = k.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
+        v = v.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
+        if past_key_value is not None:
+            k = torch.cat([past_key_value[0], k], dim=2)
+            v = torch.cat([past_key_value[1], v], dim=2)
+        present = (k, v)
+        S = k.size(2)
+        p_drop = self.attn_dropout.p if self.training else 0.0
+        if attention_mask is None and S == T:
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
+        else:
+            causal = torch.tril(torch.ones(S, S, device=q.device, dtype=torch.bool))[-T:, :]
+            bias = torch.zeros(T, S, device=q.device, dtype=q.dtype).masked_fill(~causal, float('-inf'))
+            if attention_mask is not None:
+                bias = bias + attention_mask
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=p_drop)
+        o = o.transpose(1, 2).contiguous().view(B, T, self.n_embd)
+        return self.resid_dropout(self.c_proj(o)), present
+
+
+CPTMLP = nn.ModuleDict          # the reference keeps the MLP as a ModuleDict {'fc_in', 'fc_out'} (:177-180)
+
+
+class CPTBlock(nn.Module):
+    def __init__(self, config, bit_widths: list, quantizer_per_bit: dict = None, gradient_bits: int = 8,
+                 shared_lora_rank: int = 16, shared_lora_alpha: int = 32):
+        super().__init__()
+        self.ln_1 = nn.LayerNorm(config.n_embd, eps=config.layer_norm_epsilon)
+        self.ln_2 = nn.LayerNorm(config.n_embd, eps=config.layer_norm_epsilon)
+        self.bit_widths = bit_widths
+        kw = dict(shared_lora_rank=shared_lora_rank, shared_lora_alpha=shared_lora_alpha)
+        self.attn = CPTSelfAttention(config, bit_widths, quantizer_per_bit, gradient_bits, shared_lora_rank, shared_lora_alpha)
+        self.mlp = nn.ModuleDict({
+            'fc_in': CPTLinear(config.n_embd, 4 * config.n_embd, bit_widths, quantizer_per_bit, gradient_bits, **kw),
+            'fc_out': CPTLinear(4 * config.n_embd, config.n_embd, bit_widths, quantizer_per_bit, gradient_bits, **kw)})
+        self.mlp_dropout = nn.Dropout(config.embd_pdrop)
+
+    def set_precision(self, num_bits: int):
+        self.attn.set_precision(num_bits)
+        self.mlp['fc_in'].set_precision(num_bits)
+        self.mlp['fc_out'].set_precision(num_bits)
+
+    def forward(self, hidden_states, attention_mask=None, past_key_value=None):
+        a, present = self.attn(self.ln_1(hidden_states), attention_mask, past_key_value)
+        hidden_states = hidden_states + a
+        m = self.mlp['fc_out'](F.gelu(self.mlp['fc_in'](self.ln_2(hidden_states))))
+        return hidden_states + self.mlp_dropout(m), present
+
+
+class CPTModel(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        mc = config['model']
+        self.wte = nn.Embedding(mc.vocab_size, mc.n_embd)
+        self.wpe = nn.Embedding(mc.n_positions, mc.n_embd)
+        self.drop = nn.Dropout(mc.embd_pdrop)
+        self.h = nn.ModuleList([
+            CPTBlock(mc, mc.bit_widths, mc.quantizer_per_bit, mc.gradient_bits, mc.shared_lora_rank, mc.shared_lora_alpha)
+            for _ in range(mc.n_layer)])
+        self.ln_f = nn.LayerNorm(mc.n_embd, eps=mc.layer_norm_epsilon)
+        self.lm_head = CPTLinear(mc.n_embd, mc.vocab_size, mc.bit_widths, mc.quantizer_per_bit, mc.gradient_bits,
+                                 bias=False, shared_lora_rank=mc.shared_lora_rank, shared_lora_alpha=mc.shared_lora_alpha)
+        self.apply(self._init_weights)
+        self.current_precision = config['training'].target_bits
+
+    def _init_weights(self, module):
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+
+    def set_precision(self, num_bits: int):
+        self.current_precision = num_bits
+        for block in self.h:
+            block.set_precision(num_bits)
+        self.lm_head.set_precision(num_bits)
+
+    def forward(self, input_ids, attention_mask=None, past_key_values=None, labels=None, use_cache=False):
+        from transformers.modeling_outputs import CausalLMOutputWithPast
+        B, T = input_ids.shape
+        pos = torch.arange(T, dtype=torch.long, device=input_ids.device).unsqueeze(0).expand(B, -1)
+        hidden_states = self.drop(self.wte(input_ids) + self.wpe(pos))
+        if attention_mask is not None:
+            attention_mask = (1.0 - attention_mask.unsqueeze(1).unsqueeze(2)) * -10000.0
+        presents = [] if use_cache else None
+        for i, block in enumerate(self.h):
+            pkv = past_key_values[i] if past_key_values is not None else None
+            hidden_states, present = block(hidden_states, attention_mask, pkv)
+            if use_cache:
+                presents.append(present)
+        hidden_states = self.ln_f(hidden_states)
+        logits = self.lm_head(hidden_states)
+        loss = None
+        if labels is not None:
+            targets = torch.full_like(labels, -100)
+            targets[..., :-1] = labels[..., 1:]
+            loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=presents,
+                                      hidden_states=hidden_states, attentions=None)
+
+    def disable_lora_for_calibration(self):
+        for module in self.modules():
+            if isinstance(module, (CPTLinear, LoRAAdapter)):
+                module.calibration_mode = True
+
+    def enable_lora_after_calibration(self):
+        for module in self.modules():
+            if isinstance(module, (CPTLinear, LoRAAdapter)):
+                module.calibration_mode = False
+
+    def generate(self, input_ids, max_length=100, temperature=1.0, do_sample=True, **kwargs):
+        self.eval()
+        with torch.no_grad():
+            for _ in range(max_length - input_ids.size(1)):
+                nxt = self.forward(input_ids, use_cache=False).logits[:, -1, :] / temperature
+                token = torch.multinomial(F.softmax(nxt, dim=-1), num_samples=1) if do_sample \
+                    else torch.argmax(nxt, dim=-1, keepdim=True)
+                input_ids = torch.cat([input_ids, token], dim=1)
+                if kwargs.get('eos_token_id') is not None and (token == kwargs['eos_token_id']).all():
+                    break
+        return input_ids

@@ -13,6 +13,7 @@
 // tmem_full/tmem_empty mbarriers (MMA <-> epilogue) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "spq_common.cuh"
 
@@ -142,6 +143,7 @@ struct EpiParams {
     long long d_stride_n;     // 1 for row-major D; TN kernel may store transposed
     float alpha;
     float clamp_abs;          // <= 0: off
+    int debug;                // bit0: skip epilogue stores, bit1: skip MMA issue (profiling experiments only)
 };
 
 template <int BN>
@@ -256,6 +258,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint64_t bdesc = make_desc_sw128(sa + A_TILE_BYTES, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (ep.debug & 2) break;
                         // +32 B per UMMA_K inside the 128 B swizzle span: +2 in the (addr >> 4) field
                         umma_f16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                                  (kb | k) != 0 ? 1u : 0u);
@@ -303,7 +306,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
                 tmem_ld_wait();
                 const int nc = n0 + c * 32;
-                if (nc >= N) continue;                              // warp-uniform
+                if (nc >= N || (ep.debug & 1)) continue;            // warp-uniform
                 // TMEM gives each lane one output ROW (32 consecutive columns).  Writing rows straight to
                 // global memory makes every store instruction touch 32 cache lines; instead the 32 x 32
                 // block is transposed through padded shared memory and written out coalesced.  The row
@@ -660,6 +663,11 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     EpiParams ep;
     ep.row_scale = row_scale; ep.col_scale = col_scale; ep.bias = bias; ep.C = C; ep.alpha_dev = nullptr;
     ep.D = D; ep.ldc = ldc; ep.ldd = ldd; ep.d_stride_n = 1; ep.alpha = alpha; ep.clamp_abs = clamp_abs;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("SPQ_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+        ep.debug = dbg;
+    }
     const int kb1 = static_cast<int>((K + BK - 1) / BK);
     const int kb2 = static_cast<int>((K2 + BK - 1) / BK);
     cudaStream_t st = as_stream(stream);

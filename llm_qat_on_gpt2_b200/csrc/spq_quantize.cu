@@ -114,6 +114,7 @@ struct FqArgs {
     const float* col_mul;
     float mul;
     int transposed;
+    long long op_ld;      // leading dimension of the operand output (elements)
 };
 
 // block (32, 8): x -> 4 consecutive columns (VEC) or 1; y -> rows; grid-stride over row tiles.
@@ -165,17 +166,17 @@ fake_quantize_kernel(FqArgs a) {
             if (a.sign) *reinterpret_cast<char4*>(a.sign + off) = make_char4((signed char)sg[0], (signed char)sg[1], (signed char)sg[2], (signed char)sg[3]);
             if (a.operand) {
                 if (!a.transposed) {
-                    *reinterpret_cast<uint2*>(a.operand + off) = make_uint2(pack_h2(opv[0], opv[1]), pack_h2(opv[2], opv[3]));
+                    *reinterpret_cast<uint2*>(a.operand + r * a.op_ld + c0) = make_uint2(pack_h2(opv[0], opv[1]), pack_h2(opv[2], opv[3]));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) a.operand[(c0 + j) * a.rows + r] = f2h_sat(opv[j]);
+                    for (int j = 0; j < 4; ++j) a.operand[(c0 + j) * a.op_ld + r] = f2h_sat(opv[j]);
                 }
             }
         } else {
             if (a.dequant) a.dequant[off] = dq[0];
             if (a.codes) a.codes[off] = (int)code[0];
             if (a.sign) a.sign[off] = (signed char)sg[0];
-            if (a.operand) a.operand[a.transposed ? (c0 * a.rows + r) : off] = f2h_sat(opv[0]);
+            if (a.operand) a.operand[a.transposed ? (c0 * a.op_ld + r) : (r * a.op_ld + c0)] = f2h_sat(opv[0]);
         }
     }
 }
@@ -279,6 +280,38 @@ quantize_act_kernel(ActArgs a) {
     }
 }
 
+// Rows wider than the register-resident limit, or not 16-byte aligned (LM-head gradients, N = 50257):
+// one CTA per row, two passes (the second pass hits L2), output rows `ld_out` apart.
+__global__ void __launch_bounds__(256)
+rowscale_wide_kernel(const float* __restrict__ x, long long M, long long K, unsigned short* __restrict__ out,
+                     long long ld_out, float* __restrict__ row_scale) {
+    __shared__ float s_red[8];
+    const int tid = threadIdx.x;
+    for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+        const float* p = x + row * K;
+        float amax = 0.f;
+        for (long long c = tid; c < K; c += 256) amax = fmaxf(amax, fabsf(__ldg(p + c)));
+        amax = warp_fmax(amax);
+        __syncthreads();
+        if ((tid & 31) == 0) s_red[tid >> 5] = amax;
+        __syncthreads();
+        amax = s_red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) amax = fmaxf(amax, s_red[w]);
+        int E = 0;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = 8;
+        E = E < -100 ? -100 : E;
+        const float down = exp2f(static_cast<float>(8 - E));
+        if (tid == 0 && row_scale) row_scale[row] = exp2f(static_cast<float>(E - 8));
+        unsigned short* o = out + row * ld_out;
+        for (long long c = 2 * tid; c < K; c += 512) {
+            const float a = __ldg(p + c) * down;
+            if (c + 1 < K) *reinterpret_cast<unsigned int*>(o + c) = pack_h2(a, __ldg(p + c + 1) * down);
+            else o[c] = f2h_sat(a);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) ste_backward_kernel(const float* __restrict__ g, long long n, int clampit, float* __restrict__ out) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
     for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -346,7 +379,7 @@ using namespace spq::quant;
 extern "C" int spq_fake_quantize(const float* x, int64_t rows, int64_t cols, const float* scale, const float* zero_point,
                                  int bcast, int qtype, int bits, int symmetric, float* dequant, int32_t* codes, int8_t* sign,
                                  spq_half_t* operand, int operand_kind, const float* row_mul, const float* col_mul, float mul,
-                                 int operand_transposed, spq_stream_t stream) {
+                                 int operand_transposed, int64_t operand_ld, spq_stream_t stream) {
     SPQ_REQUIRE(x && scale && zero_point, "spq_fake_quantize: null pointer");
     SPQ_REQUIRE(rows > 0 && cols > 0, "spq_fake_quantize: empty tensor");
     SPQ_REQUIRE(bits >= 1 && bits < 32, "spq_fake_quantize: bits %d outside [1, 31]", bits);
@@ -357,9 +390,11 @@ extern "C" int spq_fake_quantize(const float* x, int64_t rows, int64_t cols, con
     a.qp = make_qparams(bits, symmetric);
     a.dequant = dequant; a.codes = codes; a.sign = sign; a.operand = operand; a.operand_kind = operand_kind;
     a.row_mul = row_mul; a.col_mul = col_mul; a.mul = mul; a.transposed = operand_transposed;
+    a.op_ld = operand_ld > 0 ? operand_ld : (operand_transposed ? rows : cols);
+    SPQ_REQUIRE(!operand || a.op_ld >= (operand_transposed ? rows : cols), "spq_fake_quantize: operand_ld too small");
     const bool vec = (cols % 4 == 0) && aligned16(x) && (!dequant || aligned16(dequant)) && (!codes || aligned16(codes)) &&
                      (!sign || (reinterpret_cast<uintptr_t>(sign) & 3u) == 0) &&
-                     (!operand || (reinterpret_cast<uintptr_t>(operand) & 7u) == 0);
+                     (!operand || ((reinterpret_cast<uintptr_t>(operand) & 7u) == 0 && (operand_transposed || (a.op_ld & 3) == 0)));
     const long long col_threads = vec ? cols / 4 : cols;
     const unsigned gx = static_cast<unsigned>((col_threads + 31) / 32);
     long long gy = (static_cast<long long>(sm_count()) * 8 + gx - 1) / gx;
@@ -402,11 +437,20 @@ extern "C" int spq_quantize_act(const float* x, int64_t M, int64_t K, const floa
     return SPQ_ERR_INVALID;
 }
 
-extern "C" int spq_rowscale_f16(const float* g, int64_t M, int64_t N, float premul, spq_half_t* out, float* row_scale,
+extern "C" int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out, float* row_scale,
                                 spq_stream_t stream) {
-    SPQ_REQUIRE(premul == 1.0f, "spq_rowscale_f16: premul != 1 is not implemented");
-    return spq_quantize_act(g, M, N, nullptr, nullptr, SPQ_PER_TENSOR, -1, 8, 1, SPQ_OPERAND_RAW, nullptr, 1.0f, nullptr, out,
-                            row_scale, stream);
+    SPQ_REQUIRE(g && out && M > 0 && N > 0, "spq_rowscale_f16: bad arguments");
+    if (ld_out <= 0) ld_out = N;
+    SPQ_REQUIRE(ld_out >= N, "spq_rowscale_f16: ld_out < N");
+    if (ld_out == N && (N % 4) == 0 && N <= 8192 && aligned16(g))
+        return spq_quantize_act(g, M, N, nullptr, nullptr, SPQ_PER_TENSOR, -1, 8, 1, SPQ_OPERAND_RAW, nullptr, 1.0f, nullptr,
+                                out, row_scale, stream);
+    SPQ_REQUIRE((ld_out % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0, "spq_rowscale_f16: ld_out must be even");
+    long long ctas = static_cast<long long>(sm_count()) * 8;
+    if (ctas > M) ctas = M;
+    rowscale_wide_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(g, M, N, out, ld_out, row_scale);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
 }
 
 extern "C" int spq_ste_backward(const float* grad, int64_t n, int qtype, float* out, spq_stream_t stream) {

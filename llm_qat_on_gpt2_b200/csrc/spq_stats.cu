@@ -175,13 +175,24 @@ stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ 
         stat_max[idx] = b;
     };
     if (!collapse) {
-        const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        // 32 channels per block, 8 lanes share the fold over the `chunks` partials of a channel
+        // (a single thread walking ~200 dependent-latency loads made this kernel as slow as the
+        // streaming pass itself)
+        __shared__ float fa[8][33], fb[8][33];
+        const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        const long long c = static_cast<long long>(blockIdx.x) * 32 + cl;
+        float a = INFINITY, b = -INFINITY;
         if (c < C) {
-            float a = pmin[c], b = pmax[c];
-            for (int k = 1; k < chunks; ++k) {
+            for (int k = sl; k < chunks; k += 8) {
                 a = nan_min(a, pmin[static_cast<long long>(k) * C + c]);
                 b = nan_max(b, pmax[static_cast<long long>(k) * C + c]);
             }
+        }
+        fa[sl][cl] = a; fb[sl][cl] = b;
+        __syncthreads();
+        if (sl == 0 && c < C) {
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { a = nan_min(a, fa[w][cl]); b = nan_max(b, fb[w][cl]); }
             emit(c, a, b);
         }
     } else {
@@ -277,7 +288,7 @@ extern "C" int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int 
         SPQ_LAUNCH_OK();
     }
     const int collapse = (bcast == SPQ_PER_TENSOR) ? 1 : 0;
-    const unsigned fgrid = collapse ? 1u : static_cast<unsigned>((C + 255) / 256);
+    const unsigned fgrid = collapse ? 1u : static_cast<unsigned>((C + 31) / 32);
     if (log_mode)
         stats_finalize_kernel<true><<<fgrid, 256, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
     else

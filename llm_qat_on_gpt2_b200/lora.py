@@ -50,7 +50,7 @@ def _to_f16_operand(x2d, row_mul=None, col_mul=None, mul=1.0, transposed=False):
     """fp16(x * row_mul[:,None] * col_mul[None,:] * mul) through the quantise kernel's raw mode."""
     one, zero = _dummy_params(x2d.device)
     rows, cols = x2d.shape
-    out = torch.empty((cols, rows) if transposed else (rows, cols), dtype=torch.float16, device=x2d.device)
+    out = _lib.empty_f16_padded(cols, rows, x2d.device) if transposed else _lib.empty_f16_padded(rows, cols, x2d.device)
     _lib.fake_quantize(x2d, one, zero, _lib.PER_TENSOR, _lib.MINMAX, 8, True, operand=out,
                        operand_kind=_lib.OPERAND_RAW, row_mul=row_mul, col_mul=col_mul, mul=mul,
                        operand_transposed=transposed)
@@ -81,7 +81,7 @@ def _quantized_operand(q, w, row_mul=None, col_mul=None, mul=1.0, transposed=Fal
     sc, zp, bcast = _quantizer_params(q, w)
     w2 = w.detach().float().contiguous()
     rows, cols = w2.shape
-    out = torch.empty((cols, rows) if transposed else (rows, cols), dtype=torch.float16, device=w.device)
+    out = _lib.empty_f16_padded(cols, rows, w.device) if transposed else _lib.empty_f16_padded(rows, cols, w.device)
     _lib.fake_quantize(w2, sc, zp, bcast, _lib.QTYPE[q.quantizer_type], q.num_bits, q.symmetric, operand=out,
                        operand_kind=_lib.OPERAND_DEQUANT, row_mul=row_mul, col_mul=col_mul, mul=mul,
                        operand_transposed=transposed)
@@ -96,9 +96,9 @@ def _norm_pow2(absmax: torch.Tensor, target_log2: int = 8) -> torch.Tensor:
 def _rowscaled_f16(x2d: torch.Tensor):
     """Row-scaled fp16 copy of a float32 matrix: returns (x16, row_scale) with x = x16 * row_scale."""
     M, K = x2d.shape
-    x16 = torch.empty((M, K), dtype=torch.float16, device=x2d.device)
+    x16 = _lib.empty_f16_padded(M, K, x2d.device)
     rs = torch.empty(M, dtype=torch.float32, device=x2d.device)
-    _lib.quantize_act(x2d, None, None, _lib.PER_TENSOR, -1, 8, True, _lib.OPERAND_RAW, None, 1.0, None, x16, rs)
+    _lib.rowscale_f16(x2d, x16, rs)
     return x16, rs
 
 
@@ -275,7 +275,7 @@ class _SPLinearFn(torch.autograd.Function):
     """Fused forward / STE backward of SPLinearWithLoRA at a quantised precision."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits):
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False):
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
         act = base['act']
@@ -287,7 +287,7 @@ class _SPLinearFn(torch.autograd.Function):
         rs = torch.empty(M, dtype=torch.float32, device=x.device) if use_lora else None
         _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
                           act['kind'], act['col_mul'], act['mul'], a_q, a_raw, rs)
-        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
         t = None
         if use_lora:
@@ -374,7 +374,7 @@ class _SPLinearFn(torch.autograd.Function):
                 gw = _lib.ste_backward(gw, _lib.LOG)
         if ctx.has_bias and need_b:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None
+        return gx, gw, gb, gA, gB, None, None, None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -517,9 +517,13 @@ class SPLinearWithLoRA(nn.Module):
         return ent[1], ent[2]
 
     # ---------------------------------------------------------------- forward (reference :127-150)
-    def forward(self, x):
+    def forward(self, x, out_half=False):
+        """Reference signature is forward(x) -> float32.  `out_half=True` (used by SPAttention when the
+        attention kernel runs in fp16) makes the GEMM epilogue store fp16 directly instead of float32
+        followed by a cast."""
         if self.current_bits >= 32:
-            return linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache)
+            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache)
+            return y.half() if out_half else y
 
         bits_key = f'{self.current_bits}bit'
         if bits_key not in self.quantizers_weight or bits_key not in self.quantizers_input:
@@ -532,7 +536,7 @@ class SPLinearWithLoRA(nn.Module):
             lora_on = active_lora.enabled and active_lora.scaling != 0 and not self.calibration_mode
             return _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
                                      active_lora.lora_A if lora_on else None,
-                                     active_lora.lora_B if lora_on else None, self, self.current_bits)
+                                     active_lora.lora_B if lora_on else None, self, self.current_bits, out_half)
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
         # reference, module by module (this is the calibration pass; errors surface as upstream).
@@ -542,6 +546,6 @@ class SPLinearWithLoRA(nn.Module):
         else:
             weight_quantized, cache = self._calibration_weight(self.current_bits, weight_quantizer)
         base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache)
-        if self.calibration_mode:
-            return base_output
-        return base_output + active_lora(x)
+        if not self.calibration_mode:
+            base_output = base_output + active_lora(x)
+        return base_output.half() if out_half else base_output

@@ -56,15 +56,13 @@ class SPAttention(nn.Module):
     def forward(self, hidden_states, attention_mask=None):
         # attention_mask is accepted and ignored, as in the reference (:58-76)
         B, T, C = hidden_states.shape
-        qkv = self.c_attn(hidden_states)
+        half = self.attention_dtype == 'fp16'
+        qkv = self.c_attn(hidden_states, out_half=True) if half else self.c_attn(hidden_states)
         q, k, v = qkv.split(self.n_embd, dim=2)
         q = q.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
         k = k.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
         v = v.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
-        if self.attention_dtype == 'fp16':
-            o = F.scaled_dot_product_attention(q.half(), k.half(), v.half(), is_causal=True).float()
-        else:
-            o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
         o = o.transpose(1, 2).contiguous().view(B, T, C)
         return self.c_proj(o)
 
@@ -288,9 +286,12 @@ class SPLMHeadModel(nn.Module):
 
         loss = None
         if labels is not None:
-            shift_logits = logits[..., :-1, :].contiguous()
-            shift_labels = labels[..., 1:].contiguous()
-            loss = F.cross_entropy(shift_logits.view(-1, shift_logits.size(-1)), shift_labels.view(-1))
+            # next-token loss of the reference (:441-449) without its 2 x [B,T,V] shifted copies:
+            # position t is scored against labels[t+1]; the last position is ignored, so the mean
+            # runs over the same B*(T-1) terms
+            targets = torch.full_like(labels, -100)
+            targets[..., :-1] = labels[..., 1:]
+            loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100)
 
         if return_dict or output_hidden_states:
             return {'loss': loss, 'logits': logits, 'hidden_states': all_hidden_states}

@@ -19,4 +19,14 @@ for _ in range(reps):
     _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
+Bt = B.t().contiguous()
+for _ in range(3):
+    ref = A @ Bt
+torch.cuda.synchronize()
+e0.record()
+for _ in range(reps):
+    ref = A @ Bt
+e1.record(); torch.cuda.synchronize()
+ms_ref = e0.elapsed_time(e1) / reps
+print(f"cuBLAS   {M}x{N}x{K} out=f16: {ms_ref*1e3:.1f} us  {2.0*M*N*K/ms_ref/1e9:.0f} TFLOP/s")
 print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")
