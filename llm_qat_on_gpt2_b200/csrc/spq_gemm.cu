@@ -5,10 +5,11 @@
 // 144-150): the operands are the fp16 code / dequant tensors produced by spq_quantize.cu, the
 // LoRA up-projection is folded in as one more K segment (A2, B2) of the same accumulator.
 //
-// Layout of one CTA (192 threads, persistent over output tiles):
+// Layout of one CTA (320 threads, persistent over output tiles):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5  epilogue: TMEM lane quadrant (warp_idx % 4) -> registers -> global
+//   warps 2..9  epilogue: TMEM lane quadrant (warp_idx % 4), column half ((warp_idx - 2) / 4):
+//               tcgen05.ld -> scale/clamp/bias in registers -> swizzled smem tile -> TMA bulk store
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), two TMEM accumulators with
 // tmem_full/tmem_empty mbarriers (MMA <-> epilogue) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
@@ -23,10 +24,11 @@ namespace gemm {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // 64 fp16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;     // 2 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
-constexpr int STG_LD = 36;      // floats per staged row: 32 + 4 pad (keeps 16 B alignment, conflict-free v4 access)
+constexpr int STG_TILE_BYTES = 32 * 32 * 4;   // per-epilogue-warp 32 x 32 fp32 staging tile, 128B-XOR-swizzled
 
 __device__ int g_abort = 0;    // watchdog: set when a pipeline wait timed out
 
@@ -144,6 +146,7 @@ struct EpiParams {
     float alpha;
     float clamp_abs;          // <= 0: off
     int debug;                // bit0: skip epilogue stores, bit1: skip MMA issue (profiling experiments only)
+    int tma_store;            // 1: D is written with TMA bulk tensor stores (fp32, 16 B aligned rows, no residual)
 };
 
 template <int BN>
@@ -152,9 +155,12 @@ struct SmemLayout {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
     static constexpr int EPI_BYTES = 2 * BN * 4;      // col_scale + bias of the tile
-    static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;   // per-epilogue-warp 32 x 32 fp32 transpose buffer (padded rows)
+    static constexpr int STG_BYTES = EPI_WARPS * STG_TILE_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+    // order: [stages][staging tiles][col_scale|bias][barriers]; the dynamic smem base must be 1024 B aligned
+    // (checked at run time) -- there is no room for alignment slack at BN = 256
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + STG_BYTES + EPI_BYTES + BAR_BYTES;
+    static_assert(TOTAL <= 232448, "shared memory budget");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -163,16 +169,13 @@ template <int BN, bool OUT_HALF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                int M, int N, int kb1, int kb2, EpiParams ep) {
+                const __grid_constant__ CUtensorMap tmD, int M, int N, int kb1, int kb2, EpiParams ep) {
     using L = SmemLayout<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    // 1024 B alignment for the 128B swizzle.  Offset arithmetic on the __shared__ symbol (not an integer
-    // round trip) so that the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST.
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* epi_cs = reinterpret_cast<float*>(smem + L::STAGES * L::STAGE_BYTES);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stg_all = smem + L::STAGES * L::STAGE_BYTES;                       // EPI_WARPS x 4 KB, 1024 B aligned
+    float* epi_cs = reinterpret_cast<float*>(stg_all + L::STG_BYTES);
     float* epi_bias = epi_cs + BN;
-    float* stg_all = epi_bias + BN;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::STAGES * L::STAGE_BYTES + L::EPI_BYTES + L::STG_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_bias + BN);
     uint64_t* empty_bar = full_bar + L::STAGES;
     uint64_t* tmem_full = empty_bar + L::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -185,6 +188,12 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_tiles = n_tiles * m_tiles;
     const int kb_total = kb1 + kb2;
 
+    // the 128B swizzle of TMA / UMMA / the staging tiles assumes a 1024 B aligned base
+    if ((smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) atomicExch(&g_abort, 2);
+        return;
+    }
+
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -192,13 +201,14 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmB2);
         }
+        if (ep.tma_store) tma_prefetch_desc(&tmD);
         for (int s = 0; s < L::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);     // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], EPI_WARPS);     // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -271,108 +281,155 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // ===================================================== epilogue (warps 2..5)
+        // ===================================================== epilogue (warps 2..9)
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int epi_tid = threadIdx.x - 64;         // 0..127
+        const int half = (warp - 2) >> 2;             // which half of the tile's columns
+        const int epi_tid = threadIdx.x - 64;         // 0..255
+        constexpr int CHUNKS = (BN / 2) / 32 > 0 ? (BN / 2) / 32 : 1;   // 32-column chunks per warp
+        constexpr int COLS_PER_HALF = BN / 2 >= 32 ? BN / 2 : 32;
+        float* stg = reinterpret_cast<float*>(stg_all + (warp - 2) * STG_TILE_BYTES);
+        const uint32_t stg_u32 = smem_u32(stg);
         int acc = 0;
         uint32_t acc_phase = 0;
+        bool store_pending = false;
         const float alpha = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f);
+        const bool active = (BN >= 64) || (half == 0);   // BN = 32 would leave the second half idle (not instantiated)
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t / n_tiles) * BM;
             const int n0 = (t % n_tiles) * BN;
             // stage this tile's per-column parameters (previous tile's readers are done: barrier 1)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int j = epi_tid; j < BN; j += 128) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int j = epi_tid; j < BN; j += 256) {
                 const int n = n0 + j;
                 epi_cs[j] = (ep.col_scale && n < N) ? __ldg(ep.col_scale + n) : 1.0f;
                 epi_bias[j] = (ep.bias && n < N) ? __ldg(ep.bias + n) : 0.0f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m0 + quad * 32 + lane;
-            const bool row_ok = row < M;
-            const float rs = alpha * ((ep.row_scale && row_ok) ? __ldg(ep.row_scale + row) : 1.0f);
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            float* stg = stg_all + (warp - 2) * 32 * STG_LD;       // this warp's transpose buffer
-            const int rbase = m0 + quad * 32;                      // first global row of this warp's 32 x BN strip
-            const bool d_vec = OUT_HALF ? (((ep.ldd & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.D) & 15u) == 0))
-                                        : (((ep.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.D) & 15u) == 0));
-            const bool c_vec = ep.C && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
+            const int rbase = m0 + quad * 32;                       // first global row of this warp's strip
+            const int row = rbase + lane;
+            const float rs = alpha * ((ep.row_scale && row < M) ? __ldg(ep.row_scale + row) : 1.0f);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + half * COLS_PER_HALF);
+            const int sw = lane & 7;                                // 128B swizzle: 16 B chunk index ^ (row % 8)
+            if (active) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
-                tmem_ld_wait();
-                const int nc = n0 + c * 32;
-                if (nc >= N || (ep.debug & 1)) continue;            // warp-uniform
-                // TMEM gives each lane one output ROW (32 consecutive columns).  Writing rows straight to
-                // global memory makes every store instruction touch 32 cache lines; instead the 32 x 32
-                // block is transposed through padded shared memory and written out coalesced.  The row
-                // scale is applied before the transpose (one value per lane), column scale / clamp / bias /
-                // residual after it (each lane then owns fixed columns).
-                float* srow = stg + lane * STG_LD;
+                for (int c = 0; c < CHUNKS; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+                    tmem_ld_wait();
+                    const int cl = half * COLS_PER_HALF + c * 32;   // first column of the chunk inside the tile
+                    const int nc = n0 + cl;
+                    if (nc >= N || rbase >= M || (ep.debug & 1)) continue;      // warp-uniform
+                    if (store_pending) {                            // the previous TMA store must have read the tile
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        store_pending = false;
+                    }
+                    if (ep.tma_store) {
+                        // finish the arithmetic in registers (this lane owns one row, 32 columns), write the row
+                        // into the swizzled tile, then one lane hands the 32 x 32 block to the TMA engine
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(srow + j) =
-                        make_float4(__uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
-                                    __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
-                __syncwarp();
-                const bool full = (nc + 32 <= N);
-                if (full && d_vec && (!ep.C || c_vec)) {
-                    // 8 lanes cover one 128 B row segment; one instruction writes 4 rows
-                    const int rsub = lane >> 3, cq = (lane & 7) * 4;
-                    const float4 cs4 = *reinterpret_cast<const float4*>(epi_cs + c * 32 + cq);
-                    const float4 bi4 = *reinterpret_cast<const float4*>(epi_bias + c * 32 + cq);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rl = i * 4 + rsub;
-                        const long long gr = rbase + rl;
-                        if (gr < M) {
-                            float4 o = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cq);
-                            o.x *= cs4.x; o.y *= cs4.y; o.z *= cs4.z; o.w *= cs4.w;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 cs4 = *reinterpret_cast<const float4*>(epi_cs + cl + j);
+                            const float4 bi4 = *reinterpret_cast<const float4*>(epi_bias + cl + j);
+                            float4 o;
+                            o.x = __uint_as_float(v[j]) * rs * cs4.x;     o.y = __uint_as_float(v[j + 1]) * rs * cs4.y;
+                            o.z = __uint_as_float(v[j + 2]) * rs * cs4.z; o.w = __uint_as_float(v[j + 3]) * rs * cs4.w;
                             if (ep.clamp_abs > 0.f) {
                                 o.x = fminf(fmaxf(o.x, -ep.clamp_abs), ep.clamp_abs); o.y = fminf(fmaxf(o.y, -ep.clamp_abs), ep.clamp_abs);
                                 o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
                             }
                             o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
-                            if (ep.C) {
-                                const float4 cv = *reinterpret_cast<const float4*>(ep.C + gr * ep.ldc + nc + cq);
-                                o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
-                            }
-                            if constexpr (OUT_HALF) {
-                                *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(ep.D) + gr * ep.ldd + nc + cq) =
-                                    make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
-                            } else {
-                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.D) + gr * ep.ldd + nc + cq) = o;
-                            }
+                            *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
                         }
-                    }
-                } else {
-                    // unaligned / ragged: one row per instruction, lane = column (still coalesced)
-                    const bool col_ok = nc + lane < N;
-                    const float cs1 = epi_cs[c * 32 + lane], bi1 = epi_bias[c * 32 + lane];
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&tmD)),
+                                         "r"(stg_u32), "r"(nc), "r"(rbase)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        store_pending = true;
+                    } else {
+                        // general path (fp16 output, residual input, unaligned D): row scale before the transpose,
+                        // column scale / clamp / bias / residual after it, coalesced stores from the swizzled tile
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) =
+                                make_float4(__uint_as_float(v[j]) * rs, __uint_as_float(v[j + 1]) * rs,
+                                            __uint_as_float(v[j + 2]) * rs, __uint_as_float(v[j + 3]) * rs);
+                        __syncwarp();
+                        const bool full = (nc + 32 <= N);
+                        const bool d_vec = OUT_HALF ? (((ep.ldd & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.D) & 15u) == 0))
+                                                    : (((ep.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.D) & 15u) == 0));
+                        const bool c_vec = ep.C && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
+                        if (full && d_vec && (!ep.C || c_vec)) {
+                            // 8 lanes cover one 128 B row segment; one instruction writes 4 rows
+                            const int rsub = lane >> 3, cq = lane & 7;
+                            const float4 cs4 = *reinterpret_cast<const float4*>(epi_cs + cl + cq * 4);
+                            const float4 bi4 = *reinterpret_cast<const float4*>(epi_bias + cl + cq * 4);
+                            long long doff = static_cast<long long>(rbase + rsub) * ep.ldd + nc + cq * 4;
+                            long long coff = static_cast<long long>(rbase + rsub) * ep.ldc + nc + cq * 4;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rl = i * 4 + rsub;
+                                if (rbase + rl < M) {
+                                    float4 o = *reinterpret_cast<const float4*>(stg + rl * 32 + ((cq ^ (rl & 7)) << 2));
+                                    o.x *= cs4.x; o.y *= cs4.y; o.z *= cs4.z; o.w *= cs4.w;
+                                    if (ep.clamp_abs > 0.f) {
+                                        o.x = fminf(fmaxf(o.x, -ep.clamp_abs), ep.clamp_abs); o.y = fminf(fmaxf(o.y, -ep.clamp_abs), ep.clamp_abs);
+                                        o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
+                                    }
+                                    o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
+                                    if (ep.C) {
+                                        const float4 cv = *reinterpret_cast<const float4*>(ep.C + coff);
+                                        o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
+                                    }
+                                    if constexpr (OUT_HALF) {
+                                        *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(ep.D) + doff) =
+                                            make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                    } else {
+                                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.D) + doff) = o;
+                                    }
+                                }
+                                doff += 4 * ep.ldd;
+                                coff += 4 * ep.ldc;
+                            }
+                        } else {
+                            // unaligned / ragged: one row per instruction, lane = column (still coalesced)
+                            const bool col_ok = nc + lane < N;
+                            const float cs1 = epi_cs[cl + lane], bi1 = epi_bias[cl + lane];
+                            long long doff = static_cast<long long>(rbase) * ep.ldd + nc + lane;
+                            long long coff = static_cast<long long>(rbase) * ep.ldc + nc + lane;
 #pragma unroll 4
-                    for (int rl = 0; rl < 32; ++rl) {
-                        const long long gr = rbase + rl;
-                        if (gr < M && col_ok) {
-                            float o = stg[rl * STG_LD + lane] * cs1;
-                            if (ep.clamp_abs > 0.f) o = fminf(fmaxf(o, -ep.clamp_abs), ep.clamp_abs);
-                            o += bi1;
-                            if (ep.C) o += ep.C[gr * ep.ldc + nc + lane];
-                            if constexpr (OUT_HALF) reinterpret_cast<unsigned short*>(ep.D)[gr * ep.ldd + nc + lane] = f2h_sat(o);
-                            else reinterpret_cast<float*>(ep.D)[gr * ep.ldd + nc + lane] = o;
+                            for (int rl = 0; rl < 32; ++rl) {
+                                if (rbase + rl < M && col_ok) {
+                                    float o = stg[rl * 32 + ((((lane >> 2) ^ (rl & 7)) << 2) | (lane & 3))] * cs1;
+                                    if (ep.clamp_abs > 0.f) o = fminf(fmaxf(o, -ep.clamp_abs), ep.clamp_abs);
+                                    o += bi1;
+                                    if (ep.C) o += ep.C[coff];
+                                    if constexpr (OUT_HALF) reinterpret_cast<unsigned short*>(ep.D)[doff] = f2h_sat(o);
+                                    else reinterpret_cast<float*>(ep.D)[doff] = o;
+                                }
+                                doff += ep.ldd;
+                                coff += ep.ldc;
+                            }
                         }
+                        __syncwarp();                               // the tile is reused by the next chunk
                     }
                 }
-                __syncwarp();                                        // staging buffer is reused by the next chunk
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 
     tcgen05_fence_before();
@@ -424,9 +481,30 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
     return SPQ_OK;
 }
 
+// fp32 row-major D [M, N], leading dimension ldd (elements): box = 32 columns x 32 rows, 128B swizzle
+static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SPQ_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (output) failed (%d)", static_cast<int>(r));
+        return SPQ_ERR_CUDA;
+    }
+    return SPQ_OK;
+}
+
 template <int BN, bool OUT_HALF>
-static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2, int M,
-                     int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
+static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
+                     const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -435,7 +513,7 @@ static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    qgemm_nt_kernel<BN, OUT_HALF><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, M, N, kb1, kb2, ep);
+    qgemm_nt_kernel<BN, OUT_HALF><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
@@ -672,14 +750,18 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     const int kb2 = static_cast<int>((K2 + BK - 1) / BK);
     cudaStream_t st = as_stream(stream);
     const int m = static_cast<int>(M), n = static_cast<int>(N);
+    // TMA store path: fp32 output with 16-byte aligned rows and no residual input
+    CUtensorMap tD = tA;
+    ep.tma_store = (!d_is_half && !C && (ldd % 4) == 0 && aligned16(D) && !(ep.debug & 4)) ? 1 : 0;
+    if (ep.tma_store && (rc = make_tmap_out(&tD, D, M, N, ldd)) != SPQ_OK) return rc;
     if (d_is_half) {
-        if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
-        if (bn == 128) return launch_nt<128, true>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
-        return launch_nt<64, true>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+        if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        if (bn == 128) return launch_nt<128, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        return launch_nt<64, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     }
-    if (bn == 256) return launch_nt<256, false>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
-    if (bn == 128) return launch_nt<128, false>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
-    return launch_nt<64, false>(tA, tB, tA2, tB2, m, n, kb1, kb2, ep, st);
+    if (bn == 256) return launch_nt<256, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+    if (bn == 128) return launch_nt<128, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+    return launch_nt<64, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
 }
 
 extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq, int64_t Mred, int64_t I, int64_t J,

@@ -1,0 +1,175 @@
+"""GPU parity tests of the CPT (part2) variant against fixtures generated from the unmodified
+reference (tests/golden/make_golden_cpt.py).  pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype=torch.float32)
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def calibrate(m, bits, x_batches):
+    m.set_precision(bits)
+    qw = m.quantizer_weight
+    qw.set_num_bits(bits); qw.start_calibration()
+    with torch.no_grad():
+        qw(m.linear.weight.data)
+    qw.finish_calibration()
+    qi = m.quantizer_input
+    qi.set_num_bits(bits); qi.start_calibration()
+    m.calibration_mode = True
+    with torch.no_grad():
+        for xb in x_batches:
+            m(xb)
+    m.calibration_mode = False
+    qi.finish_calibration()
+    lq = m.lora_weight_quantizers[f"{bits}bit"]
+    lq.set_num_bits(bits); lq.start_calibration()
+    with torch.no_grad():
+        lq(m.shared_lora.lora_A); lq(m.shared_lora.lora_B)
+    lq.finish_calibration()
+
+
+def test_cpt_linear_against_golden():
+    from llm_qat_on_gpt2_b200.cpt import CPTLinear
+    g = np.load(os.path.join(GOLDEN, "cpt_linear.npz"))
+    K, N, r = [int(v) for v in g["meta"]]
+    m = CPTLinear(K, N, bit_widths=[4, 8, 32], quantizer_per_bit={4: "minmax", 8: "log", 32: None},
+                  gradient_bits=8, shared_lora_rank=r, shared_lora_alpha=16).cuda()
+    with torch.no_grad():
+        m.linear.weight.copy_(dev(g["weight"])); m.linear.bias.copy_(dev(g["bias"]))
+        m.shared_lora.lora_A.copy_(dev(g["lora_A"])); m.shared_lora.lora_B.copy_(dev(g["lora_B"]))
+    m.train()
+    xc = [dev(x) for x in g["x_calib"]]
+    x, gy = dev(g["x"]), dev(g["grad_y"])
+    for bits in (8, 4):
+        calibrate(m, bits, xc)
+        exact = bits == 4                                   # min-max parameters are bit-exact, log within 1 ulp
+        for nm, q in (("qw", m.quantizer_weight), ("qi", m.quantizer_input), ("lq", m.lora_weight_quantizers[f"{bits}bit"])):
+            for suffix, table in (("scale", q.scales), ("zp", q.zero_points)):
+                got, want = table[bits].cpu().numpy(), g[f"{nm}{bits}_{suffix}"]
+                assert got.shape == want.shape, (nm, bits, suffix)
+                if exact:
+                    assert np.array_equal(got, want), (nm, bits, suffix)
+                else:
+                    d = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+                    assert d.max() <= 4, (nm, bits, suffix, d.max())
+        m.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        y = m(xg)
+        y.backward(gy)
+        assert rel_fro(y.detach().cpu().numpy(), g[f"y{bits}"]) <= TOL
+        for got, key in ((xg.grad, "gx"), (m.linear.weight.grad, "gw"), (m.linear.bias.grad, "gb"),
+                         (m.shared_lora.lora_A.grad, "gA"), (m.shared_lora.lora_B.grad, "gB")):
+            assert rel_fro(got.cpu().numpy(), g[f"{key}{bits}"]) <= TOL, (key, bits, rel_fro(got.cpu().numpy(), g[f"{key}{bits}"]))
+    # cycling back needs no recalibration
+    m.set_precision(8)
+    with torch.no_grad():
+        assert rel_fro(m(x).cpu().numpy(), g["y8_again"]) <= TOL
+    # gradient quantisers: collect on one backward, quantise the next
+    for gq in (m.shared_lora.grad_quantizer_A, m.shared_lora.grad_quantizer_B):
+        gq.start_calibration()
+    m.zero_grad(); m(x.clone()).backward(gy)
+    for gq in (m.shared_lora.grad_quantizer_A, m.shared_lora.grad_quantizer_B):
+        gq.finish_calibration()
+    assert tuple(m.shared_lora.grad_quantizer_A.scales[8].shape) == g["gqA_scale"].shape
+    m.zero_grad(); m(x.clone()).backward(gy)
+    # 8-bit fake quantisation of a gradient that itself carries 3e-4 of GEMM rounding: a few codes
+    # may differ by one step (1/127 of the channel range), so the bar is 2 steps of 254 on the max
+    for got, key in ((m.shared_lora.lora_A.grad, "gA8_gq"), (m.shared_lora.lora_B.grad, "gB8_gq")):
+        gn, want = got.cpu().numpy(), g[key]
+        assert rel_fro(gn, want) <= 1e-2, (key, rel_fro(gn, want))
+    keys = sorted(m.state_dict().keys())
+    assert keys == sorted(str(k) for k in g["state_keys"])
+    with torch.no_grad():
+        m.set_precision(32)
+        assert rel_fro(m(x).cpu().numpy(), g["y32"]) <= TOL
+    with pytest.raises(ValueError):
+        m.set_precision(5)
+
+
+def test_cpt_quantizer_state_roundtrip_and_eval_passthrough():
+    from llm_qat_on_gpt2_b200.cpt import LearnableFakeQuantize
+    q = LearnableFakeQuantize(8, channel_dim=-1, quantizer_type="log", is_input=True).cuda()
+    x = torch.randn(4, 10, 32, device="cuda")
+    q.eval()
+    assert q(x) is x                                        # uncalibrated width outside training: pass-through
+    q.train()
+    with pytest.raises(RuntimeError, match="not calibrated"):
+        q(x)
+    for bits in (8, 4):
+        q.set_num_bits(bits); q.start_calibration(); q(x); q.finish_calibration()
+    assert q.calibrated_bits == {4, 8}
+    sd = q.state_dict()
+    assert {"_scales_4", "_scales_8", "_zero_points_4", "_zero_points_8", "_calibrated_bits", "running_min", "running_max"} <= set(sd)
+    q2 = LearnableFakeQuantize(8, channel_dim=-1, quantizer_type="log", is_input=True).cuda()
+    q2.load_state_dict(sd)
+    assert q2.calibrated_bits == {4, 8} and torch.equal(q2.scales[4], q.scales[4])
+    q2.set_num_bits(4); q.set_num_bits(4)
+    assert torch.equal(q2(x), q(x))
+
+
+def test_cpt_model_forward_backward_smoke():
+    """Tiny CPTModel: calibrate two widths, cycle precision per step, loss finite, LoRA grads flow
+    through the quantised LM head (vocab 211 -> odd leading dimensions on every GEMM path)."""
+    from types import SimpleNamespace
+    from llm_qat_on_gpt2_b200.cpt import CPTLinear, CPTModel
+    mc = SimpleNamespace(vocab_size=211, n_positions=32, n_embd=64, n_layer=2, n_head=4, embd_pdrop=0.0,
+                         layer_norm_epsilon=1e-5, bit_widths=[4, 8, 32], quantizer_per_bit={4: "minmax", 8: "log", 32: None},
+                         gradient_bits=8, shared_lora_rank=8, shared_lora_alpha=16)
+    model = CPTModel({"model": mc, "training": SimpleNamespace(target_bits=8)}).cuda()
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, CPTLinear):
+                mod.shared_lora.lora_B.normal_(0, 0.02)
+    ids = torch.randint(0, 211, (2, 32), device="cuda")
+    lins = [m for m in model.modules() if isinstance(m, CPTLinear)]
+    for bits in (8, 4):
+        model.set_precision(bits)
+        for m in lins:
+            m.quantizer_weight.set_num_bits(bits); m.quantizer_weight.start_calibration()
+            with torch.no_grad():
+                m.quantizer_weight(m.linear.weight.data)
+            m.quantizer_weight.finish_calibration()
+            m.quantizer_input.set_num_bits(bits); m.quantizer_input.start_calibration()
+        model.disable_lora_for_calibration()
+        with torch.no_grad():
+            model(ids)
+        model.enable_lora_after_calibration()
+        for m in lins:
+            m.quantizer_input.finish_calibration()
+            lq = m.lora_weight_quantizers[f"{bits}bit"]
+            lq.set_num_bits(bits); lq.start_calibration()
+            with torch.no_grad():
+                lq(m.shared_lora.lora_A); lq(m.shared_lora.lora_B)
+            lq.finish_calibration()
+    model.train()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    for m in lins:
+        m.shared_lora.lora_A.requires_grad_(True); m.shared_lora.lora_B.requires_grad_(True)
+    ref32 = None
+    for bits in (8, 4, 8, 32):
+        model.set_precision(bits)
+        model.zero_grad()
+        out = model(ids, labels=ids)
+        assert torch.isfinite(out.loss), bits
+        if bits < 32:
+            out.loss.backward()
+            gA = model.lm_head.shared_lora.lora_A.grad
+            assert gA is not None and torch.isfinite(gA).all() and gA.abs().sum() > 0
+        else:
+            ref32 = out.logits
+    assert ref32.shape == (2, 32, 211)
