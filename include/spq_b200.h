@@ -103,6 +103,18 @@ SPQ_API int spq_quantize_act(const float* x, int64_t M, int64_t K,
                      int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
                      spq_half_t* a_q, spq_half_t* a_raw, float* raw_row_scale, spq_stream_t stream);
 
+/* Scale preparation for the fused linear (host-side glue of p1/lora.py:141-150 made one launch):
+ * from the input quantiser's calibrated (scale, zero_point) [in_n = 1 or K], the per-row absmax of
+ * the dequantised weight [N] and, optionally, |q(A)| [K, r] of the active LoRA adapter, computes the
+ * per-K factor the weight operand absorbs, the activation operand multiplier, the power-of-two row
+ * normaliser pw[n] (and 1/pw) and lora_vec[0:r] = tau, [r:2r] = 1/tau, [2r:3r] = lora_scaling/tau
+ * (tau: static power-of-two pre-scale of t = x q(A) derived from the calibrated input bound). */
+SPQ_API int spq_prep_linear_scales(const float* in_scale, const float* in_zero_point, int64_t in_n,
+                           int qtype, int bits, int symmetric, int64_t K,
+                           const float* w_rowmax, int64_t N, const float* aq_abs, int64_t r,
+                           float lora_scaling, float* absorb, float* act_mul, float* pw, float* inv_pw,
+                           float* lora_vec, spq_stream_t stream);
+
 /* STE backward (p1/quantization_methods.py:25-28, 82-90): identity (min-max) or clamp to
  * [-10, 10] (log).  out may alias grad. */
 SPQ_API int spq_ste_backward(const float* grad, int64_t n, int qtype, float* out, spq_stream_t stream);

@@ -526,6 +526,7 @@ static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
 // blocks 8 KB apart (LBO), 8-row groups 1 KB apart (SBO).  The reduction (over tokens) is split
 // across CTAs; partial tiles are combined with fp32 atomics (RED) into the pre-zeroed D.
 constexpr int TN_BOX_BYTES = 64 * 128;   // 64 reduction rows x 64 fp16
+constexpr int TN_THREADS = 192;           // TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quadrant)
 
 template <int BJ>
 struct TnSmem {
@@ -547,7 +548,7 @@ struct TnEpi {
 };
 
 template <int BJ>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 qgemm_tn_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, int I, int J, int kb_total,
                 int kb_per_split, int j_tiles, TnEpi ep) {
     using L = TnSmem<BJ>;
@@ -670,7 +671,7 @@ static int launch_tn(const CUtensorMap& tP, const CUtensorMap& tQ, int I, int J,
     const int per = (kb_total + splits - 1) / splits;
     splits = (kb_total + per - 1) / per;
     dim3 grid(tiles, splits);
-    qgemm_tn_kernel<BJ><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tP, tQ, I, J, kb_total, per, j_tiles, ep);
+    qgemm_tn_kernel<BJ><<<grid, TN_THREADS, L::TOTAL, stream>>>(tP, tQ, I, J, kb_total, per, j_tiles, ep);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

@@ -1,0 +1,148 @@
+// One-launch preparation of every scale vector a fused SPLinearWithLoRA forward needs after its
+// input quantiser has been (re)calibrated.  Replaces ~100 tiny elementwise launches per layer
+// (exp2 / ceil / where / amax ... on K- and N-sized vectors) that made the calibrate+forward step
+// launch-bound.  Single CTA: the vectors are at most a few thousand elements long.
+//
+// Given the activation quantiser's (scale, zero_point) [K or 1] and the per-row absmax of the
+// dequantised weight, it produces
+//   absorb[k]   what the weight operand must be multiplied by per input channel
+//               (min-max: scale[k] / code_mul;  log: 2^(ceil(log_max[k]) - 8))
+//   act_mul[k]  what the activation operand is multiplied by (min-max: unused = 1;  log: 1 / absorb[k])
+//   pw[n], inv_pw[n]   power-of-two row normaliser of the weight operand and its reciprocal
+//   lora[0:r] = tau, lora[r:2r] = 1/tau, lora[2r:3r] = scaling/tau   with tau the static pre-scale of
+//               t = x q(A), chosen from the bound  max_j sum_k xbound[k] |q(A)[k,j]|
+#include "spq_common.cuh"
+
+namespace spq {
+namespace prep {
+
+__device__ __forceinline__ float pow2_ceil(float x) {       // smallest power of two >= x (x > 0, finite)
+    int e;
+    const float f = frexpf(x, &e);                           // x = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.0f, f == 0.5f ? e - 1 : e);
+}
+
+__device__ __forceinline__ float block_max(float v, float* s_red) {
+    v = warp_fmax(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float m = s_red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+    return m;
+}
+
+struct PrepArgs {
+    const float* in_scale; const float* in_zp; int in_n;     // 1 or K
+    int qtype, bits, symmetric;
+    long long K, N, r;
+    const float* w_rowmax;                                   // [N]
+    const float* aq_abs;                                     // [K, r] or null
+    float lora_scaling;
+    float* absorb; float* act_mul; float* pw; float* inv_pw; float* lora;
+};
+
+__device__ __forceinline__ void chan(const PrepArgs& a, long long k, float& absorb, float& act_mul, float& xbound) {
+    const float sc = __ldg(a.in_scale + (a.in_n == 1 ? 0 : k));
+    const float zp = __ldg(a.in_zp + (a.in_n == 1 ? 0 : k));
+    if (a.qtype == SPQ_MINMAX) {
+        const int shift = a.bits > 11 ? a.bits - 11 : 0;     // codes beyond 11 bits are pre-scaled to stay in fp16 range
+        absorb = ldexpf(sc, shift);
+        act_mul = 1.0f;
+        if (a.symmetric) {
+            xbound = sc * static_cast<float>((1ll << (a.bits - 1)) - 1);
+        } else {
+            const float full = static_cast<float>((1ll << a.bits) - 1);
+            xbound = fmaxf(fabsf(zp), fabsf(full - zp)) * sc;
+        }
+    } else {
+        float lmax = zp + fmaxf(sc, 0.f);                    // log_min + log_range
+        lmax = fminf(fmaxf(lmax, -100.f), 100.f);
+        const float e = ceilf(lmax);
+        absorb = exp2f(e - 8.0f);
+        act_mul = exp2f(8.0f - e);
+        xbound = exp2f(lmax);
+    }
+}
+
+__global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
+    __shared__ float s_red[32];
+    __shared__ float s_t[1024];
+    const int tid = threadIdx.x;
+    float amax = 0.f;
+    for (long long k = tid; k < a.K; k += blockDim.x) {
+        float ab, am, xb;
+        chan(a, k, ab, am, xb);
+        a.absorb[k] = ab;
+        a.act_mul[k] = am;
+        amax = fmaxf(amax, ab);
+    }
+    const float absorb_max = block_max(amax, s_red);
+    for (long long n = tid; n < a.N; n += blockDim.x) {
+        const float wm = __ldg(a.w_rowmax + n) * absorb_max;
+        const float p = (wm > 0.f && wm < INFINITY) ? pow2_ceil(wm) * 0.00390625f : 1.0f;   // row max -> (128, 256]
+        a.pw[n] = p;
+        a.inv_pw[n] = 1.0f / p;
+    }
+    if (a.aq_abs != nullptr && a.r > 0) {
+        // tsum[j] = sum_k xbound[k] * |Aq[k, j]|;  thread -> column j = i % r when r divides the block
+        const long long r = a.r;
+        float tmax = 0.f;
+        if (r <= 1024 && (1024 % r) == 0) {
+            const long long j = tid % r, k0 = tid / r, kstep = 1024 / r;
+            float acc = 0.f;
+            for (long long k = k0; k < a.K; k += kstep) {
+                float ab, am, xb;
+                chan(a, k, ab, am, xb);
+                acc += xb * __ldg(a.aq_abs + k * r + j);
+            }
+            s_t[tid] = acc;
+            __syncthreads();
+            if (tid < r) {
+                float t = 0.f;
+                for (long long q = tid; q < 1024; q += r) t += s_t[q];
+                tmax = t;
+            }
+        } else {
+            for (long long j = tid; j < r; j += blockDim.x) {
+                float acc = 0.f;
+                for (long long k = 0; k < a.K; ++k) {
+                    float ab, am, xb;
+                    chan(a, k, ab, am, xb);
+                    acc += xb * __ldg(a.aq_abs + k * r + j);
+                }
+                tmax = fmaxf(tmax, acc);
+            }
+        }
+        tmax = block_max(tmax, s_red);
+        const float tau = (tmax > 0.f && tmax < INFINITY) ? 16384.0f / pow2_ceil(tmax) : 1.0f;
+        for (long long j = tid; j < r; j += blockDim.x) {
+            a.lora[j] = tau;
+            a.lora[r + j] = 1.0f / tau;
+            a.lora[2 * r + j] = a.lora_scaling / tau;
+        }
+    }
+}
+
+}  // namespace prep
+}  // namespace spq
+
+using namespace spq;
+
+extern "C" int spq_prep_linear_scales(const float* in_scale, const float* in_zero_point, int64_t in_n, int qtype, int bits,
+                                      int symmetric, int64_t K, const float* w_rowmax, int64_t N, const float* aq_abs,
+                                      int64_t r, float lora_scaling, float* absorb, float* act_mul, float* pw, float* inv_pw,
+                                      float* lora_vec, spq_stream_t stream) {
+    SPQ_REQUIRE(in_scale && in_zero_point && w_rowmax && absorb && act_mul && pw && inv_pw, "spq_prep_linear_scales: null pointer");
+    SPQ_REQUIRE(K > 0 && N > 0 && (in_n == 1 || in_n == K), "spq_prep_linear_scales: input scale must have 1 or K elements");
+    SPQ_REQUIRE(bits >= 1 && bits < 32 && (qtype == SPQ_MINMAX || qtype == SPQ_LOG), "spq_prep_linear_scales: bad quantiser");
+    SPQ_REQUIRE(aq_abs == nullptr || (r > 0 && lora_vec), "spq_prep_linear_scales: LoRA outputs missing");
+    prep::PrepArgs a;
+    a.in_scale = in_scale; a.in_zp = in_zero_point; a.in_n = static_cast<int>(in_n);
+    a.qtype = qtype; a.bits = bits; a.symmetric = symmetric; a.K = K; a.N = N; a.r = aq_abs ? r : 0;
+    a.w_rowmax = w_rowmax; a.aq_abs = aq_abs; a.lora_scaling = lora_scaling;
+    a.absorb = absorb; a.act_mul = act_mul; a.pw = pw; a.inv_pw = inv_pw; a.lora = lora_vec;
+    prep::prep_linear_scales_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}

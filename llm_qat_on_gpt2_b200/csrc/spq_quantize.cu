@@ -56,40 +56,55 @@ __device__ __forceinline__ float log_prelevel(float l, float log_min, float rang
     return __fmul_rn(ln, qp.full);
 }
 
-__device__ __forceinline__ LogOut log_elem(float x, float log_min, float log_range, const QParams& qp) {
+// Per-channel constants of the log quantiser that do not depend on the element.
+struct LogCh {
+    float log_min, log_range, range_c, inv_range;
+};
+__device__ __forceinline__ LogCh make_logch(float log_min, float log_range) {
+    LogCh c;
+    c.log_min = log_min;
+    c.log_range = log_range;
+    c.range_c = (log_range < LOG_EPS) ? LOG_EPS : log_range;          // :43 clamp(min=eps)
+    c.inv_range = __frcp_rn(c.range_c);
+    return c;
+}
+
+// Level index: bit-exact w.r.t. the reference arithmetic (correctly rounded log2, IEEE division).
+// Fast path: lg2.approx + reciprocal multiply + one FMA; its result can differ from the exact
+// pre-rounding value by at most `band`, so whenever it lies that close to a rounding tie the
+// element is re-evaluated with the exact sequence.  ~3e-4 of the elements at 8 bits.
+__device__ __forceinline__ LogOut log_elem(float x, const LogCh& ch, const QParams& qp) {
     LogOut o;
     const float ax = fabsf(x);
-    const bool zero = ax < LOG_EPS;                        // :36
+    const bool zero = ax < LOG_EPS;                                      // :36
     o.sign = zero ? 0.f : ((x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f));
-    const float axc = (ax < LOG_EPS) ? LOG_EPS : ax;       // :40 clamp(min=eps)
-    const float range_c = (log_range < LOG_EPS) ? LOG_EPS : log_range;   // :43
+    const float axc = (ax < LOG_EPS) ? LOG_EPS : ax;                     // :40 clamp(min=eps), >= 1e-5: never denormal
     const float nl = qp.symmetric ? qp.n_sym : qp.full;
+    const float lev_mul = qp.symmetric ? 2.f * nl : nl;
 
-    float l = log2f(axc);
-    float v = log_prelevel(l, log_min, range_c, qp);
+    float l = __log2f(axc);                                              // |error| < 2^-20 on this range
+    float ln = fminf(fmaxf((l - ch.log_min) * ch.inv_range, 0.f), 1.f);
+    float v = qp.symmetric ? fmaf(ln, lev_mul, -nl) : ln * lev_mul;
     float r = rintf(v);
-    // distance of v from the nearest rounding tie, against the band a 2-ulp error of l can move it
     const float tie_dist = fabsf(fabsf(v - r) - 0.5f);
-    const float lev_mul = (qp.symmetric ? 2.f : 1.f) * nl;
-    const float band = (lev_mul / range_c) * (fabsf(l) * 9.5367431640625e-07f + 1e-12f) + fabsf(v) * 9.5367431640625e-07f + 1e-9f;
-    if (tie_dist <= band) {                               // rare: exact path
+    const float band = lev_mul * (fmaf(fabsf(l), 4.76837158203125e-07f, 1.9073486328125e-06f) * ch.inv_range + 9.5367431640625e-07f) +
+                       fabsf(v) * 4.76837158203125e-07f + 1e-9f;
+    if (tie_dist <= band) {                                              // rare: the reference's exact sequence
         l = log2_cr(axc);
-        v = log_prelevel(l, log_min, range_c, qp);
+        v = log_prelevel(l, ch.log_min, ch.range_c, qp);
         r = rintf(v);
     }
     float qn;
-    if (qp.symmetric) {                                   // :50-56, :63
+    if (qp.symmetric) {                                                  // :50-56, :63 (value only: tolerance-level)
         r = fminf(fmaxf(r, -nl), nl);
-        const float qv = __fmul_rn(__fadd_rn(__fdiv_rn(r, __fmul_rn(2.f, nl)), 0.5f), qp.full);
-        qn = __fdiv_rn(qv, qp.full);
-    } else {                                              // :57-60, :65
+        qn = fmaf(r, __frcp_rn(lev_mul), 0.5f);
+    } else {                                                             // :57-60, :65
         r = fminf(fmaxf(r, 0.f), nl);
-        qn = __fdiv_rn(r, nl);
+        qn = r * __frcp_rn(nl);
     }
     o.level = r;
-    const float x_hat = __fadd_rn(__fmul_rn(qn, log_range), log_min);   // :67
-    const float mag = exp2f(x_hat);                                     // :69 (tolerance-level op)
-    o.dq = zero ? 0.f : __fmul_rn(mag, o.sign);                         // :71-74
+    const float mag = exp2f(fmaf(qn, ch.log_range, ch.log_min));         // :67-69
+    o.dq = zero ? 0.f : mag * o.sign;                                    // :71-74
     return o;
 }
 
@@ -153,7 +168,7 @@ fake_quantize_kernel(FqArgs a) {
                 const MinMaxOut o = minmax_elem(xv[j], sj, zj, a.qp);
                 dq[j] = o.dq; code[j] = o.code; centered = o.centered; sg[j] = 0.f;
             } else {
-                const LogOut o = log_elem(xv[j], zj, sj, a.qp);
+                const LogOut o = log_elem(xv[j], make_logch(zj, sj), a.qp);
                 dq[j] = o.dq; code[j] = o.level; centered = o.level; sg[j] = o.sign;
             }
             const float base = (a.operand_kind == SPQ_OPERAND_CODE) ? centered : (a.operand_kind == SPQ_OPERAND_DEQUANT ? dq[j] : xv[j]);
@@ -207,7 +222,8 @@ quantize_act_kernel(ActArgs a) {
     const int tid = threadIdx.x;
     __shared__ float s_red[8];
     // per-column parameters of this thread's columns
-    float s[NV][4], z[NV][4], cm[NV][4];
+    // min-max: s = scale, z = zero point.  log: s = log_range, z = log_min, ir = 1 / max(log_range, eps).
+    float s[NV][4], z[NV][4], cm[NV][4], ir[NV][4];
     if constexpr (QTYPE >= 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -217,7 +233,8 @@ quantize_act_kernel(ActArgs a) {
                 const bool ok = c + j < a.K;
                 s[i][j] = ok ? bparam(a.scale, a.bcast, 0, c + j) : 1.f;
                 z[i][j] = ok ? bparam(a.zp, a.bcast, 0, c + j) : 0.f;
-                cm[i][j] = (ok && a.col_mul) ? __ldg(a.col_mul + c + j) : 1.f;
+                cm[i][j] = ((ok && a.col_mul) ? __ldg(a.col_mul + c + j) : 1.f) * a.mul;
+                ir[i][j] = (QTYPE == SPQ_LOG) ? make_logch(z[i][j], s[i][j]).inv_range : 0.f;
             }
         }
     }
@@ -268,10 +285,13 @@ quantize_act_kernel(ActArgs a) {
                             const MinMaxOut r = minmax_elem(xv[j], s[i][j], z[i][j], a.qp);
                             base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.centered : r.dq;
                         } else {
-                            const LogOut r = log_elem(xv[j], z[i][j], s[i][j], a.qp);
+                            LogCh ch;
+                            ch.log_min = z[i][j]; ch.log_range = s[i][j]; ch.inv_range = ir[i][j];
+                            ch.range_c = (s[i][j] < LOG_EPS) ? LOG_EPS : s[i][j];
+                            const LogOut r = log_elem(xv[j], ch, a.qp);
                             base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.level : r.dq;
                         }
-                        o[j] = base * cm[i][j] * a.mul;
+                        o[j] = base * cm[i][j];
                     }
                     *reinterpret_cast<uint2*>(a.a_q + row * a.K + c) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
                 }

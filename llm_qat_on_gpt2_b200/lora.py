@@ -434,28 +434,39 @@ class SPLinearWithLoRA(nn.Module):
         return self.lora_adapters[f'{self.current_bits}bit']
 
     # ---------------------------------------------------------------- operand caches
-    def _operands_for(self, bits, want_lora):
-        key = f'{bits}bit'
-        qi, qw, lo = self.quantizers_input[key], self.quantizers_weight[key], self.lora_adapters[key]
+    # Three levels, so that each event only rebuilds what depends on it:
+    #   weight level  (W, weight quantiser)          : q(W) fp32, its row absmax; backward: column scale, W^T operand
+    #   lora level    (A, B, their quantisers)       : |q(A)|, A operand, q(B); backward: B operand
+    #   input level   (+ input quantiser calibration): per-K absorb factor, activation multiplier, row
+    #                                                  normaliser, W operand, LoRA-B operand -- 3 launches
+    def _weight_level(self, bits):
+        qw = self.quantizers_weight[f'{bits}bit']
         W = self.linear.weight
-        ent = self._op_cache.setdefault(bits, {'base': None, 'lora': None, 'bwd': None})
-        base_key = (W.data_ptr(), W._version, qw.generation, qi.generation)
-        base = ent['base']
-        if base is None or base['key'] != base_key:
+        ent = self._op_cache.setdefault(bits, {})
+        key = (W.data_ptr(), W._version, qw.generation)
+        wl = ent.get('weight')
+        if wl is None or wl['key'] != key:
             with torch.no_grad():
-                act = _act_config(qi, self.in_features)
                 wq = _dequant(qw, W)
-                pw = _norm_pow2((wq.abs() * act['absorb']).amax(dim=1))
-                B_op = _quantized_operand(qw, W, row_mul=1.0 / pw, col_mul=act['absorb'])
-            base = ent['base'] = dict(key=base_key, act=act, wq=wq, pw=pw, B_op=B_op)
-            ent['lora'] = None
-            ent['bwd'] = None
-        if not want_lora:
-            return base, None
-        lkey = (base_key, lo.lora_A.data_ptr(), lo.lora_A._version, lo.lora_B.data_ptr(), lo.lora_B._version,
-                lo.quantize_A.generation, lo.quantize_B.generation)
-        lora = ent['lora']
-        if lora is None or lora['key'] != lkey:
+                wl = ent['weight'] = dict(key=key, wq=wq, wmax_row=wq.abs().amax(dim=1).contiguous(), bwd=None)
+        return wl
+
+    def _weight_level_bwd(self, bits):
+        wl = self._weight_level(bits)
+        if wl['bwd'] is None:
+            with torch.no_grad():
+                pk = _norm_pow2(wl['wq'].abs().amax(dim=0))                                  # [K]
+                wl['bwd'] = dict(pk=pk, inv_pk=(1.0 / pk).contiguous(),
+                                 WT_op=_to_f16_operand(wl['wq'], col_mul=(1.0 / pk).contiguous(), transposed=True))   # [K, N]
+        return wl['bwd']
+
+    def _lora_level(self, bits):
+        lo = self.lora_adapters[f'{bits}bit']
+        ent = self._op_cache.setdefault(bits, {})
+        key = (lo.lora_A.data_ptr(), lo.lora_A._version, lo.lora_B.data_ptr(), lo.lora_B._version,
+               lo.quantize_A.generation, lo.quantize_B.generation)
+        ll = ent.get('lora')
+        if ll is None or ll['key'] != key:
             for qq in (lo.quantize_A, lo.quantize_B):
                 if not qq.ready():
                     # same exception the reference raises from quantize_A/B (p1/lora.py:49-50)
@@ -463,46 +474,79 @@ class SPLinearWithLoRA(nn.Module):
                         f"Quantizer not calibrated. Please run calibration first for {qq.quantizer_type} quantizer.")
             with torch.no_grad():
                 K, r = lo.lora_A.shape
-                aq = _dequant(lo.quantize_A, lo.lora_A)            # [K, r]
-                pa = _norm_pow2(aq.abs().amax(dim=0), 0)            # |A'| <= 1
-                A_op = _quantized_operand(lo.quantize_A, lo.lora_A, col_mul=1.0 / pa, transposed=True)   # [r, K]
-                # |t| <= sum_k xbound[k] |Aq[k,r]| for inputs inside the calibrated range: static pre-scale of t
-                xb = qi.abs_bound().detach().float().reshape(-1).expand(K)
-                tmax = (xb[:, None] * aq.abs()).sum(dim=0).max()
-                tmul = torch.where(tmax > 0, (2.0 ** 14) / pow2_ceil(tmax), torch.ones_like(tmax))
-                tmul_vec = tmul.expand(r).contiguous()
-                Bl_op = _quantized_operand(lo.quantize_B, lo.lora_B,
-                                           row_mul=(lo.scaling / tmul).expand(r).contiguous(),
-                                           col_mul=1.0 / base['pw'], transposed=True)                    # [N, r]
-            lora = ent['lora'] = dict(key=lkey, rank=r, A_op=A_op, pa=pa, Bl_op=Bl_op, tmul_vec=tmul_vec,
-                                      inv_tmul_vec=(1.0 / tmul_vec).contiguous(), scaling=float(lo.scaling),
-                                      qtype_A=lo.quantize_A.quantizer_type, qtype_B=lo.quantize_B.quantizer_type)
-            ent['bwd'] = None
+                aq = _dequant(lo.quantize_A, lo.lora_A)                                      # [K, r]
+                aq_abs = aq.abs().contiguous()
+                pa = _norm_pow2(aq_abs.amax(dim=0), 0)                                       # |A'| <= 1
+                A_op = _to_f16_operand(aq, col_mul=(1.0 / pa).contiguous(), transposed=True)  # [r, K]
+                bq = _dequant(lo.quantize_B, lo.lora_B)                                      # [r, N]
+            ll = ent['lora'] = dict(key=key, rank=r, aq=aq, aq_abs=aq_abs, pa=pa, A_op=A_op, bq=bq,
+                                    scaling=float(lo.scaling), qtype_A=lo.quantize_A.quantizer_type,
+                                    qtype_B=lo.quantize_B.quantizer_type, bwd=None, bwd_key=None)
+        return ll
+
+    def _operands_for(self, bits, want_lora):
+        qi = self.quantizers_input[f'{bits}bit']
+        K, N = self.in_features, self.out_features
+        wl = self._weight_level(bits)
+        ll = self._lora_level(bits) if want_lora else None
+        ent = self._op_cache[bits]
+        key = (wl['key'], qi.generation, None if ll is None else ll['key'])
+        il = ent.get('input')
+        if il is not None and il['key'] == key:
+            return il['base'], il['lora']
+        if il is not None and ll is None and il['key'][:2] == key[:2]:
+            return il['base'], None                       # same weight + calibration, LoRA just switched off
+        dev = wl['wq'].device
+        with torch.no_grad():
+            sc = qi.scale.detach().float().reshape(-1).contiguous()
+            zp = qi.zero_point.detach().float().reshape(-1)
+            if zp.numel() != sc.numel():
+                zp = zp.expand_as(sc)
+            zp = zp.contiguous()
+            if sc.numel() not in (1, K):
+                raise NotImplementedError(f"input quantiser scale of {sc.numel()} elements for in_features={K}")
+            qtype = _lib.QTYPE[qi.quantizer_type]
+            vec = torch.empty(2 * K + 2 * N, dtype=torch.float32, device=dev)
+            absorb, act_mul, pw, inv_pw = vec[:K], vec[K:2 * K], vec[2 * K:2 * K + N], vec[2 * K + N:]
+            r = 0 if ll is None else ll['rank']
+            lora_vec = torch.empty(3 * r, dtype=torch.float32, device=dev) if ll is not None else None
+            _lib.prep_linear_scales(sc, zp, qtype, qi.num_bits, qi.symmetric, K, wl['wmax_row'], N,
+                                    None if ll is None else ll['aq_abs'], r, 0.0 if ll is None else ll['scaling'],
+                                    absorb, act_mul, pw, inv_pw, lora_vec)
+            if qi.quantizer_type == 'minmax':
+                kind, col_mul, mul = _lib.OPERAND_CODE, None, 2.0 ** -max(0, qi.num_bits - 11)
+            else:
+                kind, col_mul, mul = _lib.OPERAND_DEQUANT, act_mul, 1.0
+            act = dict(scale=sc, zp=zp, bcast=_lib.PER_TENSOR if sc.numel() == 1 else _lib.PER_COL, kind=kind,
+                       col_mul=col_mul, mul=mul, absorb=absorb, qtype=qtype, bits=qi.num_bits,
+                       symmetric=qi.symmetric, input_qtype=qi.quantizer_type)
+            base = dict(key=key[:2], act=act, pw=pw, B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))
+            lora = None
+            if ll is not None:
+                tmul_vec, inv_tmul_vec, bl_rowmul = lora_vec[:r], lora_vec[r:2 * r], lora_vec[2 * r:]
+                lora = dict(key=key, rank=r, A_op=ll['A_op'], pa=ll['pa'], tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
+                            Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=inv_pw, transposed=True),   # [N, r]
+                            scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'])
+        ent['input'] = dict(key=key, base=base, lora=lora)
         return base, lora
 
     def _backward_operands_for(self, bits, want_lora):
-        base, lora = self._operands_for(bits, want_lora)
-        ent = self._op_cache[bits]
-        bkey = (base['key'], None if lora is None else lora['key'])
-        bw = ent['bwd']
-        if bw is not None and bw['key'] == bkey:
-            return bw
-        key = f'{bits}bit'
-        qw, lo = self.quantizers_weight[key], self.lora_adapters[key]
-        W = self.linear.weight
-        with torch.no_grad():
-            pk = _norm_pow2(base['wq'].abs().amax(dim=0))                                   # [K]
-            bw = dict(key=bkey, pk=pk, WT_op=_quantized_operand(qw, W, col_mul=1.0 / pk, transposed=True), lora=None)
-            if lora is not None:
-                N = self.out_features
-                dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
-                bq = _dequant(lo.quantize_B, lo.lora_B)                                     # [r, N]
-                pb = _norm_pow2(bq.abs().amax(dim=1) * abs(lo.scaling), 0)                  # [r]
-                bw['lora'] = dict(
-                    pb=pb, dt_mul=dt_mul,
-                    B_rn_op=_quantized_operand(lo.quantize_B, lo.lora_B, row_mul=1.0 / pb, mul=lo.scaling),      # [r, N]
-                    A_kr_op=_quantized_operand(lo.quantize_A, lo.lora_A, row_mul=1.0 / pk, mul=1.0 / dt_mul))    # [K, r]
-        ent['bwd'] = bw
+        wb = self._weight_level_bwd(bits)
+        bw = dict(pk=wb['pk'], WT_op=wb['WT_op'], lora=None)
+        if want_lora:
+            ll = self._lora_level(bits)
+            wkey = self._weight_level(bits)['key']
+            if ll['bwd'] is None or ll['bwd_key'] != wkey:
+                with torch.no_grad():
+                    N = self.out_features
+                    dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
+                    pb = _norm_pow2(ll['bq'].abs().amax(dim=1) * abs(ll['scaling']), 0)     # [r]
+                    ll['bwd'] = dict(
+                        pb=pb, dt_mul=dt_mul,
+                        B_rn_op=_to_f16_operand(ll['bq'], row_mul=(1.0 / pb).contiguous(), mul=ll['scaling']),        # [r, N]
+                        A_kr_op=_to_f16_operand(ll['aq'], row_mul=wb['inv_pk'], mul=1.0 / dt_mul))                      # [K, r]
+                    ll['bwd_key'] = wkey
+            bw['lora'] = ll['bwd']
         return bw
 
     def _calibration_weight(self, bits, weight_quantizer):
