@@ -11,6 +11,8 @@
 // with the correctly rounded logarithm (log2_cr, via double), which is the oracle's definition,
 // so the level index is exact everywhere while the double-precision unit is touched by < 0.1 %
 // of the elements at 8 bits.
+#include <stdlib.h>
+
 #include "spq_common.cuh"
 
 namespace spq {
@@ -23,26 +25,51 @@ struct QParams {
     int symmetric;
     float n_sym;    // 2^(b-1) - 1
     float full;     // 2^b - 1
+    int debug;      // profiling experiments only: bit0 = never take the exact slow path
 };
 
 // ---------------------------------------------------------------- element arithmetic
+// Every quantiser below has a FAST path (reciprocal multiplies, lg2.approx, FMA contraction) whose
+// pre-rounding value provably differs from the reference arithmetic by less than a per-channel
+// `band`; whenever the fast value lies within that band of a rounding tie, the element is redone
+// with the EXACT sequence (IEEE division, correctly rounded log2, separate roundings).  The integer
+// code / level index is therefore bit-identical to the reference everywhere, at ~20 instructions
+// per element instead of ~100.  Dequantised VALUES are tolerance-level quantities (rel 1e-3 in
+// BASELINE.json; ~1e-6 here) and always use the fast formulas.
 struct MinMaxOut { float dq; float code; float centered; };
 
-__device__ __forceinline__ MinMaxOut minmax_elem(float x, float s, float zp, const QParams& qp) {
+struct MmCol {            // per-channel constants, min-max
+    float s, inv_s, zp;
+};
+__device__ __forceinline__ MmCol make_mmcol(float s, float zp) {
+    MmCol c;
+    c.s = s; c.zp = zp;
+    c.inv_s = __frcp_rn(s);
+    return c;
+}
+
+__device__ __forceinline__ MinMaxOut minmax_elem(float x, const MmCol& c, const QParams& qp) {
     MinMaxOut o;
-    if (qp.symmetric) {                                   // :13-16
-        float q = rintf(__fdiv_rn(x, s));
-        q = fminf(fmaxf(q, -qp.n_sym), qp.n_sym);
-        o.code = q;
-        o.centered = q;
-        o.dq = __fmul_rn(q, s);
-    } else {                                              // :17-20
-        float q = rintf(__fadd_rn(__fdiv_rn(x, s), zp));
-        q = fminf(fmaxf(q, 0.f), qp.full);
-        o.code = q;
-        o.centered = __fsub_rn(q, zp);
-        o.dq = __fmul_rn(o.centered, s);
+    // reference: q = round(x / s [+ zp]) (p1/quantization_methods.py:14 / :18)
+    float t = qp.symmetric ? x * c.inv_s : fmaf(x, c.inv_s, c.zp);
+    float q = rintf(t);
+    const float tie_dist = fabsf(fabsf(t - q) - 0.5f);
+    // |t - exact| <= |t| * 2^-21 (reciprocal, product and, if asymmetric, sum roundings); beyond the clamp
+    // range the rounding cannot matter
+    const float tmag = fminf(fabsf(t), 4.0f * qp.full) + (qp.symmetric ? 0.f : qp.full);   // |x/s| <= |t| + zp
+    if (tie_dist <= tmag * 4.76837158203125e-07f && !(qp.debug & 1)) {
+        t = qp.symmetric ? __fdiv_rn(x, c.s) : __fadd_rn(__fdiv_rn(x, c.s), c.zp);
+        q = rintf(t);
     }
+    if (qp.symmetric) {                                   // :15-16
+        q = fminf(fmaxf(q, -qp.n_sym), qp.n_sym);
+        o.centered = q;
+    } else {                                              // :19-20
+        q = fminf(fmaxf(q, 0.f), qp.full);
+        o.centered = __fsub_rn(q, c.zp);
+    }
+    o.code = q;
+    o.dq = __fmul_rn(o.centered, c.s);
     return o;
 }
 
@@ -56,55 +83,57 @@ __device__ __forceinline__ float log_prelevel(float l, float log_min, float rang
     return __fmul_rn(ln, qp.full);
 }
 
-// Per-channel constants of the log quantiser that do not depend on the element.
-struct LogCh {
-    float log_min, log_range, range_c, inv_range;
+struct LogCol {           // per-channel constants, log
+    float log_min, log_range, range_c;
+    float inv, c0;        // ln = sat(l * inv + c0),  inv = 1 / max(range, eps), c0 = -log_min * inv
+    float band;           // |v_fast - v_exact| bound (see make_logcol)
+    float out_add;        // added to the dequantised exponent: log2 of a power-of-two output multiplier
 };
-__device__ __forceinline__ LogCh make_logch(float log_min, float log_range) {
-    LogCh c;
-    c.log_min = log_min;
-    c.log_range = log_range;
+__device__ __forceinline__ LogCol make_logcol(float log_min, float log_range, const QParams& qp, float out_add = 0.f) {
+    LogCol c;
+    c.log_min = log_min; c.log_range = log_range; c.out_add = out_add;
     c.range_c = (log_range < LOG_EPS) ? LOG_EPS : log_range;          // :43 clamp(min=eps)
-    c.inv_range = __frcp_rn(c.range_c);
+    c.inv = __frcp_rn(c.range_c);
+    c.c0 = -log_min * c.inv;
+    const float nl = qp.symmetric ? qp.n_sym : qp.full;
+    const float lev_mul = qp.symmetric ? 2.f * nl : nl;
+    // l ranges over [log_min, log_min + range] where it matters (outside, ln saturates and v = +-n exactly).
+    // Error budget of the fast pre-rounding value:  lg2.approx 2^-20, roundings of l*inv, c0 and the FMA
+    // 3 * Lmax * inv * 2^-23 + 2^-23, then v = ln * lev_mul - n: n * 2^-22.  Doubled for margin.
+    const float lmax = fmaxf(fabsf(log_min), fabsf(log_min + log_range));
+    c.band = 2.0f * (lev_mul * (c.inv * (9.5367431640625e-07f + 3.0f * lmax * 1.1920928955078125e-07f) + 1.1920928955078125e-07f) +
+                     nl * 2.384185791015625e-07f) + 1e-9f;
     return c;
 }
 
-// Level index: bit-exact w.r.t. the reference arithmetic (correctly rounded log2, IEEE division).
-// Fast path: lg2.approx + reciprocal multiply + one FMA; its result can differ from the exact
-// pre-rounding value by at most `band`, so whenever it lies that close to a rounding tie the
-// element is re-evaluated with the exact sequence.  ~3e-4 of the elements at 8 bits.
-__device__ __forceinline__ LogOut log_elem(float x, const LogCh& ch, const QParams& qp) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ LogOut log_elem(float x, const LogCol& ch, const QParams& qp) {
     LogOut o;
     const float ax = fabsf(x);
     const bool zero = ax < LOG_EPS;                                      // :36
-    o.sign = zero ? 0.f : ((x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f));
-    const float axc = (ax < LOG_EPS) ? LOG_EPS : ax;                     // :40 clamp(min=eps), >= 1e-5: never denormal
+    const float axc = fmaxf(ax, LOG_EPS);                                // :40 clamp(min=eps): >= 1e-5, never denormal
     const float nl = qp.symmetric ? qp.n_sym : qp.full;
     const float lev_mul = qp.symmetric ? 2.f * nl : nl;
 
-    float l = __log2f(axc);                                              // |error| < 2^-20 on this range
-    float ln = fminf(fmaxf((l - ch.log_min) * ch.inv_range, 0.f), 1.f);
-    float v = qp.symmetric ? fmaf(ln, lev_mul, -nl) : ln * lev_mul;
+    float v = __saturatef(fmaf(__log2f(axc), ch.inv, ch.c0));            // ln in [0, 1]
+    v = qp.symmetric ? fmaf(v, lev_mul, -nl) : v * lev_mul;
     float r = rintf(v);
-    const float tie_dist = fabsf(fabsf(v - r) - 0.5f);
-    const float band = lev_mul * (fmaf(fabsf(l), 4.76837158203125e-07f, 1.9073486328125e-06f) * ch.inv_range + 9.5367431640625e-07f) +
-                       fabsf(v) * 4.76837158203125e-07f + 1e-9f;
-    if (tie_dist <= band) {                                              // rare: the reference's exact sequence
-        l = log2_cr(axc);
-        v = log_prelevel(l, ch.log_min, ch.range_c, qp);
+    if (fabsf(fabsf(v - r) - 0.5f) <= ch.band && !(qp.debug & 1)) {      // near a tie: the reference's exact sequence
+        v = log_prelevel(log2_cr(axc), ch.log_min, ch.range_c, qp);
         r = rintf(v);
-    }
-    float qn;
-    if (qp.symmetric) {                                                  // :50-56, :63 (value only: tolerance-level)
-        r = fminf(fmaxf(r, -nl), nl);
-        qn = fmaf(r, __frcp_rn(lev_mul), 0.5f);
-    } else {                                                             // :57-60, :65
-        r = fminf(fmaxf(r, 0.f), nl);
-        qn = r * __frcp_rn(nl);
+        r = qp.symmetric ? fminf(fmaxf(r, -nl), nl) : fminf(fmaxf(r, 0.f), nl);
     }
     o.level = r;
-    const float mag = exp2f(fmaf(qn, ch.log_range, ch.log_min));         // :67-69
-    o.dq = zero ? 0.f : mag * o.sign;                                    // :71-74
+    // value (:50-74): qn = L/(2n) + 0.5 (symmetric) or L/n; 2^(qn * range + log_min) * sign, 0 under the zero mask
+    const float qn = qp.symmetric ? fmaf(r, __frcp_rn(lev_mul), 0.5f) : r * __frcp_rn(nl);
+    const float mag = ex2_approx(fmaf(qn, ch.log_range, ch.log_min + ch.out_add));
+    o.sign = zero ? 0.f : copysignf(1.0f, x);
+    o.dq = zero ? 0.f : copysignf(mag, x);
     return o;
 }
 
@@ -165,10 +194,10 @@ fake_quantize_kernel(FqArgs a) {
             const float zj = (a.bcast == SPQ_PER_ROW) ? zr : z[j];
             float centered;
             if constexpr (QTYPE == SPQ_MINMAX) {
-                const MinMaxOut o = minmax_elem(xv[j], sj, zj, a.qp);
+                const MinMaxOut o = minmax_elem(xv[j], make_mmcol(sj, zj), a.qp);
                 dq[j] = o.dq; code[j] = o.code; centered = o.centered; sg[j] = 0.f;
             } else {
-                const LogOut o = log_elem(xv[j], make_logch(zj, sj), a.qp);
+                const LogOut o = log_elem(xv[j], make_logcol(zj, sj, a.qp), a.qp);
                 dq[j] = o.dq; code[j] = o.level; centered = o.level; sg[j] = o.sign;
             }
             const float base = (a.operand_kind == SPQ_OPERAND_CODE) ? centered : (a.operand_kind == SPQ_OPERAND_DEQUANT ? dq[j] : xv[j]);
@@ -215,15 +244,16 @@ struct ActArgs {
     float* raw_row_scale;
 };
 
-template <int QTYPE, int NV>   // QTYPE: -1 none, 0 minmax, 1 log; NV float4 chunks per thread
-__global__ void __launch_bounds__(256)
+template <int QTYPE, int NV>   // QTYPE: -1 none, 0 minmax, 1 log; NV float4 chunks per thread (1 for K <= 4096)
+__global__ void __launch_bounds__(1024)
 quantize_act_kernel(ActArgs a) {
     const int G = blockDim.x;
     const int tid = threadIdx.x;
-    __shared__ float s_red[8];
-    // per-column parameters of this thread's columns
-    // min-max: s = scale, z = zero point.  log: s = log_range, z = log_min, ir = 1 / max(log_range, eps).
-    float s[NV][4], z[NV][4], cm[NV][4], ir[NV][4];
+    __shared__ float s_red[32];
+    // per-column constants of this thread's 4 * NV columns (registers, reused for every row)
+    MmCol mm[NV][4];
+    LogCol lg[NV][4];
+    float cm[NV][4];
     if constexpr (QTYPE >= 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -231,10 +261,11 @@ quantize_act_kernel(ActArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool ok = c + j < a.K;
-                s[i][j] = ok ? bparam(a.scale, a.bcast, 0, c + j) : 1.f;
-                z[i][j] = ok ? bparam(a.zp, a.bcast, 0, c + j) : 0.f;
+                const float sc = ok ? bparam(a.scale, a.bcast, 0, c + j) : 1.f;
+                const float zp = ok ? bparam(a.zp, a.bcast, 0, c + j) : 0.f;
                 cm[i][j] = ((ok && a.col_mul) ? __ldg(a.col_mul + c + j) : 1.f) * a.mul;
-                ir[i][j] = (QTYPE == SPQ_LOG) ? make_logch(z[i][j], s[i][j]).inv_range : 0.f;
+                if constexpr (QTYPE == SPQ_MINMAX) mm[i][j] = make_mmcol(sc, zp);
+                else lg[i][j] = make_logcol(zp, sc, a.qp);
             }
         }
     }
@@ -248,6 +279,30 @@ quantize_act_kernel(ActArgs a) {
             v[i] = (c < a.K) ? ld_stream_f4(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
         }
+        if constexpr (QTYPE >= 0) {
+            // quantised operand first: independent of the row reduction below
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const long long c = (static_cast<long long>(i) * G + tid) * 4;
+                if (c < a.K) {
+                    const float xv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float base;
+                        if constexpr (QTYPE == SPQ_MINMAX) {
+                            const MinMaxOut r = minmax_elem(xv[j], mm[i][j], a.qp);
+                            base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.centered : r.dq;
+                        } else {
+                            const LogOut r = log_elem(xv[j], lg[i][j], a.qp);
+                            base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.level : r.dq;
+                        }
+                        o[j] = base * cm[i][j];
+                    }
+                    *reinterpret_cast<uint2*>(a.a_q + row * a.K + c) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
+                }
+            }
+        }
         if (a.a_raw) {
             amax = warp_fmax(amax);
             if (G > 32) {
@@ -255,7 +310,7 @@ quantize_act_kernel(ActArgs a) {
                 if ((tid & 31) == 0) s_red[tid >> 5] = amax;
                 __syncthreads();
                 amax = s_red[0];
-                for (int w = 1; w < (G >> 5); ++w) amax = fmaxf(amax, s_red[w]);
+                for (int w = 1; w < ((G + 31) >> 5); ++w) amax = fmaxf(amax, s_red[w]);
             }
             // amax in [2^(E-1), 2^E)  ->  raw = x * 2^(8-E) in (-256, 256); inf/0 rows: scale 1
             int E = 0;
@@ -269,32 +324,6 @@ quantize_act_kernel(ActArgs a) {
                 if (c < a.K)
                     *reinterpret_cast<uint2*>(a.a_raw + row * a.K + c) =
                         make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
-            }
-        }
-        if constexpr (QTYPE >= 0) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const long long c = (static_cast<long long>(i) * G + tid) * 4;
-                if (c < a.K) {
-                    const float xv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float base;
-                        if constexpr (QTYPE == SPQ_MINMAX) {
-                            const MinMaxOut r = minmax_elem(xv[j], s[i][j], z[i][j], a.qp);
-                            base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.centered : r.dq;
-                        } else {
-                            LogCh ch;
-                            ch.log_min = z[i][j]; ch.log_range = s[i][j]; ch.inv_range = ir[i][j];
-                            ch.range_c = (s[i][j] < LOG_EPS) ? LOG_EPS : s[i][j];
-                            const LogOut r = log_elem(xv[j], ch, a.qp);
-                            base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.level : r.dq;
-                        }
-                        o[j] = base * cm[i][j];
-                    }
-                    *reinterpret_cast<uint2*>(a.a_q + row * a.K + c) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
-                }
             }
         }
     }
@@ -358,34 +387,33 @@ static QParams make_qparams(int bits, int symmetric) {
     q.symmetric = symmetric;
     q.n_sym = static_cast<float>(static_cast<double>(1ull << (bits - 1)) - 1.0);
     q.full = static_cast<float>(static_cast<double>(1ull << bits) - 1.0);
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("SPQ_QUANT_DEBUG"); dbg = e ? atoi(e) : 0; }
+        q.debug = dbg;
+    }
     return q;
 }
 
 template <int QTYPE>
 static int launch_act(const ActArgs& a, cudaStream_t st) {
+    // one float4 per thread when the row fits a CTA (K <= 4096): few registers, no idle lanes
     const long long nvec = (a.K + 3) / 4;
-    int G, NV;
-    if (nvec <= 32) { G = 32; NV = 1; }
-    else if (nvec <= 64) { G = 32; NV = 2; }
-    else if (nvec <= 128) { G = 32; NV = 4; }
-    else if (nvec <= 256) { G = 64; NV = 4; }
-    else if (nvec <= 512) { G = 128; NV = 4; }
-    else if (nvec <= 1024) { G = 256; NV = 4; }
-    else if (nvec <= 2048) { G = 256; NV = 8; }
-    else {
+    if (nvec > 2048) {
         set_error("spq_quantize_act: K = %lld > 8192 is not supported by the row-resident kernel", a.K);
         return SPQ_ERR_UNSUPPORTED;
     }
-    long long ctas = static_cast<long long>(sm_count()) * (2048 / G > 32 ? 32 : 2048 / G);
-    if (NV == 8) ctas = static_cast<long long>(sm_count()) * 4;
+    const int NV = nvec > 1024 ? 2 : 1;
+    int G = static_cast<int>((nvec + NV - 1) / NV);
+    G = (G + 31) / 32 * 32;
+    int per_sm = 2048 / G;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    long long ctas = static_cast<long long>(sm_count()) * per_sm;
     if (ctas > a.M) ctas = a.M;
     const unsigned grid = static_cast<unsigned>(ctas);
-    switch (NV) {
-        case 1: quantize_act_kernel<QTYPE, 1><<<grid, G, 0, st>>>(a); break;
-        case 2: quantize_act_kernel<QTYPE, 2><<<grid, G, 0, st>>>(a); break;
-        case 4: quantize_act_kernel<QTYPE, 4><<<grid, G, 0, st>>>(a); break;
-        default: quantize_act_kernel<QTYPE, 8><<<grid, G, 0, st>>>(a); break;
-    }
+    if (NV == 1) quantize_act_kernel<QTYPE, 1><<<grid, G, 0, st>>>(a);
+    else quantize_act_kernel<QTYPE, 2><<<grid, G, 0, st>>>(a);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
