@@ -92,28 +92,30 @@ SPQ_API int spq_fake_quantize(const float* x, int64_t rows, int64_t cols,
                       spq_half_t* operand, int operand_kind, const float* row_mul, const float* col_mul,
                       float mul, int operand_transposed, int64_t operand_ld, spq_stream_t stream);
 
-/* Fused activation-side quantise for SPLinearWithLoRA.forward (p1/lora.py:141,149): one pass
- * over x [M, K] (per-column or per-tensor scale) produces
- *   a_q   [M, K] fp16 : the quantised GEMM operand (code or dequant * col_mul), and
- *   a_raw [M, K] fp16 : the UNquantised x scaled per row by a power of two (the LoRA branch
- *                       reads x, not q(x)), with raw_row_scale[m] the factor to multiply back.
- * qtype < 0 skips a_q (32-bit / calibration pass: only the row-scaled raw operand). */
+/* Fused activation-side quantise for SPLinearWithLoRA.forward (p1/lora.py:141,149): one elementwise
+ * pass over x [M, K] (per-column or per-tensor calibrated scale) produces
+ *   a_q   [M, K] fp16 : the quantised GEMM operand (code or dequant) * col_mul[k] * mul, and
+ *   a_raw [M, K] fp16 : the UNquantised x * raw_col_mul[k] (the LoRA branch reads x, not q(x));
+ *                       raw_col_mul is a power of two per input channel chosen from the calibrated
+ *                       bound (spq_prep_linear_scales), the conversion saturates.  a_raw is optional. */
 SPQ_API int spq_quantize_act(const float* x, int64_t M, int64_t K,
                      const float* scale, const float* zero_point, int bcast,
                      int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
-                     spq_half_t* a_q, spq_half_t* a_raw, float* raw_row_scale, spq_stream_t stream);
+                     spq_half_t* a_q, spq_half_t* a_raw, const float* raw_col_mul, spq_stream_t stream);
 
 /* Scale preparation for the fused linear (host-side glue of p1/lora.py:141-150 made one launch):
  * from the input quantiser's calibrated (scale, zero_point) [in_n = 1 or K], the per-row absmax of
  * the dequantised weight [N] and, optionally, |q(A)| [K, r] of the active LoRA adapter, computes the
- * per-K factor the weight operand absorbs, the activation operand multiplier, the power-of-two row
- * normaliser pw[n] (and 1/pw) and lora_vec[0:r] = tau, [r:2r] = 1/tau, [2r:3r] = lora_scaling/tau
- * (tau: static power-of-two pre-scale of t = x q(A) derived from the calibrated input bound). */
+ * per-K factor the weight operand absorbs, the activation operand multiplier, the power-of-two
+ * multiplier of the raw fp16 operand per input channel (and its inverse), the power-of-two row
+ * normaliser pw[n] (and 1/pw) and lora_vec (5 r floats) = tau | 1/tau | lora_scaling/tau | pa | 1/pa
+ * (tau: static pre-scale of t = x q(A) from the calibrated input bound; pa[j]: normaliser of column
+ * j of q(A)[k,j] / raw_mul[k], the operand of the LoRA down-projection). */
 SPQ_API int spq_prep_linear_scales(const float* in_scale, const float* in_zero_point, int64_t in_n,
                            int qtype, int bits, int symmetric, int64_t K,
                            const float* w_rowmax, int64_t N, const float* aq_abs, int64_t r,
-                           float lora_scaling, float* absorb, float* act_mul, float* pw, float* inv_pw,
-                           float* lora_vec, spq_stream_t stream);
+                           float lora_scaling, float* absorb, float* act_mul, float* raw_mul,
+                           float* inv_raw_mul, float* pw, float* inv_pw, float* lora_vec, spq_stream_t stream);
 
 /* STE backward (p1/quantization_methods.py:25-28, 82-90): identity (min-max) or clamp to
  * [-10, 10] (log).  out may alias grad. */

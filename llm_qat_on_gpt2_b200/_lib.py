@@ -41,7 +41,7 @@ SIGNATURES = {
                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "spq_prep_linear_scales": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int64,
                                        c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_void_p]),
+                                       c_void_p, c_void_p, c_void_p]),
     "spq_ste_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "spq_qgemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                           c_void_p, c_int64, c_void_p, c_int64, c_int64,
@@ -176,21 +176,22 @@ def fake_quantize(x2d, scale, zp, bcast, qtype, bits, symmetric, dequant=None, c
                                             _stream()), "spq_fake_quantize")
 
 
-def quantize_act(x2d, scale, zp, bcast, qtype, bits, symmetric, operand_kind, col_mul, mul, a_q, a_raw, raw_row_scale):
-    _req_cuda(x2d, scale, zp, col_mul, a_q, a_raw, raw_row_scale)
+def quantize_act(x2d, scale, zp, bcast, qtype, bits, symmetric, operand_kind, col_mul, mul, a_q, a_raw, raw_col_mul):
+    _req_cuda(x2d, scale, zp, col_mul, a_q, a_raw, raw_col_mul)
     assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
     M, K = x2d.shape
     _check(load_library().spq_quantize_act(x2d.data_ptr(), M, K, _ptr(scale), _ptr(zp), bcast, qtype, bits,
                                            int(symmetric), operand_kind, _ptr(col_mul), float(mul), _ptr(a_q),
-                                           _ptr(a_raw), _ptr(raw_row_scale), _stream()), "spq_quantize_act")
+                                           _ptr(a_raw), _ptr(raw_col_mul), _stream()), "spq_quantize_act")
 
 
 def prep_linear_scales(in_scale, in_zp, qtype, bits, symmetric, K, w_rowmax, N, aq_abs, r, lora_scaling,
-                       absorb, act_mul, pw, inv_pw, lora_vec):
-    _req_cuda(in_scale, in_zp, w_rowmax, aq_abs, absorb, act_mul, pw, inv_pw, lora_vec)
+                       absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec):
+    _req_cuda(in_scale, in_zp, w_rowmax, aq_abs, absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
     _check(load_library().spq_prep_linear_scales(in_scale.data_ptr(), in_zp.data_ptr(), in_scale.numel(), qtype, bits,
                                                  int(symmetric), K, w_rowmax.data_ptr(), N, _ptr(aq_abs), r,
-                                                 float(lora_scaling), absorb.data_ptr(), act_mul.data_ptr(), pw.data_ptr(),
+                                                 float(lora_scaling), absorb.data_ptr(), act_mul.data_ptr(),
+                                                 raw_mul.data_ptr(), inv_raw_mul.data_ptr(), pw.data_ptr(),
                                                  inv_pw.data_ptr(), _ptr(lora_vec), _stream()), "spq_prep_linear_scales")
 
 

@@ -8,9 +8,12 @@
 //   absorb[k]   what the weight operand must be multiplied by per input channel
 //               (min-max: scale[k] / code_mul;  log: 2^(ceil(log_max[k]) - 8))
 //   act_mul[k]  what the activation operand is multiplied by (min-max: unused = 1;  log: 1 / absorb[k])
+//   raw_mul[k], inv_raw_mul[k]  power of two mapping the calibrated bound of input channel k to (8, 16]:
+//               multiplier of the raw (unquantised) fp16 operand the LoRA branch reads, and its inverse
 //   pw[n], inv_pw[n]   power-of-two row normaliser of the weight operand and its reciprocal
-//   lora[0:r] = tau, lora[r:2r] = 1/tau, lora[2r:3r] = scaling/tau   with tau the static pre-scale of
-//               t = x q(A), chosen from the bound  max_j sum_k xbound[k] |q(A)[k,j]|
+//   lora[0:r] = tau, [r:2r] = 1/tau, [2r:3r] = scaling/tau, [3r:4r] = pa, [4r:5r] = 1/pa   with tau the
+//               static pre-scale of t = x q(A), chosen from the bound  max_j sum_k xbound[k] |q(A)[k,j]|,
+//               and pa[j] the power-of-two normaliser of column j of q(A)[k,j] / raw_mul[k]
 #include "spq_common.cuh"
 
 namespace spq {
@@ -39,7 +42,7 @@ struct PrepArgs {
     const float* w_rowmax;                                   // [N]
     const float* aq_abs;                                     // [K, r] or null
     float lora_scaling;
-    float* absorb; float* act_mul; float* pw; float* inv_pw; float* lora;
+    float* absorb; float* act_mul; float* raw_mul; float* inv_raw_mul; float* pw; float* inv_pw; float* lora;
 };
 
 __device__ __forceinline__ void chan(const PrepArgs& a, long long k, float& absorb, float& act_mul, float& xbound) {
@@ -75,6 +78,9 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
         chan(a, k, ab, am, xb);
         a.absorb[k] = ab;
         a.act_mul[k] = am;
+        const float rmul = (xb > 0.f && xb < INFINITY) ? 16.0f / pow2_ceil(xb) : 1.0f;
+        a.raw_mul[k] = rmul;
+        a.inv_raw_mul[k] = 1.0f / rmul;
         amax = fmaxf(amax, ab);
     }
     const float absorb_max = block_max(amax, s_red);
@@ -85,33 +91,47 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
         a.inv_pw[n] = 1.0f / p;
     }
     if (a.aq_abs != nullptr && a.r > 0) {
-        // tsum[j] = sum_k xbound[k] * |Aq[k, j]|;  thread -> column j = i % r when r divides the block
+        // per LoRA column j:  tsum[j] = sum_k xbound[k] |Aq[k,j]|,  amx[j] = max_k |Aq[k,j]| / raw_mul[k]
         const long long r = a.r;
+        __shared__ float s_m[1024];
         float tmax = 0.f;
         if (r <= 1024 && (1024 % r) == 0) {
             const long long j = tid % r, k0 = tid / r, kstep = 1024 / r;
-            float acc = 0.f;
+            float acc = 0.f, mx = 0.f;
             for (long long k = k0; k < a.K; k += kstep) {
                 float ab, am, xb;
                 chan(a, k, ab, am, xb);
-                acc += xb * __ldg(a.aq_abs + k * r + j);
+                const float av = __ldg(a.aq_abs + k * r + j);
+                const float rmul = (xb > 0.f && xb < INFINITY) ? 16.0f / pow2_ceil(xb) : 1.0f;
+                acc += xb * av;
+                mx = fmaxf(mx, av / rmul);
             }
             s_t[tid] = acc;
+            s_m[tid] = mx;
             __syncthreads();
             if (tid < r) {
-                float t = 0.f;
-                for (long long q = tid; q < 1024; q += r) t += s_t[q];
+                float t = 0.f, m = 0.f;
+                for (long long q = tid; q < 1024; q += r) { t += s_t[q]; m = fmaxf(m, s_m[q]); }
                 tmax = t;
+                const float pa = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
+                a.lora[3 * r + tid] = pa;
+                a.lora[4 * r + tid] = 1.0f / pa;
             }
         } else {
             for (long long j = tid; j < r; j += blockDim.x) {
-                float acc = 0.f;
+                float acc = 0.f, m = 0.f;
                 for (long long k = 0; k < a.K; ++k) {
                     float ab, am, xb;
                     chan(a, k, ab, am, xb);
-                    acc += xb * __ldg(a.aq_abs + k * r + j);
+                    const float av = __ldg(a.aq_abs + k * r + j);
+                    const float rmul = (xb > 0.f && xb < INFINITY) ? 16.0f / pow2_ceil(xb) : 1.0f;
+                    acc += xb * av;
+                    m = fmaxf(m, av / rmul);
                 }
                 tmax = fmaxf(tmax, acc);
+                const float pa = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
+                a.lora[3 * r + j] = pa;
+                a.lora[4 * r + j] = 1.0f / pa;
             }
         }
         tmax = block_max(tmax, s_red);
@@ -131,9 +151,10 @@ using namespace spq;
 
 extern "C" int spq_prep_linear_scales(const float* in_scale, const float* in_zero_point, int64_t in_n, int qtype, int bits,
                                       int symmetric, int64_t K, const float* w_rowmax, int64_t N, const float* aq_abs,
-                                      int64_t r, float lora_scaling, float* absorb, float* act_mul, float* pw, float* inv_pw,
-                                      float* lora_vec, spq_stream_t stream) {
-    SPQ_REQUIRE(in_scale && in_zero_point && w_rowmax && absorb && act_mul && pw && inv_pw, "spq_prep_linear_scales: null pointer");
+                                      int64_t r, float lora_scaling, float* absorb, float* act_mul, float* raw_mul,
+                                      float* inv_raw_mul, float* pw, float* inv_pw, float* lora_vec, spq_stream_t stream) {
+    SPQ_REQUIRE(in_scale && in_zero_point && w_rowmax && absorb && act_mul && raw_mul && inv_raw_mul && pw && inv_pw,
+                "spq_prep_linear_scales: null pointer");
     SPQ_REQUIRE(K > 0 && N > 0 && (in_n == 1 || in_n == K), "spq_prep_linear_scales: input scale must have 1 or K elements");
     SPQ_REQUIRE(bits >= 1 && bits < 32 && (qtype == SPQ_MINMAX || qtype == SPQ_LOG), "spq_prep_linear_scales: bad quantiser");
     SPQ_REQUIRE(aq_abs == nullptr || (r > 0 && lora_vec), "spq_prep_linear_scales: LoRA outputs missing");
@@ -141,7 +162,8 @@ extern "C" int spq_prep_linear_scales(const float* in_scale, const float* in_zer
     a.in_scale = in_scale; a.in_zp = in_zero_point; a.in_n = static_cast<int>(in_n);
     a.qtype = qtype; a.bits = bits; a.symmetric = symmetric; a.K = K; a.N = N; a.r = aq_abs ? r : 0;
     a.w_rowmax = w_rowmax; a.aq_abs = aq_abs; a.lora_scaling = lora_scaling;
-    a.absorb = absorb; a.act_mul = act_mul; a.pw = pw; a.inv_pw = inv_pw; a.lora = lora_vec;
+    a.absorb = absorb; a.act_mul = act_mul; a.raw_mul = raw_mul; a.inv_raw_mul = inv_raw_mul;
+    a.pw = pw; a.inv_pw = inv_pw; a.lora = lora_vec;
     prep::prep_linear_scales_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
     SPQ_LAUNCH_OK();
     return SPQ_OK;

@@ -241,34 +241,19 @@ struct ActArgs {
     float mul;
     unsigned short* a_q;
     unsigned short* a_raw;
-    float* raw_row_scale;
+    float* raw_row_scale;       // row-scaled variant only
+    const float* raw_col_mul;   // elementwise variant: per-column multiplier of the raw operand
 };
 
-template <int QTYPE, int NV>   // QTYPE: -1 none, 0 minmax, 1 log; NV float4 chunks per thread (1 for K <= 4096)
-__global__ void __launch_bounds__(1024)
-quantize_act_kernel(ActArgs a) {
+// Row-scaled raw operand (no quantiser): one CTA of G threads owns a row at a time, the row stays in
+// registers (NV float4 per thread), its absmax gives the power-of-two scale.  Used where no calibrated
+// bound exists: calibration pass, 32-bit path, LM head, gradients.
+template <int NV>
+__global__ void __launch_bounds__(256)
+rowscale_kernel(ActArgs a) {
     const int G = blockDim.x;
     const int tid = threadIdx.x;
-    __shared__ float s_red[32];
-    // per-column constants of this thread's 4 * NV columns (registers, reused for every row)
-    MmCol mm[NV][4];
-    LogCol lg[NV][4];
-    float cm[NV][4];
-    if constexpr (QTYPE >= 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const long long c = (static_cast<long long>(i) * G + tid) * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool ok = c + j < a.K;
-                const float sc = ok ? bparam(a.scale, a.bcast, 0, c + j) : 1.f;
-                const float zp = ok ? bparam(a.zp, a.bcast, 0, c + j) : 0.f;
-                cm[i][j] = ((ok && a.col_mul) ? __ldg(a.col_mul + c + j) : 1.f) * a.mul;
-                if constexpr (QTYPE == SPQ_MINMAX) mm[i][j] = make_mmcol(sc, zp);
-                else lg[i][j] = make_logcol(zp, sc, a.qp);
-            }
-        }
-    }
+    __shared__ float s_red[8];
     for (long long row = blockIdx.x; row < a.M; row += gridDim.x) {
         const float* px = a.x + row * a.K;
         float4 v[NV];
@@ -279,54 +264,81 @@ quantize_act_kernel(ActArgs a) {
             v[i] = (c < a.K) ? ld_stream_f4(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
         }
-        if constexpr (QTYPE >= 0) {
-            // quantised operand first: independent of the row reduction below
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const long long c = (static_cast<long long>(i) * G + tid) * 4;
-                if (c < a.K) {
-                    const float xv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float base;
-                        if constexpr (QTYPE == SPQ_MINMAX) {
-                            const MinMaxOut r = minmax_elem(xv[j], mm[i][j], a.qp);
-                            base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.centered : r.dq;
-                        } else {
-                            const LogOut r = log_elem(xv[j], lg[i][j], a.qp);
-                            base = (a.operand_kind == SPQ_OPERAND_CODE) ? r.level : r.dq;
-                        }
-                        o[j] = base * cm[i][j];
-                    }
-                    *reinterpret_cast<uint2*>(a.a_q + row * a.K + c) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
-                }
-            }
+        amax = warp_fmax(amax);
+        if (G > 32) {
+            __syncthreads();                      // s_red reuse across rows
+            if ((tid & 31) == 0) s_red[tid >> 5] = amax;
+            __syncthreads();
+            amax = s_red[0];
+            for (int w = 1; w < (G >> 5); ++w) amax = fmaxf(amax, s_red[w]);
         }
-        if (a.a_raw) {
-            amax = warp_fmax(amax);
-            if (G > 32) {
-                __syncthreads();                      // s_red reuse across rows
-                if ((tid & 31) == 0) s_red[tid >> 5] = amax;
-                __syncthreads();
-                amax = s_red[0];
-                for (int w = 1; w < ((G + 31) >> 5); ++w) amax = fmaxf(amax, s_red[w]);
-            }
-            // amax in [2^(E-1), 2^E)  ->  raw = x * 2^(8-E) in (-256, 256); inf/0 rows: scale 1
-            int E = 0;
-            if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = 8;
-            E = E < -100 ? -100 : E;
-            const float down = exp2f(static_cast<float>(8 - E));
-            if (tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = exp2f(static_cast<float>(E - 8));
+        // amax in [2^(E-1), 2^E)  ->  raw = x * 2^(8-E) in (-256, 256); inf/0 rows: scale 1
+        int E = 0;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = 8;
+        E = E < -100 ? -100 : E;
+        const float down = exp2f(static_cast<float>(8 - E));
+        if (tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = exp2f(static_cast<float>(E - 8));
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const long long c = (static_cast<long long>(i) * G + tid) * 4;
-                if (c < a.K)
-                    *reinterpret_cast<uint2*>(a.a_raw + row * a.K + c) =
-                        make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
-            }
+        for (int i = 0; i < NV; ++i) {
+            const long long c = (static_cast<long long>(i) * G + tid) * 4;
+            if (c < a.K)
+                *reinterpret_cast<uint2*>(a.a_raw + row * a.K + c) =
+                    make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
         }
     }
+}
+
+// Fused activation-side kernel (calibrated quantiser): purely elementwise.  Thread = 4 consecutive
+// columns (their constants live in registers), block (32, 8) strides over rows with four 16-byte loads
+// in flight per thread; writes the quantised operand and, for the LoRA branch, the raw operand scaled
+// per COLUMN by a power of two derived from the calibrated bound (saturating conversion).
+template <int QTYPE>
+__global__ void __launch_bounds__(256)
+quantize_act_kernel(ActArgs a) {
+    const long long c0 = (static_cast<long long>(blockIdx.x) * 32 + threadIdx.x) * 4;
+    if (c0 >= a.K) return;
+    MmCol mm[4];
+    LogCol lg[4];
+    float cm[4], rm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float sc = bparam(a.scale, a.bcast, 0, c0 + j);
+        const float zp = bparam(a.zp, a.bcast, 0, c0 + j);
+        cm[j] = (a.col_mul ? __ldg(a.col_mul + c0 + j) : 1.f) * a.mul;
+        rm[j] = a.raw_col_mul ? __ldg(a.raw_col_mul + c0 + j) : 1.f;
+        if constexpr (QTYPE == SPQ_MINMAX) mm[j] = make_mmcol(sc, zp);
+        else lg[j] = make_logcol(zp, sc, a.qp);
+    }
+    const long long rstep = static_cast<long long>(gridDim.y) * 8;
+    auto one = [&](long long r, const float4& v) {
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float base;
+            if constexpr (QTYPE == SPQ_MINMAX) {
+                const MinMaxOut q = minmax_elem(xv[j], mm[j], a.qp);
+                base = (a.operand_kind == SPQ_OPERAND_CODE) ? q.centered : q.dq;
+            } else {
+                const LogOut q = log_elem(xv[j], lg[j], a.qp);
+                base = (a.operand_kind == SPQ_OPERAND_CODE) ? q.level : q.dq;
+            }
+            o[j] = base * cm[j];
+        }
+        *reinterpret_cast<uint2*>(a.a_q + r * a.K + c0) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
+        if (a.a_raw)
+            *reinterpret_cast<uint2*>(a.a_raw + r * a.K + c0) =
+                make_uint2(pack_h2(xv[0] * rm[0], xv[1] * rm[1]), pack_h2(xv[2] * rm[2], xv[3] * rm[3]));
+    };
+    long long r = static_cast<long long>(blockIdx.y) * 8 + threadIdx.y;
+    for (; r + 3 * rstep < a.M; r += 4 * rstep) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(a.x + (r + u * rstep) * a.K + c0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one(r + u * rstep, v[u]);
+    }
+    for (; r < a.M; r += rstep) one(r, ld_stream_f4(a.x + r * a.K + c0));
 }
 
 // Rows wider than the register-resident limit, or not 16-byte aligned (LM-head gradients, N = 50257):
@@ -395,25 +407,39 @@ static QParams make_qparams(int bits, int symmetric) {
     return q;
 }
 
-template <int QTYPE>
-static int launch_act(const ActArgs& a, cudaStream_t st) {
-    // one float4 per thread when the row fits a CTA (K <= 4096): few registers, no idle lanes
+static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
     const long long nvec = (a.K + 3) / 4;
-    if (nvec > 2048) {
-        set_error("spq_quantize_act: K = %lld > 8192 is not supported by the row-resident kernel", a.K);
-        return SPQ_ERR_UNSUPPORTED;
-    }
-    const int NV = nvec > 1024 ? 2 : 1;
-    int G = static_cast<int>((nvec + NV - 1) / NV);
-    G = (G + 31) / 32 * 32;
-    int per_sm = 2048 / G;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16) per_sm = 16;
-    long long ctas = static_cast<long long>(sm_count()) * per_sm;
+    int G, NV;
+    if (nvec <= 32) { G = 32; NV = 1; }
+    else if (nvec <= 64) { G = 32; NV = 2; }
+    else if (nvec <= 128) { G = 32; NV = 4; }
+    else if (nvec <= 256) { G = 64; NV = 4; }
+    else if (nvec <= 512) { G = 128; NV = 4; }
+    else if (nvec <= 1024) { G = 256; NV = 4; }
+    else { G = 256; NV = 8; }
+    long long ctas = static_cast<long long>(sm_count()) * (2048 / G > 32 ? 32 : 2048 / G);
+    if (NV == 8) ctas = static_cast<long long>(sm_count()) * 4;
     if (ctas > a.M) ctas = a.M;
     const unsigned grid = static_cast<unsigned>(ctas);
-    if (NV == 1) quantize_act_kernel<QTYPE, 1><<<grid, G, 0, st>>>(a);
-    else quantize_act_kernel<QTYPE, 2><<<grid, G, 0, st>>>(a);
+    switch (NV) {
+        case 1: rowscale_kernel<1><<<grid, G, 0, st>>>(a); break;
+        case 2: rowscale_kernel<2><<<grid, G, 0, st>>>(a); break;
+        case 4: rowscale_kernel<4><<<grid, G, 0, st>>>(a); break;
+        default: rowscale_kernel<8><<<grid, G, 0, st>>>(a); break;
+    }
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+template <int QTYPE>
+static int launch_act(const ActArgs& a, cudaStream_t st) {
+    const unsigned gx = static_cast<unsigned>((a.K / 4 + 31) / 32);
+    long long gy = (static_cast<long long>(sm_count()) * 8 + gx - 1) / gx;
+    const long long max_gy = (a.M + 31) / 32;            // at least 4 rows per thread
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    quantize_act_kernel<QTYPE><<<dim3(gx, static_cast<unsigned>(gy)), dim3(32, 8), 0, st>>>(a);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
@@ -465,24 +491,21 @@ extern "C" int spq_fake_quantize(const float* x, int64_t rows, int64_t cols, con
 
 extern "C" int spq_quantize_act(const float* x, int64_t M, int64_t K, const float* scale, const float* zero_point, int bcast,
                                 int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
-                                spq_half_t* a_q, spq_half_t* a_raw, float* raw_row_scale, spq_stream_t stream) {
+                                spq_half_t* a_q, spq_half_t* a_raw, const float* raw_col_mul, spq_stream_t stream) {
     SPQ_REQUIRE(x && M > 0 && K > 0, "spq_quantize_act: bad input");
     SPQ_REQUIRE((K % 4) == 0 && aligned16(x), "spq_quantize_act: K must be a multiple of 4 and x 16-byte aligned");
-    SPQ_REQUIRE(qtype < 0 || (scale && zero_point && a_q), "spq_quantize_act: quantised output requested without parameters");
-    SPQ_REQUIRE(qtype < 0 || bcast == SPQ_PER_COL || bcast == SPQ_PER_TENSOR, "spq_quantize_act: per-row scales are not an activation layout");
-    SPQ_REQUIRE(qtype >= 0 || a_raw, "spq_quantize_act: nothing to do");
-    SPQ_REQUIRE(qtype < 0 || (bits >= 1 && bits < 32), "spq_quantize_act: bits %d", bits);
+    SPQ_REQUIRE(qtype == SPQ_MINMAX || qtype == SPQ_LOG, "spq_quantize_act: unknown quantizer type %d", qtype);
+    SPQ_REQUIRE(scale && zero_point && a_q, "spq_quantize_act: missing parameters or output");
+    SPQ_REQUIRE(bcast == SPQ_PER_COL || bcast == SPQ_PER_TENSOR, "spq_quantize_act: per-row scales are not an activation layout");
+    SPQ_REQUIRE(bits >= 1 && bits < 32, "spq_quantize_act: bits %d", bits);
     ActArgs a;
     a.x = x; a.M = M; a.K = K; a.scale = scale; a.zp = zero_point; a.bcast = bcast;
-    a.qp = make_qparams(qtype < 0 ? 8 : bits, symmetric);
+    a.qp = make_qparams(bits, symmetric);
     a.operand_kind = operand_kind; a.col_mul = col_mul; a.mul = mul;
-    a.a_q = a_q; a.a_raw = a_raw; a.raw_row_scale = raw_row_scale;
+    a.a_q = a_q; a.a_raw = a_raw; a.raw_row_scale = nullptr; a.raw_col_mul = raw_col_mul;
     cudaStream_t st = as_stream(stream);
-    if (qtype < 0) return launch_act<-1>(a, st);
     if (qtype == SPQ_MINMAX) return launch_act<SPQ_MINMAX>(a, st);
-    if (qtype == SPQ_LOG) return launch_act<SPQ_LOG>(a, st);
-    set_error("spq_quantize_act: unknown quantizer type %d", qtype);
-    return SPQ_ERR_INVALID;
+    return launch_act<SPQ_LOG>(a, st);
 }
 
 extern "C" int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out, float* row_scale,
@@ -490,9 +513,14 @@ extern "C" int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t
     SPQ_REQUIRE(g && out && M > 0 && N > 0, "spq_rowscale_f16: bad arguments");
     if (ld_out <= 0) ld_out = N;
     SPQ_REQUIRE(ld_out >= N, "spq_rowscale_f16: ld_out < N");
-    if (ld_out == N && (N % 4) == 0 && N <= 8192 && aligned16(g))
-        return spq_quantize_act(g, M, N, nullptr, nullptr, SPQ_PER_TENSOR, -1, 8, 1, SPQ_OPERAND_RAW, nullptr, 1.0f, nullptr,
-                                out, row_scale, stream);
+    if (ld_out == N && (N % 4) == 0 && N <= 8192 && aligned16(g)) {
+        ActArgs a;
+        a.x = g; a.M = M; a.K = N; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
+        a.qp = make_qparams(8, 1);
+        a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
+        a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr;
+        return launch_rowscale(a, as_stream(stream));
+    }
     SPQ_REQUIRE((ld_out % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0, "spq_rowscale_f16: ld_out must be even");
     long long ctas = static_cast<long long>(sm_count()) * 8;
     if (ctas > M) ctas = M;

@@ -284,16 +284,15 @@ class _SPLinearFn(torch.autograd.Function):
         M = x2d.shape[0]
         a_q = torch.empty((M, K), dtype=torch.float16, device=x.device)
         a_raw = torch.empty((M, K), dtype=torch.float16, device=x.device) if use_lora else None
-        rs = torch.empty(M, dtype=torch.float32, device=x.device) if use_lora else None
         _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
-                          act['kind'], act['col_mul'], act['mul'], a_q, a_raw, rs)
+                          act['kind'], act['col_mul'], act['mul'], a_q, a_raw, act['raw_mul'] if use_lora else None)
         y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
         t = None
         if use_lora:
             r = lo['rank']
             t = torch.empty((M, r), dtype=torch.float32, device=x.device)
-            _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, row_scale=rs, col_scale=lo['pa'])
+            _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, col_scale=lo['pa'])
             t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f)
         else:
@@ -306,12 +305,12 @@ class _SPLinearFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         ctx.bw = mod._backward_operands_for(bits, use_lora) if any(need[:5]) else None
         ctx.weight_qtype = mod.quantizers_weight[f'{bits}bit'].quantizer_type
-        ctx.save_for_backward(a_q if need[1] else None, a_raw, rs, t)
+        ctx.save_for_backward(a_q if need[1] else None, a_raw, t)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gy):
-        a_q, a_raw, rs, t = ctx.saved_tensors
+        a_q, a_raw, t = ctx.saved_tensors
         base, lo, bw = ctx.base, ctx.lo, ctx.bw
         M, N, K = ctx.dims
         g2d = _as_2d_f32(gy, N)
@@ -334,12 +333,11 @@ class _SPLinearFn(torch.autograd.Function):
                 if need_x:
                     dt16 = _to_f16_operand(dtn, mul=lb['dt_mul'])
                 if need_A:
-                    # dA[k,r] = sum_m x[m,k] dt[m,r]; token scales rs*eg folded into dt
-                    xmax = rs.max()
-                    fold = (rs / xmax) * (eg / gmax)
-                    dt2 = _to_f16_operand(dtn, row_mul=fold, mul=lb['dt_mul'])
+                    # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; token scale eg folded into dt
+                    dt2 = _to_f16_operand(dtn, row_mul=(eg / gmax).contiguous(), mul=lb['dt_mul'])
                     gA = torch.empty((K, r), dtype=torch.float32, device=dev)
-                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=(gmax * xmax).reshape(1).contiguous())
+                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax.reshape(1).contiguous(),
+                                 i_scale=act['inv_raw_mul'])
                     if lo['qtype_A'] == 'log':
                         gA = _lib.ste_backward(gA, _lib.LOG)
             if need_B:
@@ -476,10 +474,8 @@ class SPLinearWithLoRA(nn.Module):
                 K, r = lo.lora_A.shape
                 aq = _dequant(lo.quantize_A, lo.lora_A)                                      # [K, r]
                 aq_abs = aq.abs().contiguous()
-                pa = _norm_pow2(aq_abs.amax(dim=0), 0)                                       # |A'| <= 1
-                A_op = _to_f16_operand(aq, col_mul=(1.0 / pa).contiguous(), transposed=True)  # [r, K]
                 bq = _dequant(lo.quantize_B, lo.lora_B)                                      # [r, N]
-            ll = ent['lora'] = dict(key=key, rank=r, aq=aq, aq_abs=aq_abs, pa=pa, A_op=A_op, bq=bq,
+            ll = ent['lora'] = dict(key=key, rank=r, aq=aq, aq_abs=aq_abs, bq=bq,
                                     scaling=float(lo.scaling), qtype_A=lo.quantize_A.quantizer_type,
                                     qtype_B=lo.quantize_B.quantizer_type, bwd=None, bwd_key=None)
         return ll
@@ -506,25 +502,29 @@ class SPLinearWithLoRA(nn.Module):
             if sc.numel() not in (1, K):
                 raise NotImplementedError(f"input quantiser scale of {sc.numel()} elements for in_features={K}")
             qtype = _lib.QTYPE[qi.quantizer_type]
-            vec = torch.empty(2 * K + 2 * N, dtype=torch.float32, device=dev)
-            absorb, act_mul, pw, inv_pw = vec[:K], vec[K:2 * K], vec[2 * K:2 * K + N], vec[2 * K + N:]
+            vec = torch.empty(4 * K + 2 * N, dtype=torch.float32, device=dev)
+            absorb, act_mul, raw_mul, inv_raw_mul = vec[:K], vec[K:2 * K], vec[2 * K:3 * K], vec[3 * K:4 * K]
+            pw, inv_pw = vec[4 * K:4 * K + N], vec[4 * K + N:]
             r = 0 if ll is None else ll['rank']
-            lora_vec = torch.empty(3 * r, dtype=torch.float32, device=dev) if ll is not None else None
+            lora_vec = torch.empty(5 * r, dtype=torch.float32, device=dev) if ll is not None else None
             _lib.prep_linear_scales(sc, zp, qtype, qi.num_bits, qi.symmetric, K, wl['wmax_row'], N,
                                     None if ll is None else ll['aq_abs'], r, 0.0 if ll is None else ll['scaling'],
-                                    absorb, act_mul, pw, inv_pw, lora_vec)
+                                    absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
             if qi.quantizer_type == 'minmax':
                 kind, col_mul, mul = _lib.OPERAND_CODE, None, 2.0 ** -max(0, qi.num_bits - 11)
             else:
                 kind, col_mul, mul = _lib.OPERAND_DEQUANT, act_mul, 1.0
             act = dict(scale=sc, zp=zp, bcast=_lib.PER_TENSOR if sc.numel() == 1 else _lib.PER_COL, kind=kind,
-                       col_mul=col_mul, mul=mul, absorb=absorb, qtype=qtype, bits=qi.num_bits,
-                       symmetric=qi.symmetric, input_qtype=qi.quantizer_type)
+                       col_mul=col_mul, mul=mul, absorb=absorb, raw_mul=raw_mul, inv_raw_mul=inv_raw_mul, qtype=qtype,
+                       bits=qi.num_bits, symmetric=qi.symmetric, input_qtype=qi.quantizer_type)
             base = dict(key=key[:2], act=act, pw=pw, B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))
             lora = None
             if ll is not None:
-                tmul_vec, inv_tmul_vec, bl_rowmul = lora_vec[:r], lora_vec[r:2 * r], lora_vec[2 * r:]
-                lora = dict(key=key, rank=r, A_op=ll['A_op'], pa=ll['pa'], tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
+                tmul_vec, inv_tmul_vec, bl_rowmul = lora_vec[:r], lora_vec[r:2 * r], lora_vec[2 * r:3 * r]
+                pa, inv_pa = lora_vec[3 * r:4 * r], lora_vec[4 * r:]
+                # A operand of the down-projection: q(A)[k,j] / (raw_mul[k] pa[j]), stored [r, K]
+                A_op = _to_f16_operand(ll['aq'], row_mul=inv_raw_mul, col_mul=inv_pa, transposed=True)
+                lora = dict(key=key, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
                             Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=inv_pw, transposed=True),   # [N, r]
                             scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'])
         ent['input'] = dict(key=key, base=base, lora=lora)

@@ -173,27 +173,42 @@ def test_quantize_codes_bit_exact_large(lib, qtype, bits, symmetric, layout):
 
 
 def test_quantize_act_operands(lib):
-    """Fused activation kernel: code operand exact, raw operand = x up to fp16 rounding."""
+    """Fused activation kernel: code operand exact, raw operand = x * 2^e[k] up to fp16 rounding;
+    row-scaled variant (uncalibrated paths): x = x16 * row_scale with power-of-two row scales."""
     M, K = 777, 768
     x = heavy_tailed((M, K), 5)
+    raw_mul = (2.0 ** np.random.default_rng(0).integers(-3, 4, K)).astype(np.float32)
     for qtype, bits in (("minmax", 4), ("minmax", 8), ("log", 8)):
         o = QuantizerState(bits, channel_dim=-1, quantizer_type=qtype, is_input=True)
         o.start_calibration(); collect_statistics(o, x); finish_calibration(o)
         a_q = torch.empty((M, K), dtype=torch.float16, device="cuda")
         a_raw = torch.empty((M, K), dtype=torch.float16, device="cuda")
-        rs = torch.empty(M, dtype=torch.float32, device="cuda")
         lib.quantize_act(dev(x), dev(o.scale.reshape(-1)), dev(o.zero_point.reshape(-1)), lib.PER_COL,
-                         lib.QTYPE[qtype], bits, True, lib.OPERAND_CODE, None, 1.0, a_q, a_raw, rs)
+                         lib.QTYPE[qtype], bits, True, lib.OPERAND_CODE, None, 1.0, a_q, a_raw, dev(raw_mul))
         if qtype == "minmax":
             _, codes = minmax_quantize(x, o.scale.reshape(1, -1), o.zero_point.reshape(1, -1), bits, True)
         else:
             _, codes, _, _ = log_quantize(x, o.zero_point.reshape(1, -1), o.scale.reshape(1, -1), bits, True)
         assert np.array_equal(a_q.float().cpu().numpy(), codes.astype(np.float32))
-        back = a_raw.float().cpu().numpy() * rs.cpu().numpy()[:, None]
-        amax = np.abs(x).max(axis=1, keepdims=True)
-        assert np.max(np.abs(back - x) / amax) <= 2.0 ** -10
-        r = rs.cpu().numpy()
-        assert np.array_equal(np.log2(r), np.round(np.log2(r)))          # powers of two
+        want = np.clip(x * raw_mul[None, :], -65504, 65504)
+        got = a_raw.float().cpu().numpy()
+        assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)) <= 2.0 ** -10
+    x16 = torch.empty((M, K), dtype=torch.float16, device="cuda")
+    rs = torch.empty(M, dtype=torch.float32, device="cuda")
+    lib.rowscale_f16(dev(x), x16, rs)
+    back = x16.float().cpu().numpy() * rs.cpu().numpy()[:, None]
+    amax = np.abs(x).max(axis=1, keepdims=True)
+    assert np.max(np.abs(back - x) / amax) <= 2.0 ** -10
+    r = rs.cpu().numpy()
+    assert np.array_equal(np.log2(r), np.round(np.log2(r)))          # powers of two
+    # odd width / padded leading dimension (LM-head gradients)
+    xo = heavy_tailed((33, 211), 9)
+    buf = lib.empty_f16_padded(33, 211, "cuda")
+    rs2 = torch.empty(33, dtype=torch.float32, device="cuda")
+    lib.rowscale_f16(dev(xo), buf, rs2)
+    assert buf.stride(0) == 216
+    back = buf.float().cpu().numpy() * rs2.cpu().numpy()[:, None]
+    assert np.max(np.abs(back - xo) / np.abs(xo).max(axis=1, keepdims=True)) <= 2.0 ** -10
 
 
 # --------------------------------------------------------------------------- GEMM

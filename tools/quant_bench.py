@@ -13,17 +13,18 @@ x[:, 5] *= 20
 a_q = torch.empty(M, K, device="cuda", dtype=torch.float16)
 a_raw = torch.empty(M, K, device="cuda", dtype=torch.float16)
 rs = torch.empty(M, device="cuda")
+rawm = torch.full((K,), 0.5, device="cuda")
 if mode == "log":
     lmin = torch.full((K,), -16.6, device="cuda"); lrng = torch.full((K,), 19.0, device="cuda")
     cm = torch.full((K,), 2.0 ** 5, device="cuda")
-    call = lambda: _lib.quantize_act(x, lrng, lmin, _lib.PER_COL, _lib.LOG, 8, True, _lib.OPERAND_DEQUANT, cm, 1.0, a_q, a_raw, rs)
+    call = lambda: _lib.quantize_act(x, lrng, lmin, _lib.PER_COL, _lib.LOG, 8, True, _lib.OPERAND_DEQUANT, cm, 1.0, a_q, a_raw, rawm)
     nbytes = M * K * 8
 elif mode == "minmax":
     sc = torch.full((K,), 4.0 / 7, device="cuda"); zp = torch.zeros(K, device="cuda")
-    call = lambda: _lib.quantize_act(x, sc, zp, _lib.PER_COL, _lib.MINMAX, 4, True, _lib.OPERAND_CODE, None, 1.0, a_q, a_raw, rs)
+    call = lambda: _lib.quantize_act(x, sc, zp, _lib.PER_COL, _lib.MINMAX, 4, True, _lib.OPERAND_CODE, None, 1.0, a_q, a_raw, rawm)
     nbytes = M * K * 8
 else:
-    call = lambda: _lib.quantize_act(x, None, None, _lib.PER_TENSOR, -1, 8, True, _lib.OPERAND_RAW, None, 1.0, None, a_raw, rs)
+    call = lambda: _lib.rowscale_f16(x, a_raw, rs)
     nbytes = M * K * 6
 for _ in range(3):
     call()
