@@ -37,6 +37,8 @@ struct QParams {
 // per element instead of ~100.  Dequantised VALUES are tolerance-level quantities (rel 1e-3 in
 // BASELINE.json; ~1e-6 here) and always use the fast formulas.
 struct MinMaxOut { float dq; float code; float centered; };
+__device__ __noinline__ float minmax_code_exact(float x, float s, float zp, int symmetric);
+__device__ __noinline__ float log_level_exact(float axc, float log_min, float range_c, int symmetric, float n_sym, float full);
 
 struct MmCol {            // per-channel constants, min-max
     float s, inv_s, zp;
@@ -58,8 +60,7 @@ __device__ __forceinline__ MinMaxOut minmax_elem(float x, const MmCol& c, const 
     // range the rounding cannot matter
     const float tmag = fminf(fabsf(t), 4.0f * qp.full) + (qp.symmetric ? 0.f : qp.full);   // |x/s| <= |t| + zp
     if (tie_dist <= tmag * 4.76837158203125e-07f && !(qp.debug & 1)) {
-        t = qp.symmetric ? __fdiv_rn(x, c.s) : __fadd_rn(__fdiv_rn(x, c.s), c.zp);
-        q = rintf(t);
+        q = minmax_code_exact(x, c.s, c.zp, qp.symmetric);
     }
     if (qp.symmetric) {                                   // :15-16
         q = fminf(fmaxf(q, -qp.n_sym), qp.n_sym);
@@ -81,6 +82,18 @@ __device__ __forceinline__ float log_prelevel(float l, float log_min, float rang
     ln = fminf(fmaxf(ln, 0.f), 1.f);
     if (qp.symmetric) return __fmul_rn(__fmul_rn(__fsub_rn(ln, 0.5f), 2.f), qp.n_sym);
     return __fmul_rn(ln, qp.full);
+}
+
+// The exact sequences, OUT OF LINE: they are taken by < 0.1 % of the elements, and inlined next to every
+// unrolled fast path they push the hot loop past the instruction caches (64 KB of code, stall_no_inst).
+__device__ __noinline__ float log_level_exact(float axc, float log_min, float range_c, int symmetric, float n_sym, float full) {
+    QParams qp;
+    qp.bits = 0; qp.symmetric = symmetric; qp.n_sym = n_sym; qp.full = full; qp.debug = 0;
+    float r = rintf(log_prelevel(log2_cr(axc), log_min, range_c, qp));
+    return symmetric ? fminf(fmaxf(r, -n_sym), n_sym) : fminf(fmaxf(r, 0.f), full);
+}
+__device__ __noinline__ float minmax_code_exact(float x, float s, float zp, int symmetric) {
+    return rintf(symmetric ? __fdiv_rn(x, s) : __fadd_rn(__fdiv_rn(x, s), zp));
 }
 
 struct LogCol {           // per-channel constants, log
@@ -124,9 +137,7 @@ __device__ __forceinline__ LogOut log_elem(float x, const LogCol& ch, const QPar
     v = qp.symmetric ? fmaf(v, lev_mul, -nl) : v * lev_mul;
     float r = rintf(v);
     if (fabsf(fabsf(v - r) - 0.5f) <= ch.band && !(qp.debug & 1)) {      // near a tie: the reference's exact sequence
-        v = log_prelevel(log2_cr(axc), ch.log_min, ch.range_c, qp);
-        r = rintf(v);
-        r = qp.symmetric ? fminf(fmaxf(r, -nl), nl) : fminf(fmaxf(r, 0.f), nl);
+        r = log_level_exact(axc, ch.log_min, ch.range_c, qp.symmetric, qp.n_sym, qp.full);
     }
     o.level = r;
     // value (:50-74): qn = L/(2n) + 0.5 (symmetric) or L/n; 2^(qn * range + log_min) * sign, 0 under the zero mask
