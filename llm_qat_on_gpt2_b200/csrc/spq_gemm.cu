@@ -145,7 +145,8 @@ struct EpiParams {
     long long d_stride_n;     // 1 for row-major D; TN kernel may store transposed
     float alpha;
     float clamp_abs;          // <= 0: off
-    int debug;                // bit0: skip epilogue stores, bit1: skip MMA issue (profiling experiments only)
+    int debug;                // profiling experiments only: 1 skip epilogue after tcgen05.ld, 2 skip MMA issue,
+                              // 4 disable the TMA-store path, 8 skip the TMA store instruction, 16 skip the staging writes
     int tma_store;            // 1: D is written with TMA bulk tensor stores (fp32, 16 B aligned rows, no residual)
 };
 
@@ -343,11 +344,12 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
                             }
                             o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
-                            *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
+                            if (!(ep.debug & 16)) *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
+                            else if (o.x == 1.2345e-30f) ep.alpha_dev = nullptr;
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(ep.debug & 8)) {
                             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                              reinterpret_cast<uint64_t>(&tmD)),
                                          "r"(stg_u32), "r"(nc), "r"(rbase)

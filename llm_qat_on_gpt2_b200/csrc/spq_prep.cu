@@ -71,6 +71,7 @@ __device__ __forceinline__ void chan(const PrepArgs& a, long long k, float& abso
 __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
     __shared__ float s_red[32];
     __shared__ float s_t[1024];
+    __shared__ float s_xb[4096];        // calibrated bound per input channel (K <= 4096: else recomputed)
     const int tid = threadIdx.x;
     float amax = 0.f;
     for (long long k = tid; k < a.K; k += blockDim.x) {
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
         const float rmul = (xb > 0.f && xb < INFINITY) ? 16.0f / pow2_ceil(xb) : 1.0f;
         a.raw_mul[k] = rmul;
         a.inv_raw_mul[k] = 1.0f / rmul;
+        if (k < 4096) s_xb[k] = xb;
         amax = fmaxf(amax, ab);
     }
     const float absorb_max = block_max(amax, s_red);
@@ -99,12 +101,13 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
             const long long j = tid % r, k0 = tid / r, kstep = 1024 / r;
             float acc = 0.f, mx = 0.f;
             for (long long k = k0; k < a.K; k += kstep) {
-                float ab, am, xb;
-                chan(a, k, ab, am, xb);
+                float xb;
+                if (k < 4096) xb = s_xb[k];
+                else { float ab, am; chan(a, k, ab, am, xb); }
                 const float av = __ldg(a.aq_abs + k * r + j);
-                const float rmul = (xb > 0.f && xb < INFINITY) ? 16.0f / pow2_ceil(xb) : 1.0f;
+                const float inv_rmul = (xb > 0.f && xb < INFINITY) ? pow2_ceil(xb) * 0.0625f : 1.0f;
                 acc += xb * av;
-                mx = fmaxf(mx, av / rmul);
+                mx = fmaxf(mx, av * inv_rmul);
             }
             s_t[tid] = acc;
             s_m[tid] = mx;
