@@ -148,6 +148,37 @@ __device__ __forceinline__ LogOut log_elem(float x, const LogCol& ch, const QPar
     return o;
 }
 
+// ---- branch-free split of the two quantisers, for kernels that process 4 elements at a time:
+//   *_fast  : level / code from the fast arithmetic + "needs the exact path" flag, no branch
+//   *_value : operand value from the final level / code
+// so that the four independent dependency chains of a float4 interleave and at most ONE (rarely
+// taken) fix-up branch is executed per float4 instead of one per element.
+__device__ __forceinline__ float log_level_fast(float x, const LogCol& ch, const QParams& qp, bool& tie) {
+    const float nl = qp.symmetric ? qp.n_sym : qp.full;
+    const float lev_mul = qp.symmetric ? 2.f * nl : nl;
+    float v = __saturatef(fmaf(__log2f(fmaxf(fabsf(x), LOG_EPS)), ch.inv, ch.c0));
+    v = qp.symmetric ? fmaf(v, lev_mul, -nl) : v * lev_mul;
+    const float r = rintf(v);
+    tie = fabsf(fabsf(v - r) - 0.5f) <= ch.band;
+    return r;
+}
+__device__ __forceinline__ float log_value(float x, float r, const LogCol& ch, const QParams& qp, float inv_lev) {
+    const float qn = qp.symmetric ? fmaf(r, inv_lev, 0.5f) : r * inv_lev;
+    const float mag = ex2_approx(fmaf(qn, ch.log_range, ch.log_min + ch.out_add));
+    return (fabsf(x) < LOG_EPS) ? 0.f : copysignf(mag, x);
+}
+__device__ __forceinline__ float minmax_code_fast(float x, const MmCol& c, const QParams& qp, bool& tie) {
+    const float t = qp.symmetric ? x * c.inv_s : fmaf(x, c.inv_s, c.zp);
+    const float q = rintf(t);
+    const float tmag = fminf(fabsf(t), 4.0f * qp.full) + (qp.symmetric ? 0.f : qp.full);
+    tie = fabsf(fabsf(t - q) - 0.5f) <= tmag * 4.76837158203125e-07f;
+    return q;
+}
+__device__ __forceinline__ float minmax_centered(float q, const MmCol& c, const QParams& qp) {
+    if (qp.symmetric) return fminf(fmaxf(q, -qp.n_sym), qp.n_sym);
+    return __fsub_rn(fminf(fmaxf(q, 0.f), qp.full), c.zp);
+}
+
 __device__ __forceinline__ float bparam(const float* p, int bcast, long long row, long long col) {
     return bcast == SPQ_PER_TENSOR ? __ldg(p) : (bcast == SPQ_PER_ROW ? __ldg(p + row) : __ldg(p + col));
 }
@@ -304,7 +335,7 @@ rowscale_kernel(ActArgs a) {
 // in flight per thread; writes the quantised operand and, for the LoRA branch, the raw operand scaled
 // per COLUMN by a power of two derived from the calibrated bound (saturating conversion).
 template <int QTYPE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 quantize_act_kernel(ActArgs a) {
     const long long c0 = (static_cast<long long>(blockIdx.x) * 32 + threadIdx.x) * 4;
     if (c0 >= a.K) return;
@@ -321,18 +352,38 @@ quantize_act_kernel(ActArgs a) {
         else lg[j] = make_logcol(zp, sc, a.qp);
     }
     const long long rstep = static_cast<long long>(gridDim.y) * 8;
+    const float nl_ = a.qp.symmetric ? a.qp.n_sym : a.qp.full;
+    const float inv_lev = __frcp_rn(a.qp.symmetric ? 2.f * nl_ : nl_);
+    const bool no_exact = (a.qp.debug & 1) != 0;
     auto one = [&](long long r, const float4& v) {
         const float xv[4] = {v.x, v.y, v.z, v.w};
+        float q[4];
+        bool tie[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_fast(xv[j], mm[j], a.qp, tie[j]);
+            else q[j] = log_level_fast(xv[j], lg[j], a.qp, tie[j]);
+        }
+        if ((tie[0] | tie[1] | tie[2] | tie[3]) && !no_exact) {           // rare: redo the flagged elements exactly
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (tie[j]) {
+                    if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_exact(xv[j], mm[j].s, mm[j].zp, a.qp.symmetric);
+                    else q[j] = log_level_exact(fmaxf(fabsf(xv[j]), LOG_EPS), lg[j].log_min, lg[j].range_c, a.qp.symmetric,
+                                                a.qp.n_sym, a.qp.full);
+                }
+            }
+        }
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float base;
             if constexpr (QTYPE == SPQ_MINMAX) {
-                const MinMaxOut q = minmax_elem(xv[j], mm[j], a.qp);
-                base = (a.operand_kind == SPQ_OPERAND_CODE) ? q.centered : q.dq;
+                const float cen = minmax_centered(q[j], mm[j], a.qp);
+                base = (a.operand_kind == SPQ_OPERAND_CODE) ? cen : __fmul_rn(cen, mm[j].s);
             } else {
-                const LogOut q = log_elem(xv[j], lg[j], a.qp);
-                base = (a.operand_kind == SPQ_OPERAND_CODE) ? q.level : q.dq;
+                const float lvl = a.qp.symmetric ? fminf(fmaxf(q[j], -nl_), nl_) : fminf(fmaxf(q[j], 0.f), nl_);
+                base = (a.operand_kind == SPQ_OPERAND_CODE) ? lvl : log_value(xv[j], lvl, lg[j], a.qp, inv_lev);
             }
             o[j] = base * cm[j];
         }
