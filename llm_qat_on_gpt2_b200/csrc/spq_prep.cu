@@ -97,7 +97,52 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
         const long long r = a.r;
         __shared__ float s_m[1024];
         float tmax = 0.f;
-        if (r <= 1024 && (1024 % r) == 0) {
+        if ((r % 4) == 0 && r <= 4096 && (1024 % (r / 4)) == 0 && aligned16_dev(a.aq_abs)) {
+            // thread -> 4 consecutive LoRA columns (one float4 per k), k strided; 4 loads in flight
+            const long long g = r / 4, jg = (tid % g) * 4, k0 = tid / g, kstep = 1024 / g;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, mx[4] = {0.f, 0.f, 0.f, 0.f};
+            auto fold = [&](long long k, const float4& av) {
+                float xb;
+                if (k < 4096) xb = s_xb[k];
+                else { float ab, am; chan(a, k, ab, am, xb); }
+                const float inv_rmul = (xb > 0.f && xb < INFINITY) ? pow2_ceil(xb) * 0.0625f : 1.0f;
+                acc[0] += xb * av.x; acc[1] += xb * av.y; acc[2] += xb * av.z; acc[3] += xb * av.w;
+                mx[0] = fmaxf(mx[0], av.x * inv_rmul); mx[1] = fmaxf(mx[1], av.y * inv_rmul);
+                mx[2] = fmaxf(mx[2], av.z * inv_rmul); mx[3] = fmaxf(mx[3], av.w * inv_rmul);
+            };
+            long long k = k0;
+            for (; k + 3 * kstep < a.K; k += 4 * kstep) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(a.aq_abs + (k + u * kstep) * r + jg);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fold(k + u * kstep, v[u]);
+            }
+            for (; k < a.K; k += kstep) fold(k, *reinterpret_cast<const float4*>(a.aq_abs + k * r + jg));
+            // fold the kstep partial results of each column: column j lives in threads with tid % g == j / 4
+            __shared__ float s_acc[4][1024];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s_acc[u][tid] = acc[u]; }
+            __syncthreads();
+            float colsum = 0.f;
+            if (tid < r) {
+                const long long gj = tid / 4, u = tid % 4;
+                for (long long q = gj; q < 1024; q += g) colsum += s_acc[u][q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s_acc[u][tid] = mx[u]; }
+            __syncthreads();
+            if (tid < r) {
+                const long long gj = tid / 4, u = tid % 4;
+                float m = 0.f;
+                for (long long q = gj; q < 1024; q += g) m = fmaxf(m, s_acc[u][q]);
+                tmax = colsum;
+                const float pa = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
+                a.lora[3 * r + tid] = pa;
+                a.lora[4 * r + tid] = 1.0f / pa;
+            }
+        } else if (r <= 1024 && (1024 % r) == 0) {
             const long long j = tid % r, k0 = tid / r, kstep = 1024 / r;
             float acc = 0.f, mx = 0.f;
             for (long long k = k0; k < a.K; k += kstep) {

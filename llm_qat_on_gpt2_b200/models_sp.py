@@ -24,11 +24,6 @@ from .lora import SPLinearWithLoRA, _FpWeightCache, linear_fp
 from .switchable_batchnorm import SwitchableLayerNorm
 
 
-def _flash_only():
-    from torch.nn.attention import SDPBackend, sdpa_kernel
-    return sdpa_kernel([SDPBackend.FLASH_ATTENTION, SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH])
-
-
 def _sp_linear(config, n_in, n_out, bit_widths):
     return SPLinearWithLoRA(n_in, n_out, bit_widths=bit_widths,
                             lora_rank_per_bit=config.lora_rank_per_bit,
@@ -67,14 +62,7 @@ class SPAttention(nn.Module):
         q = q.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
         k = k.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
         v = v.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
-        if half:
-            # flash backend: reads the strided q/k/v views of the fused qkv buffer directly and writes its
-            # output in [B, T, H, D] memory order, so the transpose below is free (the cuDNN backend that
-            # torch prefers on sm_100 returns [B, H, T, D] memory and costs a strided copy per layer)
-            with _flash_only():
-                o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
-        else:
-            o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True)     # torch picks cuDNN's sm_100 fused attention
         o = o.transpose(1, 2).contiguous().view(B, T, C)
         return self.c_proj(o)
 
