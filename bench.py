@@ -121,6 +121,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (numpy / BLAS read
+    # these at import time, and nothing numeric has been imported yet in this process)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cpu_threads())
     base, sec_per_step, _ = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,

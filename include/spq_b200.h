@@ -124,10 +124,11 @@ SPQ_API int spq_ste_backward(const float* grad, int64_t n, int qtype, float* out
 /* ---- (c) fused quant-GEMM -------------------------------------------------------------------
  * Replaces F.linear(q(x), q(W), b) + LoRALayer.forward (p1/lora.py:45-54, 144-150):
  *   D[m,n] = epi( sum_k A[m,k] B[n,k]  +  sum_j A2[m,j] B2[n,j] )
- *   epi(v) = clamp(v * alpha * row_scale[m] * col_scale[n], +-clamp_abs) + bias[n] + C[m,n]
+ *   epi(v) = act( clamp(v * alpha * row_scale[m] * col_scale[n], +-clamp_abs) + bias[n] + C[m,n] )
  * A, B, A2, B2 are fp16, K-contiguous ("K-major"), leading dimensions in elements (multiples of
  * 8); the second segment (the LoRA up-projection folded in as extra K) is optional (K2 = 0).
- * row_scale, col_scale, bias, C are nullable; clamp_abs <= 0 disables the clamp.  D is float32,
+ * row_scale, col_scale, bias, C are nullable; clamp_abs <= 0 disables the clamp; activation 0 = none,
+ * 1 = exact erf GELU (nn.GELU(), p1/models_sp.py:114, fused here for the no-grad MLP path).  D is float32,
  * or fp16 (saturating) when d_is_half.  TMA-fed tcgen05.mma (kind::f16, fp32 accumulation in
  * TMEM), persistent over the SMs.
  */
@@ -136,7 +137,7 @@ SPQ_API int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
               const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
               float alpha, const float* row_scale, const float* col_scale, const float* bias,
               float clamp_abs, const float* C, int64_t ldc,
-              void* D, int64_t ldd, int d_is_half, spq_stream_t stream);
+              void* D, int64_t ldd, int d_is_half, int activation, spq_stream_t stream);
 
 /* Transposed-operand GEMM for the weight-gradient shaped products of the STE backward
  * (dA = x^T dT, dB = t^T dY, optional dW = dY^T q(x); torch autograd of p1/lora.py:51-52, 144):
@@ -165,6 +166,13 @@ SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weig
  * kernel takes over when the row does not fit the register-resident one or is unaligned). */
 SPQ_API int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                      float* row_scale, spq_stream_t stream);
+
+/* ---- consumer of the path: next-token cross-entropy, forward only -----------
+ * Replaces nn.CrossEntropyLoss over re-materialised shifted logits (p1/models_sp.py:441-449) for
+ * no-grad evaluation: row_loss[m] = logsumexp(logits[m, 0:V]) - logits[m, targets[m]], row_valid[m] = 1,
+ * or both 0 where targets[m] == ignore_index.  Rows of `logits` are `ld` floats apart (ld >= V). */
+SPQ_API int spq_cross_entropy_fwd(const float* logits, int64_t M, int64_t V, int64_t ld, const int64_t* targets,
+                          int64_t ignore_index, float* row_loss, float* row_valid, spq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ SIGNATURES = {
     "spq_qgemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                           c_void_p, c_int64, c_void_p, c_int64, c_int64,
                           c_float, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,
-                          c_void_p, c_int64, c_int, c_void_p]),
+                          c_void_p, c_int64, c_int, c_int, c_void_p]),
     "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "spq_layernorm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
@@ -54,6 +54,7 @@ SIGNATURES = {
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spq_cross_entropy_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_rowscale_f16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
@@ -208,7 +209,7 @@ def ste_backward(grad, qtype: int):
 
 
 def qgemm(A, B, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None, col_scale=None, bias=None,
-          clamp_abs=0.0, C=None):
+          clamp_abs=0.0, C=None, activation=0):
     """out[M,N] = epi(A[M,K] B[N,K]^T + A2[M,K2] B2[N,K2]^T); A/B fp16 row-major, out fp32 or fp16."""
     _req_cuda(A, B, out, A2, B2, row_scale, col_scale, bias, C)
     assert A.dtype == torch.float16 and B.dtype == torch.float16
@@ -220,7 +221,7 @@ def qgemm(A, B, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None,
                                     0 if B2 is None else B2.stride(0), K2, float(alpha), _ptr(row_scale),
                                     _ptr(col_scale), _ptr(bias), float(clamp_abs), _ptr(C),
                                     0 if C is None else C.stride(0), out.data_ptr(), out.stride(0), int(d_half),
-                                    _stream()), "spq_qgemm")
+                                    int(activation), _stream()), "spq_qgemm")
     return out
 
 
@@ -260,6 +261,21 @@ def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias):
     _check(lib.spq_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                  rows, cols, dx.data_ptr(), _ptr(dweight), _ptr(dbias), ws.data_ptr(), ws.numel(),
                                  _stream()), "spq_layernorm_bwd")
+
+
+def cross_entropy_fwd(logits2d, targets, ignore_index=-100):
+    """Mean cross-entropy over rows whose target != ignore_index; logits2d may have a padded row stride."""
+    _req_cuda(logits2d, targets)
+    assert logits2d.dim() == 2 and logits2d.stride(1) == 1 and logits2d.dtype == torch.float32
+    M, V = logits2d.shape
+    tg = targets.reshape(-1).to(torch.int64).contiguous()
+    assert tg.numel() == M
+    out = torch.empty((2, M), dtype=torch.float32, device=logits2d.device)
+    _check(load_library().spq_cross_entropy_fwd(logits2d.data_ptr(), M, V, logits2d.stride(0), tg.data_ptr(),
+                                                int(ignore_index), out[0].data_ptr(), out[1].data_ptr(), _stream()),
+           "spq_cross_entropy_fwd")
+    sums = out.sum(dim=1)
+    return sums[0] / sums[1]
 
 
 def rowscale_f16(g2d, out, row_scale):

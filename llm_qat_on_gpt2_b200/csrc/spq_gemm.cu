@@ -134,6 +134,8 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int umma_m, int umma_n, in
            | (static_cast<uint32_t>(umma_n >> 3) << 17) | (static_cast<uint32_t>(umma_m >> 4) << 24);
 }
 
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+
 struct EpiParams {
     const float* row_scale;   // [M] or null
     const float* col_scale;   // [N] or null
@@ -148,6 +150,7 @@ struct EpiParams {
     int debug;                // profiling experiments only: 1 skip epilogue after tcgen05.ld, 2 skip MMA issue,
                               // 4 disable the TMA-store path, 8 skip the TMA store instruction, 16 skip the staging writes
     int tma_store;            // 1: D is written with TMA bulk tensor stores (fp32, 16 B aligned rows, no residual)
+    int act;                  // 0: none, 1: exact (erf) GELU applied after the bias
 };
 
 template <int BN>
@@ -344,6 +347,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
                             }
                             o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
+                            if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                             if (!(ep.debug & 16)) *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
                             else if (o.x == 1.2345e-30f) ep.alpha_dev = nullptr;
                         }
@@ -392,6 +396,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                         const float4 cv = *reinterpret_cast<const float4*>(ep.C + coff);
                                         o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
                                     }
+                                    if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                                     if constexpr (OUT_HALF) {
                                         *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(ep.D) + doff) =
                                             make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
@@ -415,6 +420,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                     if (ep.clamp_abs > 0.f) o = fminf(fmaxf(o, -ep.clamp_abs), ep.clamp_abs);
                                     o += bi1;
                                     if (ep.C) o += ep.C[coff];
+                                    if (ep.act == 1) o = gelu_erf(o);
                                     if constexpr (OUT_HALF) reinterpret_cast<unsigned short*>(ep.D)[doff] = f2h_sat(o);
                                     else reinterpret_cast<float*>(ep.D)[doff] = o;
                                 }
@@ -704,7 +710,8 @@ extern "C" int spq_debug_status(int* aborted_host) {
 extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
                          int64_t K, const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
                          float alpha, const float* row_scale, const float* col_scale, const float* bias, float clamp_abs,
-                         const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, spq_stream_t stream) {
+                         const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, int activation,
+                         spq_stream_t stream) {
     SPQ_REQUIRE(A && B && D, "spq_qgemm: null operand");
     SPQ_REQUIRE(M > 0 && N > 0 && K > 0, "spq_qgemm: empty problem %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
     SPQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "spq_qgemm: dimension overflow");
@@ -744,6 +751,7 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     EpiParams ep;
     ep.row_scale = row_scale; ep.col_scale = col_scale; ep.bias = bias; ep.C = C; ep.alpha_dev = nullptr;
     ep.D = D; ep.ldc = ldc; ep.ldd = ldd; ep.d_stride_n = 1; ep.alpha = alpha; ep.clamp_abs = clamp_abs;
+    ep.act = activation;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("SPQ_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }

@@ -146,20 +146,24 @@ class _LinearFpFn(torch.autograd.Function):
     """y = x W^T + b with fp16 operands / fp32 accumulation on spq_qgemm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache):
+    def forward(ctx, x, weight, bias, cache, activation=0):
         N, K = weight.shape
         x2d = _as_2d_f32(x, K)
         M = x2d.shape[0]
         x16, rs = _rowscaled_f16(x2d)
         w16, pw = cache.get(weight, transposed=False)
-        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-        _lib.qgemm(x16, w16, M, N, K, y, row_scale=rs, col_scale=pw,
-                   bias=None if bias is None else bias.detach().float().contiguous())
+        # rows padded to 16 bytes (matters for N = 50257): the GEMM then stores through TMA; the caller
+        # gets a [..., N] view of the padded buffer
+        ld = (N + 3) // 4 * 4
+        ybuf = torch.empty((M, ld), dtype=torch.float32, device=x.device)
+        _lib.qgemm(x16, w16, M, N, K, ybuf[:, :N] if ld != N else ybuf, row_scale=rs, col_scale=pw,
+                   bias=None if bias is None else bias.detach().float().contiguous(), activation=activation)
         ctx.cache = cache
         ctx.x_shape = x.shape
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x16, rs, weight)
-        return y.view(*x.shape[:-1], N)
+        y = ybuf.view(*x.shape[:-1], ld)
+        return y[..., :N] if ld != N else y
 
     @staticmethod
     def backward(ctx, gy):
@@ -184,11 +188,14 @@ class _LinearFpFn(torch.autograd.Function):
             _lib.gemm_tn(g16, x2, gw, alpha=1.0, alpha_dev=(gmax * xmax).reshape(1).contiguous())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
-def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None):
-    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache())
+def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0):
+    """`activation=1` fuses the exact-erf GELU into the GEMM epilogue; only valid without autograd."""
+    if activation and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise RuntimeError("fused activation epilogue is a no-grad fast path")
+    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -275,7 +282,7 @@ class _SPLinearFn(torch.autograd.Function):
     """Fused forward / STE backward of SPLinearWithLoRA at a quantised precision."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False):
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0):
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
         act = base['act']
@@ -294,9 +301,10 @@ class _SPLinearFn(torch.autograd.Function):
             t = torch.empty((M, r), dtype=torch.float32, device=x.device)
             _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, col_scale=lo['pa'])
             t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
-            _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f)
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f,
+                       activation=activation)
         else:
-            _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f)
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f, activation=activation)
         ctx.use_lora = use_lora
         ctx.x_shape = x.shape
         ctx.has_bias = bias is not None
@@ -372,7 +380,7 @@ class _SPLinearFn(torch.autograd.Function):
                 gw = _lib.ste_backward(gw, _lib.LOG)
         if ctx.has_bias and need_b:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None, None
+        return gx, gw, gb, gA, gB, None, None, None, None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -561,12 +569,17 @@ class SPLinearWithLoRA(nn.Module):
         return ent[1], ent[2]
 
     # ---------------------------------------------------------------- forward (reference :127-150)
-    def forward(self, x, out_half=False):
-        """Reference signature is forward(x) -> float32.  `out_half=True` (used by SPAttention when the
-        attention kernel runs in fp16) makes the GEMM epilogue store fp16 directly instead of float32
-        followed by a cast."""
+    def forward(self, x, out_half=False, fuse_gelu=False):
+        """Reference signature is forward(x) -> float32.  Two internal extensions used by the model
+        wrapper: `out_half=True` (SPAttention with fp16 attention) stores fp16 from the GEMM epilogue
+        instead of float32 followed by a cast; `fuse_gelu=True` (SPMLP under no_grad) applies the exact
+        erf GELU in the epilogue instead of a separate elementwise pass."""
+        act = 1 if (fuse_gelu and not torch.is_grad_enabled()) else 0
+        post_gelu = fuse_gelu and not act
         if self.current_bits >= 32:
-            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache)
+            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act)
+            if post_gelu:
+                y = torch.nn.functional.gelu(y)
             return y.half() if out_half else y
 
         bits_key = f'{self.current_bits}bit'
@@ -578,9 +591,10 @@ class SPLinearWithLoRA(nn.Module):
 
         if input_quantizer.ready() and weight_quantizer.ready():
             lora_on = active_lora.enabled and active_lora.scaling != 0 and not self.calibration_mode
-            return _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
-                                     active_lora.lora_A if lora_on else None,
-                                     active_lora.lora_B if lora_on else None, self, self.current_bits, out_half)
+            y = _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
+                                  active_lora.lora_A if lora_on else None,
+                                  active_lora.lora_B if lora_on else None, self, self.current_bits, out_half, act)
+            return torch.nn.functional.gelu(y) if post_gelu else y
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
         # reference, module by module (this is the calibration pass; errors surface as upstream).
@@ -589,7 +603,10 @@ class SPLinearWithLoRA(nn.Module):
             weight_quantized, cache = weight_quantizer(self.linear.weight), None
         else:
             weight_quantized, cache = self._calibration_weight(self.current_bits, weight_quantizer)
-        base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache)
+        fuse_here = act and self.calibration_mode            # GELU follows the LoRA add when LoRA is on
+        base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0)
         if not self.calibration_mode:
             base_output = base_output + active_lora(x)
+        if fuse_gelu and not fuse_here:
+            base_output = torch.nn.functional.gelu(base_output)
         return base_output.half() if out_half else base_output

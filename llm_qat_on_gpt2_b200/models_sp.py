@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint
 
+from . import _lib
 from .lora import SPLinearWithLoRA, _FpWeightCache, linear_fp
 from .switchable_batchnorm import SwitchableLayerNorm
 
@@ -90,7 +91,8 @@ class SPMLP(nn.Module):
         return bits
 
     def forward(self, hidden_states):
-        return self.c_proj(self.act(self.c_fc(hidden_states)))
+        # exact-erf GELU: fused into c_fc's GEMM epilogue when autograd is off, a separate pass otherwise
+        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True))
 
 
 class SPBlock(nn.Module):
@@ -291,7 +293,11 @@ class SPLMHeadModel(nn.Module):
             # runs over the same B*(T-1) terms
             targets = torch.full_like(labels, -100)
             targets[..., :-1] = labels[..., 1:]
-            loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100)
+            if torch.is_grad_enabled() and logits.requires_grad:
+                loss = F.cross_entropy(logits.reshape(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100)
+            else:
+                # evaluation: one fused pass over the (stride-padded) logits
+                loss = _lib.cross_entropy_fwd(logits.view(-1, logits.size(-1)), targets)
 
         if return_dict or output_hidden_states:
             return {'loss': loss, 'logits': logits, 'hidden_states': all_hidden_states}

@@ -323,3 +323,35 @@ def test_ste_backward(lib):
     x.grad = None
     apply_log_quantization(x, torch.full((1, 40), -10.0, device="cuda"), torch.full((1, 40), 15.0, device="cuda"), 8, True).backward(g)
     assert torch.equal(x.grad, g.clamp(-10, 10))
+
+
+def test_qgemm_gelu_epilogue(lib):
+    torch.manual_seed(5)
+    M, N, K = 300, 520, 192
+    A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    bias = torch.randn(N, device="cuda"); cs = torch.rand(N, device="cuda") + 0.5
+    out = torch.empty(M, N, device="cuda")
+    lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, activation=1)
+    ref = torch.nn.functional.gelu(((A.double() @ B.double().t()) * cs.double() + bias.double()).float())
+    assert ((out.double() - ref.double()).norm() / ref.double().norm()) <= 1e-5
+    # padded output rows (odd N): view of a wider buffer, TMA store clips at N
+    N2 = 211
+    B2 = (torch.randn(N2, K, device="cuda") * 0.1).half()
+    buf = torch.full((M, 212), 7.0, device="cuda")
+    lib.qgemm(A, B2, M, N2, K, buf[:, :N2])
+    ref = (A.double() @ B2.double().t())
+    assert ((buf[:, :N2].double() - ref).norm() / ref.norm()) <= 1e-5
+    assert torch.all(buf[:, N2:] == 7.0)                 # padding untouched
+    assert lib.debug_status() == 0
+
+
+@pytest.mark.parametrize("M,V,ld", [(64, 211, 212), (37, 50257, 50260), (128, 1000, 1000), (5, 33, 33)])
+def test_cross_entropy_fwd(lib, M, V, ld):
+    torch.manual_seed(V)
+    buf = torch.randn(M, ld, device="cuda") * 5
+    logits = buf[:, :V]
+    tg = torch.randint(0, V, (M,), device="cuda")
+    tg[::7] = -100
+    got = lib.cross_entropy_fwd(logits, tg)
+    want = torch.nn.functional.cross_entropy(logits.double(), tg, ignore_index=-100)
+    assert abs(got.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))

@@ -269,3 +269,27 @@ def test_tiny_model_against_golden_and_oracle():
     assert any("lora_adapters.4bit.lora_A" in n for n in got) and any("ln_1.weights.4" in n for n in got)
     assert not any("lora_adapters.8bit" in n for n in got)
     assert model.transformer.h[0].attn.c_attn.linear.weight.grad is None
+
+
+def test_eval_fast_paths_match_autograd_paths():
+    """no_grad fast paths (GELU in the GEMM epilogue, fused cross-entropy on stride-padded logits)
+    give the same numbers as the differentiable composition."""
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel
+    torch.manual_seed(0)
+    model = SPLMHeadModel(_tiny_config()).cuda().eval()
+    ids = torch.randint(0, 211, (2, 32), device="cuda")
+    _calibrate_model(model, 8, [ids])
+    for bits in (8, 32):
+        model.set_precision(bits)
+        with torch.no_grad():
+            fast = model(ids, labels=ids)
+        for p in model.parameters():
+            p.requires_grad_(False)
+        model.transformer.h[0].ln_1.weights[str(bits)].requires_grad_(True)
+        slow = model(ids, labels=ids)
+        assert slow["logits"].requires_grad
+        assert tuple(fast["logits"].shape) == (2, 32, 211)
+        assert rel_fro(fast["logits"].cpu().numpy(), slow["logits"].detach().cpu().numpy()) <= 1e-5
+        assert abs(fast["loss"].item() - slow["loss"].item()) <= 1e-4 * abs(slow["loss"].item())
+        slow["loss"].backward()                       # LM-head backward with the odd vocab width
+        assert torch.isfinite(model.transformer.h[0].ln_1.weights[str(bits)].grad).all()
