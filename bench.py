@@ -46,6 +46,10 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--cpu-sample-batch", type=int, default=1, help="sequences in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=3,
+                    help="optimizer steps of the distillation training step timed after the main metric (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=32, help="per-GPU sequences of the training step (p1/config_sp.py:46)")
+    ap.add_argument("--train-seq", type=int, default=256, help="sequence length of the training step (p1/config_sp.py:47)")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="for ncu launch lists: warm up, run exactly one un-instrumented step, print nothing else")
     return ap.parse_args()
@@ -323,6 +327,10 @@ def gpu_arm(args):
     ms_e2e = t0.elapsed_time(t1)
     clocks = sampler.stop() if rank == 0 else None
 
+    train = None
+    if args.train_steps > 0:
+        train = train_section(args, model, linears, key, dev, world, rank, group, barrier)
+
     if world > 1:
         t = torch.tensor([ms_value, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,12 +363,78 @@ def gpu_arm(args):
                          "peak_source": peaks["source"] + ", bf16 dense sustained",
                          "launches": n_gemm, "share_of_step": gemm_ms / ms_value if ms_value else None},
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             base, _, _ = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=1, warmup=0)
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_section(args, model, linears, key, dev, world, rank, group, barrier):
+    """BASELINE.json configs[2]: one switchable-precision distillation step per optimizer step --
+    32-bit teacher forward (no grad), LoRA quantisers recalibrated (p1/train_sp.py:125-163, 362-364),
+    8-bit student forward + STE backward on KL(T=3) (p1/distillation_manager.py:64-80), all-reduce of
+    the gradients that exist (active LoRA A/B + active LayerNorm pairs), AdamW on those parameters.
+    Batch-sharded: every rank runs the reference's 32 x 256 micro-batch (weak scaling)."""
+    import torch
+    import torch.nn.functional as F
+    import torch.distributed as dist
+    from llm_qat_on_gpt2_b200 import _lib, dp
+    B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
+    model.train()
+    for n, p in model.named_parameters():
+        p.requires_grad_((f"lora_adapters.{key}.lora_" in n) or n.endswith(f"weights.{BITS}") or n.endswith(f"biases.{BITS}"))
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
+    lora_q = [q for m in linears for q in (m.lora_adapters[key].quantize_A, m.lora_adapters[key].quantize_B)]
+    lora_w = [w for m in linears for w in (m.lora_adapters[key].lora_A, m.lora_adapters[key].lora_B)]
+    gen = torch.Generator().manual_seed(99 + rank)
+    # the input quantisers keep the calibration of the last forward step (static during training)
+
+    def one_step(ids):
+        with torch.no_grad():
+            model.set_precision(32)
+            t_logits = model(ids)
+            for q, w in zip(lora_q, lora_w):
+                q.start_calibration(); q(w.data)
+            dp.finish_calibration_many(lora_q, None)          # parameters are replicated: no exchange needed
+        model.set_precision(BITS)
+        s_logits = model(ids)
+        t_lp = F.log_softmax(t_logits[..., :-1, :].reshape(-1, V) / Tmp, dim=-1)
+        s_lp = F.log_softmax(s_logits[..., :-1, :].reshape(-1, V) / Tmp, dim=-1)
+        loss = F.kl_div(s_lp, t_lp, reduction="batchmean", log_target=True) * (Tmp * Tmp)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        n = dp.allreduce_gradients(params, group)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss, n
+
+    batches = [torch.randint(0, V, (B, T), generator=gen).to(dev) for _ in range(args.train_steps + 2)]
+    for i in range(2):
+        loss, n_red = one_step(batches[i])
+    barrier()
+    l0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.train_steps):
+        loss, n_red = one_step(batches[2 + i])
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    model.eval()
+    return {"metric": "GPT-2 SP distillation training step tokens/s (32-bit teacher fwd + 8-bit student fwd/bwd + grad all-reduce + AdamW)",
+            "value": B * T * world * args.train_steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / args.train_steps,
+            "steps": args.train_steps, "per_gpu_batch": B, "seq_len": T, "loss": float(loss.item()),
+            "allreduced_grad_elements": int(n_red), "trainable_params": int(sum(p.numel() for p in params)),
+            "gpu_launches": int(_lib.launch_count() - l0)}
 
 
 def main():

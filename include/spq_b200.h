@@ -129,7 +129,8 @@ SPQ_API int spq_ste_backward(const float* grad, int64_t n, int qtype, float* out
  * 8); the second segment (the LoRA up-projection folded in as extra K) is optional (K2 = 0).
  * row_scale, col_scale, bias, C are nullable; clamp_abs <= 0 disables the clamp; activation 0 = none,
  * 1 = exact erf GELU (nn.GELU(), p1/models_sp.py:114, fused here for the no-grad MLP path).  D is float32,
- * or fp16 (saturating) when d_is_half.  TMA-fed tcgen05.mma (kind::f16, fp32 accumulation in
+ * or fp16 (saturating) when d_is_half.  When N is not a multiple of 4 and ldd >= 4*ceil(N/4), the 1-3
+ * floats of row padding after column N may be overwritten (16-byte store granularity).  TMA-fed tcgen05.mma (kind::f16, fp32 accumulation in
  * TMEM), persistent over the SMs.
  */
 SPQ_API int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb,

@@ -763,7 +763,9 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     const int m = static_cast<int>(M), n = static_cast<int>(N);
     // TMA store path: fp32 output with 16-byte aligned rows and no residual input
     CUtensorMap tD = tA;
-    ep.tma_store = (!d_is_half && !C && (ldd % 4) == 0 && aligned16(D) && !(ep.debug & 4)) ? 1 : 0;
+    // (TMA clips the inner dimension at 16-byte granularity: with N % 4 != 0 the 1-3 floats of row padding
+    // after column N are overwritten too, so the row must have that padding: ldd >= 4 * ceil(N / 4))
+    ep.tma_store = (!d_is_half && !C && (ldd % 4) == 0 && ldd >= (N + 3) / 4 * 4 && aligned16(D) && !(ep.debug & 4)) ? 1 : 0;
     if (ep.tma_store && (rc = make_tmap_out(&tD, D, M, N, ldd)) != SPQ_OK) return rc;
     if (d_is_half) {
         if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
