@@ -229,6 +229,10 @@ def gpu_arm(args):
     torch.manual_seed(0)               # identical replicas on every rank
     model = SPLMHeadModel(cfg).to(dev).eval()
     with torch.no_grad():
+        # GPT-2's initializer_range (0.02) for the embeddings / tied LM head: torch's default N(0,1) gives
+        # logits of magnitude ~sqrt(768) * 30, a one-hot softmax and vanishing distillation gradients
+        model.transformer.wte.weight.normal_(0, 0.02)
+        model.transformer.wpe.weight.normal_(0, 0.01)
         for n, p in model.named_parameters():
             if n.endswith("lora_B"):
                 p.normal_(0, 0.02)     # non-trivial LoRA branch

@@ -134,7 +134,18 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int umma_m, int umma_n, in
            | (static_cast<uint32_t>(umma_n >> 3) << 17) | (static_cast<uint32_t>(umma_m >> 4) << 24);
 }
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// Exact-form (erf) GELU of nn.GELU().  erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. <= 1e-7 |v|
+// on the output): ~14 instructions instead of erff()'s ~30, which matters in an epilogue-bound kernel.
+__device__ __forceinline__ float gelu_erf(float v) {
+    const float x = fabsf(v) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-x * x);          // erf(|v| / sqrt 2)
+    return 0.5f * v * (1.0f + copysignf(e, v));
+}
 
 struct EpiParams {
     const float* row_scale;   // [M] or null
