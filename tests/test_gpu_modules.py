@@ -289,7 +289,8 @@ def test_eval_fast_paths_match_autograd_paths():
         slow = model(ids, labels=ids)
         assert slow["logits"].requires_grad
         assert tuple(fast["logits"].shape) == (2, 32, 211)
-        assert rel_fro(fast["logits"].cpu().numpy(), slow["logits"].detach().cpu().numpy()) <= 1e-5
-        assert abs(fast["loss"].item() - slow["loss"].item()) <= 1e-4 * abs(slow["loss"].item())
+        # the epilogue GELU uses a 1.5e-7-accurate erf: a handful of 8-bit codes flip downstream
+        assert rel_fro(fast["logits"].cpu().numpy(), slow["logits"].detach().cpu().numpy()) <= TOL
+        assert abs(fast["loss"].item() - slow["loss"].item()) <= TOL * abs(slow["loss"].item())
         slow["loss"].backward()                       # LM-head backward with the odd vocab width
         assert torch.isfinite(model.transformer.h[0].ln_1.weights[str(bits)].grad).all()
