@@ -50,6 +50,8 @@ def parse_args():
                     help="optimizer steps of the distillation training step timed after the main metric (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU sequences of the training step (p1/config_sp.py:46)")
     ap.add_argument("--train-seq", type=int, default=256, help="sequence length of the training step (p1/config_sp.py:47)")
+    ap.add_argument("--profile-train-step", action="store_true",
+                    help="for ncu launch lists: run the training section with one NVTX-ranged step")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="for ncu launch lists: warm up, run exactly one un-instrumented step, print nothing else")
     return ap.parse_args()
@@ -291,6 +293,10 @@ def gpu_arm(args):
     for i in range(args.warmup):
         step(dev_ids[i])
     barrier()
+    if args.profile_train_step:
+        train_section(args, model, linears, key, dev, world, rank, group, barrier)
+        print(json.dumps({"profile_train_step": True}), flush=True)
+        return
     if args.profile_one_step:
         n0 = _lib.launch_count()
         torch.cuda.nvtx.range_push("spq_step")
@@ -421,6 +427,11 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     for i in range(2):
         loss, n_red = one_step(batches[i])
     barrier()
+    if args.profile_train_step:
+        torch.cuda.nvtx.range_push("spq_train_step")
+        one_step(batches[2])
+        torch.cuda.nvtx.range_pop()
+        barrier()
     l0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()

@@ -494,12 +494,13 @@ class SPLinearWithLoRA(nn.Module):
         wl = self._weight_level(bits)
         ll = self._lora_level(bits) if want_lora else None
         ent = self._op_cache[bits]
-        key = (wl['key'], qi.generation, None if ll is None else ll['key'])
+        bkey = (wl['key'], qi.generation)
+        lkey = None if ll is None else (bkey, ll['key'])
         il = ent.get('input')
-        if il is not None and il['key'] == key:
-            return il['base'], il['lora']
-        if il is not None and ll is None and il['key'][:2] == key[:2]:
-            return il['base'], None                       # same weight + calibration, LoRA just switched off
+        base = il['base'] if (il is not None and il['base']['key'] == bkey) else None
+        lora = il['lora'] if (il is not None and il['lora'] is not None and il['lora']['key'] == lkey) else None
+        if base is not None and (ll is None or lora is not None):
+            return base, (lora if ll is not None else None)
         dev = wl['wq'].device
         with torch.no_grad():
             sc = qi.scale.detach().float().reshape(-1).contiguous()
@@ -510,6 +511,8 @@ class SPLinearWithLoRA(nn.Module):
             if sc.numel() not in (1, K):
                 raise NotImplementedError(f"input quantiser scale of {sc.numel()} elements for in_features={K}")
             qtype = _lib.QTYPE[qi.quantizer_type]
+            # one launch computes every scale vector (the base part is recomputed identically when only
+            # the LoRA level changed; it is K + N elements)
             vec = torch.empty(4 * K + 2 * N, dtype=torch.float32, device=dev)
             absorb, act_mul, raw_mul, inv_raw_mul = vec[:K], vec[K:2 * K], vec[2 * K:3 * K], vec[3 * K:4 * K]
             pw, inv_pw = vec[4 * K:4 * K + N], vec[4 * K + N:]
@@ -518,25 +521,26 @@ class SPLinearWithLoRA(nn.Module):
             _lib.prep_linear_scales(sc, zp, qtype, qi.num_bits, qi.symmetric, K, wl['wmax_row'], N,
                                     None if ll is None else ll['aq_abs'], r, 0.0 if ll is None else ll['scaling'],
                                     absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
-            if qi.quantizer_type == 'minmax':
-                kind, col_mul, mul = _lib.OPERAND_CODE, None, 2.0 ** -max(0, qi.num_bits - 11)
-            else:
-                kind, col_mul, mul = _lib.OPERAND_DEQUANT, act_mul, 1.0
-            act = dict(scale=sc, zp=zp, bcast=_lib.PER_TENSOR if sc.numel() == 1 else _lib.PER_COL, kind=kind,
-                       col_mul=col_mul, mul=mul, absorb=absorb, raw_mul=raw_mul, inv_raw_mul=inv_raw_mul, qtype=qtype,
-                       bits=qi.num_bits, symmetric=qi.symmetric, input_qtype=qi.quantizer_type)
-            base = dict(key=key[:2], act=act, pw=pw, B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))
-            lora = None
+            if base is None:
+                if qi.quantizer_type == 'minmax':
+                    kind, col_mul, mul = _lib.OPERAND_CODE, None, 2.0 ** -max(0, qi.num_bits - 11)
+                else:
+                    kind, col_mul, mul = _lib.OPERAND_DEQUANT, act_mul, 1.0
+                act = dict(scale=sc, zp=zp, bcast=_lib.PER_TENSOR if sc.numel() == 1 else _lib.PER_COL, kind=kind,
+                           col_mul=col_mul, mul=mul, absorb=absorb, raw_mul=raw_mul, inv_raw_mul=inv_raw_mul, qtype=qtype,
+                           bits=qi.num_bits, symmetric=qi.symmetric, input_qtype=qi.quantizer_type)
+                base = dict(key=bkey, act=act, pw=pw, inv_pw=inv_pw,
+                            B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))      # the big one: [N, K]
             if ll is not None:
                 tmul_vec, inv_tmul_vec, bl_rowmul = lora_vec[:r], lora_vec[r:2 * r], lora_vec[2 * r:3 * r]
                 pa, inv_pa = lora_vec[3 * r:4 * r], lora_vec[4 * r:]
                 # A operand of the down-projection: q(A)[k,j] / (raw_mul[k] pa[j]), stored [r, K]
-                A_op = _to_f16_operand(ll['aq'], row_mul=inv_raw_mul, col_mul=inv_pa, transposed=True)
-                lora = dict(key=key, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
-                            Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=inv_pw, transposed=True),   # [N, r]
+                A_op = _to_f16_operand(ll['aq'], row_mul=base['act']['inv_raw_mul'], col_mul=inv_pa, transposed=True)
+                lora = dict(key=lkey, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
+                            Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=base['inv_pw'], transposed=True),   # [N, r]
                             scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'])
-        ent['input'] = dict(key=key, base=base, lora=lora)
-        return base, lora
+        ent['input'] = dict(base=base, lora=lora if ll is not None else (il['lora'] if il is not None and base is il['base'] else None))
+        return base, (lora if ll is not None else None)
 
     def _backward_operands_for(self, bits, want_lora):
         wb = self._weight_level_bwd(bits)
