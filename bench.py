@@ -413,9 +413,11 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
             dp.finish_calibration_many(lora_q, None)          # parameters are replicated: no exchange needed
         model.set_precision(BITS)
         s_logits = model(ids)
-        t_lp = F.log_softmax(t_logits[..., :-1, :].reshape(-1, V) / Tmp, dim=-1)
-        s_lp = F.log_softmax(s_logits[..., :-1, :].reshape(-1, V) / Tmp, dim=-1)
-        loss = F.kl_div(s_lp, t_lp, reduction="batchmean", log_target=True) * (Tmp * Tmp)
+        # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows,
+        # written on the strided [:, :-1] views so that no [B*T, V] slice copy is materialised
+        t_lp = F.log_softmax(t_logits[:, :-1, :] / Tmp, dim=-1)
+        s_lp = F.log_softmax(s_logits[:, :-1, :] / Tmp, dim=-1)
+        loss = F.kl_div(s_lp, t_lp, reduction="sum", log_target=True) * (Tmp * Tmp / (B * (T - 1)))
         opt.zero_grad(set_to_none=True)
         loss.backward()
         n = dp.allreduce_gradients(params, group)
@@ -428,9 +430,11 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
         loss, n_red = one_step(batches[i])
     barrier()
     if args.profile_train_step:
-        torch.cuda.nvtx.range_push("spq_train_step")
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()              # ncu --profile-from-start off: forward AND the autograd thread
         one_step(batches[2])
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         barrier()
     l0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

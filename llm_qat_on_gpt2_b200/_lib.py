@@ -40,7 +40,7 @@ SIGNATURES = {
     "spq_quantize_act": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "spq_prep_linear_scales": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int64,
-                                       c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "spq_ste_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "spq_qgemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
@@ -186,11 +186,11 @@ def quantize_act(x2d, scale, zp, bcast, qtype, bits, symmetric, operand_kind, co
                                            _ptr(a_raw), _ptr(raw_col_mul), _stream()), "spq_quantize_act")
 
 
-def prep_linear_scales(in_scale, in_zp, qtype, bits, symmetric, K, w_rowmax, N, aq_abs, r, lora_scaling,
+def prep_linear_scales(in_scale, in_zp, qtype, bits, symmetric, K, w_rowmax, N, aq_abs, bq, r, lora_scaling,
                        absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec):
-    _req_cuda(in_scale, in_zp, w_rowmax, aq_abs, absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
+    _req_cuda(in_scale, in_zp, w_rowmax, aq_abs, bq, absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
     _check(load_library().spq_prep_linear_scales(in_scale.data_ptr(), in_zp.data_ptr(), in_scale.numel(), qtype, bits,
-                                                 int(symmetric), K, w_rowmax.data_ptr(), N, _ptr(aq_abs), r,
+                                                 int(symmetric), K, w_rowmax.data_ptr(), N, _ptr(aq_abs), _ptr(bq), r,
                                                  float(lora_scaling), absorb.data_ptr(), act_mul.data_ptr(),
                                                  raw_mul.data_ptr(), inv_raw_mul.data_ptr(), pw.data_ptr(),
                                                  inv_pw.data_ptr(), _ptr(lora_vec), _stream()), "spq_prep_linear_scales")

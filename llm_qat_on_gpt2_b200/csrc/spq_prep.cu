@@ -40,7 +40,8 @@ struct PrepArgs {
     int qtype, bits, symmetric;
     long long K, N, r;
     const float* w_rowmax;                                   // [N]
-    const float* aq_abs;                                     // [K, r] or null
+    const float* aq_abs;                                     // [K, r] q(A) (sign ignored) or null
+    const float* bq;                                         // [r, N] q(B) or null -> lora[5r:6r] = pb, [6r:7r] = 1/pb
     float lora_scaling;
     float* absorb; float* act_mul; float* raw_mul; float* inv_raw_mul; float* pw; float* inv_pw; float* lora;
 };
@@ -116,9 +117,12 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(a.aq_abs + (k + u * kstep) * r + jg);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) fold(k + u * kstep, v[u]);
+                for (int u = 0; u < 4; ++u) fold(k + u * kstep, make_float4(fabsf(v[u].x), fabsf(v[u].y), fabsf(v[u].z), fabsf(v[u].w)));
             }
-            for (; k < a.K; k += kstep) fold(k, *reinterpret_cast<const float4*>(a.aq_abs + k * r + jg));
+            for (; k < a.K; k += kstep) {
+                const float4 q = *reinterpret_cast<const float4*>(a.aq_abs + k * r + jg);
+                fold(k, make_float4(fabsf(q.x), fabsf(q.y), fabsf(q.z), fabsf(q.w)));
+            }
             // fold the kstep partial results of each column: column j lives in threads with tid % g == j / 4
             __shared__ float s_acc[4][1024];
 #pragma unroll
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
                 float xb;
                 if (k < 4096) xb = s_xb[k];
                 else { float ab, am; chan(a, k, ab, am, xb); }
-                const float av = __ldg(a.aq_abs + k * r + j);
+                const float av = fabsf(__ldg(a.aq_abs + k * r + j));
                 const float inv_rmul = (xb > 0.f && xb < INFINITY) ? pow2_ceil(xb) * 0.0625f : 1.0f;
                 acc += xb * av;
                 mx = fmaxf(mx, av * inv_rmul);
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
                 for (long long k = 0; k < a.K; ++k) {
                     float ab, am, xb;
                     chan(a, k, ab, am, xb);
-                    const float av = __ldg(a.aq_abs + k * r + j);
+                    const float av = fabsf(__ldg(a.aq_abs + k * r + j));
                     const float rmul = (xb > 0.f && xb < INFINITY) ? 16.0f / pow2_ceil(xb) : 1.0f;
                     acc += xb * av;
                     m = fmaxf(m, av / rmul);
@@ -180,6 +184,20 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
                 const float pa = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
                 a.lora[3 * r + j] = pa;
                 a.lora[4 * r + j] = 1.0f / pa;
+            }
+        }
+        if (a.bq != nullptr) {
+            // pb[j] = power-of-two normaliser of row j of scaling * q(B)  (operand of dT = dY q(B)^T)
+            const int warp = tid >> 5, lane = tid & 31;
+            for (long long j = warp; j < r; j += 32) {
+                float m = 0.f;
+                for (long long n = lane; n < a.N; n += 32) m = fmaxf(m, fabsf(__ldg(a.bq + j * a.N + n)));
+                m = warp_fmax(m) * fabsf(a.lora_scaling);
+                if (lane == 0) {
+                    const float pb = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
+                    a.lora[5 * r + j] = pb;
+                    a.lora[6 * r + j] = 1.0f / pb;
+                }
             }
         }
         tmax = block_max(tmax, s_red);
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
 using namespace spq;
 
 extern "C" int spq_prep_linear_scales(const float* in_scale, const float* in_zero_point, int64_t in_n, int qtype, int bits,
-                                      int symmetric, int64_t K, const float* w_rowmax, int64_t N, const float* aq_abs,
+                                      int symmetric, int64_t K, const float* w_rowmax, int64_t N, const float* aq_abs, const float* bq,
                                       int64_t r, float lora_scaling, float* absorb, float* act_mul, float* raw_mul,
                                       float* inv_raw_mul, float* pw, float* inv_pw, float* lora_vec, spq_stream_t stream) {
     SPQ_REQUIRE(in_scale && in_zero_point && w_rowmax && absorb && act_mul && raw_mul && inv_raw_mul && pw && inv_pw,
@@ -209,7 +227,7 @@ extern "C" int spq_prep_linear_scales(const float* in_scale, const float* in_zer
     prep::PrepArgs a;
     a.in_scale = in_scale; a.in_zp = in_zero_point; a.in_n = static_cast<int>(in_n);
     a.qtype = qtype; a.bits = bits; a.symmetric = symmetric; a.K = K; a.N = N; a.r = aq_abs ? r : 0;
-    a.w_rowmax = w_rowmax; a.aq_abs = aq_abs; a.lora_scaling = lora_scaling;
+    a.w_rowmax = w_rowmax; a.aq_abs = aq_abs; a.bq = aq_abs ? bq : nullptr; a.lora_scaling = lora_scaling;
     a.absorb = absorb; a.act_mul = act_mul; a.raw_mul = raw_mul; a.inv_raw_mul = inv_raw_mul;
     a.pw = pw; a.inv_pw = inv_pw; a.lora = lora_vec;
     prep::prep_linear_scales_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);

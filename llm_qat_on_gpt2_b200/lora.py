@@ -328,7 +328,11 @@ class _SPLinearFn(torch.autograd.Function):
         gx = gw = gb = gA = gB = None
         need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
         clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
-        gmax = eg.max() if (need_w or (ctx.use_lora and (need_A or need_B))) else None
+        gmax = egn = gmax1 = None
+        if need_w or (ctx.use_lora and (need_A or need_B)):
+            gmax = eg.max()
+            gmax1 = gmax.reshape(1)
+            egn = eg / gmax                                  # token scales relative to the largest one (<= 1)
 
         dt16 = None
         if ctx.use_lora and (need_x or need_A or need_B):
@@ -342,17 +346,17 @@ class _SPLinearFn(torch.autograd.Function):
                     dt16 = _to_f16_operand(dtn, mul=lb['dt_mul'])
                 if need_A:
                     # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; token scale eg folded into dt
-                    dt2 = _to_f16_operand(dtn, row_mul=(eg / gmax).contiguous(), mul=lb['dt_mul'])
+                    dt2 = _to_f16_operand(dtn, row_mul=egn, mul=lb['dt_mul'])
                     gA = torch.empty((K, r), dtype=torch.float32, device=dev)
-                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax.reshape(1).contiguous(),
+                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1,
                                  i_scale=act['inv_raw_mul'])
                     if lo['qtype_A'] == 'log':
                         gA = _lib.ste_backward(gA, _lib.LOG)
             if need_B:
                 # dB[r,n] = scaling * sum_m t[m,r] dY[m,n]; token scales folded into t
-                t2 = _to_f16_operand(t, row_mul=(eg / gmax).contiguous(), col_mul=lo['tmul_vec'])
+                t2 = _to_f16_operand(t, row_mul=egn, col_mul=lo['tmul_vec'])
                 gB = torch.empty((r, N), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax.reshape(1).contiguous(),
+                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1,
                              j_scale=lo['inv_tmul_vec'], transposed_out=True)
                 if lo['qtype_B'] == 'log':
                     gB = _lib.ste_backward(gB, _lib.LOG)
@@ -375,7 +379,7 @@ class _SPLinearFn(torch.autograd.Function):
             # dW[n,k] = sum_m dY[m,n] q(x)[m,k];  q(x)[m,k] = a_q[m,k] * absorb[k]
             gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax).expand(M).contiguous())
             gw = torch.empty((N, K), dtype=torch.float32, device=dev)
-            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax.reshape(1).contiguous(), j_scale=act['absorb'])
+            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax1, j_scale=act['absorb'])
             if ctx.weight_qtype == 'log':
                 gw = _lib.ste_backward(gw, _lib.LOG)
         if ctx.has_bias and need_b:
@@ -481,9 +485,8 @@ class SPLinearWithLoRA(nn.Module):
             with torch.no_grad():
                 K, r = lo.lora_A.shape
                 aq = _dequant(lo.quantize_A, lo.lora_A)                                      # [K, r]
-                aq_abs = aq.abs().contiguous()
                 bq = _dequant(lo.quantize_B, lo.lora_B)                                      # [r, N]
-            ll = ent['lora'] = dict(key=key, rank=r, aq=aq, aq_abs=aq_abs, bq=bq,
+            ll = ent['lora'] = dict(key=key, rank=r, aq=aq, aq_abs=aq, bq=bq,
                                     scaling=float(lo.scaling), qtype_A=lo.quantize_A.quantizer_type,
                                     qtype_B=lo.quantize_B.quantizer_type, bwd=None, bwd_key=None)
         return ll
@@ -517,9 +520,10 @@ class SPLinearWithLoRA(nn.Module):
             absorb, act_mul, raw_mul, inv_raw_mul = vec[:K], vec[K:2 * K], vec[2 * K:3 * K], vec[3 * K:4 * K]
             pw, inv_pw = vec[4 * K:4 * K + N], vec[4 * K + N:]
             r = 0 if ll is None else ll['rank']
-            lora_vec = torch.empty(5 * r, dtype=torch.float32, device=dev) if ll is not None else None
+            lora_vec = torch.empty(7 * r, dtype=torch.float32, device=dev) if ll is not None else None
             _lib.prep_linear_scales(sc, zp, qtype, qi.num_bits, qi.symmetric, K, wl['wmax_row'], N,
-                                    None if ll is None else ll['aq_abs'], r, 0.0 if ll is None else ll['scaling'],
+                                    None if ll is None else ll['aq_abs'], None if ll is None else ll['bq'], r,
+                                    0.0 if ll is None else ll['scaling'],
                                     absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
             if base is None:
                 if qi.quantizer_type == 'minmax':
@@ -533,12 +537,13 @@ class SPLinearWithLoRA(nn.Module):
                             B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))      # the big one: [N, K]
             if ll is not None:
                 tmul_vec, inv_tmul_vec, bl_rowmul = lora_vec[:r], lora_vec[r:2 * r], lora_vec[2 * r:3 * r]
-                pa, inv_pa = lora_vec[3 * r:4 * r], lora_vec[4 * r:]
+                pa, inv_pa = lora_vec[3 * r:4 * r], lora_vec[4 * r:5 * r]
                 # A operand of the down-projection: q(A)[k,j] / (raw_mul[k] pa[j]), stored [r, K]
                 A_op = _to_f16_operand(ll['aq'], row_mul=base['act']['inv_raw_mul'], col_mul=inv_pa, transposed=True)
                 lora = dict(key=lkey, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
                             Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=base['inv_pw'], transposed=True),   # [N, r]
-                            scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'])
+                            scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'],
+                            pb=lora_vec[5 * r:6 * r], inv_pb=lora_vec[6 * r:])
         ent['input'] = dict(base=base, lora=lora if ll is not None else (il['lora'] if il is not None and base is il['base'] else None))
         return base, (lora if ll is not None else None)
 
@@ -546,18 +551,18 @@ class SPLinearWithLoRA(nn.Module):
         wb = self._weight_level_bwd(bits)
         bw = dict(pk=wb['pk'], WT_op=wb['WT_op'], lora=None)
         if want_lora:
+            _, lora = self._operands_for(bits, True)
             ll = self._lora_level(bits)
-            wkey = self._weight_level(bits)['key']
-            if ll['bwd'] is None or ll['bwd_key'] != wkey:
+            bkey = (self._weight_level(bits)['key'], lora['key'])
+            if ll['bwd'] is None or ll['bwd_key'] != bkey:
                 with torch.no_grad():
                     N = self.out_features
                     dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
-                    pb = _norm_pow2(ll['bq'].abs().amax(dim=1) * abs(ll['scaling']), 0)     # [r]
                     ll['bwd'] = dict(
-                        pb=pb, dt_mul=dt_mul,
-                        B_rn_op=_to_f16_operand(ll['bq'], row_mul=(1.0 / pb).contiguous(), mul=ll['scaling']),        # [r, N]
+                        pb=lora['pb'], dt_mul=dt_mul,
+                        B_rn_op=_to_f16_operand(ll['bq'], row_mul=lora['inv_pb'], mul=ll['scaling']),                 # [r, N]
                         A_kr_op=_to_f16_operand(ll['aq'], row_mul=wb['inv_pk'], mul=1.0 / dt_mul))                      # [K, r]
-                    ll['bwd_key'] = wkey
+                    ll['bwd_key'] = bkey
             bw['lora'] = ll['bwd']
         return bw
 
