@@ -141,18 +141,29 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
 }
 
+// Fold the per-CTA partial column sums: 32 columns per block, 8 lanes share the `parts` rows of a column
+// (one thread walking ~600 dependent-latency loads per column made this as slow as the backward itself).
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int parts, long long C,
                        float* __restrict__ out_a, float* __restrict__ out_b) {
-    const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float fa[8][33], fb[8][33];
+    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const long long c = static_cast<long long>(blockIdx.x) * 32 + cl;
     float a = 0.f, b = 0.f;
-    for (int p = 0; p < parts; ++p) {
-        a += part_a[static_cast<long long>(p) * C + c];
-        b += part_b[static_cast<long long>(p) * C + c];
+    if (c < C) {
+        for (int p = sl; p < parts; p += 8) {
+            a += part_a[static_cast<long long>(p) * C + c];
+            b += part_b[static_cast<long long>(p) * C + c];
+        }
     }
-    if (out_a) out_a[c] = a;
-    if (out_b) out_b[c] = b;
+    fa[sl][cl] = a; fb[sl][cl] = b;
+    __syncthreads();
+    if (sl == 0 && c < C) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { a += fa[w][cl]; b += fb[w][cl]; }
+        if (out_a) out_a[c] = a;
+        if (out_b) out_b[c] = b;
+    }
 }
 
 struct Cfg { int G, NV; unsigned grid; };
@@ -232,7 +243,7 @@ extern "C" int spq_layernorm_bwd(const float* dy, const float* x, const float* w
     }
     SPQ_LAUNCH_OK();
     if (dweight || dbias) {
-        colsum_finalize_kernel<<<static_cast<unsigned>((cols + 255) / 256), 256, 0, st>>>(pdw, pdb, static_cast<int>(c.grid), cols,
+        colsum_finalize_kernel<<<static_cast<unsigned>((cols + 31) / 32), 256, 0, st>>>(pdw, pdb, static_cast<int>(c.grid), cols,
                                                                                             dweight, dbias);
         SPQ_LAUNCH_OK();
     }
