@@ -151,7 +151,7 @@ rowstats_kernel(const float* __restrict__ x, long long rows, long long cols, flo
 // Fold `chunks` partials per channel, apply the log transform, merge into the running statistics.
 // collapse != 0: per-tensor -- all channels fold into stat[0] (single block).
 template <bool LOG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax, long long C, int chunks, int collapse,
                       float eps, int accumulate, const int32_t* __restrict__ flags, float* __restrict__ stat_min,
                       float* __restrict__ stat_max, int32_t* __restrict__ state) {
@@ -175,15 +175,16 @@ stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ 
         stat_max[idx] = b;
     };
     if (!collapse) {
-        // 32 channels per block, 8 lanes share the fold over the `chunks` partials of a channel
-        // (a single thread walking ~200 dependent-latency loads made this kernel as slow as the
-        // streaming pass itself)
-        __shared__ float fa[8][33], fb[8][33];
-        const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        // 32 channels per block, blockDim/32 lanes share the fold over the `chunks` partials of a
+        // channel (a single thread walking ~200 dependent-latency loads made this kernel as slow as
+        // the streaming pass itself)
+        __shared__ float fa[32][33], fb[32][33];
+        const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5, nl = blockDim.x >> 5;
         const long long c = static_cast<long long>(blockIdx.x) * 32 + cl;
         float a = INFINITY, b = -INFINITY;
         if (c < C) {
-            for (int k = sl; k < chunks; k += 8) {
+#pragma unroll 4
+            for (int k = sl; k < chunks; k += nl) {
                 a = nan_min(a, pmin[static_cast<long long>(k) * C + c]);
                 b = nan_max(b, pmax[static_cast<long long>(k) * C + c]);
             }
@@ -191,8 +192,7 @@ stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ 
         fa[sl][cl] = a; fb[sl][cl] = b;
         __syncthreads();
         if (sl == 0 && c < C) {
-#pragma unroll
-            for (int w = 1; w < 8; ++w) { a = nan_min(a, fa[w][cl]); b = nan_max(b, fb[w][cl]); }
+            for (int w = 1; w < nl; ++w) { a = nan_min(a, fa[w][cl]); b = nan_max(b, fb[w][cl]); }
             emit(c, a, b);
         }
     } else {
@@ -200,7 +200,7 @@ stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ 
         const long long total = C * chunks;
         for (long long i = threadIdx.x; i < total; i += blockDim.x) { a = nan_min(a, pmin[i]); b = nan_max(b, pmax[i]); }
         a = warp_min(a); b = warp_max(b);
-        __shared__ float sa[8], sb[8];
+        __shared__ float sa[32], sb[32];
         if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -289,10 +289,11 @@ extern "C" int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int 
     }
     const int collapse = (bcast == SPQ_PER_TENSOR) ? 1 : 0;
     const unsigned fgrid = collapse ? 1u : static_cast<unsigned>((C + 31) / 32);
+    const unsigned fthreads = (!collapse && chunks > 64) ? 1024u : 256u;
     if (log_mode)
-        stats_finalize_kernel<true><<<fgrid, 256, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
+        stats_finalize_kernel<true><<<fgrid, fthreads, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
     else
-        stats_finalize_kernel<false><<<fgrid, 256, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
+        stats_finalize_kernel<false><<<fgrid, fthreads, 0, st>>>(ws.pmin, ws.pmax, C, chunks, collapse, eps, accumulate, ws.flags, stat_min, stat_max, state);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

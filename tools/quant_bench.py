@@ -23,6 +23,10 @@ elif mode == "minmax":
     sc = torch.full((K,), 4.0 / 7, device="cuda"); zp = torch.zeros(K, device="cuda")
     call = lambda: _lib.quantize_act(x, sc, zp, _lib.PER_COL, _lib.MINMAX, 4, True, _lib.OPERAND_CODE, None, 1.0, a_q, a_raw, rawm)
     nbytes = M * K * 8
+elif mode == "stats":
+    smin = torch.empty(K, device="cuda"); smax = torch.empty(K, device="cuda"); stt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    call = lambda: _lib.minmax_stats(x, _lib.PER_COL, True, 1e-5, smin, smax, accumulate=False, state=stt)
+    nbytes = M * K * 4
 else:
     call = lambda: _lib.rowscale_f16(x, a_raw, rs)
     nbytes = M * K * 6
