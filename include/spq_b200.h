@@ -58,9 +58,11 @@ SPQ_API int64_t spq_launch_count(void);
  * state[0] |= 1 when this batch had data above eps (always for min-max mode).
  * NaN propagates as in torch.min/max.  Results are bit-exact (min/max are order independent;
  * log2 is the correctly rounded float32 logarithm, taken after the reduction -- it is monotone).
+ * x_is_half: x holds float16 (the fp16 attention output feeding c_proj); values are widened exactly,
+ * so the statistics equal those of x.float().  Per-row statistics take float32 only.
  */
 SPQ_API size_t spq_stats_workspace_bytes(int64_t rows, int64_t cols, int bcast);
-SPQ_API int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int bcast, int log_mode, float eps,
+SPQ_API int spq_minmax_stats(const void* x, int x_is_half, int64_t rows, int64_t cols, int bcast, int log_mode, float eps,
                      float* stat_min, float* stat_max, int accumulate, int32_t* state,
                      void* workspace, size_t workspace_bytes, spq_stream_t stream);
 
@@ -97,8 +99,9 @@ SPQ_API int spq_fake_quantize(const float* x, int64_t rows, int64_t cols,
  *   a_q   [M, K] fp16 : the quantised GEMM operand (code or dequant) * col_mul[k] * mul, and
  *   a_raw [M, K] fp16 : the UNquantised x * raw_col_mul[k] (the LoRA branch reads x, not q(x));
  *                       raw_col_mul is a power of two per input channel chosen from the calibrated
- *                       bound (spq_prep_linear_scales), the conversion saturates.  a_raw is optional. */
-SPQ_API int spq_quantize_act(const float* x, int64_t M, int64_t K,
+ *                       bound (spq_prep_linear_scales), the conversion saturates.  a_raw is optional.
+ * x is float32, or float16 when x_is_half (widened exactly: same results as on x.float()). */
+SPQ_API int spq_quantize_act(const void* x, int x_is_half, int64_t M, int64_t K,
                      const float* scale, const float* zero_point, int bcast,
                      int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
                      spq_half_t* a_q, spq_half_t* a_raw, const float* raw_col_mul, spq_stream_t stream);
@@ -165,8 +168,9 @@ SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weig
 
 /* ---- gradient-side operand: out[m, 0:N] = fp16(g[m,n] * 2^-e[m]), e from the row's absmax,
  * row_scale[m] = 2^e[m]; rows of `out` are ld_out elements apart (0 = N).  Any N (a two-pass
- * kernel takes over when the row does not fit the register-resident one or is unaligned). */
-SPQ_API int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
+ * kernel takes over when the row does not fit the register-resident one or is unaligned).
+ * g is float32, or float16 when g_is_half (register-resident shapes only). */
+SPQ_API int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                      float* row_scale, spq_stream_t stream);
 
 /* ---- consumer of the path: next-token cross-entropy, forward only -----------

@@ -30,14 +30,14 @@ SIGNATURES = {
     "spq_debug_status": (c_int, [POINTER(c_int)]),
     "spq_launch_count": (c_int64, []),
     "spq_stats_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "spq_minmax_stats": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
+    "spq_minmax_stats": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "spq_finish_calibration": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p,
                                        c_void_p, c_void_p]),
     "spq_fake_quantize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float,
                                   c_int, c_int64, c_void_p]),
-    "spq_quantize_act": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "spq_quantize_act": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "spq_prep_linear_scales": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int64,
                                        c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -55,7 +55,7 @@ SIGNATURES = {
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "spq_cross_entropy_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "spq_rowscale_f16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "spq_rowscale_f16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -139,13 +139,13 @@ def minmax_stats(x2d: torch.Tensor, bcast: int, log_mode: bool, eps: float, stat
                  stat_max: torch.Tensor, accumulate: bool, state: Optional[torch.Tensor]):
     lib = load_library()
     _req_cuda(x2d, stat_min, stat_max, state)
-    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype in (torch.float32, torch.float16)
     rows, cols = x2d.shape
     n = {PER_TENSOR: 1, PER_ROW: rows, PER_COL: cols}[bcast]
     assert stat_min.numel() == n and stat_max.numel() == n and stat_min.is_contiguous() and stat_max.is_contiguous()
     nbytes = lib.spq_stats_workspace_bytes(rows, cols, bcast)
     ws = _workspace(nbytes, x2d.device, "stats")
-    _check(lib.spq_minmax_stats(x2d.data_ptr(), rows, cols, bcast, int(log_mode), float(eps), stat_min.data_ptr(),
+    _check(lib.spq_minmax_stats(x2d.data_ptr(), int(x2d.dtype == torch.float16), rows, cols, bcast, int(log_mode), float(eps), stat_min.data_ptr(),
                                 stat_max.data_ptr(), int(accumulate), _ptr(state), ws.data_ptr(), ws.numel(),
                                 _stream()), "spq_minmax_stats")
 
@@ -179,9 +179,9 @@ def fake_quantize(x2d, scale, zp, bcast, qtype, bits, symmetric, dequant=None, c
 
 def quantize_act(x2d, scale, zp, bcast, qtype, bits, symmetric, operand_kind, col_mul, mul, a_q, a_raw, raw_col_mul):
     _req_cuda(x2d, scale, zp, col_mul, a_q, a_raw, raw_col_mul)
-    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype in (torch.float32, torch.float16)
     M, K = x2d.shape
-    _check(load_library().spq_quantize_act(x2d.data_ptr(), M, K, _ptr(scale), _ptr(zp), bcast, qtype, bits,
+    _check(load_library().spq_quantize_act(x2d.data_ptr(), int(x2d.dtype == torch.float16), M, K, _ptr(scale), _ptr(zp), bcast, qtype, bits,
                                            int(symmetric), operand_kind, _ptr(col_mul), float(mul), _ptr(a_q),
                                            _ptr(a_raw), _ptr(raw_col_mul), _stream()), "spq_quantize_act")
 
@@ -281,8 +281,8 @@ def cross_entropy_fwd(logits2d, targets, ignore_index=-100):
 def rowscale_f16(g2d, out, row_scale):
     _req_cuda(g2d, out, row_scale)
     M, N = g2d.shape
-    assert out.stride(-1) == 1
-    _check(load_library().spq_rowscale_f16(g2d.data_ptr(), M, N, out.data_ptr(), out.stride(0), row_scale.data_ptr(),
+    assert out.stride(-1) == 1 and g2d.is_contiguous() and g2d.dtype in (torch.float32, torch.float16)
+    _check(load_library().spq_rowscale_f16(g2d.data_ptr(), int(g2d.dtype == torch.float16), M, N, out.data_ptr(), out.stride(0), row_scale.data_ptr(),
                                            _stream()), "spq_rowscale_f16")
 
 

@@ -58,6 +58,20 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     return r;
 }
 
+// typed streaming loads: the activation-side kernels accept float32 or float16 inputs (fp16 values are
+// widened exactly, so results equal those on x.float())
+template <typename XT> __device__ __forceinline__ float4 ld_stream_x4(const XT* p);
+template <> __device__ __forceinline__ float4 ld_stream_x4<float>(const float* p) { return ld_stream_f4(p); }
+template <> __device__ __forceinline__ float4 ld_stream_x4<__half>(const __half* p) {
+    unsigned lo, hi;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float ld_x1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_x1(const __half* p) { return __half2float(__ldg(p)); }
+
 __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // torch.min/max semantics: NaN wins.

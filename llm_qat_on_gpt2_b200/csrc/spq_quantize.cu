@@ -272,7 +272,8 @@ fake_quantize_kernel(FqArgs a) {
 // its absmax gives the power-of-two scale of the raw fp16 operand, and the same registers are
 // quantised into the code / dequant operand.  Per-column parameters live in registers across rows.
 struct ActArgs {
-    const float* x;
+    const void* x;        // float32, or float16 when x_half
+    int x_half;
     long long M, K;
     const float* scale;
     const float* zp;
@@ -290,20 +291,20 @@ struct ActArgs {
 // Row-scaled raw operand (no quantiser): one CTA of G threads owns a row at a time, the row stays in
 // registers (NV float4 per thread), its absmax gives the power-of-two scale.  Used where no calibrated
 // bound exists: calibration pass, 32-bit path, LM head, gradients.
-template <int NV>
+template <int NV, typename XT>
 __global__ void __launch_bounds__(256)
 rowscale_kernel(ActArgs a) {
     const int G = blockDim.x;
     const int tid = threadIdx.x;
     __shared__ float s_red[8];
     for (long long row = blockIdx.x; row < a.M; row += gridDim.x) {
-        const float* px = a.x + row * a.K;
+        const XT* px = static_cast<const XT*>(a.x) + row * a.K;
         float4 v[NV];
         float amax = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const long long c = (static_cast<long long>(i) * G + tid) * 4;
-            v[i] = (c < a.K) ? ld_stream_f4(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = (c < a.K) ? ld_stream_x4<XT>(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
         }
         amax = warp_fmax(amax);
@@ -334,7 +335,7 @@ rowscale_kernel(ActArgs a) {
 // columns (their constants live in registers), block (32, 8) strides over rows with four 16-byte loads
 // in flight per thread; writes the quantised operand and, for the LoRA branch, the raw operand scaled
 // per COLUMN by a power of two derived from the calibrated bound (saturating conversion).
-template <int QTYPE>
+template <int QTYPE, typename XT>
 __global__ void __launch_bounds__(256, 3)
 quantize_act_kernel(ActArgs a) {
     const long long c0 = (static_cast<long long>(blockIdx.x) * 32 + threadIdx.x) * 4;
@@ -396,11 +397,11 @@ quantize_act_kernel(ActArgs a) {
     for (; r + 3 * rstep < a.M; r += 4 * rstep) {
         float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(a.x + (r + u * rstep) * a.K + c0);
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream_x4<XT>(static_cast<const XT*>(a.x) + (r + u * rstep) * a.K + c0);
 #pragma unroll
         for (int u = 0; u < 4; ++u) one(r + u * rstep, v[u]);
     }
-    for (; r < a.M; r += rstep) one(r, ld_stream_f4(a.x + r * a.K + c0));
+    for (; r < a.M; r += rstep) one(r, ld_stream_x4<XT>(static_cast<const XT*>(a.x) + r * a.K + c0));
 }
 
 // Rows wider than the register-resident limit, or not 16-byte aligned (LM-head gradients, N = 50257):
@@ -483,11 +484,20 @@ static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
     if (NV == 8) ctas = static_cast<long long>(sm_count()) * 4;
     if (ctas > a.M) ctas = a.M;
     const unsigned grid = static_cast<unsigned>(ctas);
-    switch (NV) {
-        case 1: rowscale_kernel<1><<<grid, G, 0, st>>>(a); break;
-        case 2: rowscale_kernel<2><<<grid, G, 0, st>>>(a); break;
-        case 4: rowscale_kernel<4><<<grid, G, 0, st>>>(a); break;
-        default: rowscale_kernel<8><<<grid, G, 0, st>>>(a); break;
+    if (a.x_half) {
+        switch (NV) {
+            case 1: rowscale_kernel<1, __half><<<grid, G, 0, st>>>(a); break;
+            case 2: rowscale_kernel<2, __half><<<grid, G, 0, st>>>(a); break;
+            case 4: rowscale_kernel<4, __half><<<grid, G, 0, st>>>(a); break;
+            default: rowscale_kernel<8, __half><<<grid, G, 0, st>>>(a); break;
+        }
+    } else {
+        switch (NV) {
+            case 1: rowscale_kernel<1, float><<<grid, G, 0, st>>>(a); break;
+            case 2: rowscale_kernel<2, float><<<grid, G, 0, st>>>(a); break;
+            case 4: rowscale_kernel<4, float><<<grid, G, 0, st>>>(a); break;
+            default: rowscale_kernel<8, float><<<grid, G, 0, st>>>(a); break;
+        }
     }
     SPQ_LAUNCH_OK();
     return SPQ_OK;
@@ -501,7 +511,8 @@ static int launch_act(const ActArgs& a, cudaStream_t st) {
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
-    quantize_act_kernel<QTYPE><<<dim3(gx, static_cast<unsigned>(gy)), dim3(32, 8), 0, st>>>(a);
+    if (a.x_half) quantize_act_kernel<QTYPE, __half><<<dim3(gx, static_cast<unsigned>(gy)), dim3(32, 8), 0, st>>>(a);
+    else quantize_act_kernel<QTYPE, float><<<dim3(gx, static_cast<unsigned>(gy)), dim3(32, 8), 0, st>>>(a);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
@@ -551,8 +562,8 @@ extern "C" int spq_fake_quantize(const float* x, int64_t rows, int64_t cols, con
     return SPQ_OK;
 }
 
-extern "C" int spq_quantize_act(const float* x, int64_t M, int64_t K, const float* scale, const float* zero_point, int bcast,
-                                int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
+extern "C" int spq_quantize_act(const void* x, int x_is_half, int64_t M, int64_t K, const float* scale, const float* zero_point,
+                                int bcast, int qtype, int bits, int symmetric, int operand_kind, const float* col_mul, float mul,
                                 spq_half_t* a_q, spq_half_t* a_raw, const float* raw_col_mul, spq_stream_t stream) {
     SPQ_REQUIRE(x && M > 0 && K > 0, "spq_quantize_act: bad input");
     SPQ_REQUIRE((K % 4) == 0 && aligned16(x), "spq_quantize_act: K must be a multiple of 4 and x 16-byte aligned");
@@ -561,7 +572,7 @@ extern "C" int spq_quantize_act(const float* x, int64_t M, int64_t K, const floa
     SPQ_REQUIRE(bcast == SPQ_PER_COL || bcast == SPQ_PER_TENSOR, "spq_quantize_act: per-row scales are not an activation layout");
     SPQ_REQUIRE(bits >= 1 && bits < 32, "spq_quantize_act: bits %d", bits);
     ActArgs a;
-    a.x = x; a.M = M; a.K = K; a.scale = scale; a.zp = zero_point; a.bcast = bcast;
+    a.x = x; a.x_half = x_is_half ? 1 : 0; a.M = M; a.K = K; a.scale = scale; a.zp = zero_point; a.bcast = bcast;
     a.qp = make_qparams(bits, symmetric);
     a.operand_kind = operand_kind; a.col_mul = col_mul; a.mul = mul;
     a.a_q = a_q; a.a_raw = a_raw; a.raw_row_scale = nullptr; a.raw_col_mul = raw_col_mul;
@@ -570,23 +581,24 @@ extern "C" int spq_quantize_act(const float* x, int64_t M, int64_t K, const floa
     return launch_act<SPQ_LOG>(a, st);
 }
 
-extern "C" int spq_rowscale_f16(const float* g, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out, float* row_scale,
-                                spq_stream_t stream) {
+extern "C" int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
+                                float* row_scale, spq_stream_t stream) {
     SPQ_REQUIRE(g && out && M > 0 && N > 0, "spq_rowscale_f16: bad arguments");
     if (ld_out <= 0) ld_out = N;
     SPQ_REQUIRE(ld_out >= N, "spq_rowscale_f16: ld_out < N");
     if (ld_out == N && (N % 4) == 0 && N <= 8192 && aligned16(g)) {
         ActArgs a;
-        a.x = g; a.M = M; a.K = N; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
+        a.x = g; a.x_half = g_is_half ? 1 : 0; a.M = M; a.K = N; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
         a.qp = make_qparams(8, 1);
         a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
         a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr;
         return launch_rowscale(a, as_stream(stream));
     }
+    SPQ_REQUIRE(!g_is_half, "spq_rowscale_f16: float16 input needs dense rows (ld_out == N), N %% 4 == 0, N <= 8192, 16-byte alignment");
     SPQ_REQUIRE((ld_out % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0, "spq_rowscale_f16: ld_out must be even");
     long long ctas = static_cast<long long>(sm_count()) * 8;
     if (ctas > M) ctas = M;
-    rowscale_wide_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(g, M, N, out, ld_out, row_scale);
+    rowscale_wide_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(static_cast<const float*>(g), M, N, out, ld_out, row_scale);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

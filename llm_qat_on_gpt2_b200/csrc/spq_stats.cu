@@ -32,9 +32,9 @@ static inline int col_chunks(int64_t rows, int64_t cols) {
 
 // Partial reduction over rows for a tile of columns.  VEC = 4: float4 loads (cols % 4 == 0 and x
 // 16-byte aligned); VEC = 1: scalar fallback.
-template <int VEC, bool LOG>
+template <int VEC, bool LOG, typename XT>
 __global__ void __launch_bounds__(TX* TY)
-colstats_partial_kernel(const float* __restrict__ x, long long rows, long long cols, float eps, long long rows_per_chunk,
+colstats_partial_kernel(const XT* __restrict__ x, long long rows, long long cols, float eps, long long rows_per_chunk,
                         float* __restrict__ pmin, float* __restrict__ pmax, int32_t* __restrict__ flags) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const long long c0 = (static_cast<long long>(blockIdx.x) * TX + tx) * VEC;
@@ -49,14 +49,14 @@ colstats_partial_kernel(const float* __restrict__ x, long long rows, long long c
     bool any = false;
 
     if (c0 < cols) {
-        const float* p = x + c0;
+        const XT* p = x + c0;
         long long r = r_begin + ty;
         if constexpr (VEC == 4) {
             // 4 independent 16-byte loads in flight per thread
             for (; r + 3 * TY < r_end; r += 4 * TY) {
                 float4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(p + (r + u * TY) * cols);
+                for (int u = 0; u < 4; ++u) v[u] = ld_stream_x4<XT>(p + (r + u * TY) * cols);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -75,7 +75,7 @@ colstats_partial_kernel(const float* __restrict__ x, long long rows, long long c
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 if (c0 + j < cols) {
-                    float a = __ldg(p + r * cols + j);
+                    float a = ld_x1(p + r * cols + j);
                     if (LOG) a = fabsf(a);
                     nan_cols |= (a != a) ? (1u << j) : 0u;
                     if (LOG) any |= (a > eps);
@@ -248,7 +248,15 @@ extern "C" size_t spq_stats_workspace_bytes(int64_t rows, int64_t cols, int bcas
     return 256 + 2 * n * sizeof(float);
 }
 
-extern "C" int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int bcast, int log_mode, float eps,
+template <int VEC, typename XT>
+static void launch_colstats(dim3 grid, dim3 block, cudaStream_t st, int log_mode, const void* x, long long rows, long long cols,
+                            float eps, long long rpc, float* pmin, float* pmax, int32_t* flags) {
+    const XT* xt = static_cast<const XT*>(x);
+    if (log_mode) colstats_partial_kernel<VEC, true, XT><<<grid, block, 0, st>>>(xt, rows, cols, eps, rpc, pmin, pmax, flags);
+    else colstats_partial_kernel<VEC, false, XT><<<grid, block, 0, st>>>(xt, rows, cols, eps, rpc, pmin, pmax, flags);
+}
+
+extern "C" int spq_minmax_stats(const void* x, int x_is_half, int64_t rows, int64_t cols, int bcast, int log_mode, float eps,
                                 float* stat_min, float* stat_max, int accumulate, int32_t* state, void* workspace,
                                 size_t workspace_bytes, spq_stream_t stream) {
     SPQ_REQUIRE(x && stat_min && stat_max && workspace, "spq_minmax_stats: null pointer");
@@ -267,23 +275,25 @@ extern "C" int spq_minmax_stats(const float* x, int64_t rows, int64_t cols, int 
         ws.pmax = ws.pmin + C;
         const int warps = 8;
         const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
-        if (log_mode) rowstats_kernel<true><<<grid, warps * 32, 0, st>>>(x, rows, cols, eps, ws.pmin, ws.pmax, ws.flags);
-        else rowstats_kernel<false><<<grid, warps * 32, 0, st>>>(x, rows, cols, eps, ws.pmin, ws.pmax, ws.flags);
+        SPQ_REQUIRE(!x_is_half, "spq_minmax_stats: per-row (weight) statistics take float32 input");
+        const float* xf = static_cast<const float*>(x);
+        if (log_mode) rowstats_kernel<true><<<grid, warps * 32, 0, st>>>(xf, rows, cols, eps, ws.pmin, ws.pmax, ws.flags);
+        else rowstats_kernel<false><<<grid, warps * 32, 0, st>>>(xf, rows, cols, eps, ws.pmin, ws.pmax, ws.flags);
         SPQ_LAUNCH_OK();
     } else {
         C = cols; chunks = col_chunks(rows, cols);
         ws.pmax = ws.pmin + static_cast<size_t>(chunks) * C;
         const long long rpc = (rows + chunks - 1) / chunks;
-        const bool vec = ((cols & 3) == 0) && aligned16(x);
+        const bool vec = ((cols & 3) == 0) && (x_is_half ? (reinterpret_cast<uintptr_t>(x) & 7u) == 0 : aligned16(x));
         dim3 block(TX, TY);
         if (vec) {
             dim3 grid(static_cast<unsigned>((cols + COLS_PER_BLOCK_V4 - 1) / COLS_PER_BLOCK_V4), chunks);
-            if (log_mode) colstats_partial_kernel<4, true><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
-            else colstats_partial_kernel<4, false><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+            if (x_is_half) launch_colstats<4, __half>(grid, block, st, log_mode, x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+            else launch_colstats<4, float>(grid, block, st, log_mode, x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
         } else {
             dim3 grid(static_cast<unsigned>((cols + TX - 1) / TX), chunks);
-            if (log_mode) colstats_partial_kernel<1, true><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
-            else colstats_partial_kernel<1, false><<<grid, block, 0, st>>>(x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+            if (x_is_half) launch_colstats<1, __half>(grid, block, st, log_mode, x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
+            else launch_colstats<1, float>(grid, block, st, log_mode, x, rows, cols, eps, rpc, ws.pmin, ws.pmax, ws.flags);
         }
         SPQ_LAUNCH_OK();
     }

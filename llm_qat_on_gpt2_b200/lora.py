@@ -112,6 +112,16 @@ def _as_2d_f32(x: torch.Tensor, last: int) -> torch.Tensor:
     return x2.contiguous()
 
 
+def _as_2d_act(x: torch.Tensor, last: int, max_cols: int = 1 << 30) -> torch.Tensor:
+    """Layer input as a contiguous 2-D matrix.  float16 inputs (the fp16 attention output feeding c_proj)
+    stay float16 -- the activation-side kernels widen them exactly -- everything else becomes float32."""
+    if x.is_cuda and x.dtype == torch.float16 and last % 4 == 0 and last <= max_cols:
+        x2 = x.reshape(-1, last).contiguous()
+        if x2.data_ptr() % 16 == 0:
+            return x2
+    return _as_2d_f32(x, last)
+
+
 # ----------------------------------------------------------------------------------------------
 # plain (unquantised) linear on the tcgen05 GEMM: 32-bit teacher path, calibration pass, LM head
 # ----------------------------------------------------------------------------------------------
@@ -146,20 +156,20 @@ class _LinearFpFn(torch.autograd.Function):
     """y = x W^T + b with fp16 operands / fp32 accumulation on spq_qgemm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache, activation=0):
+    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False):
         N, K = weight.shape
-        x2d = _as_2d_f32(x, K)
+        x2d = _as_2d_act(x, K, max_cols=8192)
         M = x2d.shape[0]
         x16, rs = _rowscaled_f16(x2d)
         w16, pw = cache.get(weight, transposed=False)
         # rows padded to 16 bytes (matters for N = 50257): the GEMM then stores through TMA; the caller
         # gets a [..., N] view of the padded buffer
         ld = (N + 3) // 4 * 4
-        ybuf = torch.empty((M, ld), dtype=torch.float32, device=x.device)
+        ybuf = torch.empty((M, ld), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         _lib.qgemm(x16, w16, M, N, K, ybuf[:, :N] if ld != N else ybuf, row_scale=rs, col_scale=pw,
                    bias=None if bias is None else bias.detach().float().contiguous(), activation=activation)
         ctx.cache = cache
-        ctx.x_shape = x.shape
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x16, rs, weight)
         y = ybuf.view(*x.shape[:-1], ld)
@@ -177,7 +187,7 @@ class _LinearFpFn(torch.autograd.Function):
             wt16, pk = ctx.cache.get(weight, transposed=True)
             gx = torch.empty((M, K), dtype=torch.float32, device=gy.device)
             _lib.qgemm(g16, wt16, M, K, N, gx, row_scale=eg, col_scale=pk)
-            gx = gx.view(ctx.x_shape)
+            gx = gx.view(ctx.x_shape).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
             # dW[n,k] = sum_m dY[m,n] x[m,k]: the per-token scales sit inside the reduction, so they
             # are folded into one operand: x2 = x16 * (rs*eg / (max rs * max eg))
@@ -188,14 +198,15 @@ class _LinearFpFn(torch.autograd.Function):
             _lib.gemm_tn(g16, x2, gw, alpha=1.0, alpha_dev=(gmax * xmax).reshape(1).contiguous())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0):
-    """`activation=1` fuses the exact-erf GELU into the GEMM epilogue; only valid without autograd."""
-    if activation and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
-        raise RuntimeError("fused activation epilogue is a no-grad fast path")
-    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation)
+def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0, out_half: bool = False):
+    """`activation=1` fuses the exact-erf GELU into the GEMM epilogue, `out_half` stores float16 from the
+    epilogue; both are no-grad fast paths."""
+    if (activation or out_half) and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise RuntimeError("fused activation / float16 output epilogues are no-grad fast paths")
+    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation, out_half)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -287,7 +298,7 @@ class _SPLinearFn(torch.autograd.Function):
         base, lo = mod._operands_for(bits, use_lora)
         act = base['act']
         N, K = weight.shape
-        x2d = _as_2d_f32(x, K)
+        x2d = _as_2d_act(x, K)
         M = x2d.shape[0]
         a_q = torch.empty((M, K), dtype=torch.float16, device=x.device)
         a_raw = torch.empty((M, K), dtype=torch.float16, device=x.device) if use_lora else None
@@ -306,7 +317,7 @@ class _SPLinearFn(torch.autograd.Function):
         else:
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f, activation=activation)
         ctx.use_lora = use_lora
-        ctx.x_shape = x.shape
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_bias = bias is not None
         ctx.dims = (M, N, K)
         ctx.base, ctx.lo = base, lo
@@ -374,7 +385,7 @@ class _SPLinearFn(torch.autograd.Function):
                 _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in, C=gl)
             else:
                 _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in)
-            gx = gx.view(ctx.x_shape)
+            gx = gx.view(ctx.x_shape).to(ctx.x_dtype)
         if need_w:
             # dW[n,k] = sum_m dY[m,n] q(x)[m,k];  q(x)[m,k] = a_q[m,k] * absorb[k]
             gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax).expand(M).contiguous())
@@ -586,10 +597,11 @@ class SPLinearWithLoRA(nn.Module):
         act = 1 if (fuse_gelu and not torch.is_grad_enabled()) else 0
         post_gelu = fuse_gelu and not act
         if self.current_bits >= 32:
-            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act)
+            half_here = out_half and not post_gelu and not torch.is_grad_enabled()
+            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act, out_half=half_here)
             if post_gelu:
                 y = torch.nn.functional.gelu(y)
-            return y.half() if out_half else y
+            return y.half() if (out_half and not half_here) else y
 
         bits_key = f'{self.current_bits}bit'
         if bits_key not in self.quantizers_weight or bits_key not in self.quantizers_input:
@@ -613,9 +625,12 @@ class SPLinearWithLoRA(nn.Module):
         else:
             weight_quantized, cache = self._calibration_weight(self.current_bits, weight_quantizer)
         fuse_here = act and self.calibration_mode            # GELU follows the LoRA add when LoRA is on
-        base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0)
+        half_here = (out_half and self.calibration_mode and not (fuse_gelu and not fuse_here)
+                     and not torch.is_grad_enabled())
+        base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0,
+                                out_half=half_here)
         if not self.calibration_mode:
             base_output = base_output + active_lora(x)
         if fuse_gelu and not fuse_here:
             base_output = torch.nn.functional.gelu(base_output)
-        return base_output.half() if out_half else base_output
+        return base_output.half() if (out_half and not half_here) else base_output

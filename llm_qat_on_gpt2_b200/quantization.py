@@ -130,7 +130,10 @@ class LearnableFakeQuantize(nn.Module):
                                f"fallback); got a tensor on {x.device}")
         with torch.no_grad():
             xc = x.detach()
-            if xc.dtype != torch.float32:
+            keep_half = xc.dtype == torch.float16 and not (
+                self.per_channel and self.channel_dim is not None and xc.dim() > 1
+                and self.channel_dim % xc.dim() == 0)          # per-row (weight) statistics take float32
+            if xc.dtype != torch.float32 and not keep_half:
                 xc = xc.float()
             xc = xc.contiguous()
             if xc.numel() == 0:

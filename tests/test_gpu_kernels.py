@@ -358,3 +358,44 @@ def test_cross_entropy_fwd(lib, M, V, ld):
     got = lib.cross_entropy_fwd(logits, tg)
     want = torch.nn.functional.cross_entropy(logits.double(), tg, ignore_index=-100)
     assert abs(got.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4096, 768), (515, 3072), (33, 64), (7, 12)])
+def test_half_inputs_equal_widened_inputs(shape):
+    """float16 inputs to the activation-side kernels (stats, row scale, quantise) give the bits of x.float()."""
+    from llm_qat_on_gpt2_b200 import _lib
+    M, K = shape
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    xh = (torch.randn(M, K, generator=g) * 3).half().to(dev)
+    xf = xh.float()
+    for log_mode in (False, True):
+        for bcast, n in ((_lib.PER_COL, K), (_lib.PER_TENSOR, 1)):
+            outs = []
+            for x in (xf, xh):
+                mn = torch.empty(n, device=dev); mx = torch.empty(n, device=dev)
+                st = torch.zeros(1, dtype=torch.int32, device=dev)
+                _lib.minmax_stats(x, bcast, log_mode, 1e-5, mn, mx, accumulate=False, state=st)
+                outs.append((mn, mx))
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    if K % 4 == 0:
+        res = []
+        for x in (xf, xh):
+            o = torch.empty(M, K, dtype=torch.float16, device=dev); rs = torch.empty(M, device=dev)
+            _lib.rowscale_f16(x, o, rs)
+            res.append((o, rs))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        for qtype, bits, kind in ((_lib.MINMAX, 4, _lib.OPERAND_CODE), (_lib.LOG, 8, _lib.OPERAND_DEQUANT)):
+            if qtype == _lib.MINMAX:
+                sc = (xf.abs().amax(0) / 7).clamp_min(1e-5); zp = torch.zeros(K, device=dev)
+            else:
+                lg = torch.log2(xf.abs().clamp_min(1e-5))
+                zp = lg.amin(0); sc = (lg.amax(0) - zp).clamp_min(1e-5)
+            cm = torch.full((K,), 0.25, device=dev); rm = torch.full((K,), 0.5, device=dev)
+            res = []
+            for x in (xf, xh):
+                a_q = torch.empty(M, K, dtype=torch.float16, device=dev); a_raw = torch.empty(M, K, dtype=torch.float16, device=dev)
+                _lib.quantize_act(x, sc, zp, _lib.PER_COL, qtype, bits, True, kind, cm, 1.0, a_q, a_raw, rm)
+                res.append((a_q, a_raw))
+            assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -294,3 +294,42 @@ def test_eval_fast_paths_match_autograd_paths():
         assert abs(fast["loss"].item() - slow["loss"].item()) <= TOL * abs(slow["loss"].item())
         slow["loss"].backward()                       # LM-head backward with the odd vocab width
         assert torch.isfinite(model.transformer.h[0].ln_1.weights[str(bits)].grad).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qtype", ["minmax", "log"])
+def test_sp_linear_half_input_equals_float_input(qtype):
+    """A float16 layer input (fp16 attention output -> c_proj) gives the bits of the same values in float32,
+    through calibration and through the quantised forward."""
+    from llm_qat_on_gpt2_b200.lora import SPLinearWithLoRA
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    outs = []
+    xh = (torch.randn(4, 96, 256, device=dev) * 2).half()
+    for x in (xh.float(), xh):
+        torch.manual_seed(5)
+        m = SPLinearWithLoRA(256, 384, [4, 8, 32], {4: 8, 8: 8, 32: 0}, {4: 16, 8: 16, 32: 0},
+                             {4: qtype, 8: qtype, 32: None}).to(dev)
+        with torch.no_grad():
+            m.lora_adapters['8bit'].lora_B.normal_(0, 0.02)
+        m.set_precision(8)
+        with torch.no_grad():
+            m.quantizers_weight['8bit'].start_calibration(); m.quantizers_weight['8bit'](m.linear.weight)
+            m.quantizers_weight['8bit'].finish_calibration()
+            m.calibration_mode = True
+            m.quantizers_input['8bit'].start_calibration()
+            y_cal = m(x)
+            m.quantizers_input['8bit'].finish_calibration()
+            m.calibration_mode = False
+            for q in (m.lora_adapters['8bit'].quantize_A, m.lora_adapters['8bit'].quantize_B):
+                q.start_calibration()
+            q = m.lora_adapters['8bit']
+            q.quantize_A(q.lora_A); q.quantize_B(q.lora_B)
+            q.quantize_A.finish_calibration(); q.quantize_B.finish_calibration()
+            y = m(x)
+            y32 = None
+            m.set_precision(32)
+            y32 = m(x)
+        outs.append((y_cal.float(), y.float(), y32.float(), m.quantizers_input['8bit'].scale.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
