@@ -160,7 +160,7 @@ struct EpiParams {
     float clamp_abs;          // <= 0: off
     int debug;                // profiling experiments only: 1 skip epilogue after tcgen05.ld, 2 skip MMA issue,
                               // 4 disable the TMA-store path, 8 skip the TMA store instruction, 16 skip the staging writes
-    int tma_store;            // 1: D is written with TMA bulk tensor stores (fp32, 16 B aligned rows, no residual)
+    int tma_store;            // 1: D is written with TMA bulk tensor stores (16 B aligned rows; residual prefetched per lane)
     int act;                  // 0: none, 1: exact (erf) GELU applied after the bias
 };
 
@@ -180,7 +180,9 @@ struct SmemLayout {
 };
 
 // D[m,n] = epi( sum_k A[m,k] B[n,k] + sum_j A2[m,j] B2[n,j] ), all operands K-major fp16.
-template <int BN, bool OUT_HALF>
+// PRE_C: the TMA-store epilogue adds a float32 residual (separate instantiation: its 32 prefetch registers and
+// extra staging traffic stay out of the plain kernel)
+template <int BN, bool OUT_HALF, bool PRE_C>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -309,6 +311,22 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         bool store_pending = false;
         const float alpha = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f);
         const bool active = (BN >= 64) || (half == 0);   // BN = 32 would leave the second half idle (not instantiated)
+        // residual C on the TMA-store path: the warp reads the NEXT chunk's 32 x 32 block of C coalesced (8 lanes
+        // per 128 B row segment) into registers as soon as the current block has been parked in the staging tile;
+        // the block goes through the same swizzled tile, so every lane then finds its own row next to its
+        // accumulators (chunk 0 of the next tile is requested while that tile's MMA still runs)
+        constexpr bool pre_c = PRE_C;
+        float4 cn[PRE_C ? 8 : 1];
+        auto c_load = [&](int tt, int cc) {
+            const int rb = (tt / n_tiles) * BM + quad * 32 + (lane >> 3);
+            const int ncol = (tt % n_tiles) * BN + half * COLS_PER_HALF + cc * 32 + (lane & 7) * 4;
+            const float* pc = ep.C + static_cast<long long>(rb) * ep.ldc + ncol;
+#pragma unroll
+            for (int i = 0; i < (PRE_C ? 8 : 1); ++i)
+                cn[i] = (rb + i * 4 < M && ncol < N) ? *reinterpret_cast<const float4*>(pc + static_cast<long long>(i) * 4 * ep.ldc)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if constexpr (PRE_C) { if (active && static_cast<int>(blockIdx.x) < num_tiles) c_load(blockIdx.x, 0); }
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t / n_tiles) * BM;
             const int n0 = (t % n_tiles) * BN;
@@ -337,13 +355,29 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tmem_ld_wait();
                     const int cl = half * COLS_PER_HALF + c * 32;   // first column of the chunk inside the tile
                     const int nc = n0 + cl;
-                    if (nc >= N || rbase >= M || (ep.debug & 1)) continue;      // warp-uniform
+                    auto c_next = [&]() {                           // issue the next chunk's residual loads
+                        if (c + 1 < CHUNKS) c_load(t, c + 1);
+                        else if (t + static_cast<int>(gridDim.x) < num_tiles) c_load(t + gridDim.x, 0);
+                    };
+                    if (nc >= N || rbase >= M || (ep.debug & 1)) {              // warp-uniform
+                        if constexpr (PRE_C) c_next();
+                        continue;
+                    }
                     if (store_pending) {                            // the previous TMA store must have read the tile
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         __syncwarp();
                         store_pending = false;
                     }
                     if (ep.tma_store) {
+                        if constexpr (PRE_C) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rl = i * 4 + (lane >> 3);
+                                *reinterpret_cast<float4*>(stg + rl * 32 + (((lane & 7) ^ (rl & 7)) << 2)) = cn[i];
+                            }
+                            c_next();
+                            __syncwarp();
+                        }
                         // finish the arithmetic in registers (this lane owns one row, 32 columns), write the row
                         // into the swizzled tile, then one lane hands the 32 x 32 block to the TMA engine
 #pragma unroll
@@ -358,9 +392,20 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
                             }
                             o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
+                            if constexpr (PRE_C) {
+                                const float4 c4 = *reinterpret_cast<const float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2));
+                                o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
+                            }
                             if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-                            if (!(ep.debug & 16)) *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
-                            else if (o.x == 1.2345e-30f) ep.alpha_dev = nullptr;
+                            if constexpr (OUT_HALF) {
+                                // 64 B rows, 64B swizzle: 16-byte chunk index ^ ((row / 2) % 4)
+                                *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(stg) + lane * 64 +
+                                                          (((j >> 3) ^ ((lane >> 1) & 3)) << 4) + ((j & 4) << 1)) =
+                                    make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                            } else {
+                                if (!(ep.debug & 16)) *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
+                                else if (o.x == 1.2345e-30f) ep.alpha_dev = nullptr;
+                            }
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
@@ -391,7 +436,14 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const float4 cs4 = *reinterpret_cast<const float4*>(epi_cs + cl + cq * 4);
                             const float4 bi4 = *reinterpret_cast<const float4*>(epi_bias + cl + cq * 4);
                             long long doff = static_cast<long long>(rbase + rsub) * ep.ldd + nc + cq * 4;
-                            long long coff = static_cast<long long>(rbase + rsub) * ep.ldc + nc + cq * 4;
+                            const long long coff = static_cast<long long>(rbase + rsub) * ep.ldc + nc + cq * 4;
+                            float4 cv8[8];
+                            if (ep.C) {                             // all eight residual loads in flight at once
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    cv8[i] = (rbase + i * 4 + rsub < M) ? *reinterpret_cast<const float4*>(ep.C + coff + static_cast<long long>(i) * 4 * ep.ldc)
+                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int rl = i * 4 + rsub;
@@ -403,10 +455,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                         o.z = fminf(fmaxf(o.z, -ep.clamp_abs), ep.clamp_abs); o.w = fminf(fmaxf(o.w, -ep.clamp_abs), ep.clamp_abs);
                                     }
                                     o.x += bi4.x; o.y += bi4.y; o.z += bi4.z; o.w += bi4.w;
-                                    if (ep.C) {
-                                        const float4 cv = *reinterpret_cast<const float4*>(ep.C + coff);
-                                        o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
-                                    }
+                                    if (ep.C) { o.x += cv8[i].x; o.y += cv8[i].y; o.z += cv8[i].z; o.w += cv8[i].w; }
                                     if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                                     if constexpr (OUT_HALF) {
                                         *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(ep.D) + doff) =
@@ -416,7 +465,6 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                     }
                                 }
                                 doff += 4 * ep.ldd;
-                                coff += 4 * ep.ldc;
                             }
                         } else {
                             // unaligned / ragged: one row per instruction, lane = column (still coalesced)
@@ -500,19 +548,21 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
     return SPQ_OK;
 }
 
-// fp32 row-major D [M, N], leading dimension ldd (elements): box = 32 columns x 32 rows, 128B swizzle
-static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+// row-major D [M, N], leading dimension ldd (elements): box = 32 columns x 32 rows; fp32 rows of the box are
+// 128 B (128B swizzle), fp16 rows 64 B (64B swizzle) -- the swizzle keeps the per-row smem writes conflict-free
+static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, bool is_half) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return SPQ_ERR_CUDA;
     }
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * (is_half ? 2 : 4)};
     cuuint32_t box[2] = {32, 32};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+    CUresult r = enc(tm, is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                     gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     is_half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (output) failed (%d)", static_cast<int>(r));
@@ -521,18 +571,18 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_
     return SPQ_OK;
 }
 
-template <int BN, bool OUT_HALF>
+template <int BN, bool OUT_HALF, bool PRE_C = false>
 static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
                      const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF, PRE_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    qgemm_nt_kernel<BN, OUT_HALF><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
+    qgemm_nt_kernel<BN, OUT_HALF, PRE_C><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
@@ -772,16 +822,23 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     const int kb2 = static_cast<int>((K2 + BK - 1) / BK);
     cudaStream_t st = as_stream(stream);
     const int m = static_cast<int>(M), n = static_cast<int>(N);
-    // TMA store path: fp32 output with 16-byte aligned rows and no residual input
+    // TMA store path: output rows 16-byte aligned; a residual C must be float4-addressable
     CUtensorMap tD = tA;
-    // (TMA clips the inner dimension at 16-byte granularity: with N % 4 != 0 the 1-3 floats of row padding
-    // after column N are overwritten too, so the row must have that padding: ldd >= 4 * ceil(N / 4))
-    ep.tma_store = (!d_is_half && !C && (ldd % 4) == 0 && ldd >= (N + 3) / 4 * 4 && aligned16(D) && !(ep.debug & 4)) ? 1 : 0;
-    if (ep.tma_store && (rc = make_tmap_out(&tD, D, M, N, ldd)) != SPQ_OK) return rc;
+    // (TMA clips the inner dimension at 16-byte granularity: with N % 4 != 0 (fp16: N % 8) the 1-3 floats (1-7
+    // halves) of row padding after column N are overwritten too, so the row must have that padding)
+    const int64_t gran = d_is_half ? 8 : 4;
+    const bool c_ok = !C || (!d_is_half && (ldc % 4) == 0 && (N % 4) == 0 && aligned16(C));   // fp16 D + residual: general path
+    ep.tma_store = (c_ok && (ldd % gran) == 0 && ldd >= (N + gran - 1) / gran * gran && aligned16(D) && !(ep.debug & 4)) ? 1 : 0;
+    if (ep.tma_store && (rc = make_tmap_out(&tD, D, M, N, ldd, d_is_half != 0)) != SPQ_OK) return rc;
     if (d_is_half) {
         if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 128) return launch_nt<128, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         return launch_nt<64, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+    }
+    if (ep.tma_store && C) {
+        if (bn == 256) return launch_nt<256, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        if (bn == 128) return launch_nt<128, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        return launch_nt<64, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     }
     if (bn == 256) return launch_nt<256, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     if (bn == 128) return launch_nt<128, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);

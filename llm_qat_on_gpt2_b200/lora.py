@@ -156,7 +156,7 @@ class _LinearFpFn(torch.autograd.Function):
     """y = x W^T + b with fp16 operands / fp32 accumulation on spq_qgemm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False):
+    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False, residual=None):
         N, K = weight.shape
         x2d = _as_2d_act(x, K, max_cols=8192)
         M = x2d.shape[0]
@@ -167,7 +167,8 @@ class _LinearFpFn(torch.autograd.Function):
         ld = (N + 3) // 4 * 4
         ybuf = torch.empty((M, ld), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         _lib.qgemm(x16, w16, M, N, K, ybuf[:, :N] if ld != N else ybuf, row_scale=rs, col_scale=pw,
-                   bias=None if bias is None else bias.detach().float().contiguous(), activation=activation)
+                   bias=None if bias is None else bias.detach().float().contiguous(), activation=activation,
+                   C=None if residual is None else residual.reshape(M, N))
         ctx.cache = cache
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_bias = bias is not None
@@ -198,15 +199,18 @@ class _LinearFpFn(torch.autograd.Function):
             _lib.gemm_tn(g16, x2, gw, alpha=1.0, alpha_dev=(gmax * xmax).reshape(1).contiguous())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
-def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0, out_half: bool = False):
+def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0, out_half: bool = False,
+              residual=None):
     """`activation=1` fuses the exact-erf GELU into the GEMM epilogue, `out_half` stores float16 from the
-    epilogue; both are no-grad fast paths."""
-    if (activation or out_half) and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
-        raise RuntimeError("fused activation / float16 output epilogues are no-grad fast paths")
-    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation, out_half)
+    epilogue, `residual` (float32, contiguous, output-shaped) is added in the epilogue; all no-grad fast paths."""
+    if (activation or out_half or residual is not None) and torch.is_grad_enabled() and \
+            (x.requires_grad or weight.requires_grad):
+        raise RuntimeError("fused activation / float16 output / residual epilogues are no-grad fast paths")
+    return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation, out_half,
+                             residual)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -293,7 +297,7 @@ class _SPLinearFn(torch.autograd.Function):
     """Fused forward / STE backward of SPLinearWithLoRA at a quantised precision."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0):
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0, residual=None):
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
         act = base['act']
@@ -306,6 +310,7 @@ class _SPLinearFn(torch.autograd.Function):
                           act['kind'], act['col_mul'], act['mul'], a_q, a_raw, act['raw_mul'] if use_lora else None)
         y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
+        res2d = None if residual is None else residual.reshape(M, N)
         t = None
         if use_lora:
             r = lo['rank']
@@ -313,9 +318,9 @@ class _SPLinearFn(torch.autograd.Function):
             _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, col_scale=lo['pa'])
             t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f,
-                       activation=activation)
+                       activation=activation, C=res2d)
         else:
-            _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f, activation=activation)
+            _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f, activation=activation, C=res2d)
         ctx.use_lora = use_lora
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_bias = bias is not None
@@ -395,7 +400,7 @@ class _SPLinearFn(torch.autograd.Function):
                 gw = _lib.ste_backward(gw, _lib.LOG)
         if ctx.has_bias and need_b:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None, None, None
+        return gx, gw, gb, gA, gB, None, None, None, None, None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -589,16 +594,24 @@ class SPLinearWithLoRA(nn.Module):
         return ent[1], ent[2]
 
     # ---------------------------------------------------------------- forward (reference :127-150)
-    def forward(self, x, out_half=False, fuse_gelu=False):
+    def forward(self, x, out_half=False, fuse_gelu=False, residual=None):
         """Reference signature is forward(x) -> float32.  Two internal extensions used by the model
         wrapper: `out_half=True` (SPAttention with fp16 attention) stores fp16 from the GEMM epilogue
         instead of float32 followed by a cast; `fuse_gelu=True` (SPMLP under no_grad) applies the exact
-        erf GELU in the epilogue instead of a separate elementwise pass."""
+        erf GELU in the epilogue instead of a separate elementwise pass; `residual` (SPBlock's residual
+        stream) returns residual + forward(x), the add done in the GEMM epilogue when autograd is off."""
+        if residual is not None:
+            fuse_res = (not torch.is_grad_enabled() and not out_half and not fuse_gelu and residual.is_cuda
+                        and residual.dtype == torch.float32 and residual.is_contiguous()
+                        and residual.shape == x.shape[:-1] + (self.linear.out_features,))
+            if not fuse_res:
+                return residual + self.forward(x, out_half=out_half, fuse_gelu=fuse_gelu)
         act = 1 if (fuse_gelu and not torch.is_grad_enabled()) else 0
         post_gelu = fuse_gelu and not act
         if self.current_bits >= 32:
             half_here = out_half and not post_gelu and not torch.is_grad_enabled()
-            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act, out_half=half_here)
+            y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act, out_half=half_here,
+                          residual=residual)
             if post_gelu:
                 y = torch.nn.functional.gelu(y)
             return y.half() if (out_half and not half_here) else y
@@ -614,7 +627,8 @@ class SPLinearWithLoRA(nn.Module):
             lora_on = active_lora.enabled and active_lora.scaling != 0 and not self.calibration_mode
             y = _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
                                   active_lora.lora_A if lora_on else None,
-                                  active_lora.lora_B if lora_on else None, self, self.current_bits, out_half, act)
+                                  active_lora.lora_B if lora_on else None, self, self.current_bits, out_half, act,
+                                  residual)
             return torch.nn.functional.gelu(y) if post_gelu else y
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
@@ -627,10 +641,13 @@ class SPLinearWithLoRA(nn.Module):
         fuse_here = act and self.calibration_mode            # GELU follows the LoRA add when LoRA is on
         half_here = (out_half and self.calibration_mode and not (fuse_gelu and not fuse_here)
                      and not torch.is_grad_enabled())
+        res_here = residual if self.calibration_mode else None      # otherwise after the LoRA add, as upstream
         base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0,
-                                out_half=half_here)
+                                out_half=half_here, residual=res_here)
         if not self.calibration_mode:
             base_output = base_output + active_lora(x)
+            if residual is not None:
+                base_output = residual + base_output
         if fuse_gelu and not fuse_here:
             base_output = torch.nn.functional.gelu(base_output)
         return base_output.half() if (out_half and not half_here) else base_output

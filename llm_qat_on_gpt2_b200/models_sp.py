@@ -54,8 +54,9 @@ class SPAttention(nn.Module):
         self.c_proj.set_precision(bits)
         return self.current_bit_width
 
-    def forward(self, hidden_states, attention_mask=None):
-        # attention_mask is accepted and ignored, as in the reference (:58-76)
+    def forward(self, hidden_states, attention_mask=None, residual=None):
+        # attention_mask is accepted and ignored, as in the reference (:58-76); `residual` (SPBlock) is added
+        # to the projection output (inside c_proj's GEMM epilogue when autograd is off)
         B, T, C = hidden_states.shape
         half = self.attention_dtype == 'fp16'
         qkv = self.c_attn(hidden_states, out_half=True) if half else self.c_attn(hidden_states)
@@ -65,7 +66,7 @@ class SPAttention(nn.Module):
         v = v.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
         o = F.scaled_dot_product_attention(q, k, v, is_causal=True)     # torch picks cuDNN's sm_100 fused attention
         o = o.transpose(1, 2).contiguous().view(B, T, C)
-        return self.c_proj(o)
+        return self.c_proj(o, residual=residual)
 
 
 class SPMLP(nn.Module):
@@ -90,9 +91,10 @@ class SPMLP(nn.Module):
         self.c_proj.set_precision(bits)
         return bits
 
-    def forward(self, hidden_states):
-        # exact-erf GELU: fused into c_fc's GEMM epilogue when autograd is off, a separate pass otherwise
-        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True))
+    def forward(self, hidden_states, residual=None):
+        # exact-erf GELU: fused into c_fc's GEMM epilogue when autograd is off, a separate pass otherwise;
+        # `residual` (SPBlock) is added to the projection output
+        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True), residual=residual)
 
 
 class SPBlock(nn.Module):
@@ -116,8 +118,10 @@ class SPBlock(nn.Module):
         return self._forward(hidden_states, attention_mask)
 
     def _forward(self, hidden_states, attention_mask=None):
-        hidden_states = hidden_states + self.attn(self.ln_1(hidden_states), attention_mask)
-        hidden_states = hidden_states + self.mlp(self.ln_2(hidden_states))
+        # residual stream (reference :139-147): x + attn(ln_1(x)), then x + mlp(ln_2(x)); the adds ride in the
+        # c_proj epilogues when autograd is off
+        hidden_states = self.attn(self.ln_1(hidden_states), attention_mask, residual=hidden_states)
+        hidden_states = self.mlp(self.ln_2(hidden_states), residual=hidden_states)
         return hidden_states
 
 

@@ -399,3 +399,58 @@ def test_half_inputs_equal_widened_inputs(shape):
                 _lib.quantize_act(x, sc, zp, _lib.PER_COL, qtype, bits, True, kind, cm, 1.0, a_q, a_raw, rm)
                 res.append((a_q, a_raw))
             assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(515, 768, 320), (1024, 2304, 768), (300, 200, 64), (130, 72, 128), (4096, 3072, 256)])
+def test_qgemm_tma_store_half_and_residual(M, N, K):
+    """TMA-store epilogue variants: float16 D (64B-swizzled staging) and a prefetched float32 residual C,
+    including the in-place form D = C (residual stream update) and ragged edge tiles."""
+    from llm_qat_on_gpt2_b200 import _lib as lib
+    torch.manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    cs = torch.rand(N, device="cuda") + 0.5; bias = torch.randn(N, device="cuda"); rs = torch.rand(M, device="cuda") + 0.5
+    base = (A.double() @ B.double().t()) * rs.double()[:, None] * cs.double()[None, :] + bias.double()
+    # float16 output
+    outh = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    lib.qgemm(A, B, M, N, K, outh, row_scale=rs, col_scale=cs, bias=bias)
+    assert ((outh.double() - base).norm() / base.norm()) <= 1e-3
+    assert (outh.float() - base.float()).abs().max() <= 2e-3 * base.abs().max()
+    # float16 output + GELU
+    lib.qgemm(A, B, M, N, K, outh, row_scale=rs, col_scale=cs, bias=bias, activation=1)
+    refg = torch.nn.functional.gelu(base.float()).double()
+    assert ((outh.double() - refg).norm() / refg.norm()) <= 1e-3
+    # residual, separate output
+    C = torch.randn(M, N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda")
+    lib.qgemm(A, B, M, N, K, out, row_scale=rs, col_scale=cs, bias=bias, C=C)
+    ref = base + C.double()
+    assert ((out.double() - ref).norm() / ref.norm()) <= 1e-5
+    # residual, in place (D aliases C)
+    D = C.clone()
+    lib.qgemm(A, B, M, N, K, D, row_scale=rs, col_scale=cs, bias=bias, C=D)
+    assert torch.equal(D, out)
+    # residual + float16 output, row-padded residual view (ldc != N)
+    Cp = torch.randn(M, N + 4, device="cuda")
+    lib.qgemm(A, B, M, N, K, outh, row_scale=rs, col_scale=cs, bias=bias, C=Cp[:, :N])
+    ref = base + Cp[:, :N].double()
+    assert ((outh.double() - ref).norm() / ref.norm()) <= 1e-3
+    assert lib.debug_status() == 0
+
+
+@pytest.mark.gpu
+def test_qgemm_general_epilogue_still_covers_unaligned():
+    """Shapes the TMA store cannot take (N % 4 != 0 with a residual, odd leading dimensions) use the masked path."""
+    from llm_qat_on_gpt2_b200 import _lib as lib
+    torch.manual_seed(9)
+    M, N, K = 333, 203, 128
+    A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    C = torch.randn(M, N, device="cuda")
+    ref = A.double() @ B.double().t() + C.double()
+    out = torch.empty(M, N, device="cuda")
+    lib.qgemm(A, B, M, N, K, out, C=C)
+    assert ((out.double() - ref).norm() / ref.norm()) <= 1e-5
+    outh = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    lib.qgemm(A, B, M, N, K, outh, C=C)
+    assert ((outh.double() - ref).norm() / ref.norm()) <= 1e-3
+    assert lib.debug_status() == 0

@@ -333,3 +333,45 @@ def test_sp_linear_half_input_equals_float_input(qtype):
         outs.append((y_cal.float(), y.float(), y32.float(), m.quantizers_input['8bit'].scale.clone()))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_sp_linear_residual_epilogue_is_the_separate_add():
+    """forward(x, residual=r) under no_grad (residual added in the GEMM epilogue) == r + forward(x), bit for bit,
+    at a quantised precision with LoRA, at 32 bits, and during the calibration pass; with autograd on it is the
+    plain add and gradients reach the residual."""
+    from llm_qat_on_gpt2_b200.lora import SPLinearWithLoRA
+    torch.manual_seed(11)
+    dev = torch.device("cuda")
+    m = SPLinearWithLoRA(256, 384, [4, 8, 32], {4: 8, 8: 8, 32: 0}, {4: 16, 8: 16, 32: 0},
+                         {4: "minmax", 8: "log", 32: None}).to(dev)
+    x = torch.randn(3, 50, 256, device=dev)
+    r = torch.randn(3, 50, 384, device=dev)
+    with torch.no_grad():
+        for bits in (4, 8):
+            m.lora_adapters[f'{bits}bit'].lora_B.normal_(0, 0.02)
+            m.set_precision(bits)
+            wq = m.quantizers_weight[f'{bits}bit']
+            wq.start_calibration(); wq(m.linear.weight); wq.finish_calibration()
+            m.calibration_mode = True
+            iq = m.quantizers_input[f'{bits}bit']
+            iq.start_calibration()
+            y_cal = m(x, residual=r)
+            iq2_min = iq.temp_min.clone()
+            assert torch.equal(y_cal, r + m(x))          # second collection of the same batch: statistics unchanged
+            assert torch.equal(iq2_min, iq.temp_min)
+            iq.finish_calibration()
+            m.calibration_mode = False
+            lo = m.lora_adapters[f'{bits}bit']
+            for q, t in ((lo.quantize_A, lo.lora_A), (lo.quantize_B, lo.lora_B)):
+                q.start_calibration(); q(t); q.finish_calibration()
+            assert torch.equal(m(x, residual=r), r + m(x))
+        m.set_precision(32)
+        assert torch.equal(m(x, residual=r), r + m(x))
+    m.set_precision(8)
+    r2 = r.clone().requires_grad_(True)
+    y = m(x, residual=r2)
+    y.sum().backward()
+    assert torch.equal(r2.grad, torch.ones_like(r2))
+    with torch.no_grad():
+        assert (y - (r + m(x))).abs().max() <= 1e-4 * y.abs().max()

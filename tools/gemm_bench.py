@@ -1,4 +1,5 @@
-"""Time / profile one spq_qgemm shape:  python tools/gemm_bench.py M N K [reps] [half]"""
+"""Time / profile one spq_qgemm shape:  python tools/gemm_bench.py M N K [reps] [half|f32] [resid]
+(resid: the epilogue adds a float32 residual C, in place: D = C)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,13 +11,15 @@ torch.manual_seed(0)
 A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
 out = torch.empty(M, N, device="cuda", dtype=torch.float16 if half else torch.float32)
 bias = torch.randn(N, device="cuda"); cs = torch.rand(N, device="cuda")
+resid = len(sys.argv) > 6 and sys.argv[6] == "resid"
+Cres = out if resid else None
 for _ in range(3):
-    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias)
+    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, C=Cres)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
-    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias)
+    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, C=Cres)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 Bt = B.t().contiguous()
@@ -29,4 +32,4 @@ for _ in range(reps):
 e1.record(); torch.cuda.synchronize()
 ms_ref = e0.elapsed_time(e1) / reps
 print(f"cuBLAS   {M}x{N}x{K} out=f16: {ms_ref*1e3:.1f} us  {2.0*M*N*K/ms_ref/1e9:.0f} TFLOP/s")
-print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")
+print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}{' +C' if resid else ''}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")
