@@ -88,7 +88,7 @@ class _CPTLinearFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         ctx.use_lora, ctx.x_shape, ctx.has_bias, ctx.dims = use_lora, x.shape, bias is not None, (M, N, K)
         ctx.base, ctx.lo, ctx.mod = base, lo, mod
-        ctx.bw = mod._backward_operands_for(bits, use_lora) if any(need[:5]) else None
+        ctx.bits = bits                     # backward operands are built (and cached) when backward first runs
         ctx.weight_qtype = mod.quantizer_weight.quantizer_type
         keep_aq = need[1] or (use_lora and need[3])
         ctx.save_for_backward(a_q if keep_aq else None, t)
@@ -97,7 +97,8 @@ class _CPTLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         a_q, t = ctx.saved_tensors
-        base, lo, bw, mod = ctx.base, ctx.lo, ctx.bw, ctx.mod
+        base, lo, mod = ctx.base, ctx.lo, ctx.mod
+        bw = mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
         g2d = _as_2d_f32(gy, N)
         dev = gy.device

@@ -135,16 +135,21 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int umma_m, int umma_n, in
 }
 
 // Exact-form (erf) GELU of nn.GELU().  erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. <= 1e-7 |v|
-// on the output): ~14 instructions instead of erff()'s ~30, which matters in an epilogue-bound kernel.
+// on the output), arranged as 12 FMUL/FFMA + MUFU.RCP + MUFU.EX2: erff() costs ~30 instructions and the IEEE
+// reciprocal / denormal-guarded exp another ~10, which shows in an epilogue that has ~18 issue slots per element.
+//   gelu(v) = v/2 + |v|/2 * erf(|v|/sqrt 2),   erf(x) = 1 - (a1 t + ... + a5 t^5) exp(-x^2),  t = 1/(1 + p x)
 __device__ __forceinline__ float gelu_erf(float v) {
     const float x = fabsf(v) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
+    float t, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * __expf(-x * x);          // erf(|v| / sqrt 2)
-    return 0.5f * v * (1.0f + copysignf(e, v));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((v * v) * -0.72134752044448170f));   // exp(-v^2 / 2)
+    const float e = fmaf(-(p * t), ex, 1.0f);                // erf(|v| / sqrt 2)
+    const float hv = 0.5f * v;
+    return fmaf(fabsf(hv), e, hv);
 }
 
 struct EpiParams {

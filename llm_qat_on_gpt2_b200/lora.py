@@ -327,7 +327,7 @@ class _SPLinearFn(torch.autograd.Function):
         ctx.dims = (M, N, K)
         ctx.base, ctx.lo = base, lo
         need = ctx.needs_input_grad
-        ctx.bw = mod._backward_operands_for(bits, use_lora) if any(need[:5]) else None
+        ctx.mod, ctx.bits = mod, bits       # backward operands are built (and cached) when backward first runs
         ctx.weight_qtype = mod.quantizers_weight[f'{bits}bit'].quantizer_type
         ctx.save_for_backward(a_q if need[1] else None, a_raw, t)
         return y.view(*x.shape[:-1], N)
@@ -335,7 +335,8 @@ class _SPLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         a_q, a_raw, t = ctx.saved_tensors
-        base, lo, bw = ctx.base, ctx.lo, ctx.bw
+        base, lo = ctx.base, ctx.lo
+        bw = ctx.mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
         g2d = _as_2d_f32(gy, N)
         dev = gy.device

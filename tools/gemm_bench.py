@@ -1,4 +1,4 @@
-"""Time / profile one spq_qgemm shape:  python tools/gemm_bench.py M N K [reps] [half|f32] [resid]
+"""Time / profile one spq_qgemm shape:  python tools/gemm_bench.py M N K [reps] [half|f32] [resid|gelu]
 (resid: the epilogue adds a float32 residual C, in place: D = C)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,14 +12,15 @@ A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda
 out = torch.empty(M, N, device="cuda", dtype=torch.float16 if half else torch.float32)
 bias = torch.randn(N, device="cuda"); cs = torch.rand(N, device="cuda")
 resid = len(sys.argv) > 6 and sys.argv[6] == "resid"
+gelu = 1 if (len(sys.argv) > 6 and sys.argv[6] == "gelu") else 0
 Cres = out if resid else None
 for _ in range(3):
-    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, C=Cres)
+    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, C=Cres, activation=gelu)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
-    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, C=Cres)
+    _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias, C=Cres, activation=gelu)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 Bt = B.t().contiguous()
@@ -32,4 +33,4 @@ for _ in range(reps):
 e1.record(); torch.cuda.synchronize()
 ms_ref = e0.elapsed_time(e1) / reps
 print(f"cuBLAS   {M}x{N}x{K} out=f16: {ms_ref*1e3:.1f} us  {2.0*M*N*K/ms_ref/1e9:.0f} TFLOP/s")
-print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}{' +C' if resid else ''}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")
+print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}{' +C' if resid else ''}{' +gelu' if gelu else ''}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")
