@@ -153,17 +153,35 @@ def workload_name(args):
 # ------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    """SM clock / throttle-reason sampling during the timed region: NVML (the source nvidia-smi reads) polled from
+    a thread every 50 ms -- an `nvidia-smi -lms` child process takes driver locks for milliseconds per query and
+    showed up as sporadic +60 ms in the latency-sensitive end-to-end loop; it remains the fallback."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                    (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[0].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -173,18 +191,38 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                flags = ["Active" if mask & bit else "Not Active" for bit, _ in self.NVML_REASONS]
+                self.rows.append(", ".join([str(sm), str(mx), "0"] + flags))
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -200,7 +238,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml (50 ms poll)" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 def gpu_arm(args):
