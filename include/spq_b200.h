@@ -111,8 +111,8 @@ SPQ_API int spq_quantize_act(const void* x, int x_is_half, int64_t M, int64_t K,
  * the dequantised weight [N] and, optionally, |q(A)| [K, r] of the active LoRA adapter, computes the
  * per-K factor the weight operand absorbs, the activation operand multiplier, the power-of-two
  * multiplier of the raw fp16 operand per input channel (and its inverse), the power-of-two row
- * normaliser pw[n] (and 1/pw) and lora_vec (7 r floats) = tau | 1/tau | lora_scaling/tau | pa | 1/pa |
- * pb | 1/pb  (tau: static pre-scale of t = x q(A) from the calibrated input bound; pa[j]: normaliser of
+ * normaliser pw[n] (and 1/pw) and lora_vec (8 r floats) = tau | 1/tau | lora_scaling/tau | pa | 1/pa |
+ * pb | 1/pb | pa*tau  (tau: static pre-scale of t = x q(A) from the calibrated input bound; pa[j]: normaliser of
  * column j of q(A)[k,j] / raw_mul[k], the operand of the LoRA down-projection; pb[j], written when
  * bq = q(B) [r, N] is given: normaliser of row j of lora_scaling * q(B), the operand of dT = dY q(B)^T). */
 SPQ_API int spq_prep_linear_scales(const float* in_scale, const float* in_zero_point, int64_t in_n,

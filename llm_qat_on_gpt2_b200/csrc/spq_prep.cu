@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
             a.lora[j] = tau;
             a.lora[r + j] = 1.0f / tau;
             a.lora[2 * r + j] = a.lora_scaling / tau;
+            a.lora[7 * r + j] = a.lora[3 * r + j] * tau;      // pa * tau (block_max's barrier ordered the pa writes)
         }
     }
 }

@@ -297,7 +297,9 @@ class _SPLinearFn(torch.autograd.Function):
     """Fused forward / STE backward of SPLinearWithLoRA at a quantised precision."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0, residual=None):
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0, residual=None,
+                grad_mode=True):
+        # grad_mode: torch.is_grad_enabled() of the caller (always False inside Function.forward)
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
         act = base['act']
@@ -314,9 +316,15 @@ class _SPLinearFn(torch.autograd.Function):
         t = None
         if use_lora:
             r = lo['rank']
-            t = torch.empty((M, r), dtype=torch.float32, device=x.device)
-            _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, col_scale=lo['pa'])
-            t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
+            if grad_mode and any(ctx.needs_input_grad[:5]):
+                t = torch.empty((M, r), dtype=torch.float32, device=x.device)     # kept for dB
+                _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, col_scale=lo['pa'])
+                t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
+            else:
+                # nothing to save: the down-projection stores its fp16 operand directly (pa and tau are
+                # powers of two, so fp16(acc * (pa tau)) is the same value as the two-step form)
+                t16 = _lib.empty_f16_padded(M, r, x.device)
+                _lib.qgemm(a_raw, lo['A_op'], M, r, K, t16, col_scale=lo['pa_tmul'])
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f,
                        activation=activation, C=res2d)
         else:
@@ -401,7 +409,7 @@ class _SPLinearFn(torch.autograd.Function):
                 gw = _lib.ste_backward(gw, _lib.LOG)
         if ctx.has_bias and need_b:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None, None, None, None
+        return gx, gw, gb, gA, gB, None, None, None, None, None, None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -537,9 +545,12 @@ class SPLinearWithLoRA(nn.Module):
             absorb, act_mul, raw_mul, inv_raw_mul = vec[:K], vec[K:2 * K], vec[2 * K:3 * K], vec[3 * K:4 * K]
             pw, inv_pw = vec[4 * K:4 * K + N], vec[4 * K + N:]
             r = 0 if ll is None else ll['rank']
-            lora_vec = torch.empty(7 * r, dtype=torch.float32, device=dev) if ll is not None else None
+            lora_vec = torch.empty(8 * r, dtype=torch.float32, device=dev) if ll is not None else None
+            # pb (normaliser of scaling * q(B)) does not depend on the input quantiser: computed by the first
+            # prep after the LoRA level changed, reused by the recalibrations that follow
+            want_pb = ll is not None and ll.get('pb') is None
             _lib.prep_linear_scales(sc, zp, qtype, qi.num_bits, qi.symmetric, K, wl['wmax_row'], N,
-                                    None if ll is None else ll['aq_abs'], None if ll is None else ll['bq'], r,
+                                    None if ll is None else ll['aq_abs'], ll['bq'] if want_pb else None, r,
                                     0.0 if ll is None else ll['scaling'],
                                     absorb, act_mul, raw_mul, inv_raw_mul, pw, inv_pw, lora_vec)
             if base is None:
@@ -553,6 +564,8 @@ class SPLinearWithLoRA(nn.Module):
                 base = dict(key=bkey, act=act, pw=pw, inv_pw=inv_pw,
                             B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))      # the big one: [N, K]
             if ll is not None:
+                if want_pb:
+                    ll['pb'], ll['inv_pb'] = lora_vec[5 * r:6 * r].clone(), lora_vec[6 * r:7 * r].clone()
                 tmul_vec, inv_tmul_vec, bl_rowmul = lora_vec[:r], lora_vec[r:2 * r], lora_vec[2 * r:3 * r]
                 pa, inv_pa = lora_vec[3 * r:4 * r], lora_vec[4 * r:5 * r]
                 # A operand of the down-projection: q(A)[k,j] / (raw_mul[k] pa[j]), stored [r, K]
@@ -560,7 +573,7 @@ class SPLinearWithLoRA(nn.Module):
                 lora = dict(key=lkey, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
                             Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=base['inv_pw'], transposed=True),   # [N, r]
                             scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'],
-                            pb=lora_vec[5 * r:6 * r], inv_pb=lora_vec[6 * r:])
+                            pb=ll['pb'], inv_pb=ll['inv_pb'], pa_tmul=lora_vec[7 * r:])
         ent['input'] = dict(base=base, lora=lora if ll is not None else (il['lora'] if il is not None and base is il['base'] else None))
         return base, (lora if ll is not None else None)
 
@@ -629,7 +642,7 @@ class SPLinearWithLoRA(nn.Module):
             y = _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
                                   active_lora.lora_A if lora_on else None,
                                   active_lora.lora_B if lora_on else None, self, self.current_bits, out_half, act,
-                                  residual)
+                                  residual, torch.is_grad_enabled())
             return torch.nn.functional.gelu(y) if post_gelu else y
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the

@@ -374,4 +374,6 @@ def test_sp_linear_residual_epilogue_is_the_separate_add():
     y.sum().backward()
     assert torch.equal(r2.grad, torch.ones_like(r2))
     with torch.no_grad():
-        assert (y - (r + m(x))).abs().max() <= 1e-4 * y.abs().max()
+        # the no-grad forward stores the LoRA intermediate as fp16 straight from the down-projection epilogue;
+        # its scales are powers of two, so it is the value the training path rounds in two steps
+        assert torch.equal(y, r + m(x))
