@@ -185,6 +185,26 @@ struct SmemLayout {
 };
 
 // D[m,n] = epi( sum_k A[m,k] B[n,k] + sum_j A2[m,j] B2[n,j] ), all operands K-major fp16.
+// Tile order of the persistent CTAs.  Few column tiles (the layer GEMMs: 3-12): row-major, the ~148 tiles in
+// flight share one or two A row-blocks and all of B sits in L2.  Many column tiles (LM head: 197): groups of
+// GROUP_M row-blocks are swept column by column, so the tiles in flight touch ~16 A blocks x ~9 B blocks; with
+// row-major order every row-block re-read the whole 77 MB B while the 6.6 GB output stream kept evicting it
+// (ncu: 7-8 GB of DRAM reads for 0.13 GB of operands).
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
+    if (n_tiles < 2 * GROUP_M) {
+        m_blk = t / n_tiles;
+        n_blk = t - m_blk * n_tiles;
+        return;
+    }
+    const int per_group = GROUP_M * n_tiles;
+    const int g = t / per_group;
+    const int rem = t - g * per_group;
+    const int gm = min(GROUP_M, m_tiles - g * GROUP_M);     // the last group may be short
+    n_blk = rem / gm;
+    m_blk = g * GROUP_M + (rem - n_blk * gm);
+}
+
 // PRE_C: the TMA-store epilogue adds a float32 residual (separate instantiation: its 32 prefetch registers and
 // extra staging traffic stay out of the plain kernel)
 template <int BN, bool OUT_HALF, bool PRE_C>
@@ -252,8 +272,10 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / n_tiles) * BM;
-                const int n0 = (t % n_tiles) * BN;
+                int m_blk, n_blk;
+                tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
+                const int m0 = m_blk * BM;
+                const int n0 = n_blk * BN;
                 for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -323,8 +345,10 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr bool pre_c = PRE_C;
         float4 cn[PRE_C ? 8 : 1];
         auto c_load = [&](int tt, int cc) {
-            const int rb = (tt / n_tiles) * BM + quad * 32 + (lane >> 3);
-            const int ncol = (tt % n_tiles) * BN + half * COLS_PER_HALF + cc * 32 + (lane & 7) * 4;
+            int m_blk, n_blk;
+            tile_coords(tt, m_tiles, n_tiles, m_blk, n_blk);
+            const int rb = m_blk * BM + quad * 32 + (lane >> 3);
+            const int ncol = n_blk * BN + half * COLS_PER_HALF + cc * 32 + (lane & 7) * 4;
             const float* pc = ep.C + static_cast<long long>(rb) * ep.ldc + ncol;
 #pragma unroll
             for (int i = 0; i < (PRE_C ? 8 : 1); ++i)
@@ -333,8 +357,10 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
         if constexpr (PRE_C) { if (active && static_cast<int>(blockIdx.x) < num_tiles) c_load(blockIdx.x, 0); }
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m0 = (t / n_tiles) * BM;
-            const int n0 = (t % n_tiles) * BN;
+            int m_blk, n_blk;
+            tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
+            const int m0 = m_blk * BM;
+            const int n0 = n_blk * BN;
             // stage this tile's per-column parameters (previous tile's readers are done: barrier 1)
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int j = epi_tid; j < BN; j += 256) {

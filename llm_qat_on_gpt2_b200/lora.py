@@ -162,9 +162,12 @@ class _LinearFpFn(torch.autograd.Function):
         M = x2d.shape[0]
         x16, rs = _rowscaled_f16(x2d)
         w16, pw = cache.get(weight, transposed=False)
-        # rows padded to 16 bytes (matters for N = 50257): the GEMM then stores through TMA; the caller
-        # gets a [..., N] view of the padded buffer
-        ld = (N + 3) // 4 * 4
+        # odd widths (N = 50257): rows padded to 128 bytes -- the GEMM then stores through TMA, and every 32 x 32
+        # block it stores covers whole 32-byte sectors (rows merely 16-byte aligned made L2 fetch the other
+        # half of each edge sector: 8.4 GB of DRAM reads for a 6.6 GB logits store).  The caller gets a
+        # [..., N] view of the padded buffer
+        align = 64 if out_half else 32
+        ld = N if N % 4 == 0 else (N + align - 1) // align * align
         ybuf = torch.empty((M, ld), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         _lib.qgemm(x16, w16, M, N, K, ybuf[:, :N] if ld != N else ybuf, row_scale=rs, col_scale=pw,
                    bias=None if bias is None else bias.detach().float().contiguous(), activation=activation,

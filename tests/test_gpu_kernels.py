@@ -454,3 +454,20 @@ def test_qgemm_general_epilogue_still_covers_unaligned():
     lib.qgemm(A, B, M, N, K, outh, C=C)
     assert ((outh.double() - ref).norm() / ref.norm()) <= 1e-3
     assert lib.debug_status() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(2693, 8200, 64), (4100, 12001, 128)])
+def test_qgemm_grouped_tile_order(M, N, K):
+    """>= 32 column tiles switch the persistent CTAs to the grouped (16 row-blocks) sweep; the last group is short."""
+    from llm_qat_on_gpt2_b200 import _lib as lib
+    torch.manual_seed(N)
+    A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    ld = (N + 31) // 32 * 32
+    buf = torch.full((M, ld), float("nan"), device="cuda")
+    lib.qgemm(A, B, M, N, K, buf[:, :N] if ld != N else buf)
+    ref = A.double() @ B.double().t()
+    out = buf[:, :N].double()
+    assert not torch.isnan(out).any()
+    assert ((out - ref).norm() / ref.norm()) <= 1e-5
+    assert lib.debug_status() == 0
