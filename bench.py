@@ -39,7 +39,7 @@ LORA_ALPHA = {4: 64, 8: 64, 32: 0}
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
@@ -154,8 +154,10 @@ def workload_name(args):
 
 class ClockSampler:
     """SM clock / throttle-reason sampling during the timed region: NVML (the source nvidia-smi reads) polled from
-    a thread every 50 ms -- an `nvidia-smi -lms` child process takes driver locks for milliseconds per query and
-    showed up as sporadic +60 ms in the latency-sensitive end-to-end loop; it remains the fallback."""
+    a thread every 100 ms (`nvidia-smi -lms 100` as a child process is the fallback).  Either way the queries
+    perturb the device now and then: A/B runs with the sampler off (SPQ_NOCLOCKS=1) never show the single
+    +20..80 ms step that about one end-to-end region in two shows with it on (the queries themselves return in
+    ~1 ms; `max_query_ms` reports that).  The resident-input loop hides it behind its launch queue."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -168,6 +170,7 @@ class ClockSampler:
         self.proc = None
         self.nvml = None
         self._stop = threading.Event()
+        self.query_ms = (0.0, 0.0)
 
     def start(self):
         try:
@@ -196,16 +199,20 @@ class ClockSampler:
         mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
         while not self._stop.is_set():
             try:
+                q0 = time.perf_counter()
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                q1 = time.perf_counter()
                 try:
                     mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                q2 = time.perf_counter()
+                self.query_ms = (max(self.query_ms[0], (q1 - q0) * 1e3), max(self.query_ms[1], (q2 - q1) * 1e3))
                 flags = ["Active" if mask & bit else "Not Active" for bit, _ in self.NVML_REASONS]
                 self.rows.append(", ".join([str(sm), str(mx), "0"] + flags))
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.1)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -239,7 +246,8 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvml (50 ms poll)" if self.nvml is not None else "nvidia-smi -lms 100"}
+                "source": "nvml (100 ms poll)" if self.nvml is not None else "nvidia-smi -lms 100",
+                "max_query_ms": [round(v, 2) for v in self.query_ms]}
 
 
 def gpu_arm(args):
@@ -332,7 +340,7 @@ def gpu_arm(args):
     # the clock sampler attaches to NVML before the warm-up (its one-time driver work stays out of the timed
     # regions); its samples are reset when the first timed region starts
     sampler = ClockSampler(local)
-    if rank == 0 and not (args.profile_train_step or args.profile_one_step):
+    if rank == 0 and not (args.profile_train_step or args.profile_one_step) and not os.environ.get('SPQ_NOCLOCKS'):
         sampler.start()
     for i in range(args.warmup):
         step(dev_ids[i])
