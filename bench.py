@@ -68,6 +68,21 @@ def measured_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def measured_traffic():
+    """DRAM bytes per qgemm_nt launch from the committed ncu capture of one step (profiles/), or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01h_qgemm_dram_per_launch.csv")
+    try:
+        with open(path) as f:
+            for line in f:
+                if line.startswith("TOTAL("):
+                    n = int(line[len("TOTAL("):].split(" ")[0])
+                    _, _, rd, wr = line.strip().split(",")
+                    return (float(rd) + float(wr)) * 1e6 / n, "profiles/r01h_qgemm_dram_per_launch.csv (ncu, one step)"
+    except Exception:
+        pass
+    return None, "no capture committed"
+
+
 # ------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the numpy oracle on a bounded sample
 # ------------------------------------------------------------------------------------------
@@ -330,7 +345,9 @@ def gpu_arm(args):
         e0.record()
         r = orig_qgemm(A, Bm, M, N, K, out, A2=A2, B2=B2, K2=K2, **kw)
         e1.record()
-        gemm_events.append((e0, e1, 2.0 * M * N * (K + K2)))
+        # algorithmic bytes of the launch: operands once, output once, residual once
+        nbytes = 2.0 * (M + N) * (K + K2) + M * N * out.element_size() + (4.0 * M * N if kw.get("C") is not None else 0.0)
+        gemm_events.append((e0, e1, 2.0 * M * N * (K + K2), nbytes))
         return r
 
     def patch(fn):
@@ -384,8 +401,9 @@ def gpu_arm(args):
     ms_value = t0.elapsed_time(t1)
     launches = _lib.launch_count() - launches0
     patch(orig_qgemm)
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
-    gemm_flops = sum(f for _, _, f in gemm_events)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f, _ in gemm_events)
+    gemm_bytes = sum(nb for _, _, _, nb in gemm_events)
     n_gemm = len(gemm_events)
 
     # ---- timed region 2: end to end through the module API, ids from pinned host memory, loss to host
@@ -436,7 +454,11 @@ def gpu_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "spq::gemm::qgemm_nt_kernel (all launches in the timed region)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                         "frac": (achieved / peak) if (achieved and peak) else None,
+                         "traffic": measured_traffic()[0], "traffic_unit": "bytes per launch (dram__bytes_read.sum + "
+                         "dram__bytes_write.sum averaged over every qgemm_nt launch of one step)",
+                         "traffic_source": measured_traffic()[1],
+                         "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
                          "peak_source": peaks["source"] + ", bf16 dense sustained",
                          "launches": n_gemm, "share_of_step": gemm_ms / ms_value if ms_value else None},
         }

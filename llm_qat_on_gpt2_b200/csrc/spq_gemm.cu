@@ -342,7 +342,6 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // per 128 B row segment) into registers as soon as the current block has been parked in the staging tile;
         // the block goes through the same swizzled tile, so every lane then finds its own row next to its
         // accumulators (chunk 0 of the next tile is requested while that tile's MMA still runs)
-        constexpr bool pre_c = PRE_C;
         float4 cn[PRE_C ? 8 : 1];
         auto c_load = [&](int tt, int cc) {
             int m_blk, n_blk;
@@ -411,6 +410,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                         // finish the arithmetic in registers (this lane owns one row, 32 columns), write the row
                         // into the swizzled tile, then one lane hands the 32 x 32 block to the TMA engine
+                        uint2 hold = make_uint2(0u, 0u);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 cs4 = *reinterpret_cast<const float4*>(epi_cs + cl + j);
@@ -429,10 +429,16 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                             if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                             if constexpr (OUT_HALF) {
-                                // 64 B rows, 64B swizzle: 16-byte chunk index ^ ((row / 2) % 4)
-                                *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(stg) + lane * 64 +
-                                                          (((j >> 3) ^ ((lane >> 1) & 3)) << 4) + ((j & 4) << 1)) =
-                                    make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                // 64 B rows, 64B swizzle: 16-byte chunk index ^ ((row / 2) % 4); one 16-byte store
+                                // per 8 columns (8-byte stores put lanes l and l+8 on the same banks: ncu showed
+                                // 2x the ideal shared-store wavefronts)
+                                if ((j & 4) == 0) {
+                                    hold = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                } else {
+                                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + lane * 64 +
+                                                              (((j >> 3) ^ ((lane >> 1) & 3)) << 4)) =
+                                        make_uint4(hold.x, hold.y, pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                }
                             } else {
                                 if (!(ep.debug & 16)) *reinterpret_cast<float4*>(stg + lane * 32 + (((j >> 2) ^ sw) << 2)) = o;
                                 else if (o.x == 1.2345e-30f) ep.alpha_dev = nullptr;
