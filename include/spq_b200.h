@@ -173,6 +173,20 @@ SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weig
 SPQ_API int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                      float* row_scale, spq_stream_t stream);
 
+/* LM head with the log-sum-exp folded into the GEMM epilogue ("fused CE over V = 50257
+ * with the tied LM-head GEMM"; replaces lm_head + the softmax passes of nn.CrossEntropyLoss,
+ * p1/models_sp.py:436-449).  Same product and epilogue as spq_qgemm with float32 D (rows 16-byte aligned and
+ * padded: ldd >= 4*ceil(N/4)); additionally lse_part [M, lse_ld] receives, per row and per column half-tile, the
+ * pair (max, sum exp(v - max)) of the values stored.  spq_qgemm_lse_parts(M, N) is the number of pairs per row;
+ * spq_cross_entropy_from_parts folds them and reads only the target logit of each row. */
+SPQ_API int64_t spq_qgemm_lse_parts(int64_t M, int64_t N);
+SPQ_API int spq_qgemm_lse(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
+                  int64_t K, float alpha, const float* row_scale, const float* col_scale, const float* bias,
+                  float* D, int64_t ldd, float* lse_part, int64_t lse_ld, spq_stream_t stream);
+SPQ_API int spq_cross_entropy_from_parts(const float* parts, int64_t P, int64_t part_ld, const float* logits, int64_t M,
+                                 int64_t V, int64_t ld, const int64_t* targets, int64_t ignore_index,
+                                 float* row_loss, float* row_valid, spq_stream_t stream);
+
 /* ---- consumer of the path: next-token cross-entropy, forward only -----------
  * Replaces nn.CrossEntropyLoss over re-materialised shifted logits (p1/models_sp.py:441-449) for
  * no-grad evaluation: row_loss[m] = logsumexp(logits[m, 0:V]) - logits[m, targets[m]], row_valid[m] = 1,

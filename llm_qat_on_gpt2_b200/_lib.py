@@ -54,6 +54,11 @@ SIGNATURES = {
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spq_qgemm_lse_parts": (c_int64, [c_int64, c_int64]),
+    "spq_qgemm_lse": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "spq_cross_entropy_from_parts": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                             c_void_p, c_void_p, c_void_p]),
     "spq_cross_entropy_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_rowscale_f16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
 }
@@ -281,6 +286,38 @@ def cross_entropy_fwd(logits2d, targets, ignore_index=-100):
     _check(load_library().spq_cross_entropy_fwd(logits2d.data_ptr(), M, V, logits2d.stride(0), tg.data_ptr(),
                                                 int(ignore_index), out[0].data_ptr(), out[1].data_ptr(), _stream()),
            "spq_cross_entropy_fwd")
+    sums = out.sum(dim=1)
+    return sums[0] / sums[1]
+
+
+def qgemm_lse(A, B, M, N, K, out, alpha=1.0, row_scale=None, col_scale=None, bias=None):
+    """spq_qgemm with float32 `out` plus the per-row (max, sum exp) pairs of every column half-tile: returns the
+    [M, P, 2] partials for cross_entropy_from_parts.  `out` needs 16-byte aligned rows padded to a multiple of 4."""
+    lib = load_library()
+    _req_cuda(A, B, out, row_scale, col_scale, bias)
+    assert A.dtype == torch.float16 and B.dtype == torch.float16 and out.dtype == torch.float32
+    assert A.stride(-1) == 1 and B.stride(-1) == 1 and out.stride(-1) == 1
+    P = int(lib.spq_qgemm_lse_parts(M, N))
+    parts = torch.empty((M, P, 2), dtype=torch.float32, device=out.device)
+    _check(lib.spq_qgemm_lse(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, float(alpha), _ptr(row_scale),
+                             _ptr(col_scale), _ptr(bias), out.data_ptr(), out.stride(0), parts.data_ptr(), P, _stream()),
+           "spq_qgemm_lse")
+    return parts
+
+
+def cross_entropy_from_parts(parts, logits2d, targets, ignore_index=-100):
+    """Mean cross-entropy from qgemm_lse's partials; reads one logit per row."""
+    _req_cuda(parts, logits2d, targets)
+    M, V = logits2d.shape
+    assert parts.dim() == 3 and parts.shape[0] == M and parts.shape[2] == 2 and parts.is_contiguous()
+    assert logits2d.stride(1) == 1 and logits2d.dtype == torch.float32
+    tg = targets.reshape(-1).to(torch.int64).contiguous()
+    assert tg.numel() == M
+    out = torch.empty((2, M), dtype=torch.float32, device=logits2d.device)
+    _check(load_library().spq_cross_entropy_from_parts(parts.data_ptr(), parts.shape[1], parts.shape[1], logits2d.data_ptr(),
+                                                       M, V, logits2d.stride(0), tg.data_ptr(), int(ignore_index),
+                                                       out[0].data_ptr(), out[1].data_ptr(), _stream()),
+           "spq_cross_entropy_from_parts")
     sums = out.sum(dim=1)
     return sums[0] / sums[1]
 

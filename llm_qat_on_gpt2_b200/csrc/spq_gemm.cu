@@ -167,6 +167,8 @@ struct EpiParams {
                               // 4 disable the TMA-store path, 8 skip the TMA store instruction, 16 skip the staging writes
     int tma_store;            // 1: D is written with TMA bulk tensor stores (16 B aligned rows; residual prefetched per lane)
     int act;                  // 0: none, 1: exact (erf) GELU applied after the bias
+    float2* lse_part;         // LSE kernels: [M, lse_ld] (max, sum of exp(v - max)) of each row over each column half-tile
+    long long lse_ld;
 };
 
 template <int BN>
@@ -207,7 +209,9 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
 
 // PRE_C: the TMA-store epilogue adds a float32 residual (separate instantiation: its 32 prefetch registers and
 // extra staging traffic stay out of the plain kernel)
-template <int BN, bool OUT_HALF, bool PRE_C>
+// LSE: the epilogue also keeps, per output row, the running (max, sum exp) of the values it stores and writes one
+// pair per column half-tile -- the log-sum-exp of the LM head's logits without a second pass over them
+template <int BN, bool OUT_HALF, bool PRE_C, bool LSE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -377,6 +381,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(acc * BN + half * COLS_PER_HALF);
             const int sw = lane & 7;                                // 128B swizzle: 16 B chunk index ^ (row % 8)
+            float lse_m = -INFINITY, lse_s = 0.f;                   // LSE: this row over this warp's columns of the tile
             if (active) {
 #pragma unroll 1
                 for (int c = 0; c < CHUNKS; ++c) {
@@ -428,6 +433,16 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w;
                             }
                             if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                            if constexpr (LSE) {
+                                // columns >= N (ragged last tile) do not take part
+                                const float e0 = (nc + j < N) ? o.x : -INFINITY, e1 = (nc + j + 1 < N) ? o.y : -INFINITY;
+                                const float e2 = (nc + j + 2 < N) ? o.z : -INFINITY, e3 = (nc + j + 3 < N) ? o.w : -INFINITY;
+                                const float mn = fmaxf(fmaxf(lse_m, fmaxf(e0, e1)), fmaxf(e2, e3));
+                                if (mn > -INFINITY) {
+                                    lse_s = lse_s * __expf(lse_m - mn) + __expf(e0 - mn) + __expf(e1 - mn) + __expf(e2 - mn) + __expf(e3 - mn);
+                                    lse_m = mn;
+                                }
+                            }
                             if constexpr (OUT_HALF) {
                                 // 64 B rows, 64B swizzle: 16-byte chunk index ^ ((row / 2) % 4); one 16-byte store
                                 // per 8 columns (8-byte stores put lanes l and l+8 on the same banks: ncu showed
@@ -528,6 +543,9 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             }
+            if constexpr (LSE) {
+                if (row < M) ep.lse_part[static_cast<long long>(row) * ep.lse_ld + n_blk * 2 + half] = make_float2(lse_m, lse_s);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -608,18 +626,18 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_
     return SPQ_OK;
 }
 
-template <int BN, bool OUT_HALF, bool PRE_C = false>
+template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false>
 static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
                      const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF, PRE_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    qgemm_nt_kernel<BN, OUT_HALF, PRE_C><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
+    qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
@@ -805,11 +823,22 @@ extern "C" int spq_debug_status(int* aborted_host) {
     return SPQ_OK;
 }
 
-extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
-                         int64_t K, const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
-                         float alpha, const float* row_scale, const float* col_scale, const float* bias, float clamp_abs,
-                         const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, int activation,
-                         spq_stream_t stream) {
+// tile width: the widest BN that still gives every SM a tile; otherwise the one with most tiles
+static int pick_bn(int64_t M, int64_t N, int sms) {
+    const long long mt = (M + BM - 1) / BM;
+    auto tiles = [&](int b) { return mt * ((N + b - 1) / b); };
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    if (tiles(256) >= sms) return 256;
+    if (tiles(128) >= sms) return 128;
+    return 64;
+}
+
+static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
+                      int64_t K, const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
+                      float alpha, const float* row_scale, const float* col_scale, const float* bias, float clamp_abs,
+                      const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, int activation,
+                      float* lse_part, int64_t lse_ld, spq_stream_t stream) {
     SPQ_REQUIRE(A && B && D, "spq_qgemm: null operand");
     SPQ_REQUIRE(M > 0 && N > 0 && K > 0, "spq_qgemm: empty problem %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
     SPQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "spq_qgemm: dimension overflow");
@@ -824,17 +853,7 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
         set_error("spq_qgemm: no CUDA device");
         return SPQ_ERR_CUDA;
     }
-    // tile width: the widest BN that still gives every SM a tile; otherwise the one with most tiles
-    int bn = 256;
-    {
-        const long long mt = (M + BM - 1) / BM;
-        auto tiles = [&](int b) { return mt * ((N + b - 1) / b); };
-        if (N <= 64) bn = 64;
-        else if (N <= 128) bn = 128;
-        else if (tiles(256) >= sms) bn = 256;
-        else if (tiles(128) >= sms) bn = 128;
-        else bn = 64;
-    }
+    const int bn = pick_bn(M, N, sms);
     CUtensorMap tA, tB, tA2, tB2;
     int rc;
     if ((rc = make_tmap(&tA, A, M, K, lda, BM)) != SPQ_OK) return rc;
@@ -850,6 +869,7 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     ep.row_scale = row_scale; ep.col_scale = col_scale; ep.bias = bias; ep.C = C; ep.alpha_dev = nullptr;
     ep.D = D; ep.ldc = ldc; ep.ldd = ldd; ep.d_stride_n = 1; ep.alpha = alpha; ep.clamp_abs = clamp_abs;
     ep.act = activation;
+    ep.lse_part = reinterpret_cast<float2*>(lse_part); ep.lse_ld = lse_ld;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("SPQ_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -867,6 +887,13 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     const bool c_ok = !C || (!d_is_half && (ldc % 4) == 0 && (N % 4) == 0 && aligned16(C));   // fp16 D + residual: general path
     ep.tma_store = (c_ok && (ldd % gran) == 0 && ldd >= (N + gran - 1) / gran * gran && aligned16(D) && !(ep.debug & 4)) ? 1 : 0;
     if (ep.tma_store && (rc = make_tmap_out(&tD, D, M, N, ldd, d_is_half != 0)) != SPQ_OK) return rc;
+    if (lse_part) {
+        SPQ_REQUIRE(ep.tma_store && !d_is_half && !C, "spq_qgemm_lse: needs float32 output with 16-byte aligned, padded rows and no residual");
+        SPQ_REQUIRE(lse_ld >= 2 * ((N + bn - 1) / bn) && (reinterpret_cast<uintptr_t>(lse_part) & 7u) == 0, "spq_qgemm_lse: partials buffer too narrow");
+        if (bn == 256) return launch_nt<256, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        if (bn == 128) return launch_nt<128, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        return launch_nt<64, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+    }
     if (d_is_half) {
         if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 128) return launch_nt<128, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
@@ -880,6 +907,30 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
     if (bn == 256) return launch_nt<256, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     if (bn == 128) return launch_nt<128, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     return launch_nt<64, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+}
+
+extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
+                         int64_t K, const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
+                         float alpha, const float* row_scale, const float* col_scale, const float* bias, float clamp_abs,
+                         const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, int activation,
+                         spq_stream_t stream) {
+    return qgemm_impl(A, lda, B, ldb, M, N, K, A2, lda2, B2, ldb2, K2, alpha, row_scale, col_scale, bias, clamp_abs, C, ldc,
+                      D, ldd, d_is_half, activation, nullptr, 0, stream);
+}
+
+extern "C" int64_t spq_qgemm_lse_parts(int64_t M, int64_t N) {
+    const int sms = sm_count();
+    if (M <= 0 || N <= 0 || sms <= 0) return 0;
+    const int bn = pick_bn(M, N, sms);
+    return 2 * ((N + bn - 1) / bn);
+}
+
+extern "C" int spq_qgemm_lse(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
+                             int64_t K, float alpha, const float* row_scale, const float* col_scale, const float* bias,
+                             float* D, int64_t ldd, float* lse_part, int64_t lse_ld, spq_stream_t stream) {
+    SPQ_REQUIRE(lse_part, "spq_qgemm_lse: null partials buffer");
+    return qgemm_impl(A, lda, B, ldb, M, N, K, nullptr, 0, nullptr, 0, 0, alpha, row_scale, col_scale, bias, 0.f, nullptr, 0,
+                      D, ldd, 0, 0, lse_part, lse_ld, stream);
 }
 
 extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq, int64_t Mred, int64_t I, int64_t J,

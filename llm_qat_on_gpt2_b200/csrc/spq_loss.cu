@@ -64,6 +64,40 @@ cross_entropy_fwd_kernel(const float* __restrict__ logits, long long M, long lon
     }
 }
 
+// Cross-entropy from the (max, sum exp) pairs the LM-head GEMM left per row and column half-tile
+// (spq_qgemm_lse): one warp per row folds the P pairs and reads the single target logit -- the 6.6 GB logits
+// matrix is not read again.
+__global__ void __launch_bounds__(256)
+cross_entropy_from_parts_kernel(const float2* __restrict__ parts, long long P, long long part_ld,
+                                const float* __restrict__ logits, long long M, long long V, long long ld,
+                                const long long* __restrict__ targets, long long ignore_index,
+                                float* __restrict__ row_loss, float* __restrict__ row_valid) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
+        const long long tgt = targets[row];
+        if (tgt == ignore_index || tgt < 0 || tgt >= V) {       // warp-uniform
+            if (lane == 0) { row_loss[row] = 0.f; row_valid[row] = 0.f; }
+            continue;
+        }
+        MS acc; acc.m = -INFINITY; acc.s = 0.f;
+        for (long long i = lane; i < P; i += 32) {
+            const float2 v = parts[row * part_ld + i];
+            MS b; b.m = v.x; b.s = v.y;
+            acc = combine(acc, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MS b; b.m = __shfl_xor_sync(0xffffffffu, acc.m, o); b.s = __shfl_xor_sync(0xffffffffu, acc.s, o);
+            acc = combine(acc, b);
+        }
+        if (lane == 0) {
+            row_loss[row] = logf(acc.s) + acc.m - __ldg(logits + row * ld + tgt);
+            row_valid[row] = 1.f;
+        }
+    }
+}
+
 }  // namespace loss
 }  // namespace spq
 
@@ -76,6 +110,21 @@ extern "C" int spq_cross_entropy_fwd(const float* logits, int64_t M, int64_t V, 
     if (ctas > M) ctas = M;
     loss::cross_entropy_fwd_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(
         logits, M, V, ld, reinterpret_cast<const long long*>(targets), ignore_index, row_loss, row_valid);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_cross_entropy_from_parts(const float* parts, int64_t P, int64_t part_ld, const float* logits, int64_t M,
+                                            int64_t V, int64_t ld, const int64_t* targets, int64_t ignore_index,
+                                            float* row_loss, float* row_valid, spq_stream_t stream) {
+    SPQ_REQUIRE(parts && logits && targets && row_loss && row_valid && M > 0 && V > 0 && ld >= V && P > 0 && part_ld >= P,
+                "spq_cross_entropy_from_parts: bad arguments");
+    long long ctas = (M + 7) / 8;
+    const long long cap = static_cast<long long>(sm_count()) * 8;
+    if (ctas > cap) ctas = cap;
+    loss::cross_entropy_from_parts_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2*>(parts), P, part_ld, logits, M, V, ld, reinterpret_cast<const long long*>(targets),
+        ignore_index, row_loss, row_valid);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

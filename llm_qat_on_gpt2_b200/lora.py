@@ -156,7 +156,7 @@ class _LinearFpFn(torch.autograd.Function):
     """y = x W^T + b with fp16 operands / fp32 accumulation on spq_qgemm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False, residual=None):
+    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False, residual=None, lse_out=None):
         N, K = weight.shape
         x2d = _as_2d_act(x, K, max_cols=8192)
         M = x2d.shape[0]
@@ -169,9 +169,14 @@ class _LinearFpFn(torch.autograd.Function):
         align = 64 if out_half else 32
         ld = N if N % 4 == 0 else (N + align - 1) // align * align
         ybuf = torch.empty((M, ld), dtype=torch.float16 if out_half else torch.float32, device=x.device)
-        _lib.qgemm(x16, w16, M, N, K, ybuf[:, :N] if ld != N else ybuf, row_scale=rs, col_scale=pw,
-                   bias=None if bias is None else bias.detach().float().contiguous(), activation=activation,
-                   C=None if residual is None else residual.reshape(M, N))
+        dview = ybuf[:, :N] if ld != N else ybuf
+        bias_f = None if bias is None else bias.detach().float().contiguous()
+        if lse_out is not None:
+            # LM head under no_grad: the epilogue also leaves the per-row log-sum-exp partials (fused CE)
+            lse_out.append(_lib.qgemm_lse(x16, w16, M, N, K, dview, row_scale=rs, col_scale=pw, bias=bias_f))
+        else:
+            _lib.qgemm(x16, w16, M, N, K, dview, row_scale=rs, col_scale=pw, bias=bias_f, activation=activation,
+                       C=None if residual is None else residual.reshape(M, N))
         ctx.cache = cache
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_bias = bias is not None
@@ -202,18 +207,19 @@ class _LinearFpFn(torch.autograd.Function):
             _lib.gemm_tn(g16, x2, gw, alpha=1.0, alpha_dev=(gmax * xmax).reshape(1).contiguous())
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2d.sum(dim=0)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0, out_half: bool = False,
-              residual=None):
+              residual=None, lse_out=None):
     """`activation=1` fuses the exact-erf GELU into the GEMM epilogue, `out_half` stores float16 from the
-    epilogue, `residual` (float32, contiguous, output-shaped) is added in the epilogue; all no-grad fast paths."""
-    if (activation or out_half or residual is not None) and torch.is_grad_enabled() and \
+    epilogue, `residual` (float32, contiguous, output-shaped) is added in the epilogue, `lse_out` (a list) receives
+    the per-row log-sum-exp partials of the output for `_lib.cross_entropy_from_parts`; all no-grad fast paths."""
+    if (activation or out_half or residual is not None or lse_out is not None) and torch.is_grad_enabled() and \
             (x.requires_grad or weight.requires_grad):
         raise RuntimeError("fused activation / float16 output / residual epilogues are no-grad fast paths")
     return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation, out_half,
-                             residual)
+                             residual, lse_out)
 
 
 # ----------------------------------------------------------------------------------------------

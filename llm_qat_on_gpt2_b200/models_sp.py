@@ -288,7 +288,12 @@ class SPLMHeadModel(nn.Module):
                                use_checkpoint=use_checkpoint, output_hidden_states=output_hidden_states)
         hidden_states, all_hidden_states = out if output_hidden_states else (out, None)
 
-        logits = linear_fp(hidden_states, self.lm_head.weight, None, self._lm_head_cache)
+        # evaluation with labels: the LM-head GEMM also leaves the per-row log-sum-exp partials, so the loss
+        # needs no second pass over the [B, T, V] logits
+        fused_ce = labels is not None and not (torch.is_grad_enabled() and
+                                               (hidden_states.requires_grad or self.lm_head.weight.requires_grad))
+        lse_parts = [] if fused_ce else None
+        logits = linear_fp(hidden_states, self.lm_head.weight, None, self._lm_head_cache, lse_out=lse_parts)
 
         loss = None
         if labels is not None:
@@ -297,7 +302,9 @@ class SPLMHeadModel(nn.Module):
             # runs over the same B*(T-1) terms
             targets = torch.full_like(labels, -100)
             targets[..., :-1] = labels[..., 1:]
-            if torch.is_grad_enabled() and logits.requires_grad:
+            if fused_ce and lse_parts:
+                loss = _lib.cross_entropy_from_parts(lse_parts[0], logits.view(-1, logits.size(-1)), targets)
+            elif torch.is_grad_enabled() and logits.requires_grad:
                 loss = F.cross_entropy(logits.reshape(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100)
             else:
                 # evaluation: one fused pass over the (stride-padded) logits

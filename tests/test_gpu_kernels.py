@@ -471,3 +471,32 @@ def test_qgemm_grouped_tile_order(M, N, K):
     assert not torch.isnan(out).any()
     assert ((out - ref).norm() / ref.norm()) <= 1e-5
     assert lib.debug_status() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,V,K", [(300, 211, 64), (1024, 50257, 128), (130, 1000, 64), (4096, 2304, 64)])
+def test_qgemm_lse_and_cross_entropy_from_parts(M, V, K):
+    """LM head with the log-sum-exp folded into the epilogue: same logits as spq_qgemm bit for bit, loss equal to
+    float64 cross-entropy of those logits (ignore_index rows excluded, ragged last column tile masked)."""
+    from llm_qat_on_gpt2_b200 import _lib as lib
+    torch.manual_seed(V)
+    A = torch.randn(M, K, device="cuda").half(); B = (torch.randn(V, K, device="cuda") * 0.3).half()
+    rs = torch.rand(M, device="cuda") + 0.5; cs = torch.rand(V, device="cuda") + 0.5
+    ld = V if V % 4 == 0 else (V + 31) // 32 * 32
+    buf = torch.full((M, ld), 1e30, device="cuda"); ref_buf = torch.full((M, ld), 1e30, device="cuda")
+    logits = buf[:, :V] if ld != V else buf
+    ref_logits = ref_buf[:, :V] if ld != V else ref_buf
+    parts = lib.qgemm_lse(A, B, M, V, K, logits, row_scale=rs, col_scale=cs)
+    lib.qgemm(A, B, M, V, K, ref_logits, row_scale=rs, col_scale=cs)
+    assert torch.equal(logits, ref_logits)
+    tg = torch.randint(0, V, (M,), device="cuda")
+    tg[::5] = -100
+    got = lib.cross_entropy_from_parts(parts, logits, tg)
+    want = torch.nn.functional.cross_entropy(logits.double(), tg, ignore_index=-100)
+    assert abs(got.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
+    # per-row log-sum-exp from the partials
+    m = parts[..., 0]; s_ = parts[..., 1]
+    mm = m.max(dim=1).values
+    lse = mm + torch.log((s_ * torch.exp(m - mm[:, None])).sum(dim=1))
+    assert float((lse.double() - torch.logsumexp(logits.double(), dim=1)).abs().max()) <= 1e-4
+    assert lib.debug_status() == 0
