@@ -481,7 +481,7 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     import torch
     import torch.nn.functional as F
     import torch.distributed as dist
-    from llm_qat_on_gpt2_b200 import _lib, dp
+    from llm_qat_on_gpt2_b200 import _lib, dp, calibrate_many
     B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
     model.train()
     for n, p in model.named_parameters():
@@ -497,9 +497,7 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
         with torch.no_grad():
             model.set_precision(32)
             t_logits = model(ids)
-            for q, w in zip(lora_q, lora_w):
-                q.start_calibration(); q(w.data)
-            dp.finish_calibration_many(lora_q, None)          # parameters are replicated: no exchange needed
+            calibrate_many(lora_q, [w.data for w in lora_w])  # one launch; parameters are replicated: no exchange
         model.set_precision(BITS)
         s_logits = model(ids)
         # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows,

@@ -66,6 +66,27 @@ SPQ_API int spq_minmax_stats(const void* x, int x_is_half, int64_t rows, int64_t
                      float* stat_min, float* stat_max, int accumulate, int32_t* state,
                      void* workspace, size_t workspace_bytes, spq_stream_t stream);
 
+/* Single-batch calibration of many small tensors in ONE launch: start_calibration + one collected batch +
+ * finish_calibration for each job (the LoRA A/B quantisers of every linear are recalibrated on their own weights
+ * each training step, p1/train_sp.py:125-163).  Same statistics, log transform, scale and zero-point as
+ * spq_minmax_stats + spq_finish_calibration, bit for bit.  `jobs_dev` is an array of SpqCalibJob in device
+ * memory; max_blocks >= the largest per-job block count (per column: ceil(cols/32); per row: ceil(rows/8);
+ * per tensor: 1).  flags_dev[job] = 1 unless a log-mode job saw no |x| > eps (the caller then redoes that job
+ * through the single-tensor path, which implements the reference's default-shape behaviour). */
+typedef struct SpqCalibJob {
+    const float* x;          /* [rows, cols] float32, dense */
+    int64_t rows, cols;
+    float* rmin; float* rmax; float* scale; float* zp;   /* outputs, one per channel */
+    int32_t bcast;           /* SPQ_PER_COL / SPQ_PER_ROW / SPQ_PER_TENSOR */
+    int32_t qtype;           /* SPQ_MINMAX / SPQ_LOG */
+    int32_t symmetric;
+    float levels;            /* quant_max - quant_min of the min-max range (2^(b-1)-1 symmetric, 2^b-1 otherwise) */
+    float eps;
+    int32_t pad_;
+} SpqCalibJob;
+SPQ_API int spq_calibrate_many(const SpqCalibJob* jobs_dev, int32_t n_jobs, int32_t max_blocks, int32_t* flags_dev,
+                       spq_stream_t stream);
+
 /* Replaces LearnableFakeQuantize.finish_calibration (p1/quantization.py:104-139): scale and
  * zero-point (min-max: symmetric or asymmetric; log: zero_point = log_min, scale = log_range)
  * from n running statistics.  True IEEE division, as torch-CPU. */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "spq_stats_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "spq_minmax_stats": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spq_calibrate_many": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "spq_finish_calibration": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p,
                                        c_void_p, c_void_p]),
     "spq_fake_quantize": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -160,6 +161,17 @@ def minmax_stats(x2d: torch.Tensor, bcast: int, log_mode: bool, eps: float, stat
     _check(lib.spq_minmax_stats(x2d.data_ptr(), int(x2d.dtype == torch.float16), rows, cols, bcast, int(log_mode), float(eps), stat_min.data_ptr(),
                                 stat_max.data_ptr(), int(accumulate), _ptr(state), ws.data_ptr(), ws.numel(),
                                 _stream()), "spq_minmax_stats")
+
+
+CALIB_JOB_FORMAT = "QqqQQQQiiiffi"        # struct SpqCalibJob (include/spq_b200.h), 80 bytes
+
+
+def calibrate_many(jobs_dev: torch.Tensor, n_jobs: int, max_blocks: int, flags_dev: torch.Tensor):
+    """One launch calibrating n_jobs small tensors; jobs_dev is the packed SpqCalibJob table (uint8, on device)."""
+    _req_cuda(jobs_dev, flags_dev)
+    assert jobs_dev.dtype == torch.uint8 and jobs_dev.numel() >= 80 * n_jobs and flags_dev.dtype == torch.int32
+    _check(load_library().spq_calibrate_many(jobs_dev.data_ptr(), n_jobs, max_blocks, flags_dev.data_ptr(), _stream()),
+           "spq_calibrate_many")
 
 
 def finish_calibration(rmin, rmax, qtype: int, symmetric: bool, bits: int, eps: float, scale, zp):

@@ -211,27 +211,133 @@ stats_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0 && state && any) atomicOr(state, 1);
 }
 
+// scale / zero-point from calibrated statistics (p1/quantization.py:104-139)
+__device__ __forceinline__ void finish_one(float lo, float hi, int qtype, int symmetric, float levels, float eps,
+                                           float& scale, float& zp) {
+    if (qtype == SPQ_LOG) {                       // :110-116
+        zp = lo;
+        scale = __fsub_rn(hi, lo);
+    } else if (symmetric) {                       // :118-122
+        float a = nan_max(fabsf(lo), fabsf(hi));
+        a = (a < eps) ? eps : a;
+        scale = __fdiv_rn(a, levels);
+        zp = 0.f;
+    } else {                                      // :123-127
+        float r = __fsub_rn(hi, lo);
+        r = (r < eps) ? eps : r;
+        const float s = __fdiv_rn(r, levels);
+        scale = s;
+        zp = rintf(__fdiv_rn(-lo, s));
+    }
+}
+
 __global__ void finish_calibration_kernel(const float* __restrict__ rmin, const float* __restrict__ rmax, long long n, int qtype,
                                           int symmetric, float levels, float eps, float* __restrict__ scale,
                                           float* __restrict__ zp) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float lo = rmin[i], hi = rmax[i];
-    if (qtype == SPQ_LOG) {                       // p1/quantization.py:110-116
-        zp[i] = lo;
-        scale[i] = __fsub_rn(hi, lo);
-    } else if (symmetric) {                       // :118-122
-        float a = nan_max(fabsf(lo), fabsf(hi));
-        a = (a < eps) ? eps : a;
-        scale[i] = __fdiv_rn(a, levels);
-        zp[i] = 0.f;
-    } else {                                      // :123-127
-        float r = __fsub_rn(hi, lo);
-        r = (r < eps) ? eps : r;
-        const float s = __fdiv_rn(r, levels);
-        scale[i] = s;
-        zp[i] = rintf(__fdiv_rn(-lo, s));
+    float s, z;
+    finish_one(rmin[i], rmax[i], qtype, symmetric, levels, eps, s, z);
+    scale[i] = s;
+    zp[i] = z;
+}
+
+// Single-batch calibration of MANY small tensors in one launch (the LoRA A/B quantisers of all 48 linears are
+// recalibrated on their own weights every training step, p1/train_sp.py:125-163: 96 x (memset + 3 kernels) made
+// that phase host-bound).  blockIdx.y = job; per-column jobs: blockIdx.x = block of 32 columns, 8 row lanes;
+// per-row jobs: blockIdx.x = block of 8 rows, one warp each; per-tensor jobs: block 0 only.  Statistics,
+// log transform and scale / zero-point are those of spq_minmax_stats + spq_finish_calibration bit for bit;
+// flags[job] = any(|x| > eps) (log mode; 1 otherwise) -- a log job without data is redone by the caller.
+__global__ void __launch_bounds__(256)
+calibrate_many_kernel(const SpqCalibJob* __restrict__ jobs, int32_t* __restrict__ flags) {
+    const SpqCalibJob jb = jobs[blockIdx.y];
+    const bool LOG = jb.qtype == SPQ_LOG;
+    const float eps = jb.eps;
+    const float levels = jb.levels;
+    __shared__ float s_a[8][33], s_b[8][33];
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    bool any = false;
+    auto tf = [&](float a) { return LOG ? log2_cr(a < eps ? eps : a) : a; };      // clamp keeps NaN
+    if (jb.bcast == SPQ_PER_COL) {
+        const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+        const long long c = static_cast<long long>(blockIdx.x) * 32 + cl;
+        if (static_cast<long long>(blockIdx.x) * 32 >= jb.cols) return;
+        float a = INFINITY, b = -INFINITY;
+        bool isnan_ = false;
+        if (c < jb.cols) {
+            for (long long r = rl; r < jb.rows; r += 8) {
+                float v = __ldg(jb.x + r * jb.cols + c);
+                if (LOG) v = fabsf(v);
+                isnan_ |= (v != v);
+                any |= (v > eps);
+                a = fminf(a, v); b = fmaxf(b, v);
+            }
+        }
+        if (isnan_) { a = NAN; b = NAN; }
+        s_a[rl][cl] = a; s_b[rl][cl] = b;
+        if (LOG && any) s_any = 1;
+        __syncthreads();
+        if (rl == 0 && c < jb.cols) {
+#pragma unroll
+            for (int w = 1; w < 8; ++w) { a = nan_min(a, s_a[w][cl]); b = nan_max(b, s_b[w][cl]); }
+            a = tf(a); b = tf(b);
+            float s, z;
+            finish_one(a, b, jb.qtype, jb.symmetric, levels, eps, s, z);
+            jb.rmin[c] = a; jb.rmax[c] = b; jb.scale[c] = s; jb.zp[c] = z;
+        }
+    } else if (jb.bcast == SPQ_PER_ROW) {
+        const int lane = threadIdx.x & 31;
+        const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+        if (static_cast<long long>(blockIdx.x) * 8 >= jb.rows) return;
+        float a = INFINITY, b = -INFINITY;
+        bool isnan_ = false;
+        if (r < jb.rows) {
+            for (long long c = lane; c < jb.cols; c += 32) {
+                float v = __ldg(jb.x + r * jb.cols + c);
+                if (LOG) v = fabsf(v);
+                isnan_ |= (v != v);
+                any |= (v > eps);
+                a = fminf(a, v); b = fmaxf(b, v);
+            }
+        }
+        if (__any_sync(0xffffffffu, isnan_)) { a = NAN; b = NAN; }
+        a = warp_min(a); b = warp_max(b);
+        if (LOG && any) s_any = 1;
+        __syncthreads();
+        if (lane == 0 && r < jb.rows) {
+            a = tf(a); b = tf(b);
+            float s, z;
+            finish_one(a, b, jb.qtype, jb.symmetric, levels, eps, s, z);
+            jb.rmin[r] = a; jb.rmax[r] = b; jb.scale[r] = s; jb.zp[r] = z;
+        }
+    } else {
+        if (blockIdx.x != 0) return;
+        float a = INFINITY, b = -INFINITY;
+        bool isnan_ = false;
+        const long long total = jb.rows * jb.cols;
+        for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+            float v = __ldg(jb.x + i);
+            if (LOG) v = fabsf(v);
+            isnan_ |= (v != v);
+            any |= (v > eps);
+            a = fminf(a, v); b = fmaxf(b, v);
+        }
+        if (isnan_) { a = NAN; b = NAN; }
+        a = warp_min(a); b = warp_max(b);
+        if ((threadIdx.x & 31) == 0) { s_a[0][threadIdx.x >> 5] = a; s_b[0][threadIdx.x >> 5] = b; }
+        if (LOG && any) s_any = 1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) { a = nan_min(a, s_a[0][w]); b = nan_max(b, s_b[0][w]); }
+            a = tf(a); b = tf(b);
+            float s, z;
+            finish_one(a, b, jb.qtype, jb.symmetric, levels, eps, s, z);
+            jb.rmin[0] = a; jb.rmax[0] = b; jb.scale[0] = s; jb.zp[0] = z;
+        }
     }
+    if (threadIdx.x == 0 && (!LOG || s_any)) atomicOr(flags + blockIdx.y, 1);
 }
 
 }  // namespace stats
@@ -315,6 +421,16 @@ extern "C" int spq_finish_calibration(const float* running_min, const float* run
     const double levels = symmetric ? (static_cast<double>(1ull << (bits - 1)) - 1.0) : (static_cast<double>(1ull << bits) - 1.0);
     finish_calibration_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream)>>>(
         running_min, running_max, n, qtype, symmetric, static_cast<float>(levels), eps, scale, zero_point);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_calibrate_many(const SpqCalibJob* jobs_dev, int32_t n_jobs, int32_t max_blocks, int32_t* flags_dev,
+                                  spq_stream_t stream) {
+    SPQ_REQUIRE(jobs_dev && flags_dev && n_jobs > 0 && max_blocks > 0 && n_jobs <= 65535, "spq_calibrate_many: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    SPQ_CUDA_OK(cudaMemsetAsync(flags_dev, 0, sizeof(int32_t) * static_cast<size_t>(n_jobs), st));
+    calibrate_many_kernel<<<dim3(static_cast<unsigned>(max_blocks), static_cast<unsigned>(n_jobs)), 256, 0, st>>>(jobs_dev, flags_dev);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

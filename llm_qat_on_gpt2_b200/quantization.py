@@ -235,6 +235,82 @@ class LearnableFakeQuantize(nn.Module):
         return torch.maximum((self.zero_point).abs(), (hi - self.zero_point).abs()) * self.scale
 
 
+_calib_tables = {}
+
+
+def calibrate_many(quantizers, tensors) -> None:
+    """`q.start_calibration(); q(w); q.finish_calibration()` for every pair, in ONE kernel launch and one
+    device->host read (spq_calibrate_many).  The reference recalibrates the LoRA A/B quantisers of all linears
+    on their own weights every training step (p1/train_sp.py:125-163); one launch per quantiser phase made that
+    part of the step host-bound.  Results are bit-identical to the per-quantiser calls (tests/test_gpu_modules.py).
+    32-bit quantisers and log quantisers whose tensor has no |x| > eps take the single-tensor path."""
+    import struct
+    qs, ws = list(quantizers), list(tensors)
+    if len(qs) != len(ws):
+        raise ValueError("calibrate_many: one tensor per quantiser")
+    fast, slow = [], []
+    for q, w in zip(qs, ws):
+        ok = (q.num_bits < 32 and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.numel() > 0
+              and q.stats_sync_hook is None and q.quantizer_type in ('minmax', 'log'))
+        (fast if ok else slow).append((q, w))
+    for q, w in slow:
+        q.start_calibration(); q(w); q.finish_calibration()
+    if not fast:
+        return
+    dev = fast[0][1].device
+    layouts = []
+    with torch.no_grad():
+        for q, w in fast:
+            wd = w.detach()
+            x2d, bcast, stat_shape = q._stat_layout(wd)
+            if x2d.data_ptr() != wd.data_ptr():          # interior channel dim (copy): not a weight layout
+                layouts.append(None)
+                continue
+            for name in ('running_min', 'running_max', 'scale', 'zero_point'):
+                buf = getattr(q, name)
+                if list(buf.shape) != list(stat_shape):
+                    buf.resize_(stat_shape)
+            layouts.append((x2d, bcast))
+    key = tuple((w.data_ptr(), tuple(w.shape), q.running_min.data_ptr(), q.running_max.data_ptr(), q.scale.data_ptr(),
+                 q.zero_point.data_ptr(), q.num_bits, q.symmetric, q.quantizer_type, q.eps)
+                for (q, w), lay in zip(fast, layouts) if lay is not None)
+    ent = _calib_tables.get(key)
+    if ent is None:
+        rows_b, max_blocks = [], 1
+        for (q, w), lay in zip(fast, layouts):
+            if lay is None:
+                continue
+            x2d, bcast = lay
+            rows, cols = x2d.shape
+            levels = float(2 ** (q.num_bits - 1) - 1) if q.symmetric else float(2 ** q.num_bits - 1)
+            blocks = (cols + 31) // 32 if bcast == _lib.PER_COL else (rows + 7) // 8 if bcast == _lib.PER_ROW else 1
+            max_blocks = max(max_blocks, blocks)
+            rows_b.append(struct.pack(_lib.CALIB_JOB_FORMAT, x2d.data_ptr(), rows, cols, q.running_min.data_ptr(),
+                                      q.running_max.data_ptr(), q.scale.data_ptr(), q.zero_point.data_ptr(), bcast,
+                                      _lib.QTYPE[q.quantizer_type], int(q.symmetric), levels, float(q.eps), 0))
+        table = torch.frombuffer(bytearray(b"".join(rows_b)), dtype=torch.uint8).to(dev)
+        ent = (table, len(rows_b), max_blocks, torch.zeros(len(rows_b), dtype=torch.int32, device=dev))
+        if len(_calib_tables) > 64:
+            _calib_tables.clear()
+        _calib_tables[key] = ent
+    table, n_jobs, max_blocks, flags = ent
+    if n_jobs:
+        _lib.calibrate_many(table, n_jobs, max_blocks, flags)
+        got = flags.tolist()                              # the one device->host read
+    it = iter(got if n_jobs else [])
+    for (q, w), lay in zip(fast, layouts):
+        had = next(it) if lay is not None else 0
+        if lay is None or not had:
+            q.start_calibration(); q(w); q.finish_calibration()       # no data above eps / odd layout
+            continue
+        q.calibrated = True
+        q.collecting_stats = False
+        q.num_batches_collected = 1
+        q.temp_min = q.temp_max = None
+        q._first_shape = tuple(w.shape)
+        q.generation += 1
+
+
 def pow2_ceil(t: torch.Tensor) -> torch.Tensor:
     """Smallest power of two >= t (elementwise, t > 0; zeros and non-finite map to 1)."""
     safe = torch.where(torch.isfinite(t) & (t > 0), t, torch.ones_like(t))

@@ -377,3 +377,47 @@ def test_sp_linear_residual_epilogue_is_the_separate_add():
         # the no-grad forward stores the LoRA intermediate as fp16 straight from the down-projection epilogue;
         # its scales are powers of two, so it is the value the training path rounds in two steps
         assert torch.equal(y, r + m(x))
+
+
+@pytest.mark.gpu
+def test_calibrate_many_equals_per_quantiser_calibration():
+    """One launch for many small tensors == start_calibration / forward / finish_calibration per quantiser, bit for
+    bit: per-column, per-row and per-tensor layouts, min-max (symmetric and not) and log, NaN columns, and the
+    log quantiser whose tensor is all zeros (the reference's default-shape case, taken through the slow path)."""
+    from llm_qat_on_gpt2_b200 import LearnableFakeQuantize, calibrate_many
+    torch.manual_seed(21)
+    dev = torch.device("cuda")
+    specs = []
+    for qtype in ("minmax", "log"):
+        for sym in (True, False):
+            specs += [dict(bits=8, cd=1, pc=True, qtype=qtype, sym=sym, shape=(768, 64)),
+                      dict(bits=4, cd=0, pc=True, qtype=qtype, sym=sym, shape=(64, 2304)),
+                      dict(bits=8, cd=1, pc=True, qtype=qtype, sym=sym, shape=(64, 2304)),
+                      dict(bits=6, cd=0, pc=False, qtype=qtype, sym=sym, shape=(333, 77)),
+                      dict(bits=8, cd=-1, pc=True, qtype=qtype, sym=sym, shape=(3072, 16))]
+    tensors = [torch.randn(*sp["shape"], device=dev) * (0.02 + 0.3 * i) for i, sp in enumerate(specs)]
+    tensors[2][5, 7] = float("nan")
+    tensors[1][:, 3] = 0.0
+    specs.append(dict(bits=8, cd=1, pc=True, qtype="log", sym=True, shape=(64, 2304)))
+    tensors.append(torch.zeros(64, 2304, device=dev))           # fresh lora_B: nothing above eps
+    def make(sp):
+        return LearnableFakeQuantize(sp["bits"], channel_dim=sp["cd"], quantizer_type=sp["qtype"], symmetric=sp["sym"],
+                                     per_channel=sp["pc"]).to(dev)
+    ref = [make(sp) for sp in specs]
+    for q, w in zip(ref, tensors):
+        q.start_calibration(); q(w); q.finish_calibration()
+    got = [make(sp) for sp in specs]
+    for rep in range(2):                                          # second call: cached job table, new values
+        if rep == 1:
+            for w in tensors[:-1]:
+                w.mul_(1.7)
+            for q, w in zip(ref, tensors):
+                q.start_calibration(); q(w); q.finish_calibration()
+        calibrate_many(got, tensors)
+        for a, b, sp in zip(ref, got, specs):
+            assert b.calibrated and not b.collecting_stats
+            for name in ("running_min", "running_max", "scale", "zero_point"):
+                x, y = getattr(a, name), getattr(b, name)
+                assert x.shape == y.shape, (sp, name, x.shape, y.shape)
+                assert torch.equal(x.view(torch.int32), y.view(torch.int32)), (sp, name)
+    assert torch.equal(ref[0](tensors[0]), got[0](tensors[0]))          # and the quantisers quantise alike
