@@ -481,15 +481,15 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     import torch
     import torch.nn.functional as F
     import torch.distributed as dist
-    from llm_qat_on_gpt2_b200 import _lib, dp, calibrate_many
+    from llm_qat_on_gpt2_b200 import _lib, dp
+    from llm_qat_on_gpt2_b200.training import LoRARefresher
     B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
     model.train()
     for n, p in model.named_parameters():
         p.requires_grad_((f"lora_adapters.{key}.lora_" in n) or n.endswith(f"weights.{BITS}") or n.endswith(f"biases.{BITS}"))
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
-    lora_q = [q for m in linears for q in (m.lora_adapters[key].quantize_A, m.lora_adapters[key].quantize_B)]
-    lora_w = [w for m in linears for w in (m.lora_adapters[key].lora_A, m.lora_adapters[key].lora_B)]
+    refresher = LoRARefresher(linears, BITS)
     gen = torch.Generator().manual_seed(99 + rank)
     # the input quantisers keep the calibration of the last forward step (static during training)
 
@@ -497,7 +497,8 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
         with torch.no_grad():
             model.set_precision(32)
             t_logits = model(ids)
-            calibrate_many(lora_q, [w.data for w in lora_w])  # one launch; parameters are replicated: no exchange
+            refresher.refresh()       # LoRA recalibration + operand rebuild: one CUDA-graph replay (parameters are
+                                      # replicated, so no statistics exchange is needed)
         model.set_precision(BITS)
         s_logits = model(ids)
         # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows,

@@ -605,6 +605,18 @@ class SPLinearWithLoRA(nn.Module):
             bw['lora'] = ll['bwd']
         return bw
 
+    def _restamp_lora_keys(self, bits, with_bwd=True):
+        """After a CUDA-graph replay rewrote the LoRA-level tensors in place (training.LoRARefresher): mark the
+        cached levels as built from the current parameter versions / quantiser generations."""
+        lo = self.lora_adapters[f'{bits}bit']
+        ent = self._op_cache[bits]
+        ll, il = ent['lora'], ent['input']
+        ll['key'] = (lo.lora_A.data_ptr(), lo.lora_A._version, lo.lora_B.data_ptr(), lo.lora_B._version,
+                     lo.quantize_A.generation, lo.quantize_B.generation)
+        il['lora']['key'] = (il['base']['key'], ll['key'])
+        if with_bwd and ll['bwd'] is not None:
+            ll['bwd_key'] = (self._weight_level(bits)['key'], il['lora']['key'])
+
     def _calibration_weight(self, bits, weight_quantizer):
         """q_w(W) and its fp16 operand cache for the calibration pass (inputs not quantised yet)."""
         W = self.linear.weight

@@ -238,12 +238,16 @@ class LearnableFakeQuantize(nn.Module):
 _calib_tables = {}
 
 
-def calibrate_many(quantizers, tensors) -> None:
+def calibrate_many(quantizers, tensors, defer: bool = False):
     """`q.start_calibration(); q(w); q.finish_calibration()` for every pair, in ONE kernel launch and one
     device->host read (spq_calibrate_many).  The reference recalibrates the LoRA A/B quantisers of all linears
     on their own weights every training step (p1/train_sp.py:125-163); one launch per quantiser phase made that
     part of the step host-bound.  Results are bit-identical to the per-quantiser calls (tests/test_gpu_modules.py).
-    32-bit quantisers and log quantisers whose tensor has no |x| > eps take the single-tensor path."""
+    32-bit quantisers and log quantisers whose tensor has no |x| > eps take the single-tensor path.
+
+    defer=True (CUDA-graph capture, see training.LoRARefresher): only the kernel is launched; the returned
+    callable does the host part later (flag read, quantiser state) and returns the number of quantisers that
+    had to take the single-tensor path."""
     import struct
     qs, ws = list(quantizers), list(tensors)
     if len(qs) != len(ws):
@@ -253,10 +257,12 @@ def calibrate_many(quantizers, tensors) -> None:
         ok = (q.num_bits < 32 and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.numel() > 0
               and q.stats_sync_hook is None and q.quantizer_type in ('minmax', 'log'))
         (fast if ok else slow).append((q, w))
+    if defer and slow:
+        raise RuntimeError("calibrate_many(defer=True): every quantiser must be eligible for the one-launch path")
     for q, w in slow:
         q.start_calibration(); q(w); q.finish_calibration()
     if not fast:
-        return
+        return (lambda: 0) if defer else None
     dev = fast[0][1].device
     layouts = []
     with torch.no_grad():
@@ -296,19 +302,29 @@ def calibrate_many(quantizers, tensors) -> None:
     table, n_jobs, max_blocks, flags = ent
     if n_jobs:
         _lib.calibrate_many(table, n_jobs, max_blocks, flags)
-        got = flags.tolist()                              # the one device->host read
-    it = iter(got if n_jobs else [])
-    for (q, w), lay in zip(fast, layouts):
-        had = next(it) if lay is not None else 0
-        if lay is None or not had:
-            q.start_calibration(); q(w); q.finish_calibration()       # no data above eps / odd layout
-            continue
-        q.calibrated = True
-        q.collecting_stats = False
-        q.num_batches_collected = 1
-        q.temp_min = q.temp_max = None
-        q._first_shape = tuple(w.shape)
-        q.generation += 1
+
+    def finish() -> int:
+        got = flags.tolist() if n_jobs else []            # the one device->host read
+        it = iter(got)
+        redone = 0
+        for (q, w), lay in zip(fast, layouts):
+            had = next(it) if lay is not None else 0
+            if lay is None or not had:
+                q.start_calibration(); q(w); q.finish_calibration()       # no data above eps / odd layout
+                redone += 1
+                continue
+            q.calibrated = True
+            q.collecting_stats = False
+            q.num_batches_collected = 1
+            q.temp_min = q.temp_max = None
+            q._first_shape = tuple(w.shape)
+            q.generation += 1
+        return redone
+
+    if defer:
+        return finish
+    finish()
+    return None
 
 
 def pow2_ceil(t: torch.Tensor) -> torch.Tensor:

@@ -421,3 +421,59 @@ def test_calibrate_many_equals_per_quantiser_calibration():
                 assert x.shape == y.shape, (sp, name, x.shape, y.shape)
                 assert torch.equal(x.view(torch.int32), y.view(torch.int32)), (sp, name)
     assert torch.equal(ref[0](tensors[0]), got[0](tensors[0]))          # and the quantisers quantise alike
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qtype", ["log", "minmax"])
+def test_lora_refresher_graph_equals_eager(qtype):
+    """training.LoRARefresher (CUDA-graph replay of LoRA recalibration + operand rebuild) leaves every linear in
+    the state of the eager path: forward outputs and all gradients identical over several optimizer-like updates,
+    including the first step with an all-zero lora_B (log quantiser without data -> host fallback)."""
+    import copy
+    from llm_qat_on_gpt2_b200 import calibrate_many
+    from llm_qat_on_gpt2_b200.lora import SPLinearWithLoRA
+    from llm_qat_on_gpt2_b200.training import LoRARefresher
+    torch.manual_seed(31)
+    dev = torch.device("cuda")
+    shapes = [(256, 384), (384, 256), (256, 1024)]
+    eager = [SPLinearWithLoRA(i, o, [8, 32], {8: 16, 32: 0}, {8: 32, 32: 0}, {8: qtype, 32: None}).to(dev) for i, o in shapes]
+    xs = [torch.randn(4, 33, i, device=dev) for i, _ in shapes]
+    for m, x in zip(eager, xs):
+        m.set_precision(8)
+        with torch.no_grad():
+            wq = m.quantizers_weight['8bit']; wq.start_calibration(); wq(m.linear.weight); wq.finish_calibration()
+            m.calibration_mode = True
+            iq = m.quantizers_input['8bit']; iq.start_calibration(); m(x); iq.finish_calibration()
+            m.calibration_mode = False
+    graphed = copy.deepcopy(eager)
+    ref = LoRARefresher(graphed, 8)
+    for step in range(4):
+        if step > 0:
+            with torch.no_grad():
+                for a, b in zip(eager, graphed):
+                    for name in ("lora_A", "lora_B"):
+                        d = torch.randn_like(getattr(a.lora_adapters['8bit'], name)) * 0.01
+                        getattr(a.lora_adapters['8bit'], name).add_(d)
+                        getattr(b.lora_adapters['8bit'], name).add_(d)
+        los = [m.lora_adapters['8bit'] for m in eager]
+        with torch.no_grad():
+            calibrate_many([q for lo in los for q in (lo.quantize_A, lo.quantize_B)],
+                           [w.data for lo in los for w in (lo.lora_A, lo.lora_B)])
+        ref.refresh()
+        for a, b, x in zip(eager, graphed, xs):
+            for m in (a, b):
+                for p in m.parameters():
+                    p.grad = None
+            xa = x.clone().requires_grad_(True); xb = x.clone().requires_grad_(True)
+            ya = a(xa); yb = b(xb)
+            assert torch.equal(ya, yb), step
+            g = torch.randn_like(ya)
+            ya.backward(g); yb.backward(g)
+            assert torch.equal(xa.grad, xb.grad)
+            la, lb = a.lora_adapters['8bit'], b.lora_adapters['8bit']
+            # dA / dB come from the split-K kernel (fp32 atomics: summation order varies run to run)
+            for ga, gb in ((la.lora_A.grad, lb.lora_A.grad), (la.lora_B.grad, lb.lora_B.grad)):
+                assert float((ga - gb).abs().max()) <= 1e-5 * max(float(ga.abs().max()), 1e-30)
+            for qa, qb in ((la.quantize_A, lb.quantize_A), (la.quantize_B, lb.quantize_B)):
+                assert torch.equal(qa.scale, qb.scale) and torch.equal(qa.zero_point, qb.zero_point)
+    assert ref.graph is not None
