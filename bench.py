@@ -482,7 +482,7 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     import torch.nn.functional as F
     import torch.distributed as dist
     from llm_qat_on_gpt2_b200 import _lib, dp
-    from llm_qat_on_gpt2_b200.training import LoRARefresher
+    from llm_qat_on_gpt2_b200.training import LoRARefresher, distillation_kl_loss
     B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
     model.train()
     for n, p in model.named_parameters():
@@ -501,11 +501,8 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
                                       # replicated, so no statistics exchange is needed)
         model.set_precision(BITS)
         s_logits = model(ids)
-        # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows,
-        # written on the strided [:, :-1] views so that no [B*T, V] slice copy is materialised
-        t_lp = F.log_softmax(t_logits[:, :-1, :] / Tmp, dim=-1)
-        s_lp = F.log_softmax(s_logits[:, :-1, :] / Tmp, dim=-1)
-        loss = F.kl_div(s_lp, t_lp, reduction="sum", log_target=True) * (Tmp * Tmp / (B * (T - 1)))
+        # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows, * T^2
+        loss = distillation_kl_loss(s_logits, t_logits, Tmp)     # value + gradient from one kernel
         opt.zero_grad(set_to_none=True)
         loss.backward()
         n = dp.allreduce_gradients(params, group)

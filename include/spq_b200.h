@@ -208,6 +208,15 @@ SPQ_API int spq_cross_entropy_from_parts(const float* parts, int64_t P, int64_t 
                                  int64_t V, int64_t ld, const int64_t* targets, int64_t ignore_index,
                                  float* row_loss, float* row_valid, spq_stream_t stream);
 
+/* Distillation loss of the SP training step (p1/distillation_manager.py:64-80):
+ * row_loss[m] = KL( softmax(t[m]/T) || softmax(s[m]/T) ) and, when grad != NULL, the dense [M, V] gradient
+ * grad[m,v] = grad_scale / T * (softmax(s[m]/T)[v] - softmax(t[m]/T)[v])  (grad_scale = T^2 / rows for the
+ * reference's batchmean * T^2).  Rows with m % seq_len == seq_len - 1 are ignored (seq_len = 0: none) -- the
+ * reference scores positions 0..T-2.  Logits may have padded rows (ld_s, ld_t in elements). */
+SPQ_API int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t, int64_t M, int64_t V,
+                   float temperature, int64_t seq_len, float grad_scale, float* row_loss, float* grad,
+                   spq_stream_t stream);
+
 /* ---- consumer of the path: next-token cross-entropy, forward only -----------
  * Replaces nn.CrossEntropyLoss over re-materialised shifted logits (p1/models_sp.py:441-449) for
  * no-grad evaluation: row_loss[m] = logsumexp(logits[m, 0:V]) - logits[m, targets[m]], row_valid[m] = 1,

@@ -60,6 +60,8 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "spq_cross_entropy_from_parts": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                              c_void_p, c_void_p, c_void_p]),
+    "spq_distill_kl": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float, c_int64, c_float, c_void_p,
+                               c_void_p, c_void_p]),
     "spq_cross_entropy_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_rowscale_f16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
 }
@@ -332,6 +334,20 @@ def cross_entropy_from_parts(parts, logits2d, targets, ignore_index=-100):
            "spq_cross_entropy_from_parts")
     sums = out.sum(dim=1)
     return sums[0] / sums[1]
+
+
+def distill_kl(s2d, t2d, temperature, seq_len, grad_scale, want_grad=True):
+    """Per-row KL(softmax(t/T) || softmax(s/T)) and (optionally) the dense gradient w.r.t. s; rows may be padded."""
+    _req_cuda(s2d, t2d)
+    assert s2d.dim() == 2 and t2d.shape == s2d.shape and s2d.stride(1) == 1 and t2d.stride(1) == 1
+    assert s2d.dtype == torch.float32 and t2d.dtype == torch.float32
+    M, V = s2d.shape
+    row_loss = torch.empty(M, dtype=torch.float32, device=s2d.device)
+    grad = torch.empty((M, V), dtype=torch.float32, device=s2d.device) if want_grad else None
+    _check(load_library().spq_distill_kl(s2d.data_ptr(), s2d.stride(0), t2d.data_ptr(), t2d.stride(0), M, V,
+                                         float(temperature), int(seq_len), float(grad_scale), row_loss.data_ptr(),
+                                         _ptr(grad), _stream()), "spq_distill_kl")
+    return row_loss, grad
 
 
 def rowscale_f16(g2d, out, row_scale):

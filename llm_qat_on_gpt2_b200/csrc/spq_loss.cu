@@ -98,6 +98,88 @@ cross_entropy_from_parts_kernel(const float2* __restrict__ parts, long long P, l
     }
 }
 
+// Distillation loss of the switchable-precision training step (p1/distillation_manager.py:64-80):
+//   KL( softmax(t / T) || softmax(s / T) ) per row, forward value AND the gradient w.r.t. the student logits,
+// in two passes over the two [M, V] matrices instead of torch's log_softmax x2 + kl_div + their backward
+// (~10 passes of 1.6 GB each at 32 x 256 x 50257).  One CTA per row: pass A = online (max, sum exp) of both
+// rows, pass B = loss terms and  grad[v] = g * (ps[v] - pt[v])  (the second read mostly hits L2).
+// Rows with  row % seq_len == seq_len - 1  (the last position of each sequence, excluded upstream) are skipped.
+__global__ void __launch_bounds__(256)
+distill_kl_kernel(const float* __restrict__ s_logits, long long ld_s, const float* __restrict__ t_logits, long long ld_t,
+                  long long M, long long V, float inv_T, long long seq_len, float g, float* __restrict__ row_loss,
+                  float* __restrict__ grad) {
+    __shared__ float sm[4][8];
+    __shared__ float s_lse[2];
+    __shared__ float s_part[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+        float* gr = grad ? grad + row * V : nullptr;
+        if (seq_len > 0 && (row % seq_len) == seq_len - 1) {         // block-uniform
+            if (tid == 0) row_loss[row] = 0.f;
+            if (gr) for (long long i = tid; i < V; i += 256) gr[i] = 0.f;
+            continue;
+        }
+        const float* ps_ = s_logits + row * ld_s;
+        const float* pt_ = t_logits + row * ld_t;
+        MS a; a.m = -INFINITY; a.s = 0.f;
+        MS b; b.m = -INFINITY; b.s = 0.f;
+        const bool vec = ((ld_s & 3) == 0) && ((ld_t & 3) == 0) && aligned16_dev(s_logits) && aligned16_dev(t_logits);
+        const long long v4 = vec ? (V >> 2) : 0;
+        for (long long i = tid; i < v4; i += 256) {
+            float4 x = ld_stream_f4(ps_ + 4 * i);
+            float4 y = ld_stream_f4(pt_ + 4 * i);
+            x.x *= inv_T; x.y *= inv_T; x.z *= inv_T; x.w *= inv_T;
+            y.x *= inv_T; y.y *= inv_T; y.z *= inv_T; y.w *= inv_T;
+            float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+            if (mx > a.m) { a.s *= __expf(a.m - mx); a.m = mx; }
+            a.s += __expf(x.x - a.m) + __expf(x.y - a.m) + __expf(x.z - a.m) + __expf(x.w - a.m);
+            mx = fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w));
+            if (mx > b.m) { b.s *= __expf(b.m - mx); b.m = mx; }
+            b.s += __expf(y.x - b.m) + __expf(y.y - b.m) + __expf(y.z - b.m) + __expf(y.w - b.m);
+        }
+        for (long long i = 4 * v4 + tid; i < V; i += 256) { push(a, __ldg(ps_ + i) * inv_T); push(b, __ldg(pt_ + i) * inv_T); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MS c; c.m = __shfl_xor_sync(0xffffffffu, a.m, o); c.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+            a = combine(a, c);
+            c.m = __shfl_xor_sync(0xffffffffu, b.m, o); c.s = __shfl_xor_sync(0xffffffffu, b.s, o);
+            b = combine(b, c);
+        }
+        __syncthreads();                                            // previous row's readers of sm / s_lse are done
+        if (lane == 0) { sm[0][warp] = a.m; sm[1][warp] = a.s; sm[2][warp] = b.m; sm[3][warp] = b.s; }
+        __syncthreads();
+        if (tid == 0) {
+            MS x; x.m = sm[0][0]; x.s = sm[1][0];
+            MS y; y.m = sm[2][0]; y.s = sm[3][0];
+            for (int w = 1; w < 8; ++w) {
+                MS c; c.m = sm[0][w]; c.s = sm[1][w]; x = combine(x, c);
+                c.m = sm[2][w]; c.s = sm[3][w]; y = combine(y, c);
+            }
+            s_lse[0] = x.m + logf(x.s);
+            s_lse[1] = y.m + logf(y.s);
+        }
+        __syncthreads();
+        const float lse_s = s_lse[0], lse_t = s_lse[1];
+        float acc = 0.f;
+        // pass B: lanes walk consecutive elements (coalesced loads and, for the dense gradient, stores)
+        for (long long i = tid; i < V; i += 256) {
+            const float ls = fmaf(__ldg(ps_ + i), inv_T, -lse_s);      // log softmax(s / T)
+            const float lt = fmaf(__ldg(pt_ + i), inv_T, -lse_t);
+            const float pt = __expf(lt);
+            acc = fmaf(pt, lt - ls, acc);
+            if (gr) gr[i] = g * (__expf(ls) - pt);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < 8; ++w) tot += s_part[w];
+            row_loss[row] = tot;
+        }
+    }
+}
+
 }  // namespace loss
 }  // namespace spq
 
@@ -125,6 +207,19 @@ extern "C" int spq_cross_entropy_from_parts(const float* parts, int64_t P, int64
     loss::cross_entropy_from_parts_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float2*>(parts), P, part_ld, logits, M, V, ld, reinterpret_cast<const long long*>(targets),
         ignore_index, row_loss, row_valid);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t, int64_t M, int64_t V,
+                              float temperature, int64_t seq_len, float grad_scale, float* row_loss, float* grad,
+                              spq_stream_t stream) {
+    SPQ_REQUIRE(s_logits && t_logits && row_loss && M > 0 && V > 0 && ld_s >= V && ld_t >= V && temperature > 0.f,
+                "spq_distill_kl: bad arguments");
+    long long ctas = static_cast<long long>(sm_count()) * 8;
+    if (ctas > M) ctas = M;
+    loss::distill_kl_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(
+        s_logits, ld_s, t_logits, ld_t, M, V, 1.0f / temperature, seq_len, grad_scale / temperature, row_loss, grad);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

@@ -84,3 +84,40 @@ class LoRARefresher:
             else:
                 for m, _ in self.active:
                     m._restamp_lora_keys(self.bits, self.with_bwd)
+
+
+class _DistillKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s_logits, t_logits, temperature):
+        from . import _lib
+        B, T, V = s_logits.shape
+        rows = B * (T - 1)
+
+        def as2d(x):
+            # [B, T, V] -> [B*T, V] without a copy, also for the row-padded views the LM head returns
+            if x.dtype != torch.float32:
+                x = x.float()
+            if x.stride(-1) == 1 and x.stride(0) == T * x.stride(1):
+                return x.as_strided((B * T, V), (x.stride(1), 1))
+            return x.reshape(B * T, V).contiguous()
+        s2d, t2d = as2d(s_logits.detach()), as2d(t_logits.detach())
+        row_loss, grad = _lib.distill_kl(s2d, t2d, temperature, T, temperature * temperature / rows,
+                                         want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(grad)
+        ctx.shape = s_logits.shape
+        return row_loss.sum() * (temperature * temperature / rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).view(ctx.shape) if grad is not None else None, None, None
+
+
+def distillation_kl_loss(student_logits, teacher_logits, temperature: float = 3.0):
+    """`F.kl_div(log_softmax(s[:, :-1] / T), log_softmax(t[:, :-1] / T), reduction='batchmean', log_target=True)
+    * T**2` of the reference's distillation step (p1/distillation_manager.py:64-80), value and gradient from ONE
+    kernel (spq_distill_kl) instead of ~10 elementwise passes over the [B, T, V] logits.  Logits may be the
+    row-padded views the LM head returns."""
+    if not (student_logits.is_cuda and student_logits.dim() == 3 and teacher_logits.shape == student_logits.shape):
+        raise RuntimeError("distillation_kl_loss expects CUDA logits of shape [B, T, V] (no CPU fallback)")
+    return _DistillKL.apply(student_logits, teacher_logits, float(temperature))

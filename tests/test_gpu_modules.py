@@ -477,3 +477,29 @@ def test_lora_refresher_graph_equals_eager(qtype):
             for qa, qb in ((la.quantize_A, lb.quantize_A), (la.quantize_B, lb.quantize_B)):
                 assert torch.equal(qa.scale, qb.scale) and torch.equal(qa.zero_point, qb.zero_point)
     assert ref.graph is not None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,padded", [(3, 17, 211, True), (2, 64, 50257, True), (4, 9, 1000, False)])
+def test_distillation_kl_loss_matches_torch(B, T, V, padded):
+    """training.distillation_kl_loss (one kernel: value + gradient) == the reference's log_softmax / kl_div
+    composition (p1/distillation_manager.py:64-80) evaluated in float64."""
+    import torch.nn.functional as F
+    from llm_qat_on_gpt2_b200.training import distillation_kl_loss
+    torch.manual_seed(V + T)
+    dev = torch.device("cuda")
+    Tmp = 3.0
+    ld = (V + 31) // 32 * 32 if padded else V
+    sbuf = torch.randn(B, T, ld, device=dev) * 4; tbuf = torch.randn(B, T, ld, device=dev) * 4
+    s = sbuf[..., :V].detach().requires_grad_(True)
+    t = tbuf[..., :V]
+    loss = distillation_kl_loss(s, t, Tmp)
+    loss.backward()
+    s64 = sbuf[..., :V].double().detach().requires_grad_(True)
+    ref = F.kl_div(F.log_softmax(s64[:, :-1] / Tmp, dim=-1), F.log_softmax(t.double()[:, :-1] / Tmp, dim=-1),
+                   reduction="sum", log_target=True) * (Tmp * Tmp / (B * (T - 1)))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+    gerr = (s.grad.double() - s64.grad).abs().max() / s64.grad.abs().max()
+    assert float(gerr) <= 1e-4, float(gerr)
+    assert float(s.grad[:, -1].abs().max()) == 0.0                  # the last position takes no part
