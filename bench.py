@@ -475,14 +475,16 @@ def gpu_arm(args):
 def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     """BASELINE.json configs[2]: one switchable-precision distillation step per optimizer step --
     32-bit teacher forward (no grad), LoRA quantisers recalibrated (p1/train_sp.py:125-163, 362-364),
-    8-bit student forward + STE backward on KL(T=3) (p1/distillation_manager.py:64-80), all-reduce of
+    8-bit student forward + STE backward on the distillation loss (KL(T=3) + 1e-7 * hidden-state MSE,
+    p1/distillation_manager.py:64-116), all-reduce of
     the gradients that exist (active LoRA A/B + active LayerNorm pairs), AdamW on those parameters.
     Batch-sharded: every rank runs the reference's 32 x 256 micro-batch (weak scaling)."""
     import torch
     import torch.nn.functional as F
     import torch.distributed as dist
     from llm_qat_on_gpt2_b200 import _lib, dp
-    from llm_qat_on_gpt2_b200.training import LoRARefresher, distillation_kl_loss
+    import random
+    from llm_qat_on_gpt2_b200.training import LoRARefresher, distillation_loss
     B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
     model.train()
     for n, p in model.named_parameters():
@@ -490,19 +492,21 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
     refresher = LoRARefresher(linears, BITS)
+    layer_rng = random.Random(7 + rank)
     gen = torch.Generator().manual_seed(99 + rank)
     # the input quantisers keep the calibration of the last forward step (static during training)
 
     def one_step(ids):
         with torch.no_grad():
             model.set_precision(32)
-            t_logits = model(ids)
+            t_out = model(ids, output_hidden_states=True, return_dict=True)
             refresher.refresh()       # LoRA recalibration + operand rebuild: one CUDA-graph replay (parameters are
                                       # replicated, so no statistics exchange is needed)
         model.set_precision(BITS)
-        s_logits = model(ids)
+        s_out = model(ids, output_hidden_states=True, return_dict=True)
         # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows, * T^2
-        loss = distillation_kl_loss(s_logits, t_logits, Tmp)     # value + gradient from one kernel
+        # alpha_kl * KL(T) [one kernel: value + gradient] + alpha_feature * MSE(hidden states of one random layer)
+        loss = distillation_loss(s_out, t_out, Tmp, alpha_kl=1.0, alpha_feature=1e-7, rng=layer_rng)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         n = dp.allreduce_gradients(params, group)

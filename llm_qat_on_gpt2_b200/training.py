@@ -121,3 +121,26 @@ def distillation_kl_loss(student_logits, teacher_logits, temperature: float = 3.
     if not (student_logits.is_cuda and student_logits.dim() == 3 and teacher_logits.shape == student_logits.shape):
         raise RuntimeError("distillation_kl_loss expects CUDA logits of shape [B, T, V] (no CPU fallback)")
     return _DistillKL.apply(student_logits, teacher_logits, float(temperature))
+
+
+def distillation_loss(student_outputs, teacher_outputs, temperature: float = 3.0, alpha_kl: float = 1.0,
+                      alpha_feature: float = 1e-7, feature_layers=None, accumulative: bool = False, rng=None):
+    """`DistillationManager.compute_distillation_loss` (p1/distillation_manager.py:64-116) on output dicts with
+    'logits' and (optionally) 'hidden_states': alpha_kl * KL(T) [fused kernel] + alpha_feature * MSE of the hidden
+    states of one randomly chosen layer (or the mean over `feature_layers` when accumulative).  The models return
+    detached hidden-state copies, as upstream (p1/models_sp.py:323), so the feature term carries no gradient."""
+    import random
+    import torch.nn.functional as F
+    kl = distillation_kl_loss(student_outputs['logits'], teacher_outputs['logits'], temperature)
+    feature = None
+    hs, ht = student_outputs.get('hidden_states'), teacher_outputs.get('hidden_states')
+    if hs and ht:
+        n = min(len(hs), len(ht))
+        layers = [l for l in (feature_layers or range(n)) if l < n]
+        if layers:
+            if accumulative:
+                feature = sum(F.mse_loss(hs[l], ht[l], reduction='mean') for l in layers) / len(layers)
+            else:
+                l = (rng or random).choice(layers)
+                feature = F.mse_loss(hs[l], ht[l], reduction='mean')
+    return alpha_kl * kl if feature is None else alpha_kl * kl + alpha_feature * feature

@@ -503,3 +503,25 @@ def test_distillation_kl_loss_matches_torch(B, T, V, padded):
     gerr = (s.grad.double() - s64.grad).abs().max() / s64.grad.abs().max()
     assert float(gerr) <= 1e-4, float(gerr)
     assert float(s.grad[:, -1].abs().max()) == 0.0                  # the last position takes no part
+
+
+@pytest.mark.gpu
+def test_distillation_loss_against_reference_fixture():
+    """training.distillation_loss vs DistillationManager.compute_distillation_loss of the unmodified reference
+    (tests/golden/make_golden_distill.py): loss within 1e-5 relative, gradient w.r.t. the student logits within
+    1e-4 of its largest entry (float32 softmax on both sides)."""
+    import os
+    import numpy as np
+    from llm_qat_on_gpt2_b200.training import distillation_loss
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "distill_kl.npz"))
+    dev = torch.device("cuda")
+    s = torch.tensor(g["s_logits"], device=dev).requires_grad_(True)
+    t = torch.tensor(g["t_logits"], device=dev)
+    hs = [torch.tensor(h, device=dev) for h in g["s_hidden"]]
+    ht = [torch.tensor(h, device=dev) for h in g["t_hidden"]]
+    loss = distillation_loss({'logits': s, 'hidden_states': hs}, {'logits': t, 'hidden_states': ht},
+                             float(g["temperature"]), float(g["alpha_kl"]), float(g["alpha_feature"]), accumulative=True)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    ref_grad = torch.tensor(g["grad"], device=dev)
+    assert float((s.grad - ref_grad).abs().max()) <= 1e-4 * float(ref_grad.abs().max())
