@@ -525,3 +525,29 @@ def test_distillation_loss_against_reference_fixture():
     assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     ref_grad = torch.tensor(g["grad"], device=dev)
     assert float((s.grad - ref_grad).abs().max()) <= 1e-4 * float(ref_grad.abs().max())
+
+
+@pytest.mark.gpu
+def test_export_integer_weights_roundtrip():
+    """deploy.export_integer_weights: codes and scales of the calibrated weight quantisers reproduce the
+    fake-quantised weights exactly (min-max), int8 storage when the codes fit."""
+    from llm_qat_on_gpt2_b200.deploy import export_integer_weights
+    from llm_qat_on_gpt2_b200.lora import SPLinearWithLoRA
+    torch.manual_seed(5)
+    dev = torch.device("cuda")
+    net = torch.nn.ModuleDict({"a": SPLinearWithLoRA(64, 96, [4, 8, 32], {4: 4, 8: 4, 32: 0}, {4: 8, 8: 8, 32: 0},
+                                                     {4: "minmax", 8: "minmax", 32: None}),
+                               "b": SPLinearWithLoRA(96, 64, [4, 8, 32], {4: 4, 8: 4, 32: 0}, {4: 8, 8: 8, 32: 0},
+                                                     {4: "minmax", 8: "minmax", 32: None})}).to(dev)
+    for m in net.values():
+        m.set_precision(8)
+        q = m.quantizers_weight["8bit"]
+        q.start_calibration(); q(m.linear.weight.data); q.finish_calibration()
+    out = export_integer_weights(net, 8)
+    for name, m in net.items():
+        codes, scale = out[f"{name}.codes"], out[f"{name}.scale"]
+        assert codes.dtype == torch.int8 and codes.shape == m.linear.weight.shape
+        dq = m.quantizers_weight["8bit"](m.linear.weight.data).cpu()
+        assert torch.equal(codes.float() * scale, dq)
+    with pytest.raises(RuntimeError):
+        export_integer_weights(net, 4)                      # 4-bit quantisers were never calibrated
