@@ -7,5 +7,7 @@ LoRAAdapter, CPTLinear and the GPT-2 wrapper classes around them.
 from .quantization import GradientQuantizer, LearnableFakeQuantize
 from .cpt_model import LoRAAdapter, CPTLinear, CPTSelfAttention, CPTMLP, CPTBlock, CPTModel
 
-__all__ = ["GradientQuantizer", "LearnableFakeQuantize", "LoRAAdapter", "CPTLinear", "CPTSelfAttention",
+from .cyclic_scheduler import CyclicPrecisionScheduler, PrecisionRangeTest
+
+__all__ = ["CyclicPrecisionScheduler", "PrecisionRangeTest", "GradientQuantizer", "LearnableFakeQuantize", "LoRAAdapter", "CPTLinear", "CPTSelfAttention",
            "CPTMLP", "CPTBlock", "CPTModel"]
