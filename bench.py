@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--bits", type=int, default=8, choices=[4, 8],
+                    help="precision of the measured step: 8 = log quantisers (the headline configuration), 4 = min-max")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
     ap.add_argument("--seq", type=int, default=1024)
@@ -159,7 +161,7 @@ def reference_arm(args):
 
 
 def workload_name(args):
-    return (f"GPT-2 small (124M) SPLMHeadModel, 8-bit log per-channel: calibration pass + quantised forward + CE, "
+    return (f"GPT-2 small (124M) SPLMHeadModel, {BITS}-bit {QUANTIZER_PER_BIT[BITS]} per-channel: calibration pass + quantised forward + CE, "
             f"batch {args.batch} x seq {args.seq} per GPU, LoRA rank 64, random-init weights")
 
 
@@ -546,7 +548,10 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
 
 
 def main():
+    global BITS, METRIC
     args = parse_args()
+    BITS = args.bits
+    METRIC = f"GPT-2 SP tokens/s at {BITS}-bit (calibration pass + quantised forward)"
     if args.impl == "reference":
         reference_arm(args)
     else:
