@@ -20,9 +20,14 @@ namespace spq {
 namespace prep {
 
 __device__ __forceinline__ float pow2_ceil(float x) {       // smallest power of two >= x (x > 0, finite)
-    int e;
-    const float f = frexpf(x, &e);                           // x = f * 2^e, f in [0.5, 1)
-    return ldexpf(1.0f, f == 0.5f ? e - 1 : e);
+    const int b = __float_as_int(x);
+    const int e = b & 0x7f800000;
+    if (e != 0 && e != 0x7f000000) {                         // normal, and the result stays finite: bump the exponent
+        return __int_as_float((b & 0x007fffff) ? e + 0x00800000 : e);      // unless x already is a power of two
+    }
+    int ex;                                                   // denormal / top binade: the library route
+    const float f = frexpf(x, &ex);                           // x = f * 2^ex, f in [0.5, 1)
+    return ldexpf(1.0f, f == 0.5f ? ex - 1 : ex);
 }
 
 __device__ __forceinline__ float block_max(float v, float* s_red) {

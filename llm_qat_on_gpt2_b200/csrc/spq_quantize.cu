@@ -119,6 +119,14 @@ __device__ __forceinline__ LogCol make_logcol(float log_min, float log_range, co
     return c;
 }
 
+// lg2.approx with flush-to-zero: the argument is max(|x|, 1e-5), never subnormal, so the result is the one of
+// __log2f() without the three instructions it spends on rescaling subnormal inputs
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -133,7 +141,7 @@ __device__ __forceinline__ LogOut log_elem(float x, const LogCol& ch, const QPar
     const float nl = qp.symmetric ? qp.n_sym : qp.full;
     const float lev_mul = qp.symmetric ? 2.f * nl : nl;
 
-    float v = __saturatef(fmaf(__log2f(axc), ch.inv, ch.c0));            // ln in [0, 1]
+    float v = __saturatef(fmaf(lg2_approx(axc), ch.inv, ch.c0));            // ln in [0, 1]
     v = qp.symmetric ? fmaf(v, lev_mul, -nl) : v * lev_mul;
     float r = rintf(v);
     if (fabsf(fabsf(v - r) - 0.5f) <= ch.band && !(qp.debug & 1)) {      // near a tie: the reference's exact sequence
@@ -156,7 +164,7 @@ __device__ __forceinline__ LogOut log_elem(float x, const LogCol& ch, const QPar
 __device__ __forceinline__ float log_level_fast(float x, const LogCol& ch, const QParams& qp, bool& tie) {
     const float nl = qp.symmetric ? qp.n_sym : qp.full;
     const float lev_mul = qp.symmetric ? 2.f * nl : nl;
-    float v = __saturatef(fmaf(__log2f(fmaxf(fabsf(x), LOG_EPS)), ch.inv, ch.c0));
+    float v = __saturatef(fmaf(lg2_approx(fmaxf(fabsf(x), LOG_EPS)), ch.inv, ch.c0));
     v = qp.symmetric ? fmaf(v, lev_mul, -nl) : v * lev_mul;
     const float r = rintf(v);
     tie = fabsf(fabsf(v - r) - 0.5f) <= ch.band;
