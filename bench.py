@@ -352,9 +352,20 @@ def gpu_arm(args):
         gemm_events.append((e0, e1, 2.0 * M * N * (K + K2), nbytes))
         return r
 
+    orig_qgemm_lse = _lib.qgemm_lse
+
+    def timed_qgemm_lse(A, Bm, M, N, K, out, **kw):          # the LM head (same kernel, log-sum-exp epilogue)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_qgemm_lse(A, Bm, M, N, K, out, **kw)
+        e1.record()
+        gemm_events.append((e0, e1, 2.0 * M * N * K, 2.0 * (M + N) * K + 4.0 * M * N + 8.0 * M * r.shape[1]))
+        return r
+
     def patch(fn):
         import llm_qat_on_gpt2_b200.lora as lora_mod
         lora_mod._lib.qgemm = fn
+        lora_mod._lib.qgemm_lse = timed_qgemm_lse if fn is timed_qgemm else orig_qgemm_lse
 
     # the clock sampler attaches to NVML before the warm-up (its one-time driver work stays out of the timed
     # regions); its samples are reset when the first timed region starts

@@ -81,6 +81,47 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster (same TPC) run one 256-row MMA; each loads its own
+// 128 rows of A and HALF of the B tile, so every operand byte is fetched from L2 once per pair, not once per SM.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {   // same offset, in CTA `cta_rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the completion bytes are signalled on `bar_cluster_addr`, a shared::cluster address (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -171,9 +212,9 @@ struct EpiParams {
     long long lse_ld;
 };
 
-template <int BN>
+template <int BN, bool CTA2 = false>
 struct SmemLayout {
-    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int B_TILE_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;      // CTA pair: each CTA stages half of the B tile
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
     static constexpr int EPI_BYTES = 2 * BN * 4;      // col_scale + bias of the tile
@@ -211,12 +252,14 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
 // extra staging traffic stay out of the plain kernel)
 // LSE: the epilogue also keeps, per output row, the running (max, sum exp) of the values it stores and writes one
 // pair per column half-tile -- the log-sum-exp of the LM head's logits without a second pass over them
-template <int BN, bool OUT_HALF, bool PRE_C, bool LSE = false>
+// CTA2: launched as clusters of two CTAs; the pair computes 256 x BN tiles with tcgen05.mma.cta_group::2 (issued
+// by the even CTA), each CTA owning 128 rows of A, half of B in shared memory and its 128 rows of the accumulator.
+template <int BN, bool OUT_HALF, bool PRE_C, bool LSE = false, bool CTA2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmD, int M, int N, int kb1, int kb2, EpiParams ep) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, CTA2>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stg_all = smem + L::STAGES * L::STAGE_BYTES;                       // EPI_WARPS x 4 KB, 1024 B aligned
     float* epi_cs = reinterpret_cast<float*>(stg_all + L::STG_BYTES);
@@ -229,8 +272,13 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int TILE_M = CTA2 ? 2 * BM : BM;                     // rows per tile (per CTA pair in CTA2 mode)
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int row_off = static_cast<int>(cta_rank) * BM;           // this CTA's rows inside the tile
     const int n_tiles = (N + BN - 1) / BN;
-    const int m_tiles = (M + BM - 1) / BM;
+    const int m_tiles = (M + TILE_M - 1) / TILE_M;
     const int num_tiles = n_tiles * m_tiles;
     const int kb_total = kb1 + kb2;
 
@@ -254,19 +302,27 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], EPI_WARPS);     // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], EPI_WARPS * (CTA2 ? 2 : 1));     // one arrive per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                     "n"(L::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "n"(L::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "n"(L::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();           // the peer's barriers exist before anything is signalled on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
@@ -275,22 +331,35 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = tile_first; t < num_tiles; t += tile_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
-                const int m0 = m_blk * BM;
-                const int n0 = n_blk * BN;
+                const int m0 = m_blk * TILE_M + row_off;
+                const int n0 = n_blk * BN + (CTA2 ? static_cast<int>(cta_rank) * (BN / 2) : 0);   // this CTA's half of B
                 for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + A_TILE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    if (kb < kb1) {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                    if constexpr (CTA2) {
+                        // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+                        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        if (kb < kb1) {
+                            tma_load_2d_pair(sa, &tmA, lead_bar, kb * BK, m0);
+                            tma_load_2d_pair(sb, &tmB, lead_bar, kb * BK, n0);
+                        } else {
+                            tma_load_2d_pair(sa, &tmA2, lead_bar, (kb - kb1) * BK, m0);
+                            tma_load_2d_pair(sb, &tmB2, lead_bar, (kb - kb1) * BK, n0);
+                        }
                     } else {
-                        tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - kb1) * BK, m0);
-                        tma_load_2d(sb, &tmB2, &full_bar[stage], (kb - kb1) * BK, n0);
+                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        if (kb < kb1) {
+                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                        } else {
+                            tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - kb1) * BK, m0);
+                            tma_load_2d(sb, &tmB2, &full_bar[stage], (kb - kb1) * BK, n0);
+                        }
                     }
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -298,13 +367,13 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+        if (lane == 0 && cta_rank == 0) {              // CTA pair: the even CTA issues for both
+            constexpr uint32_t idesc = make_idesc_f16(TILE_M, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = tile_first; t < num_tiles; t += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -318,11 +387,20 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         if (ep.debug & 2) break;
                         // +32 B per UMMA_K inside the 128 B swizzle span: +2 in the (addr >> 4) field
-                        umma_f16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                                 (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CTA2)
+                            umma_f16_pair(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                                          (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_f16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
-                    if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+                    if constexpr (CTA2) {
+                        umma_commit_pair(&empty_bar[stage]);     // frees the slot in both CTAs
+                        if (kb == kb_total - 1) umma_commit_pair(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+                        if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -350,7 +428,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         auto c_load = [&](int tt, int cc) {
             int m_blk, n_blk;
             tile_coords(tt, m_tiles, n_tiles, m_blk, n_blk);
-            const int rb = m_blk * BM + quad * 32 + (lane >> 3);
+            const int rb = m_blk * TILE_M + row_off + quad * 32 + (lane >> 3);
             const int ncol = n_blk * BN + half * COLS_PER_HALF + cc * 32 + (lane & 7) * 4;
             const float* pc = ep.C + static_cast<long long>(rb) * ep.ldc + ncol;
 #pragma unroll
@@ -358,11 +436,11 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 cn[i] = (rb + i * 4 < M && ncol < N) ? *reinterpret_cast<const float4*>(pc + static_cast<long long>(i) * 4 * ep.ldc)
                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        if constexpr (PRE_C) { if (active && static_cast<int>(blockIdx.x) < num_tiles) c_load(blockIdx.x, 0); }
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        if constexpr (PRE_C) { if (active && tile_first < num_tiles) c_load(tile_first, 0); }
+        for (int t = tile_first; t < num_tiles; t += tile_step) {
             int m_blk, n_blk;
             tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
-            const int m0 = m_blk * BM;
+            const int m0 = m_blk * TILE_M + row_off;
             const int n0 = n_blk * BN;
             // stage this tile's per-column parameters (previous tile's readers are done: barrier 1)
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -392,7 +470,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int nc = n0 + cl;
                     auto c_next = [&]() {                           // issue the next chunk's residual loads
                         if (c + 1 < CHUNKS) c_load(t, c + 1);
-                        else if (t + static_cast<int>(gridDim.x) < num_tiles) c_load(t + gridDim.x, 0);
+                        else if (t + tile_step < num_tiles) c_load(t + tile_step, 0);
                     };
                     if (nc >= N || rbase >= M || (ep.debug & 1)) {              // warp-uniform
                         if constexpr (PRE_C) c_next();
@@ -548,7 +626,10 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader's barrier
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -556,9 +637,13 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();           // neither CTA leaves while the other can still signal it / read its smem
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(L::TMEM_COLS) : "memory");
+        if constexpr (CTA2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(L::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(L::TMEM_COLS) : "memory");
     }
 }
 
@@ -642,6 +727,42 @@ static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
     return SPQ_OK;
 }
 
+
+// CTA-pair launch: clusters of two CTAs, 256 x BN tiles, one cluster per SM pair
+template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false>
+static int launch_nt_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
+                          const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
+    using L = SmemLayout<BN, true>;
+    auto kern = qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(sm_count() & ~1));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent clusters: exactly as many as can be co-resident (a TPC with one SM fused off cannot host a pair)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        int n = 0;
+        SPQ_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        max_clusters = n > 0 ? n : 1;
+    }
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    SPQ_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep));
+    spq::count_launch();
+    return SPQ_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Transposed-operand GEMM (weight-gradient shape): D[i,j] += alpha * is[i] * js[j] * sum_m P[m,i] Q[m,j].
@@ -854,13 +975,19 @@ static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
         return SPQ_ERR_CUDA;
     }
     const int bn = pick_bn(M, N, sms);
+    // CTA-pair mode (cta_group::2, 256 x 256 tiles): wide outputs with enough 256-row tiles for every SM pair
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("SPQ_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }      // SPQ_GEMM_PAIR=0: A/B switch
+    const bool pair = pair_env != 0 && bn == 256 &&
+                      ((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn) >= sms / 2;
+    const int b_rows = pair ? bn / 2 : bn;                // rows of B each CTA stages per k-block
     CUtensorMap tA, tB, tA2, tB2;
     int rc;
     if ((rc = make_tmap(&tA, A, M, K, lda, BM)) != SPQ_OK) return rc;
-    if ((rc = make_tmap(&tB, B, N, K, ldb, bn)) != SPQ_OK) return rc;
+    if ((rc = make_tmap(&tB, B, N, K, ldb, b_rows)) != SPQ_OK) return rc;
     if (K2 > 0) {
         if ((rc = make_tmap(&tA2, A2, M, K2, lda2, BM)) != SPQ_OK) return rc;
-        if ((rc = make_tmap(&tB2, B2, N, K2, ldb2, bn)) != SPQ_OK) return rc;
+        if ((rc = make_tmap(&tB2, B2, N, K2, ldb2, b_rows)) != SPQ_OK) return rc;
     } else {
         tA2 = tA;
         tB2 = tB;
@@ -890,9 +1017,15 @@ static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
     if (lse_part) {
         SPQ_REQUIRE(ep.tma_store && !d_is_half && !C, "spq_qgemm_lse: needs float32 output with 16-byte aligned, padded rows and no residual");
         SPQ_REQUIRE(lse_ld >= 2 * ((N + bn - 1) / bn) && (reinterpret_cast<uintptr_t>(lse_part) & 7u) == 0, "spq_qgemm_lse: partials buffer too narrow");
+        if (pair) return launch_nt_pair<256, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 256) return launch_nt<256, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 128) return launch_nt<128, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         return launch_nt<64, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+    }
+    if (pair) {
+        if (d_is_half) return launch_nt_pair<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        if (ep.tma_store && C) return launch_nt_pair<256, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        return launch_nt_pair<256, false>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     }
     if (d_is_half) {
         if (bn == 256) return launch_nt<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);

@@ -32,5 +32,13 @@ for _ in range(reps):
     ref = A @ Bt
 e1.record(); torch.cuda.synchronize()
 ms_ref = e0.elapsed_time(e1) / reps
+ref32 = (A[:2048].float() @ B.float().t()) * cs + bias
+if resid:
+    ref32 = None
+if ref32 is not None and not gelu:
+    out.zero_(); _lib.qgemm(A, B, M, N, K, out, col_scale=cs, bias=bias)
+    err = ((out[:2048].float() - ref32).norm() / ref32.norm()).item()
+    bad = (out.float() - ((A.float() @ B.float().t()) * cs + bias)).abs().max().item() if M * N <= 2 ** 28 else float('nan')
+    print(f"rel err (first 2048 rows) {err:.2e}   max abs err (all rows) {bad:.3e}")
 print(f"cuBLAS   {M}x{N}x{K} out=f16: {ms_ref*1e3:.1f} us  {2.0*M*N*K/ms_ref/1e9:.0f} TFLOP/s")
 print(f"spq_qgemm {M}x{N}x{K} out={'f16' if half else 'f32'}{' +C' if resid else ''}{' +gelu' if gelu else ''}: {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s  watchdog {_lib.debug_status()}")
