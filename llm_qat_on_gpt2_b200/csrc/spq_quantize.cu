@@ -101,10 +101,11 @@ struct LogCol {           // per-channel constants, log
     float inv, c0;        // ln = sat(l * inv + c0),  inv = 1 / max(range, eps), c0 = -log_min * inv
     float band;           // |v_fast - v_exact| bound (see make_logcol)
     float out_add;        // added to the dequantised exponent: log2 of a power-of-two output multiplier
+    float e0;             // log_min + out_add
 };
 __device__ __forceinline__ LogCol make_logcol(float log_min, float log_range, const QParams& qp, float out_add = 0.f) {
     LogCol c;
-    c.log_min = log_min; c.log_range = log_range; c.out_add = out_add;
+    c.log_min = log_min; c.log_range = log_range; c.out_add = out_add; c.e0 = log_min + out_add;
     c.range_c = (log_range < LOG_EPS) ? LOG_EPS : log_range;          // :43 clamp(min=eps)
     c.inv = __frcp_rn(c.range_c);
     c.c0 = -log_min * c.inv;
@@ -150,7 +151,7 @@ __device__ __forceinline__ LogOut log_elem(float x, const LogCol& ch, const QPar
     o.level = r;
     // value (:50-74): qn = L/(2n) + 0.5 (symmetric) or L/n; 2^(qn * range + log_min) * sign, 0 under the zero mask
     const float qn = qp.symmetric ? fmaf(r, __frcp_rn(lev_mul), 0.5f) : r * __frcp_rn(nl);
-    const float mag = ex2_approx(fmaf(qn, ch.log_range, ch.log_min + ch.out_add));
+    const float mag = ex2_approx(fmaf(qn, ch.log_range, ch.e0));
     o.sign = zero ? 0.f : copysignf(1.0f, x);
     o.dq = zero ? 0.f : copysignf(mag, x);
     return o;
@@ -172,7 +173,7 @@ __device__ __forceinline__ float log_level_fast(float x, const LogCol& ch, const
 }
 __device__ __forceinline__ float log_value(float x, float r, const LogCol& ch, const QParams& qp, float inv_lev) {
     const float qn = qp.symmetric ? fmaf(r, inv_lev, 0.5f) : r * inv_lev;
-    const float mag = ex2_approx(fmaf(qn, ch.log_range, ch.log_min + ch.out_add));
+    const float mag = ex2_approx(fmaf(qn, ch.log_range, ch.e0));
     return (fabsf(x) < LOG_EPS) ? 0.f : copysignf(mag, x);
 }
 __device__ __forceinline__ float minmax_code_fast(float x, const MmCol& c, const QParams& qp, bool& tie) {
@@ -343,11 +344,17 @@ rowscale_kernel(ActArgs a) {
 // columns (their constants live in registers), block (32, 8) strides over rows with four 16-byte loads
 // in flight per thread; writes the quantised operand and, for the LoRA branch, the raw operand scaled
 // per COLUMN by a power of two derived from the calibrated bound (saturating conversion).
-template <int QTYPE, typename XT>
+// SYM / KIND >= 0: compile-time copies of qp.symmetric / operand_kind for the configurations the model uses
+// (symmetric quantisers; codes for min-max, dequantised values for log) -- the per-float4 uniform branches and
+// the duplicated code paths of the generic kernel cost ~10 % of its issue slots.
+template <int QTYPE, typename XT, int SYM = -1, int KIND = -1>
 __global__ void __launch_bounds__(256, 3)
 quantize_act_kernel(ActArgs a) {
     const long long c0 = (static_cast<long long>(blockIdx.x) * 32 + threadIdx.x) * 4;
     if (c0 >= a.K) return;
+    QParams qp = a.qp;                                 // (a copy: kernel parameters are read-only)
+    if constexpr (SYM >= 0) qp.symmetric = SYM;
+    const int kind = (KIND >= 0) ? KIND : a.operand_kind;
     MmCol mm[4];
     LogCol lg[4];
     float cm[4], rm[4];
@@ -358,28 +365,28 @@ quantize_act_kernel(ActArgs a) {
         cm[j] = (a.col_mul ? __ldg(a.col_mul + c0 + j) : 1.f) * a.mul;
         rm[j] = a.raw_col_mul ? __ldg(a.raw_col_mul + c0 + j) : 1.f;
         if constexpr (QTYPE == SPQ_MINMAX) mm[j] = make_mmcol(sc, zp);
-        else lg[j] = make_logcol(zp, sc, a.qp);
+        else lg[j] = make_logcol(zp, sc, qp);
     }
     const long long rstep = static_cast<long long>(gridDim.y) * 8;
-    const float nl_ = a.qp.symmetric ? a.qp.n_sym : a.qp.full;
-    const float inv_lev = __frcp_rn(a.qp.symmetric ? 2.f * nl_ : nl_);
-    const bool no_exact = (a.qp.debug & 1) != 0;
+    const float nl_ = qp.symmetric ? qp.n_sym : qp.full;
+    const float inv_lev = __frcp_rn(qp.symmetric ? 2.f * nl_ : nl_);
+    const bool no_exact = (qp.debug & 1) != 0;
     auto one = [&](long long r, const float4& v) {
         const float xv[4] = {v.x, v.y, v.z, v.w};
         float q[4];
         bool tie[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_fast(xv[j], mm[j], a.qp, tie[j]);
-            else q[j] = log_level_fast(xv[j], lg[j], a.qp, tie[j]);
+            if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_fast(xv[j], mm[j], qp, tie[j]);
+            else q[j] = log_level_fast(xv[j], lg[j], qp, tie[j]);
         }
         if ((tie[0] | tie[1] | tie[2] | tie[3]) && !no_exact) {           // rare: redo the flagged elements exactly
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (tie[j]) {
-                    if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_exact(xv[j], mm[j].s, mm[j].zp, a.qp.symmetric);
-                    else q[j] = log_level_exact(fmaxf(fabsf(xv[j]), LOG_EPS), lg[j].log_min, lg[j].range_c, a.qp.symmetric,
-                                                a.qp.n_sym, a.qp.full);
+                    if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_exact(xv[j], mm[j].s, mm[j].zp, qp.symmetric);
+                    else q[j] = log_level_exact(fmaxf(fabsf(xv[j]), LOG_EPS), lg[j].log_min, lg[j].range_c, qp.symmetric,
+                                                qp.n_sym, qp.full);
                 }
             }
         }
@@ -388,11 +395,12 @@ quantize_act_kernel(ActArgs a) {
         for (int j = 0; j < 4; ++j) {
             float base;
             if constexpr (QTYPE == SPQ_MINMAX) {
-                const float cen = minmax_centered(q[j], mm[j], a.qp);
-                base = (a.operand_kind == SPQ_OPERAND_CODE) ? cen : __fmul_rn(cen, mm[j].s);
+                const float cen = minmax_centered(q[j], mm[j], qp);
+                base = (kind == SPQ_OPERAND_CODE) ? cen : __fmul_rn(cen, mm[j].s);
             } else {
-                const float lvl = a.qp.symmetric ? fminf(fmaxf(q[j], -nl_), nl_) : fminf(fmaxf(q[j], 0.f), nl_);
-                base = (a.operand_kind == SPQ_OPERAND_CODE) ? lvl : log_value(xv[j], lvl, lg[j], a.qp, inv_lev);
+                // q is already in range: the fast path rounds v = sat(.) * 2n - n (or sat(.) * n), the exact path clamps
+                const float lvl = q[j];
+                base = (kind == SPQ_OPERAND_CODE) ? lvl : log_value(xv[j], lvl, lg[j], qp, inv_lev);
             }
             o[j] = base * cm[j];
         }
@@ -519,8 +527,15 @@ static int launch_act(const ActArgs& a, cudaStream_t st) {
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
-    if (a.x_half) quantize_act_kernel<QTYPE, __half><<<dim3(gx, static_cast<unsigned>(gy)), dim3(32, 8), 0, st>>>(a);
-    else quantize_act_kernel<QTYPE, float><<<dim3(gx, static_cast<unsigned>(gy)), dim3(32, 8), 0, st>>>(a);
+    const dim3 grid(gx, static_cast<unsigned>(gy)), block(32, 8);
+    constexpr int HOT_KIND = (QTYPE == SPQ_MINMAX) ? SPQ_OPERAND_CODE : SPQ_OPERAND_DEQUANT;
+    if (a.qp.symmetric && a.operand_kind == HOT_KIND) {
+        if (a.x_half) quantize_act_kernel<QTYPE, __half, 1, HOT_KIND><<<grid, block, 0, st>>>(a);
+        else quantize_act_kernel<QTYPE, float, 1, HOT_KIND><<<grid, block, 0, st>>>(a);
+    } else {
+        if (a.x_half) quantize_act_kernel<QTYPE, __half><<<grid, block, 0, st>>>(a);
+        else quantize_act_kernel<QTYPE, float><<<grid, block, 0, st>>>(a);
+    }
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
