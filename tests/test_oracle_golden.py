@@ -176,3 +176,14 @@ def test_tiny_model_against_reference():
         assert rel_fro(logits, g[f"logits{b}"]) <= 2e-2
     with pytest.raises(ValueError):
         m.set_precision(5)
+
+
+def test_distillation_loss_oracle_matches_reference_fixture():
+    """oracle.train_oracle.distillation_loss vs DistillationManager.compute_distillation_loss of the unmodified
+    reference (float32 torch on CPU): loss to 1e-6 relative, gradient to 1e-6 of its largest entry."""
+    from oracle.train_oracle import distillation_loss
+    g = np.load(os.path.join(GOLDEN, "distill_kl.npz"))
+    loss, grad = distillation_loss(g["s_logits"], g["t_logits"], float(g["temperature"]), float(g["alpha_kl"]),
+                                   float(g["alpha_feature"]), g["s_hidden"], g["t_hidden"])
+    assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert np.abs(grad - g["grad"]).max() <= 1e-6 * np.abs(g["grad"]).max()
