@@ -497,7 +497,7 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     import torch.distributed as dist
     from llm_qat_on_gpt2_b200 import _lib, dp
     import random
-    from llm_qat_on_gpt2_b200.training import LoRARefresher, distillation_loss
+    from llm_qat_on_gpt2_b200.training import GraphedNoGradForward, LoRARefresher, distillation_loss
     B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
     model.train()
     for n, p in model.named_parameters():
@@ -505,6 +505,7 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
     refresher = LoRARefresher(linears, BITS)
+    teacher = GraphedNoGradForward(model, output_hidden_states=True, return_dict=True)
     layer_rng = random.Random(7 + rank)
     gen = torch.Generator().manual_seed(99 + rank)
     # the input quantisers keep the calibration of the last forward step (static during training)
@@ -512,7 +513,7 @@ def train_section(args, model, linears, key, dev, world, rank, group, barrier):
     def one_step(ids):
         with torch.no_grad():
             model.set_precision(32)
-            t_out = model(ids, output_hidden_states=True, return_dict=True)
+            t_out = teacher(ids)              # 32-bit teacher forward: one CUDA-graph replay
             refresher.refresh()       # LoRA recalibration + operand rebuild: one CUDA-graph replay (parameters are
                                       # replicated, so no statistics exchange is needed)
         model.set_precision(BITS)

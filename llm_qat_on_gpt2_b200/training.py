@@ -144,3 +144,37 @@ def distillation_loss(student_outputs, teacher_outputs, temperature: float = 3.0
                 l = (rng or random).choice(layers)
                 feature = F.mse_loss(hs[l], ht[l], reduction='mean')
     return alpha_kl * kl if feature is None else alpha_kl * kl + alpha_feature * feature
+
+
+class GraphedNoGradForward:
+    """`model(ids, **kwargs)` under no_grad with fixed shapes -- the 32-bit teacher forward of the distillation step
+    (p1/distillation_manager.py:34-62) -- replayed as ONE CUDA graph: ~200 launches of the eager forward become one.
+    The precision must be set before the first call (the captured launches are those of that precision) and the
+    returned tensors are static buffers, overwritten by the next call."""
+
+    def __init__(self, model, **kwargs):
+        self.model, self.kwargs = model, kwargs
+        self.graph = None
+        self.ids = None
+        self.out = None
+        self._sig = None
+
+    def _signature(self, ids):
+        return (tuple(ids.shape), ids.dtype, self.model.training, self.model.get_current_precision()
+                if hasattr(self.model, 'get_current_precision') else None)
+
+    def __call__(self, ids):
+        sig = self._signature(ids)
+        if self.graph is None or sig != self._sig:
+            self.ids = ids.clone()
+            with torch.no_grad():
+                for _ in range(2):                         # warm-up: operand caches, cuDNN plans, allocator
+                    self.model(self.ids, **self.kwargs)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.out = self.model(self.ids, **self.kwargs)
+            self.graph, self._sig = g, sig
+        self.ids.copy_(ids)
+        self.graph.replay()
+        return self.out

@@ -614,3 +614,23 @@ def test_gpt2_small_against_oracle(bits):
     print(f"gpt2-small {bits}-bit: loss {out['loss'].item():.5f} vs oracle {want_loss:.5f}")
     assert cos >= (0.95 if bits == 4 else 0.98), cos
     assert abs(out["loss"].item() - want_loss) <= 2e-2 * want_loss, (out["loss"].item(), want_loss)
+
+
+@pytest.mark.gpu
+def test_graphed_no_grad_forward_equals_eager():
+    """training.GraphedNoGradForward: the CUDA-graph replay of a 32-bit (teacher) forward returns the eager result
+    bit for bit, for new token ids on every call."""
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel
+    from llm_qat_on_gpt2_b200.training import GraphedNoGradForward
+    torch.manual_seed(2)
+    model = SPLMHeadModel(_tiny_config()).cuda().eval()
+    model.set_precision(32)
+    teacher = GraphedNoGradForward(model, output_hidden_states=True, return_dict=True)
+    for step in range(3):
+        ids = torch.randint(0, 211, (2, 32), device="cuda")
+        got = teacher(ids)
+        with torch.no_grad():
+            want = model(ids, output_hidden_states=True, return_dict=True)
+        assert torch.equal(got["logits"], want["logits"]), step
+        assert all(torch.equal(a, b) for a, b in zip(got["hidden_states"], want["hidden_states"]))
+    assert teacher.graph is not None
