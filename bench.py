@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (weak scaling)")
     ap.add_argument("--seq", type=int, default=1024)
-    ap.add_argument("--cpu-sample-batch", type=int, default=1, help="sequences in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2,
+                    help="sequences (of --seq tokens) per step in the bounded CPU-arm sample; the GPU arm runs --batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=3,
                     help="optimizer steps of the distillation training step timed after the main metric (0 = skip)")
@@ -127,6 +128,16 @@ def cpu_threads():
 
 
 def run_cpu_baseline(sample_batch, seq, steps=1, warmup=0):
+    """The CPU arm: the UNMODIFIED upstream SPLMHeadModel on torch-CPU (baseline/_ref, `kind: reference`) on a bounded
+    sample of the workload; the numpy port (`kind: port`, ~4x slower than upstream) only when that copy is absent."""
+    from oracle import upstream
+    if upstream.available() and not os.environ.get("SPQ_CPU_PORT"):
+        from oracle.upstream_workload import UpstreamForwardWorkload, host_threads
+        w = UpstreamForwardWorkload(BITS, MODEL, BIT_WIDTHS, QUANTIZER_PER_BIT, LORA_RANK[BITS], sample_batch, seq)
+        dt, loss = w.run(steps, warmup)
+        import torch
+        return {"value": sample_batch * seq * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+                "os_cpu_count": os.cpu_count(), "kind": "reference", "sample": w.describe(steps, dt)}, dt / max(steps, 1), loss
     w = CpuWorkload(sample_batch, seq)
     for _ in range(warmup):
         w.step()
@@ -137,24 +148,25 @@ def run_cpu_baseline(sample_batch, seq, steps=1, warmup=0):
     dt = time.perf_counter() - t0
     return {"value": sample_batch * seq * steps / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
             "sample": f"{steps} step(s) of calibration pass + forward on {sample_batch} x {seq} tokens "
-                      f"(numpy oracle, BLAS threads = host cores), {dt:.1f} s"}, dt / max(steps, 1), loss
+                      f"(numpy oracle -- baseline/_ref absent, BLAS threads = host cores), {dt:.1f} s"}, dt / max(steps, 1), loss
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (numpy / BLAS read
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (torch / numpy / BLAS read
     # these at import time, and nothing numeric has been imported yet in this process)
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[var] = str(cpu_threads())
-    base, sec_per_step, _ = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=args.steps, warmup=min(args.warmup, 1))
+    base, sec_per_step, loss = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": base["sample"]},
-        "cpu_baseline": base,
+        "config": {"workload": workload_name(args), "sample": base["sample"],
+                   "sample_batch": args.cpu_sample_batch, "seq_len": args.seq},
+        "cpu_baseline": base, "loss": loss,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

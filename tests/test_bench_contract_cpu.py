@@ -1,4 +1,5 @@
-"""bench.py contract on CPU: the reference arm (numpy oracle on the host cores) prints ONE JSON line with the keys
+"""bench.py contract on CPU: the reference arm (the unmodified upstream model from baseline/_ref on torch-CPU; the
+numpy port only when that copy is absent) prints ONE JSON line with the keys
 the driver reads, on the GPU arm's metric / unit / config; ranks other than 0 stay silent; the GPU arm fails
 loudly without a device (no CPU fallback)."""
 import json
@@ -28,8 +29,18 @@ def test_reference_arm_prints_the_contract_line():
         assert key in d, key
     assert d["value"] > 0 and "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    from oracle import upstream
+    assert cb["kind"] == ("reference" if upstream.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["warmup"] == 0 and d["steps"] == 1                      # the arm runs exactly the K / W it was given
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_port_fallback():
+    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--seq", "32", "--cpu-sample-batch", "1"],
+             env={"SPQ_CPU_PORT": "1"})
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert json.loads(p.stdout.strip().splitlines()[-1])["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_are_silent():
