@@ -8,6 +8,11 @@
  * SPQ_OK (0) or an error code; spq_last_error() gives the message.  There is no CPU fallback:
  * on a machine without an sm_100 device the compute entry points return SPQ_ERR_CUDA.
  *
+ * Process model: ONE PROCESS PER GPU (the data-parallel layout of this path).  The SM count, the
+ * co-resident cluster count of the CTA-pair GEMM and the per-kernel shared-memory attributes are
+ * cached process-wide for the device that is current at the first call; driving several devices
+ * from one process through this library is not supported.
+ *
  * The reference (Laurence-Wu/LLM-QAT-on-gpt2) has no FFI; its boundary for this path is the
  * Python class API of part1_switchable_precision.  Each entry point below names the reference
  * code it replaces (file:line relative to the upstream repo root, p1 =
@@ -43,7 +48,10 @@ SPQ_API int spq_abi_version(void);
 SPQ_API const char* spq_last_error(void);
 /* sm count and compute capability of the current device */
 SPQ_API int spq_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* device-side watchdog: nonzero if a GEMM pipeline wait ever timed out (synchronises) */
+/* device-side watchdog (synchronises).  A GEMM pipeline wait that times out (seconds) TRAPS the kernel: the launch
+ * fails and every later CUDA call of the process -- this one included -- returns the error, so a stalled pipeline
+ * can neither hang the GPU nor produce a number.  *aborted_host reports the residual flag (2 = the dynamic
+ * shared-memory base was not 1024-byte aligned). */
 SPQ_API int spq_debug_status(int* aborted_host);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 SPQ_API int64_t spq_launch_count(void);

@@ -59,19 +59,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a broken pipeline must never hang the GPU.  On timeout the watchdog flag is set
-// and every later wait in the grid falls through, so the kernel terminates (with garbage output
-// and spq_debug_status() != 0).
+// Bounded wait: a broken pipeline must never hang the GPU, and must never pass silently.  On timeout (2^24
+// failed try_waits, seconds) the kernel TRAPS: the launch fails, the CUDA context reports the error at the next
+// synchronising call of the process (torch raises, bench.py exits non-zero without a JSON line), and no later
+// kernel can run on garbage.  g_abort is kept for the mis-aligned-smem guard (spq_debug_status()).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     for (uint32_t it = 0;; ++it) {
         if (mbar_try_wait(bar, parity)) return;
-        if ((it & 1023u) == 1023u) {
-            if (*reinterpret_cast<volatile int*>(&g_abort)) return;
-            if (it >= SPIN_LIMIT) {
-                atomicExch(&g_abort, 1);
-                return;
-            }
+        if ((it & 1023u) == 1023u && it >= SPIN_LIMIT) {
+            atomicExch(&g_abort, 1);
+            __trap();
         }
     }
 }
@@ -285,7 +283,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // the 128B swizzle of TMA / UMMA / the staging tiles assumes a 1024 B aligned base
     if ((smem_u32(smem) & 1023u) != 0) {
         if (threadIdx.x == 0) atomicExch(&g_abort, 2);
-        return;
+        __trap();
     }
 
     if (warp == 0 && lane == 0) {

@@ -66,7 +66,19 @@ def sync_calibration_stats(quantizers, group=None) -> None:
     """MIN / MAX all-reduce of the statistics collected so far by `quantizers` (objects with
     temp_min / temp_max / _stat_state), batched into two collectives plus one for the flags."""
     qs = [q for q in quantizers if q.temp_min is not None]
-    if not qs or _world(group) == 1:
+    if _world(group) == 1:
+        return
+    # every rank must bring the same quantisers (same count, same total width): a rank that collected nothing for
+    # one of them would otherwise hang or silently mis-align the bucket
+    mine = torch.tensor([len(qs), sum(q.temp_min.numel() for q in qs)], dtype=torch.int64,
+                        device=qs[0].temp_min.device if qs else _any_device(quantizers))
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        raise RuntimeError(f"sync_calibration_stats: ranks disagree on the collected quantisers "
+                           f"(this rank {mine.tolist()}, min {lo.tolist()}, max {hi.tolist()})")
+    if not qs:
         return
     mins = torch.cat([q.temp_min.reshape(-1) for q in qs])
     maxs = torch.cat([q.temp_max.reshape(-1) for q in qs])
@@ -88,13 +100,27 @@ def sync_calibration_stats(quantizers, group=None) -> None:
             foff += 1
 
 
+def _any_device(quantizers):
+    for q in quantizers:
+        st = getattr(q, "_stat_state", None)
+        if st is not None:
+            return st.device
+        buf = getattr(q, "scale", None)
+        if buf is not None:
+            return buf.device
+    return torch.device("cpu")
+
+
 def install_calibration_sync(model: torch.nn.Module, group=None) -> int:
-    """Make every LearnableFakeQuantize of `model` all-reduce its statistics inside its own
-    finish_calibration (so the reference's unmodified CalibrationManager becomes DP-correct).
-    One pair of small collectives per quantiser; `finish_calibration_many` is the batched form."""
+    """Make every ACTIVATION quantiser of `model` (is_input=True: the only statistics that depend on the batch
+    shard) all-reduce its statistics inside its own finish_calibration, so the reference's unmodified
+    CalibrationManager becomes DP-correct.  Weight and LoRA quantisers see replicated parameters and need no
+    exchange -- leaving them unhooked also keeps them eligible for the one-launch `calibrate_many` /
+    `training.LoRARefresher` path.  One pair of small collectives per quantiser; `finish_calibration_many` is the
+    batched form."""
     n = 0
     for m in model.modules():
-        if m.__class__.__name__ == "LearnableFakeQuantize":
+        if m.__class__.__name__ == "LearnableFakeQuantize" and getattr(m, "is_input", False):
             m.stats_sync_hook = lambda q, tmin, tmax, _g=group: sync_calibration_stats([q], _g)
             n += 1
     return n

@@ -294,16 +294,23 @@ def calibrate_many(quantizers, tensors, defer: bool = False):
             rows_b.append(struct.pack(_lib.CALIB_JOB_FORMAT, x2d.data_ptr(), rows, cols, q.running_min.data_ptr(),
                                       q.running_max.data_ptr(), q.scale.data_ptr(), q.zero_point.data_ptr(), bcast,
                                       _lib.QTYPE[q.quantizer_type], int(q.symmetric), levels, float(q.eps), 0))
+        if defer and torch.cuda.is_current_stream_capturing():
+            # building the job table is a pageable host->device copy: not capturable.  LoRARefresher runs the same
+            # call eagerly before it captures, so a miss here means the addresses changed in between
+            raise RuntimeError("calibrate_many(defer=True): job table not built yet; run the call once outside "
+                               "the CUDA-graph capture")
         table = torch.frombuffer(bytearray(b"".join(rows_b)), dtype=torch.uint8).to(dev)
         ent = (table, len(rows_b), max_blocks, torch.zeros(len(rows_b), dtype=torch.int32, device=dev))
-        if len(_calib_tables) > 64:
-            _calib_tables.clear()
+        while len(_calib_tables) >= 64:
+            # evict the oldest entry only; a captured graph that launches with an evicted table keeps it alive
+            # through the `finish` closure it holds (tables carry raw device pointers)
+            _calib_tables.pop(next(iter(_calib_tables)))
         _calib_tables[key] = ent
     table, n_jobs, max_blocks, flags = ent
     if n_jobs:
         _lib.calibrate_many(table, n_jobs, max_blocks, flags)
 
-    def finish() -> int:
+    def finish(_keep=ent) -> int:                         # _keep: the job table outlives any cache eviction
         got = flags.tolist() if n_jobs else []            # the one device->host read
         it = iter(got)
         redone = 0

@@ -150,7 +150,13 @@ class GraphedNoGradForward:
     """`model(ids, **kwargs)` under no_grad with fixed shapes -- the 32-bit teacher forward of the distillation step
     (p1/distillation_manager.py:34-62) -- replayed as ONE CUDA graph: ~200 launches of the eager forward become one.
     The precision must be set before the first call (the captured launches are those of that precision) and the
-    returned tensors are static buffers, overwritten by the next call."""
+    returned tensors are static buffers, overwritten by the next call.
+
+    The capture hard-wires the fp16 weight operands the model's caches held at capture time.  Upstream trains the
+    base linears and every LayerNorm pair at the teacher width (models_sp.unfreeze_weights(32)), so the signature
+    covers (data_ptr, _version) of every parameter and buffer the forward reads: any optimizer update, `.data`
+    assignment or recalibration recaptures, and the graph keeps its own references to the cached operands so that
+    an eager forward rebuilding a cache in between cannot free memory a replay would read."""
 
     def __init__(self, model, **kwargs):
         self.model, self.kwargs = model, kwargs
@@ -158,10 +164,28 @@ class GraphedNoGradForward:
         self.ids = None
         self.out = None
         self._sig = None
+        self._keep = None
 
     def _signature(self, ids):
-        return (tuple(ids.shape), ids.dtype, self.model.training, self.model.get_current_precision()
-                if hasattr(self.model, 'get_current_precision') else None)
+        prec = self.model.get_current_precision() if hasattr(self.model, 'get_current_precision') else None
+        tensors = tuple((t.data_ptr(), t._version) for t in self.model.parameters())
+        gens = tuple(m.generation for m in self.model.modules() if hasattr(m, 'generation'))
+        return (tuple(ids.shape), ids.dtype, self.model.training, prec, tensors, gens)
+
+    def _cached_operands(self):
+        keep = []
+        for m in self.model.modules():
+            for attr in ('_fp_cache', '_lm_head_cache'):
+                c = getattr(m, attr, None)
+                if c is not None:
+                    keep.append((c.fwd, c.bwd))
+            oc = getattr(m, '_op_cache', None)
+            if oc:
+                keep.append({b: dict(ent) for b, ent in oc.items()})
+            cc = getattr(m, '_calib_cache', None)
+            if cc:
+                keep.append(dict(cc))
+        return keep
 
     def __call__(self, ids):
         sig = self._signature(ids)
@@ -174,7 +198,7 @@ class GraphedNoGradForward:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self.out = self.model(self.ids, **self.kwargs)
-            self.graph, self._sig = g, sig
+            self.graph, self._sig, self._keep = g, sig, self._cached_operands()
         self.ids.copy_(ids)
         self.graph.replay()
         return self.out
