@@ -232,6 +232,21 @@ SPQ_API int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* t_l
 SPQ_API int spq_cross_entropy_fwd(const float* logits, int64_t M, int64_t V, int64_t ld, const int64_t* targets,
                           int64_t ignore_index, float* row_loss, float* row_valid, spq_stream_t stream);
 
+/* ---- optimiser step of the SP training step on flat buffers -----------------------------
+ * Replaces `scaler.unscale_; clip_grad_norm_(model.parameters(), 1.0); AdamW.step` of p1/train_sp.py:390-393 for
+ * the path's trainable parameters (LoRA A/B, LayerNorm pairs) when they live in one flat fp32 buffer (their .grad
+ * tensors are slices of a second one, which is also what the data-parallel all-reduce sends).
+ * spq_grad_sumsq: out_sumsq[0] = scale^2 * sum g[i]^2, fixed-order tree (bitwise reproducible).
+ * spq_adamw_flat: one pass over a segment; g' = g * grad_scale * min(1, max_norm / (sqrt(total_sumsq[0]) + 1e-6))
+ * (max_norm <= 0 or total_sumsq NULL: no clipping), then torch.optim.AdamW's update with decoupled weight decay
+ * and bias corrections for `step` (1-based count of updates this segment has received). */
+SPQ_API size_t spq_sumsq_workspace_bytes(void);
+SPQ_API int spq_grad_sumsq(const float* g, int64_t n, float scale, float* out_sumsq, void* workspace, size_t workspace_bytes,
+                   spq_stream_t stream);
+SPQ_API int spq_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                   const float* total_sumsq, float max_norm, spq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

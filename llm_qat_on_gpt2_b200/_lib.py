@@ -64,6 +64,10 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "spq_cross_entropy_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_rowscale_f16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "spq_sumsq_workspace_bytes": (c_size_t, []),
+    "spq_grad_sumsq": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "spq_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
+                               c_int64, c_float, c_void_p, c_float, c_void_p]),
 }
 
 _lib = None
@@ -356,6 +360,29 @@ def rowscale_f16(g2d, out, row_scale):
     assert out.stride(-1) == 1 and g2d.is_contiguous() and g2d.dtype in (torch.float32, torch.float16)
     _check(load_library().spq_rowscale_f16(g2d.data_ptr(), int(g2d.dtype == torch.float16), M, N, out.data_ptr(), out.stride(0), row_scale.data_ptr(),
                                            _stream()), "spq_rowscale_f16")
+
+
+def grad_sumsq(flat_grad: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    """out[0] = scale^2 * sum(flat_grad^2), deterministic."""
+    lib = load_library()
+    _req_cuda(flat_grad, out)
+    assert flat_grad.dtype == torch.float32 and flat_grad.is_contiguous() and out.dtype == torch.float32
+    ws = _workspace(lib.spq_sumsq_workspace_bytes(), flat_grad.device, "sumsq")
+    _check(lib.spq_grad_sumsq(flat_grad.data_ptr(), flat_grad.numel(), float(scale), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _stream()), "spq_grad_sumsq")
+
+
+def adamw_flat(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.0, total_sumsq=None,
+               max_norm=0.0):
+    """In-place AdamW on one flat float32 segment (see include/spq_b200.h)."""
+    _req_cuda(param, grad, exp_avg, exp_avg_sq, total_sumsq)
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (param, grad, exp_avg, exp_avg_sq))
+    _check(load_library().spq_adamw_flat(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+                                         float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                         int(step), float(grad_scale), _ptr(total_sumsq), float(max_norm), _stream()),
+           "spq_adamw_flat")
 
 
 def empty_f16_padded(rows: int, cols: int, device) -> torch.Tensor:

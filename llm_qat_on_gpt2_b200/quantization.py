@@ -310,16 +310,22 @@ def calibrate_many(quantizers, tensors, defer: bool = False):
     if n_jobs:
         _lib.calibrate_many(table, n_jobs, max_blocks, flags)
 
-    def finish(_keep=ent) -> int:                         # _keep: the job table outlives any cache eviction
+    def finish(redo: bool = True, _keep=ent) -> int:      # _keep: the job table outlives any cache eviction
+        """redo=False (whole-step CUDA graphs, training.SPTrainer): a log quantiser whose tensor had nothing above
+        eps keeps what the kernel wrote -- log2(eps) statistics and a zero range in the per-channel layout, the same
+        VALUES as the reference's default-shape quirk (p1/quantization.py:164-172, 194-197), so every dequantised
+        number is identical; only the buffer shape differs until the next eager calibration."""
         got = flags.tolist() if n_jobs else []            # the one device->host read
         it = iter(got)
         redone = 0
         for (q, w), lay in zip(fast, layouts):
             had = next(it) if lay is not None else 0
-            if lay is None or not had:
+            if lay is None or (not had and redo):
                 q.start_calibration(); q(w); q.finish_calibration()       # no data above eps / odd layout
                 redone += 1
                 continue
+            if not had:
+                redone += 1
             q.calibrated = True
             q.collecting_stats = False
             q.num_batches_collected = 1

@@ -50,6 +50,30 @@ class LoRARefresher:
         calibrate_many(self.quantizers, [w.data for w in self.weights])
         self._build_all()
 
+    # pieces a larger capture (SPTrainer's whole micro-step graph) composes ------------------------------------
+    def invalidate(self):
+        """Drop the LoRA-level cache entries so that the next `body()` rebuilds them (inside a capture: into the
+        graph's private pool, where every replay rewrites them in place)."""
+        for m, _ in self.active:
+            m._op_cache.get(self.bits, {}).pop('lora', None)
+            ent = m._op_cache.get(self.bits, {}).get('input')
+            if ent is not None:
+                ent['lora'] = None
+
+    def body(self):
+        """The device work of one refresh, host-sync free (capturable): one calibration launch for all LoRA
+        quantisers + the operand rebuild.  Returns the deferred host part (flag read, quantiser bookkeeping)."""
+        with torch.no_grad():
+            fin = calibrate_many(self.quantizers, [w.data for w in self.weights], defer=True)
+            for q in self.quantizers:                     # the rebuild must see "calibrated" quantisers
+                q.calibrated, q.collecting_stats = True, False
+            self._build_all()
+        return fin
+
+    def restamp(self):
+        for m, _ in self.active:
+            m._restamp_lora_keys(self.bits, self.with_bwd)
+
     def refresh(self) -> None:
         """Recalibrate the active LoRA quantisers on the current LoRA weights and rebuild every operand that
         depends on them, for all linears."""
@@ -63,16 +87,9 @@ class LoRARefresher:
                 self._eager()
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                for m, _ in self.active:                      # force a rebuild of the LoRA levels inside the capture
-                    m._op_cache.get(self.bits, {}).pop('lora', None)
-                    ent = m._op_cache.get(self.bits, {}).get('input')
-                    if ent is not None:
-                        ent['lora'] = None
+                self.invalidate()                             # force a rebuild of the LoRA levels inside the capture
                 with torch.cuda.graph(g):
-                    fin = calibrate_many(self.quantizers, [w.data for w in self.weights], defer=True)
-                    for q in self.quantizers:                 # the captured rebuild must see "calibrated" quantisers
-                        q.calibrated, q.collecting_stats = True, False
-                    self._build_all()
+                    fin = self.body()
                 self.graph, self.finish, self._sig = g, fin, self._signature()
             self.graph.replay()
             redone = self.finish()
@@ -82,8 +99,7 @@ class LoRARefresher:
                 self._build_all()
                 self._sig = None
             else:
-                for m, _ in self.active:
-                    m._restamp_lora_keys(self.bits, self.with_bwd)
+                self.restamp()
 
 
 class _DistillKL(torch.autograd.Function):
@@ -165,11 +181,28 @@ class GraphedNoGradForward:
         self.out = None
         self._sig = None
         self._keep = None
+        self._params_for = {}
+
+    def _read_params(self, prec):
+        """Parameters a forward at `prec` reads: everything except the LoRA adapters and LayerNorm pairs of OTHER
+        precisions (those change every optimizer step of a student width and must not force a recapture)."""
+        got = self._params_for.get(prec)
+        if got is None:
+            got = []
+            for n, p in self.model.named_parameters():
+                parts = n.split('.')
+                if 'lora_adapters' in parts and (prec is None or prec >= 32 or f'{prec}bit' not in parts):
+                    continue
+                if len(parts) >= 2 and parts[-2] in ('weights', 'biases') and prec is not None and parts[-1] != str(prec):
+                    continue
+                got.append(p)
+            self._params_for[prec] = got
+        return got
 
     def _signature(self, ids):
         prec = self.model.get_current_precision() if hasattr(self.model, 'get_current_precision') else None
-        tensors = tuple((t.data_ptr(), t._version) for t in self.model.parameters())
-        gens = tuple(m.generation for m in self.model.modules() if hasattr(m, 'generation'))
+        tensors = tuple((t.data_ptr(), t._version) for t in self._read_params(prec))
+        gens = tuple(m.generation for m in self.model.modules() if hasattr(m, 'generation')) if (prec or 32) < 32 else ()
         return (tuple(ids.shape), ids.dtype, self.model.training, prec, tensors, gens)
 
     def _cached_operands(self):
@@ -202,3 +235,308 @@ class GraphedNoGradForward:
         self.ids.copy_(ids)
         self.graph.replay()
         return self.out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The switchable-precision training step (BASELINE.json configs[2]; p1/train_sp.py:341-397)
+# ----------------------------------------------------------------------------------------------------------------
+
+class FlatTrainState:
+    """The path's trainable parameters -- LoRA A/B of every student width and every LayerNorm pair of the widths in
+    use (north_star (d); README.md:108-112 of the reference) -- laid out in ONE flat float32 buffer, grouped in
+    segments: [LayerNorm pairs of the teacher width | per student width b: LayerNorm pairs @b, LoRA A/B @b].
+
+      * `p.data` of each parameter is a view into `flat_param`, `p.grad` a view into `flat_grad`: autograd
+        accumulates straight into the buffer the NCCL all-reduce sends (no pack / scatter kernels, no `.grad`
+        reallocation, static addresses for CUDA graphs);
+      * AdamW state (`exp_avg`, `exp_avg_sq`) is flat too; a segment is updated only in optimizer steps in which it
+        received a gradient, with its own step count -- what torch.optim.AdamW does for parameters whose .grad is
+        None after `zero_grad(set_to_none=True)` (p1/train_sp.py:344).
+    Everything else in the model is frozen (requires_grad=False)."""
+
+    def __init__(self, model, teacher_bits, student_bits):
+        self.model = model
+        segs = {teacher_bits: []}
+        for b in student_bits:
+            segs[b] = []
+        frozen = []
+        for name, p in model.named_parameters():
+            parts = name.split('.')
+            seg = None
+            if 'lora_adapters' in parts:
+                b = int(parts[parts.index('lora_adapters') + 1][:-3])
+                if b in student_bits and parts[-1] in ('lora_A', 'lora_B'):
+                    seg = b
+            elif len(parts) >= 2 and parts[-2] in ('weights', 'biases') and parts[-1].isdigit() and int(parts[-1]) in segs:
+                seg = int(parts[-1])
+            if seg is None:
+                frozen.append(p)
+            else:
+                segs[seg].append((name, p))
+        dev = next(model.parameters()).device
+        total, self.segments, self.slots = 0, {}, {}
+        for key, items in segs.items():
+            start = total
+            for name, p in items:
+                self.slots[name] = (p, total, p.numel())
+                total += (p.numel() + 3) // 4 * 4
+            self.segments[key] = (start, total)
+        self.numel = total
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.steps = {k: 0 for k in self.segments}
+        with torch.no_grad():
+            for p in frozen:
+                p.requires_grad_(False)
+            for name, (p, off, n) in self.slots.items():
+                view = self.flat_param[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.requires_grad_(True)
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+        self.params = [p for p, _, _ in self.slots.values()]
+
+    def seg_grad(self, key):
+        a, b = self.segments[key]
+        return self.flat_grad[a:b]
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p, off, n in self.slots.values():             # something replaced a .grad (set_to_none, a new tensor)
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+
+    def bump_versions(self):
+        """The fused optimiser writes through raw pointers: tell torch (and the operand caches keyed on
+        `_version`) that the parameters changed."""
+        inc = torch.autograd.graph.increment_version
+        for p in self.params:
+            inc(p)
+
+
+class SPTrainer:
+    """One optimizer step of upstream's switchable-precision training (`train_step`, p1/train_sp.py:341-397) on
+    this repo's modules, batch-sharded data parallel:
+
+        zero_grad                                                                 :344
+        micro-step 0      : teacher width, CE loss with labels = ids, backward;   :354-356, 320-323
+                            then a no-grad forward whose logits + 13 hidden states are the distillation targets
+                            (DistillationManager.update_teacher)                   :325-326, distillation_manager.py:34-62
+        micro-steps 1..G-1: width = random.choice(student widths); LoRA quantisers recalibrated on their weights
+                            (calibrate_lora_only); forward; KL(T) * T^2 + 1e-7 * MSE(one random hidden layer);
+                            backward                                               :357-380, distillation_manager.py:64-116
+        every loss is divided by G (gradient accumulation)                         :339
+        clip_grad_norm_(1.0); AdamW step; cosine LR advanced once per micro-step   :380, 390-393
+
+    B200 mapping: each micro-step (recalibration + forward + loss + backward) is ONE CUDA-graph replay per width;
+    gradients accumulate into `FlatTrainState.flat_grad`; a segment's all-reduce (NCCL over NVLink, async) is
+    launched right after the LAST micro-step that touches it, so it overlaps the remaining micro-steps and only
+    the final width's segment is exposed; 1/world and the clip coefficient are folded into the fused AdamW kernel
+    (`spq_grad_sumsq`, `spq_adamw_flat`).  Upstream's GradScaler is a no-op here (gradients are float32; its
+    power-of-two scale cancels exactly) and is not reproduced; the teacher cache of DistillationManager is the
+    static output of the teacher graph.  All ranks draw the same widths / feature layers from `rng`."""
+
+    def __init__(self, model, bit_widths, *, grad_accum=8, lr=1e-4, weight_decay=0.01, betas=(0.9, 0.999), eps=1e-8,
+                 max_grad_norm=1.0, temperature=3.0, alpha_kl=1.0, alpha_feature=1e-7, total_lr_steps=None,
+                 group=None, rng=None, use_graphs=True):
+        import random
+        self.model = model
+        self.teacher_bits = max(bit_widths)
+        self.student_bits = [b for b in bit_widths if b != self.teacher_bits]
+        self.G, self.lr0, self.wd, self.betas, self.eps = grad_accum, lr, weight_decay, betas, eps
+        self.max_norm, self.T, self.alpha_kl, self.alpha_feature = max_grad_norm, temperature, alpha_kl, alpha_feature
+        self.total_lr_steps = total_lr_steps
+        self.group = group
+        self.rng = rng if rng is not None else random.Random(0)
+        self.use_graphs = use_graphs
+        self.world = torch.distributed.get_world_size(group) if (torch.distributed.is_available()
+                                                                  and torch.distributed.is_initialized()) else 1
+        self.state = FlatTrainState(model, self.teacher_bits, self.student_bits)
+        linears = [m for m in model.modules() if m.__class__.__name__ == 'SPLinearWithLoRA']
+        self.refreshers = {b: LoRARefresher(linears, b) for b in self.student_bits}
+        self.dev = self.state.flat_param.device
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.loss_buf = torch.zeros(grad_accum, 2, dtype=torch.float32, device=self.dev)
+        self.ids = None
+        self.graphs, self.outs, self.finishers, self.sigs = {}, {}, {}, {}
+        self._frozen = None
+        self.pool = None
+        self.micro_steps_done = 0
+        self.n_hidden = None
+        self.phase_events = None          # set to a list to record (name, start_event, end_event) per phase
+
+    # ------------------------------------------------------------------------------------------ bodies
+    def _teacher_body(self):
+        m = self.model
+        m.set_precision(self.teacher_bits)
+        self._mark_inner('teacher_forward')
+        out = m(self.ids, labels=self.ids, output_hidden_states=True, return_dict=True)
+        loss = out['loss'] / self.G
+        self._mark_inner('teacher_backward')
+        loss.backward()
+        self._mark_inner('teacher_cache_forward')
+        with torch.no_grad():                                              # DistillationManager.update_teacher
+            t = m(self.ids, output_hidden_states=True, return_dict=True)
+        return {'loss': loss.detach().reshape(1), 'logits': t['logits'], 'hidden': t['hidden_states']}
+
+    def _student_body(self, bits):
+        import torch.nn.functional as F
+        m = self.model
+        m.set_precision(bits)
+        self._mark_inner('lora_recalibration')
+        fin = self.refreshers[bits].body()                                  # calibrate_lora_only(bits)
+        self._mark_inner('student_forward')
+        out = m(self.ids, output_hidden_states=True, return_dict=True)
+        tch = self.outs[self.teacher_bits]
+        self._mark_inner('distillation_loss')
+        kl = distillation_kl_loss(out['logits'], tch['logits'], self.T)
+        with torch.no_grad():
+            hs, ht = out['hidden_states'], tch['hidden']
+            n = min(len(hs), len(ht))
+            feats = torch.stack([F.mse_loss(hs[l], ht[l], reduction='mean') for l in range(n)])
+        self._mark_inner('student_backward')
+        ((self.alpha_kl / self.G) * kl).backward()          # the feature term carries no gradient (detached copies)
+        return {'kl': kl.detach().reshape(1), 'feats': feats, 'finish': fin}
+
+    def _body(self, bits):
+        return self._teacher_body() if bits == self.teacher_bits else self._student_body(bits)
+
+    # ------------------------------------------------------------------------------------------ graphs
+    def _signature(self, bits):
+        """What a captured micro-step hard-wires beyond the live-read trainable parameters: the frozen tensors
+        (their fp16 operands are cached by address / version) and, for a student width, the calibration state."""
+        if self._frozen is None:
+            own = {id(p) for p in self.state.params}
+            self._frozen = [p for p in self.model.parameters() if id(p) not in own]
+        sig = (tuple(self.ids.shape), self.model.training, tuple((p.data_ptr(), p._version) for p in self._frozen))
+        return sig if bits == self.teacher_bits else sig + (self.refreshers[bits]._signature(),)
+
+    def _ensure(self, bits):
+        if not self.use_graphs:
+            return
+        sig = self._signature(bits)
+        if bits in self.graphs and self.sigs.get(bits) == sig:
+            return
+        # warm-up on the eager path: operand caches, cuDNN plans, workspaces, the calibration job tables
+        for _ in range(2):
+            self.outs[bits] = self._body(bits)
+        torch.cuda.synchronize()
+        if bits != self.teacher_bits:
+            self.refreshers[bits].invalidate()
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.pool):
+            self.outs[bits] = self._body(bits)
+        self.graphs[bits], self.sigs[bits] = g, self._signature(bits)
+        if bits == self.teacher_bits:
+            for b in self.student_bits:                    # the students read the teacher graph's static outputs
+                self.graphs.pop(b, None)
+        self.state.zero_grad()                                               # the warm-ups accumulated into it
+
+    def _run(self, bits):
+        if self.use_graphs:
+            self.graphs[bits].replay()
+            if bits != self.teacher_bits:
+                self.refreshers[bits].restamp()
+        else:
+            self.outs[bits] = self._body(bits)
+        return self.outs[bits]
+
+    # ------------------------------------------------------------------------------------------ LR schedule
+    def lr_at(self, micro_steps):
+        """CosineAnnealingLR(T_max = iterations * G, eta_min = 0) stepped once per micro-step (p1/train_sp.py:380, 456-457)."""
+        import math
+        if not self.total_lr_steps:
+            return self.lr0
+        return self.lr0 * (1.0 + math.cos(math.pi * micro_steps / self.total_lr_steps)) / 2.0
+
+    # ------------------------------------------------------------------------------------------ the step
+    def _mark(self, name):
+        if self.phase_events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.phase_events.append((name, e))
+        return e
+
+    def _mark_inner(self, name):
+        # phases inside a micro-step can only be separated on the eager path (a replay is one launch)
+        if not self.use_graphs and not torch.cuda.is_current_stream_capturing():
+            self._mark(name)
+
+    def train_step(self, ids):
+        """ids: [B, T] int64 token ids of this rank's shard (CUDA, or pinned host memory -> copied asynchronously).
+        Returns {'loss': total loss as upstream reports it (sum of the G micro-step losses, each / G), 'precisions': [...]}
+        -- one device->host read per optimizer step."""
+        from . import _lib
+        import torch.distributed as dist
+        st = self.state
+        if self.ids is None or self.ids.shape != ids.shape:
+            self.ids = torch.empty(ids.shape, dtype=torch.int64, device=self.dev)
+            self.graphs.clear(); self.outs.clear()
+        self.ids.copy_(ids, non_blocking=True)
+        n_layers_p1 = len(self.model.transformer.h) + 1
+        # upstream's draw order: per student micro-step, first the width (train_step), then the feature layer
+        # (compute_distillation_loss)
+        sched, layers = [self.teacher_bits], [None]
+        for _ in range(1, self.G):
+            sched.append(self.rng.choice(self.student_bits))
+            layers.append(self.rng.choice(list(range(n_layers_p1))))
+        last_use = {b: i for i, b in enumerate(sched)}
+        for b in dict.fromkeys(sched):
+            self._ensure(b)
+        self._mark('zero_grad')
+        st.zero_grad()
+        works = []
+        for i, bits in enumerate(sched):
+            self._mark(f'micro_step_{bits}')
+            out = self._run(bits)
+            if bits == self.teacher_bits:
+                self.loss_buf[i, 0:1].copy_(out['loss'])
+                self.loss_buf[i, 1].zero_()
+            else:
+                self.loss_buf[i, 0:1].copy_(out['kl'])
+                self.loss_buf[i, 1:2].copy_(out['feats'][layers[i]:layers[i] + 1])
+                self.finishers[bits] = out['finish']
+            if self.world > 1 and last_use[bits] == i:
+                # this segment is final: its all-reduce runs on NCCL's stream under the remaining micro-steps
+                works.append(dist.all_reduce(st.seg_grad(bits), op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._mark('allreduce_wait')
+        for w in works:
+            w.wait()
+        self._mark('optimizer')
+        self.micro_steps_done += self.G
+        lr = self.lr_at(self.micro_steps_done)
+        inv_world = 1.0 / self.world
+        _lib.grad_sumsq(st.flat_grad, self.sumsq, scale=inv_world)
+        for b in dict.fromkeys(sched):
+            a, e = st.segments[b]
+            if e == a:
+                continue
+            st.steps[b] += 1
+            _lib.adamw_flat(st.flat_param[a:e], st.flat_grad[a:e], st.exp_avg[a:e], st.exp_avg_sq[a:e], lr, self.betas,
+                            self.eps, self.wd, st.steps[b], grad_scale=inv_world, total_sumsq=self.sumsq,
+                            max_norm=self.max_norm)
+        st.bump_versions()
+        self._mark('end')
+        vals = self.loss_buf.tolist()                                         # the one device->host read of the step
+        for b, fin in list(self.finishers.items()):
+            fin(redo=False)
+        self.finishers.clear()
+        total = 0.0
+        for i, bits in enumerate(sched):
+            if bits == self.teacher_bits:
+                total += vals[i][0]
+            else:
+                total += (self.alpha_kl * vals[i][0] + self.alpha_feature * vals[i][1]) / self.G
+        return {'loss': total, 'precisions': sched, 'lr': lr}
+
+    def phase_times_ms(self):
+        """After a step run with `phase_events = []`: [(phase, ms)] between consecutive marks (synchronises)."""
+        torch.cuda.synchronize()
+        ev = self.phase_events or []
+        return [(ev[i][0], ev[i][1].elapsed_time(ev[i + 1][1])) for i in range(len(ev) - 1)]
