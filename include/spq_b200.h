@@ -196,7 +196,8 @@ SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weig
                       float* dbias, void* workspace, size_t workspace_bytes, spq_stream_t stream);
 
 /* ---- gradient-side operand: out[m, 0:N] = fp16(g[m,n] * 2^-e[m]), e from the row's absmax,
- * row_scale[m] = 2^e[m]; rows of `out` are ld_out elements apart (0 = N).  Any N (a two-pass
+ * row_scale[m] = 2^e[m] (an all-zero row reports the smallest scale, 2^-108, so that `max over rows` and
+ * `scale / max` ignore it; inf / NaN rows report 1); rows of `out` are ld_out elements apart (0 = N).  Any N (a two-pass
  * kernel takes over when the row does not fit the register-resident one or is unaligned).
  * g is float32, or float16 when g_is_half (register-resident shapes only). */
 SPQ_API int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,

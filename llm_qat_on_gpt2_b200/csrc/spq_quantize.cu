@@ -324,9 +324,12 @@ rowscale_kernel(ActArgs a) {
             amax = s_red[0];
             for (int w = 1; w < (G >> 5); ++w) amax = fmaxf(amax, s_red[w]);
         }
-        // amax in [2^(E-1), 2^E)  ->  raw = x * 2^(8-E) in (-256, 256); inf/0 rows: scale 1
+        // amax in [2^(E-1), 2^E)  ->  raw = x * 2^(8-E) in (-256, 256); inf / NaN rows: scale 1.  An all-zero row
+        // (the last position of every sequence in a next-token loss has no gradient) gets the SMALLEST scale, 2^-108:
+        // callers fold `scale / max over rows` into fp16 operands of token reductions, and a zero row reporting
+        // scale 1 against real rows at ~2^-20 pushed those operands into the fp16 subnormal range
         int E = 0;
-        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = 8;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;
         E = E < -100 ? -100 : E;
         const float down = exp2f(static_cast<float>(8 - E));
         if (tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = exp2f(static_cast<float>(E - 8));
@@ -439,7 +442,7 @@ rowscale_wide_kernel(const float* __restrict__ x, long long M, long long K, unsi
 #pragma unroll
         for (int w = 1; w < 8; ++w) amax = fmaxf(amax, s_red[w]);
         int E = 0;
-        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = 8;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;   // see rowscale_kernel
         E = E < -100 ? -100 : E;
         const float down = exp2f(static_cast<float>(8 - E));
         if (tid == 0 && row_scale) row_scale[row] = exp2f(static_cast<float>(E - 8));

@@ -201,6 +201,11 @@ def test_quantize_act_operands(lib):
     assert np.max(np.abs(back - x) / amax) <= 2.0 ** -10
     r = rs.cpu().numpy()
     assert np.array_equal(np.log2(r), np.round(np.log2(r)))          # powers of two
+    # an all-zero row reports the smallest scale (so `scale / max over rows` ignores it), and stays zero
+    xz = x.copy(); xz[3] = 0.0
+    lib.rowscale_f16(dev(xz), x16, rs)
+    assert float(rs[3]) == 2.0 ** -108 and float(x16[3].float().abs().max()) == 0.0
+    assert float(rs.max()) == float(np.delete(r, 3).max())
     # odd width / padded leading dimension (LM-head gradients)
     xo = heavy_tailed((33, 211), 9)
     buf = lib.empty_f16_padded(33, 211, "cuda")
