@@ -49,8 +49,12 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=2,
                     help="sequences (of --seq tokens) per step in the bounded CPU-arm sample; the GPU arm runs --batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--train-steps", type=int, default=3,
-                    help="optimizer steps of the distillation training step timed after the main metric (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=20,
+                    help="optimizer steps of upstream's train_step (8 micro-steps each) timed after the main metric (0 = skip)")
+    ap.add_argument("--train-dropout", type=float, default=0.1, help="embd_pdrop of the training step (p1/config_sp.py:9)")
+    ap.add_argument("--train-eager", action="store_true", help="run the micro-steps eagerly (no CUDA graphs): per-phase timing")
+    ap.add_argument("--train-strong", type=int, default=1, help="also time the strong-scaling shapes (global 32x256, 32x1024)")
+    ap.add_argument("--no-dp-parity", action="store_true")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU sequences of the training step (p1/config_sp.py:46)")
     ap.add_argument("--train-seq", type=int, default=256, help="sequence length of the training step (p1/config_sp.py:47)")
     ap.add_argument("--profile-train-step", action="store_true",
@@ -497,78 +501,206 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-def train_section(args, model, linears, key, dev, world, rank, group, barrier):
-    """BASELINE.json configs[2]: one switchable-precision distillation step per optimizer step --
-    32-bit teacher forward (no grad), LoRA quantisers recalibrated (p1/train_sp.py:125-163, 362-364),
-    8-bit student forward + STE backward on the distillation loss (KL(T=3) + 1e-7 * hidden-state MSE,
-    p1/distillation_manager.py:64-116), all-reduce of
-    the gradients that exist (active LoRA A/B + active LayerNorm pairs), AdamW on those parameters.
-    Batch-sharded: every rank runs the reference's 32 x 256 micro-batch (weak scaling)."""
+GRAD_ACCUM = 8                      # p1/config_sp.py:58
+# GEMM work of one optimizer step of upstream's train_step, MFLOP per token of the batch:
+#   teacher micro-step : CE forward (base 169.87 + LM head 77.19) + backward dX of both + the cache forward
+#   student micro-step : forward (base + LoRA 18.87 + LM head) + backward (dX 169.87 + LoRA 37.75 + LM head dX)
+TRAIN_MFLOP_TEACHER = 3 * (169.87 + 77.19)
+TRAIN_MFLOP_STUDENT = (169.87 + 18.87 + 77.19) + (169.87 + 37.75 + 77.19)
+
+
+def _calibrate_width(model, linears, bits, ids, group):
+    """Untimed: weight, LoRA and input quantisers of one student width (p1/train_sp.py:47-163); the input statistics
+    are MIN/MAX all-reduced across the ranks."""
     import torch
-    import torch.nn.functional as F
-    import torch.distributed as dist
-    from llm_qat_on_gpt2_b200 import _lib, dp
-    import random
-    from llm_qat_on_gpt2_b200.training import GraphedNoGradForward, LoRARefresher, distillation_loss
-    B, T, V, Tmp = args.train_batch, args.train_seq, MODEL["vocab_size"], 3.0
-    model.train()
-    for n, p in model.named_parameters():
-        p.requires_grad_((f"lora_adapters.{key}.lora_" in n) or n.endswith(f"weights.{BITS}") or n.endswith(f"biases.{BITS}"))
-    params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
-    refresher = LoRARefresher(linears, BITS)
-    teacher = GraphedNoGradForward(model, output_hidden_states=True, return_dict=True)
-    layer_rng = random.Random(7 + rank)
-    gen = torch.Generator().manual_seed(99 + rank)
-    # the input quantisers keep the calibration of the last forward step (static during training)
+    from llm_qat_on_gpt2_b200 import dp
+    key = f"{bits}bit"
+    with torch.no_grad():
+        model.set_precision(bits)
+        for m in linears:
+            qw = m.quantizers_weight[key]
+            qw.start_calibration(); qw(m.linear.weight.data); qw.finish_calibration()
+            lo = m.lora_adapters[key]
+            for qq, w in ((lo.quantize_A, lo.lora_A), (lo.quantize_B, lo.lora_B)):
+                qq.start_calibration(); qq(w.data); qq.finish_calibration()
+        iq = [m.quantizers_input[key] for m in linears]
+        for q in iq:
+            q.start_calibration()
+        model.disable_lora_for_calibration()
+        model.transformer(ids)
+        model.enable_lora_after_calibration()
+        dp.finish_calibration_many(iq, group)
 
-    def one_step(ids):
-        with torch.no_grad():
-            model.set_precision(32)
-            t_out = teacher(ids)              # 32-bit teacher forward: one CUDA-graph replay
-            refresher.refresh()       # LoRA recalibration + operand rebuild: one CUDA-graph replay (parameters are
-                                      # replicated, so no statistics exchange is needed)
-        model.set_precision(BITS)
-        s_out = model(ids, output_hidden_states=True, return_dict=True)
-        # KL over positions 0..T-2 (p1/distillation_manager.py:68-80), batchmean over the B*(T-1) rows, * T^2
-        # alpha_kl * KL(T) [one kernel: value + gradient] + alpha_feature * MSE(hidden states of one random layer)
-        loss = distillation_loss(s_out, t_out, Tmp, alpha_kl=1.0, alpha_feature=1e-7, rng=layer_rng)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        n = dp.allreduce_gradients(params, group)
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
-        opt.step()
-        return loss, n
 
-    batches = [torch.randint(0, V, (B, T), generator=gen).to(dev) for _ in range(args.train_steps + 2)]
-    for i in range(2):
-        loss, n_red = one_step(batches[i])
+def _timed_train(trainer, host_batches, dev, steps, warmup, world, barrier):
+    """(ms per optimizer step resident, ms per step end to end, last result) -- max over ranks is taken by the caller."""
+    import torch
+    dev_batches = [h.to(dev) for h in host_batches]
+    for i in range(warmup):
+        res = trainer.train_step(dev_batches[i % len(dev_batches)])
     barrier()
-    if args.profile_train_step:
-        torch.cuda.synchronize()
-        torch.cuda.profiler.start()              # ncu --profile-from-start off: forward AND the autograd thread
-        one_step(batches[2])
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        barrier()
-    l0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for i in range(args.train_steps):
-        loss, n_red = one_step(batches[2 + i])
+    for i in range(steps):
+        res = trainer.train_step(dev_batches[(warmup + i) % len(dev_batches)])
     t1.record()
     barrier()
-    ms = t0.elapsed_time(t1)
-    if world > 1:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = tt.item()
+    ms = t0.elapsed_time(t1) / steps
+    t0.record()
+    for i in range(steps):
+        res = trainer.train_step(host_batches[(warmup + i) % len(host_batches)])       # pinned host ids -> device
+    t1.record()
+    barrier()
+    return ms, t0.elapsed_time(t1) / steps, res
+
+
+def train_section(args, model, linears, key, dev, world, rank, group, barrier):
+    """BASELINE.json configs[2]: upstream's `train_step` (p1/train_sp.py:341-397) through training.SPTrainer -- per
+    optimizer step 8 micro-steps on one batch: teacher (32-bit) CE forward + backward + cache forward, then 7 student
+    micro-steps at random.choice([4, 8]) with LoRA recalibration, KL(T=3) + 1e-7 MSE, backward; gradient all-reduce
+    of the touched LoRA / LayerNorm segments (overlapped), clip 1.0, AdamW.  tokens/s = B*T*8*world / step time
+    (SURVEY section 8d).  Weak scaling: the reference's 32 x 256 per GPU; strong scaling: global 32 x 256 and
+    32 x 1024 sharded over the ranks."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from llm_qat_on_gpt2_b200 import _lib
+    from llm_qat_on_gpt2_b200.training import SPTrainer
+    V = MODEL["vocab_size"]
+    other = [b for b in BIT_WIDTHS if b < 32 and b != BITS]
+    gen = torch.Generator().manual_seed(99 + rank)
+    calib_ids = torch.randint(0, V, (args.train_batch, args.train_seq), generator=gen).to(dev)
+    for b in other:
+        _calibrate_width(model, linears, b, calib_ids, group)
+    model.train()
+    model.transformer.drop.p = args.train_dropout            # p1/config_sp.py:9 embd_pdrop = 0.1
+    out = {}
+
+    def run(tag, B, T, steps, warmup, phases=False):
+        trainer = SPTrainer(model, BIT_WIDTHS, grad_accum=GRAD_ACCUM, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0,
+                            temperature=3.0, alpha_kl=1.0, alpha_feature=1e-7, total_lr_steps=550 * GRAD_ACCUM, group=group,
+                            rng=random.Random(7), use_graphs=not args.train_eager)
+        hosts = [torch.randint(0, V, (B, T), generator=gen).pin_memory() for _ in range(4)]
+        if args.profile_train_step:
+            # for ncu launch lists (--profile-from-start off): warm up / capture, then exactly one profiled step
+            d0 = hosts[0].to(dev)
+            for _ in range(3):
+                trainer.train_step(d0)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            trainer.train_step(d0)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return {"profiled": tag}
+        l0 = _lib.launch_count()
+        ms, ms_e2e, res = _timed_train(trainer, hosts, dev, steps, warmup, world, barrier)
+        launches = (_lib.launch_count() - l0)
+        ph = None
+        if phases:
+            trainer.phase_events = []
+            trainer.train_step(hosts[0].to(dev))
+            ph = trainer.phase_times_ms()
+            trainer.phase_events = None
+        if world > 1:
+            tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms, ms_e2e = tt.tolist()
+        tokens = B * T * GRAD_ACCUM * world
+        n_student = GRAD_ACCUM - 1
+        flop = (TRAIN_MFLOP_TEACHER + n_student * TRAIN_MFLOP_STUDENT) * 1e6 * B * T       # per GPU per optimizer step
+        peak = measured_peaks()["tflops_sustained"]
+        r = {"value": tokens / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+             "per_gpu_batch": B, "seq_len": T, "micro_steps": GRAD_ACCUM, "loss": res["loss"], "precisions_last_step": res["precisions"],
+             "e2e": {"value": tokens / (ms_e2e / 1e3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * T * 8,
+                     "d2h_bytes_per_step": int(trainer.loss_buf.numel() * 4)},
+             "trainable_params": int(trainer.state.numel), "cuda_graphs": sorted(trainer.graphs),
+             # one graph replay + one loss copy (two for a student) per micro-step, the gradient memset, the
+             # norm (2 kernels) and one AdamW launch per touched segment, one all-reduce per touched segment
+             "host_launches_per_step": (GRAD_ACCUM * 3 - 1 + 1 + 2 + 3 + (3 if world > 1 else 0)) if trainer.graphs else None,
+             "lib_launches_outside_graphs": launches,
+             "roofline": {"bound": "tensor", "kernel": "all GEMMs of the optimizer step (algorithmic FLOP / whole step time)",
+                          "achieved": flop / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                          "frac": flop / (ms / 1e3) / 1e12 / peak if peak else None}}
+        if ph is not None:
+            agg = {}
+            for name, t in ph:
+                agg[name] = agg.get(name, 0.0) + t
+            r["phases_ms"] = {k: round(v, 3) for k, v in agg.items()}
+        del trainer
+        torch.cuda.empty_cache()
+        return r
+
+    B, T = args.train_batch, args.train_seq
+    out = run("weak", B, T, args.train_steps, 3, phases=True)
+    if args.profile_train_step:
+        return out
+    out["metric"] = ("GPT-2 SP train_step tokens/s (teacher CE fwd+bwd + cache fwd @32, 7 student micro-steps @random{4,8} with "
+                     "LoRA recalibration + KL/MSE distillation fwd+bwd, grad all-reduce, clip, AdamW); tokens = B*T*8 per optimizer step")
+    out["scaling"] = "weak"
+    if args.train_strong and B % world == 0:
+        for tag, gb, gt, st in (("strong_32x256", 32, 256, max(5, args.train_steps // 2)), ("strong_32x1024", 32, 1024, 5)):
+            if gb % world == 0:
+                r = run(tag, gb // world, gt, st, 2)
+                r["global_batch"], r["scaling"] = gb, "strong"
+                out[tag] = r
+    if world > 1 and not args.no_dp_parity:
+        out["dp_parity"] = dp_parity_section(args, model, linears, dev, world, rank, group)
+    model.transformer.drop.p = 0.0
     model.eval()
-    return {"metric": "GPT-2 SP distillation training step tokens/s (32-bit teacher fwd + 8-bit student fwd/bwd + grad all-reduce + AdamW)",
-            "value": B * T * world * args.train_steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / args.train_steps,
-            "steps": args.train_steps, "per_gpu_batch": B, "seq_len": T, "loss": float(loss.item()),
-            "allreduced_grad_elements": int(n_red), "trainable_params": int(sum(p.numel() for p in params)),
-            "gpu_launches": int(_lib.launch_count() - l0)}
+    return out
+
+
+def dp_parity_section(args, model, linears, dev, world, rank, group):
+    """Untimed, N > 1: (1) the calibrated input-quantiser parameters are bit-identical on every rank and equal to a
+    single-process calibration of the gathered global batch; (2) the all-reduced gradient of one optimizer step
+    equals the gradient a single process computes on the global batch."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from llm_qat_on_gpt2_b200.training import SPTrainer
+    V, Bp, T = MODEL["vocab_size"], 4, args.train_seq
+    gen = torch.Generator().manual_seed(4242 + rank)
+    ids = torch.randint(0, V, (Bp, T), generator=gen).to(dev)
+    gathered = [torch.empty_like(ids) for _ in range(world)]
+    dist.all_gather(gathered, ids)
+    global_ids = torch.cat(gathered, dim=0)
+    res = {}
+    # ---- (1) calibration
+    def params():
+        return torch.cat([torch.cat([q.scale.reshape(-1), q.zero_point.reshape(-1)])
+                          for m in linears for q in (m.quantizers_input[f"{BITS}bit"],)]).view(torch.int32).clone()
+    _calibrate_width(model, linears, BITS, ids, group)                 # sharded, MIN/MAX all-reduced
+    mine = params()
+    ref0 = mine.clone()
+    dist.broadcast(ref0, src=0)
+    same = torch.tensor([int(torch.equal(mine, ref0))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    _calibrate_width(model, linears, BITS, global_ids, None)           # single-process on the whole batch
+    single = params()
+    d = (single.long() - mine.long()).abs()
+    res["calibration"] = {"ranks_bit_identical": bool(same.item()), "vs_single_process_max_ulp": int(d.max()),
+                          "vs_single_process_differing": int((d > 0).sum()), "parameters": int(d.numel())}
+    # ---- (2) gradients: lr = 0 keeps the replicas' parameters untouched
+    p_drop, model.transformer.drop.p = model.transformer.drop.p, 0.0
+    def grads(batch, data_parallel):
+        tr = SPTrainer(model, BIT_WIDTHS, grad_accum=3, lr=0.0, weight_decay=0.0, group=group, rng=random.Random(3),
+                       use_graphs=False)
+        if not data_parallel:
+            tr.world = 1
+        tr.train_step(batch)
+        g = tr.state.flat_grad.clone() / tr.world
+        del tr
+        return g
+    g_dp = grads(ids, True)
+    g_single = grads(global_ids, False)
+    rel = float((g_dp.double() - g_single.double()).norm() / g_single.double().norm())
+    model.transformer.drop.p = p_drop
+    res["gradient"] = {"rel_allreduced_vs_single_process": rel, "elements": int(g_dp.numel()),
+                       "per_rank_batch": Bp, "global_batch": Bp * world, "micro_steps": 3}
+    ok = res["calibration"]["ranks_bit_identical"] and res["calibration"]["vs_single_process_max_ulp"] == 0 and rel <= 1e-4
+    res["ok"] = bool(ok)
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
