@@ -659,6 +659,7 @@ def dp_parity_section(args, model, linears, dev, world, rank, group):
     import torch.distributed as dist
     from llm_qat_on_gpt2_b200.training import SPTrainer
     V, Bp, T = MODEL["vocab_size"], 4, args.train_seq
+    p_drop, model.transformer.drop.p = model.transformer.drop.p, 0.0      # parity needs the same function on every rank
     gen = torch.Generator().manual_seed(4242 + rank)
     ids = torch.randint(0, V, (Bp, T), generator=gen).to(dev)
     gathered = [torch.empty_like(ids) for _ in range(world)]
@@ -681,7 +682,6 @@ def dp_parity_section(args, model, linears, dev, world, rank, group):
     res["calibration"] = {"ranks_bit_identical": bool(same.item()), "vs_single_process_max_ulp": int(d.max()),
                           "vs_single_process_differing": int((d > 0).sum()), "parameters": int(d.numel())}
     # ---- (2) gradients: lr = 0 keeps the replicas' parameters untouched
-    p_drop, model.transformer.drop.p = model.transformer.drop.p, 0.0
     def grads(batch, data_parallel):
         tr = SPTrainer(model, BIT_WIDTHS, grad_accum=3, lr=0.0, weight_decay=0.0, group=group, rng=random.Random(3),
                        use_graphs=False)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPQ_ABI_VERSION 1
+#define SPQ_ABI_VERSION 2
 #define SPQ_API __attribute__((visibility("default")))
 
 typedef void* spq_stream_t;          /* cudaStream_t */
@@ -175,17 +175,21 @@ SPQ_API int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
 
 /* Transposed-operand GEMM for the weight-gradient shaped products of the STE backward
  * (dA = x^T dT, dB = t^T dY, optional dW = dY^T q(x); torch autograd of p1/lora.py:51-52, 144):
- *   D[i,j] = alpha * alpha_dev[0] * i_scale[i] * j_scale[j] * sum_m P[m,i] Q[m,j]
+ *   D[i,j] = clamp( alpha * alpha_dev[0] * i_scale[i] * j_scale[j] * sum_m P[m,i] Q[m,j], +-clamp_abs )
  * P: [Mred, I] fp16, Q: [Mred, J] fp16, row-major (leading dimensions multiples of 8): both are
  * MN-major tcgen05 operands loaded by TMA without a transpose.  D is a dense float32 matrix
- * addressed D[i * d_stride_i + j * d_stride_j] (one of the strides is 1, so the result can be
- * written transposed); it is zeroed here and accumulated with fp32 atomics because the reduction
- * over Mred is split across CTAs.  alpha_dev (device scalar), i_scale, j_scale are nullable.
- * Per-reduction-row scales cannot be applied here: fold them into P or Q. */
+ * addressed D[i * d_stride_i + j * d_stride_j], either [I, J] row-major or its transpose [J, I].
+ * The reduction over Mred is split across CTAs; each split writes its partial tile to its own plane of
+ * `workspace` (spq_gemm_tn_workspace_bytes) and a second kernel folds the planes in a fixed order, so the
+ * result is bitwise reproducible (no atomics).  clamp_abs > 0 applies the log quantiser's STE clamp
+ * (p1/quantization_methods.py:82-90) to the finished gradient.  alpha_dev (device scalar), i_scale, j_scale
+ * are nullable.  Per-reduction-row scales cannot be applied here: fold them into P or Q. */
+SPQ_API size_t spq_gemm_tn_workspace_bytes(int64_t Mred, int64_t I, int64_t J);
 SPQ_API int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq,
                 int64_t Mred, int64_t I, int64_t J, float alpha, const float* alpha_dev,
-                const float* i_scale, const float* j_scale,
-                float* D, int64_t d_stride_i, int64_t d_stride_j, spq_stream_t stream);
+                const float* i_scale, const float* j_scale, float clamp_abs,
+                float* D, int64_t d_stride_i, int64_t d_stride_j, void* workspace, size_t workspace_bytes,
+                spq_stream_t stream);
 
 /* ---- SwitchableLayerNorm (p1/switchable_batchnorm.py:102-109) ------------------------------ */
 SPQ_API int spq_layernorm_fwd(const float* x, int64_t rows, int64_t cols, const float* weight, const float* bias,
@@ -202,6 +206,19 @@ SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weig
  * g is float32, or float16 when g_is_half (register-resident shapes only). */
 SPQ_API int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                      float* row_scale, spq_stream_t stream);
+/* same, and max_scale[0] = max over rows of row_scale (what the token-reduction GEMMs fold the scales against) */
+SPQ_API int spq_rowscale_f16_max(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
+                         float* row_scale, float* max_scale, spq_stream_t stream);
+
+/* fp16 operands of the LoRA gradient GEMMs in one pass (STE backward of p1/lora.py:45-54):
+ *   dt16 = fp16(dtn * dt_mul)                       (dX += dT q(A)^T; token scale applied in that GEMM's epilogue)
+ *   dt2  = fp16(dtn * dt_mul * row_scale / max)     (dA = x^T dT: reduction over tokens, scale folded in)
+ *   t2   = fp16(t16 * row_scale / max)              (dB = t^T dY)
+ * dtn [M, r] float32 is the down-projected gradient per token scale, t16 [M, r] (leading dimension ld_t16) the fp16
+ * down-projection saved by the forward; row_scale / max_scale come from spq_rowscale_f16_max.  Any output may be NULL. */
+SPQ_API int spq_lora_bwd_prep(const float* dtn, const spq_half_t* t16, int64_t ld_t16, const float* row_scale,
+                      const float* max_scale, int64_t M, int64_t r, float dt_mul, spq_half_t* dt16, spq_half_t* dt2,
+                      spq_half_t* t2, spq_stream_t stream);
 
 /* LM head with the log-sum-exp folded into the GEMM epilogue ("fused CE over V = 50257
  * with the tied LM-head GEMM"; replaces lm_head + the softmax passes of nn.CrossEntropyLoss,
@@ -225,6 +242,20 @@ SPQ_API int spq_cross_entropy_from_parts(const float* parts, int64_t P, int64_t 
 SPQ_API int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t, int64_t M, int64_t V,
                    float temperature, int64_t seq_len, float grad_scale, float* row_loss, float* grad,
                    spq_stream_t stream);
+
+/* Softmax loss over the LM-head logits whose gradient is emitted as the fp16 operand of the LM-head backward GEMM
+ * (the float32 [B, T, V] dlogits matrix is never materialised).
+ *   kind 0: distillation KL of p1/distillation_manager.py:64-80 (as spq_distill_kl);  d = softmax(s/T) - softmax(t/T)
+ *   kind 1: next-token cross-entropy of p1/models_sp.py:441-449 (targets already shifted; rows whose target is
+ *           ignore_index or out of range are not scored);                              d = softmax(s) - onehot(target)
+ * row_loss[m] as spq_distill_kl / spq_cross_entropy_fwd, row_valid[m] (nullable) 1 for scored rows;
+ * g16[m, 0:V] = fp16(d * 2^(8-E[m])), row_scale[m] = 2^(E[m]-8) (unscored rows: zeros, scale 2^-108),
+ * max_scale[0] = max_m row_scale[m]; g16 rows are ld_g (even, >= V) elements apart, the padding is zeroed.
+ * The caller's scalar factor (T/rows for kind 0, 1/scored-rows for kind 1) multiplies row_scale. */
+SPQ_API int spq_softmax_loss_grad16(int kind, const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t,
+                            const int64_t* targets, int64_t ignore_index, int64_t M, int64_t V, float temperature,
+                            int64_t seq_len, float* row_loss, float* row_valid, spq_half_t* g16, int64_t ld_g,
+                            float* row_scale, float* max_scale, spq_stream_t stream);
 
 /* ---- consumer of the path: next-token cross-entropy, forward only -----------
  * Replaces nn.CrossEntropyLoss over re-materialised shifted logits (p1/models_sp.py:441-449) for

@@ -21,6 +21,7 @@ PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
 MINMAX, LOG = 0, 1
 OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW = 0, 1, 2
 QTYPE = {"minmax": MINMAX, "log": LOG}
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); must list every SPQ_API symbol of include/spq_b200.h
 SIGNATURES = {
@@ -48,8 +49,14 @@ SIGNATURES = {
                           c_void_p, c_int64, c_void_p, c_int64, c_int64,
                           c_float, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,
                           c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "spq_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
-                            c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+                            c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "spq_rowscale_f16_max": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "spq_lora_bwd_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "spq_softmax_loss_grad16": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                        c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_layernorm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
@@ -87,8 +94,8 @@ def load_library(path: str = LIB_PATH):
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.spq_abi_version() != 1:
-        raise RuntimeError(f"libspq_b200 ABI version {lib.spq_abi_version()} != 1")
+    if lib.spq_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libspq_b200 ABI version {lib.spq_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -255,8 +262,10 @@ def qgemm(A, B, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None,
     return out
 
 
-def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, transposed_out=False):
-    """out[I,J] (or out[J,I] when transposed_out) = alpha * P[Mred,I]^T Q[Mred,J]; fp16 in, fp32 out."""
+def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, transposed_out=False, clamp_abs=0.0):
+    """out[I,J] (or out[J,I] when transposed_out) = clamp(alpha * P[Mred,I]^T Q[Mred,J]); fp16 in, fp32 out.
+    Deterministic (split reduction folded in a fixed order); clamp_abs > 0 applies the log STE clamp."""
+    lib = load_library()
     _req_cuda(P, Q, out, alpha_dev, i_scale, j_scale)
     assert P.dtype == torch.float16 and Q.dtype == torch.float16 and out.dtype == torch.float32
     assert P.stride(-1) == 1 and Q.stride(-1) == 1 and out.is_contiguous()
@@ -269,9 +278,10 @@ def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, tr
     else:
         assert tuple(out.shape) == (I, J)
         si, sj = J, 1
-    _check(load_library().spq_gemm_tn(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), Mred, I, J, float(alpha),
-                                      _ptr(alpha_dev), _ptr(i_scale), _ptr(j_scale), out.data_ptr(), si, sj,
-                                      _stream()), "spq_gemm_tn")
+    ws = _workspace(lib.spq_gemm_tn_workspace_bytes(Mred, I, J), out.device, "gemm_tn")
+    _check(lib.spq_gemm_tn(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), Mred, I, J, float(alpha),
+                           _ptr(alpha_dev), _ptr(i_scale), _ptr(j_scale), float(clamp_abs), out.data_ptr(), si, sj,
+                           ws.data_ptr(), ws.numel(), _stream()), "spq_gemm_tn")
     return out
 
 
@@ -383,6 +393,64 @@ def adamw_flat(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, s
                                          float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
                                          int(step), float(grad_scale), _ptr(total_sumsq), float(max_norm), _stream()),
            "spq_adamw_flat")
+
+
+def rowscale_f16_max(g2d, out, row_scale, max_scale):
+    """rowscale_f16 that also leaves max(row_scale) in the device scalar `max_scale`."""
+    _req_cuda(g2d, out, row_scale, max_scale)
+    M, N = g2d.shape
+    assert out.stride(-1) == 1 and g2d.is_contiguous() and g2d.dtype in (torch.float32, torch.float16)
+    _check(load_library().spq_rowscale_f16_max(g2d.data_ptr(), int(g2d.dtype == torch.float16), M, N, out.data_ptr(), out.stride(0),
+                                               row_scale.data_ptr(), max_scale.data_ptr(), _stream()), "spq_rowscale_f16_max")
+
+
+def lora_bwd_prep(dtn, t16, row_scale, max_scale, dt_mul, want_dt16=True, want_dt2=True, want_t2=True):
+    """(dt16, dt2, t2) fp16 operands of the LoRA gradient GEMMs in one launch (see include/spq_b200.h)."""
+    _req_cuda(dtn, t16, row_scale, max_scale)
+    src = dtn if dtn is not None else t16
+    M, r = src.shape
+    dev = src.device
+    if r % 4:
+        # odd ranks (no reference configuration has one): the same arithmetic with torch device ops
+        e = (row_scale / max_scale).unsqueeze(1)
+        d = None if dtn is None else dtn * dt_mul
+        return (d.half() if (d is not None and want_dt16) else None, (d * e).half() if (d is not None and want_dt2) else None,
+                (t16.float() * e).half() if (t16 is not None and want_t2) else None)
+    dt16 = torch.empty((M, r), dtype=torch.float16, device=dev) if (dtn is not None and want_dt16) else None
+    dt2 = torch.empty((M, r), dtype=torch.float16, device=dev) if (dtn is not None and want_dt2) else None
+    t2 = torch.empty((M, r), dtype=torch.float16, device=dev) if (t16 is not None and want_t2) else None
+    assert dtn is None or (dtn.dtype == torch.float32 and dtn.is_contiguous())
+    assert t16 is None or (t16.dtype == torch.float16 and t16.stride(-1) == 1)
+    _check(load_library().spq_lora_bwd_prep(_ptr(dtn), _ptr(t16), 0 if t16 is None else t16.stride(0), row_scale.data_ptr(),
+                                            max_scale.data_ptr(), M, r, float(dt_mul), _ptr(dt16), _ptr(dt2), _ptr(t2),
+                                            _stream()), "spq_lora_bwd_prep")
+    return dt16, dt2, t2
+
+
+def softmax_loss_grad16(s2d, kind, *, t2d=None, targets=None, temperature=1.0, seq_len=0, ignore_index=-100):
+    """kind 'kl' | 'ce' -> (row_loss [M], row_valid [M], g16 [M, V] fp16 view (padded rows), row_scale [M], max_scale [1])."""
+    _req_cuda(s2d, t2d, targets)
+    assert s2d.dim() == 2 and s2d.stride(1) == 1 and s2d.dtype == torch.float32
+    M, V = s2d.shape
+    dev = s2d.device
+    ld = (V + 7) // 8 * 8
+    gbuf = torch.empty((M, ld), dtype=torch.float16, device=dev)
+    row_loss = torch.empty(M, dtype=torch.float32, device=dev)
+    row_valid = torch.empty(M, dtype=torch.float32, device=dev)
+    row_scale = torch.empty(M, dtype=torch.float32, device=dev)
+    max_scale = torch.empty(1, dtype=torch.float32, device=dev)
+    if kind == 'kl':
+        assert t2d is not None and t2d.shape == s2d.shape and t2d.stride(1) == 1 and t2d.dtype == torch.float32
+        tg = None
+    else:
+        tg = targets.reshape(-1).to(torch.int64).contiguous()
+        assert tg.numel() == M
+    _check(load_library().spq_softmax_loss_grad16(0 if kind == 'kl' else 1, s2d.data_ptr(), s2d.stride(0), _ptr(t2d),
+                                                  0 if t2d is None else t2d.stride(0), _ptr(tg), int(ignore_index), M, V,
+                                                  float(temperature), int(seq_len), row_loss.data_ptr(), row_valid.data_ptr(),
+                                                  gbuf.data_ptr(), ld, row_scale.data_ptr(), max_scale.data_ptr(), _stream()),
+           "spq_softmax_loss_grad16")
+    return row_loss, row_valid, (gbuf[:, :V] if ld != V else gbuf), row_scale, max_scale
 
 
 def empty_f16_padded(rows: int, cols: int, device) -> torch.Tensor:

@@ -782,12 +782,9 @@ struct TnSmem {
 };
 
 struct TnEpi {
-    const float* i_scale;
-    const float* j_scale;
-    const float* alpha_dev;
-    float* D;
-    long long stride_i, stride_j;
-    float alpha;
+    float* part;                   // [splits][I * J] partial results, each in D's own layout
+    long long stride_i, stride_j;  // D (and every partial) is addressed [i * stride_i + j * stride_j]
+    long long plane;               // I * J
 };
 
 template <int BJ>
@@ -865,28 +862,35 @@ qgemm_tn_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
             }
         }
     } else if (nkb > 0) {
+        // epilogue: this CTA's partial tile goes to its own plane of the workspace (no atomics: the planes are
+        // folded in a fixed order by tn_reduce_kernel, so the result is bitwise reproducible)
         const int quad = warp & 3;
         mbar_wait(&tmem_full[0], 0);
         tcgen05_fence_after();
         const int i = i0 + quad * 32 + lane;
         const bool i_ok = i < I;
-        const float a = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f) * ((ep.i_scale && i_ok) ? __ldg(ep.i_scale + i) : 1.0f);
+        float* base = ep.part + static_cast<long long>(blockIdx.y) * ep.plane + static_cast<long long>(i) * ep.stride_i;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const bool row_vec = ep.stride_j == 1 && (ep.stride_i & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.part) & 15u) == 0 &&
+                             (ep.plane & 3) == 0;
 #pragma unroll 1
         for (int c = 0; c < BJ / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
             tmem_ld_wait();
-            if (i_ok) {
+            const int jb = j0 + c * 32;
+            if (!i_ok || jb >= J) continue;
+            if (row_vec && jb + 32 <= J) {
+                // D row-major: the lane owns 128 contiguous bytes of its row
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = j0 + c * 32 + jj;
-                    if (j < J) {
-                        const float js = ep.j_scale ? __ldg(ep.j_scale + j) : 1.0f;
-                        atomicAdd(ep.D + static_cast<long long>(i) * ep.stride_i + static_cast<long long>(j) * ep.stride_j,
-                                  __uint_as_float(v[jj]) * a * js);
-                    }
-                }
+                for (int jj = 0; jj < 32; jj += 4)
+                    *reinterpret_cast<float4*>(base + jb + jj) = make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                                                                             __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+            } else {
+                // D stored transposed (stride_i == 1): for each j the 32 lanes write 32 consecutive floats
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj)
+                    if (jb + jj < J) base[static_cast<long long>(jb + jj) * ep.stride_j] = __uint_as_float(v[jj]);
             }
         }
     }
@@ -898,21 +902,81 @@ qgemm_tn_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
     }
 }
 
+struct TnReduce {
+    const float* part;
+    int splits;
+    long long plane, I, J, stride_i, stride_j;
+    const float* i_scale;
+    const float* j_scale;
+    const float* alpha_dev;
+    float alpha, clamp_abs;
+    float* D;
+};
+
+// D[e] = clamp(alpha * alpha_dev * is[i] * js[j] * sum_s part[s][e]): the splits are added in index order.
+__global__ void __launch_bounds__(256) tn_reduce_kernel(TnReduce a) {
+    const float al = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.0f);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const bool vec = (a.plane & 3) == 0 && (reinterpret_cast<uintptr_t>(a.part) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.D) & 15u) == 0 &&
+                     (((a.stride_j == 1) ? a.J : a.I) & 3) == 0;
+    if (vec) {
+        for (long long e4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e4 < (a.plane >> 2); e4 += stride) {
+            const long long e = e4 << 2;
+            float4 acc = *reinterpret_cast<const float4*>(a.part + e);
+            for (int s = 1; s < a.splits; ++s) {
+                const float4 p = *reinterpret_cast<const float4*>(a.part + static_cast<long long>(s) * a.plane + e);
+                acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+            }
+            float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                long long i, j;
+                if (a.stride_j == 1) { i = (e + u) / a.J; j = (e + u) - i * a.J; }
+                else { j = (e + u) / a.I; i = (e + u) - j * a.I; }
+                float v = o[u] * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f);
+                if (a.clamp_abs > 0.f) v = fminf(fmaxf(v, -a.clamp_abs), a.clamp_abs);
+                o[u] = v;
+            }
+            *reinterpret_cast<float4*>(a.D + e) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    } else {
+        for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < a.plane; e += stride) {
+            float acc = a.part[e];
+            for (int s = 1; s < a.splits; ++s) acc += a.part[static_cast<long long>(s) * a.plane + e];
+            long long i, j;
+            if (a.stride_j == 1) { i = e / a.J; j = e - i * a.J; }
+            else { j = e / a.I; i = e - j * a.I; }
+            float v = acc * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f);
+            if (a.clamp_abs > 0.f) v = fminf(fmaxf(v, -a.clamp_abs), a.clamp_abs);
+            a.D[e] = v;
+        }
+    }
+}
+
+// reduction splits: enough CTAs for two waves, never more than the k-blocks there are
+static void tn_splits(int64_t Mred, int64_t I, int64_t J, int bj, int& splits, int& per, int& j_tiles, int& tiles) {
+    const int i_tiles = static_cast<int>((I + BM - 1) / BM);
+    j_tiles = static_cast<int>((J + bj - 1) / bj);
+    tiles = i_tiles * j_tiles;
+    const int kb_total = static_cast<int>((Mred + 63) / 64);
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    splits = (2 * sms + tiles - 1) / tiles;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;
+}
+static int tn_bj(int64_t J) { return J <= 64 ? 64 : J <= 128 ? 128 : 256; }
+
 template <int BJ>
-static int launch_tn(const CUtensorMap& tP, const CUtensorMap& tQ, int I, int J, int kb_total, const TnEpi& ep, cudaStream_t stream) {
+static int launch_tn(const CUtensorMap& tP, const CUtensorMap& tQ, int I, int J, int kb_total, int splits, int per, int j_tiles,
+                     int tiles, const TnEpi& ep, cudaStream_t stream) {
     using L = TnSmem<BJ>;
     static bool attr_set = false;
     if (!attr_set) {
         SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_tn_kernel<BJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    const int i_tiles = (I + BM - 1) / BM, j_tiles = (J + BJ - 1) / BJ;
-    const int tiles = i_tiles * j_tiles;
-    int splits = (2 * sm_count() + tiles - 1) / tiles;
-    if (splits > kb_total) splits = kb_total;
-    if (splits < 1) splits = 1;
-    const int per = (kb_total + splits - 1) / splits;
-    splits = (kb_total + per - 1) / per;
     dim3 grid(tiles, splits);
     qgemm_tn_kernel<BJ><<<grid, TN_THREADS, L::TOTAL, stream>>>(tP, tQ, I, J, kb_total, per, j_tiles, ep);
     SPQ_LAUNCH_OK();
@@ -1064,31 +1128,52 @@ extern "C" int spq_qgemm_lse(const spq_half_t* A, int64_t lda, const spq_half_t*
                       D, ldd, 0, 0, lse_part, lse_ld, stream);
 }
 
+extern "C" size_t spq_gemm_tn_workspace_bytes(int64_t Mred, int64_t I, int64_t J) {
+    if (Mred <= 0 || I <= 0 || J <= 0) return 0;
+    int splits, per, j_tiles, tiles;
+    tn_splits(Mred, I, J, tn_bj(J), splits, per, j_tiles, tiles);
+    return static_cast<size_t>(splits) * static_cast<size_t>(I) * static_cast<size_t>(J) * sizeof(float);
+}
+
 extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq, int64_t Mred, int64_t I, int64_t J,
-                           float alpha, const float* alpha_dev, const float* i_scale, const float* j_scale, float* D,
-                           int64_t d_stride_i, int64_t d_stride_j, spq_stream_t stream) {
-    SPQ_REQUIRE(P && Q && D, "spq_gemm_tn: null operand");
+                           float alpha, const float* alpha_dev, const float* i_scale, const float* j_scale, float clamp_abs,
+                           float* D, int64_t d_stride_i, int64_t d_stride_j, void* workspace, size_t workspace_bytes,
+                           spq_stream_t stream) {
+    SPQ_REQUIRE(P && Q && D && workspace, "spq_gemm_tn: null operand");
     SPQ_REQUIRE(Mred > 0 && I > 0 && J > 0 && Mred < (1ll << 31) && I < (1ll << 31) && J < (1ll << 31), "spq_gemm_tn: bad shape");
     SPQ_REQUIRE((ldp % 8) == 0 && (ldq % 8) == 0 && ldp >= I && ldq >= J && aligned16(P) && aligned16(Q),
                 "spq_gemm_tn: leading dimensions must be multiples of 8 and operands 16-byte aligned");
-    SPQ_REQUIRE((d_stride_i == 1) != (d_stride_j == 1) || (I == 1 || J == 1), "spq_gemm_tn: D must be contiguous along i or j");
+    SPQ_REQUIRE((d_stride_i == 1 && d_stride_j == I) || (d_stride_j == 1 && d_stride_i == J),
+                "spq_gemm_tn: D must be dense, [I, J] row-major or its transpose");
+    SPQ_REQUIRE(workspace_bytes >= spq_gemm_tn_workspace_bytes(Mred, I, J) && aligned16(workspace), "spq_gemm_tn: workspace too small");
     if (sm_count() <= 0) {
         set_error("spq_gemm_tn: no CUDA device");
         return SPQ_ERR_CUDA;
     }
     cudaStream_t st = as_stream(stream);
-    // D is dense [I, J] (or [J, I] when stored transposed): zero it, the CTAs accumulate into it
-    SPQ_CUDA_OK(cudaMemsetAsync(D, 0, static_cast<size_t>(I) * static_cast<size_t>(J) * sizeof(float), st));
     CUtensorMap tP, tQ;
     int rc;
     if ((rc = make_tmap_mn(&tP, P, Mred, I, ldp)) != SPQ_OK) return rc;
     if ((rc = make_tmap_mn(&tQ, Q, Mred, J, ldq)) != SPQ_OK) return rc;
+    const int bj = tn_bj(J);
+    int splits, per, j_tiles, tiles;
+    tn_splits(Mred, I, J, bj, splits, per, j_tiles, tiles);
     TnEpi ep;
-    ep.i_scale = i_scale; ep.j_scale = j_scale; ep.alpha_dev = alpha_dev; ep.D = D;
-    ep.stride_i = d_stride_i; ep.stride_j = d_stride_j; ep.alpha = alpha;
+    ep.part = static_cast<float*>(workspace); ep.stride_i = d_stride_i; ep.stride_j = d_stride_j; ep.plane = I * J;
     const int kb_total = static_cast<int>((Mred + 63) / 64);
     const int i = static_cast<int>(I), j = static_cast<int>(J);
-    if (J <= 64) return launch_tn<64>(tP, tQ, i, j, kb_total, ep, st);
-    if (J <= 128) return launch_tn<128>(tP, tQ, i, j, kb_total, ep, st);
-    return launch_tn<256>(tP, tQ, i, j, kb_total, ep, st);
+    if (bj == 64) rc = launch_tn<64>(tP, tQ, i, j, kb_total, splits, per, j_tiles, tiles, ep, st);
+    else if (bj == 128) rc = launch_tn<128>(tP, tQ, i, j, kb_total, splits, per, j_tiles, tiles, ep, st);
+    else rc = launch_tn<256>(tP, tQ, i, j, kb_total, splits, per, j_tiles, tiles, ep, st);
+    if (rc != SPQ_OK) return rc;
+    TnReduce ra;
+    ra.part = ep.part; ra.splits = splits; ra.plane = ep.plane; ra.I = I; ra.J = J; ra.stride_i = d_stride_i; ra.stride_j = d_stride_j;
+    ra.i_scale = i_scale; ra.j_scale = j_scale; ra.alpha_dev = alpha_dev; ra.alpha = alpha; ra.clamp_abs = clamp_abs; ra.D = D;
+    long long blocks = (ep.plane / 4 + 255) / 256;
+    const long long cap = static_cast<long long>(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    tn_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ra);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
 }

@@ -180,6 +180,167 @@ distill_kl_kernel(const float* __restrict__ s_logits, long long ld_s, const floa
     }
 }
 
+
+// Softmax loss over the LM-head logits with the gradient emitted AS THE fp16 OPERAND of the LM-head backward GEMM
+// (SURVEY section 8 f1 / VERDICT r01 item 7: the float32 [B, T, V] dlogits matrix is never materialised):
+//   KIND 0 (distillation, p1/distillation_manager.py:64-80): row_loss = KL(softmax(t/T) || softmax(s/T)),
+//           d[v] = softmax(s/T)[v] - softmax(t/T)[v]        (caller scale: T^2/rows * 1/T)
+//   KIND 1 (next-token cross-entropy, p1/models_sp.py:441-449): row_loss = logsumexp(s) - s[target],
+//           d[v] = softmax(s)[v] - [v == target]            (caller scale: 1 / number of scored rows)
+// Output: g16[m, v] = fp16(d[v] * 2^(8-E[m])), row_scale[m] = 2^(E[m]-8) with 2^(E-1) <= max_v |d| < 2^E (rows that are
+// not scored -- the last position of each sequence, ignored targets -- are zero with the smallest scale 2^-108, the
+// convention of spq_rowscale_f16), max_scale[0] = max_m row_scale[m].
+// One 1024-thread CTA per row and ONE CTA per SM: 148 rows x 2 x 201 KB stay in L2, so of the three passes (online
+// max / sum-exp; loss + max|d|; scaled store) only the first reads HBM.  Algorithmic bytes: 4 (8 for KIND 0) read +
+// 2 written per logit.
+template <int KIND>
+__global__ void __launch_bounds__(1024, 1)
+softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, const float* __restrict__ t_logits, long long ld_t,
+                           const long long* __restrict__ targets, long long ignore_index, long long M, long long V, float inv_T,
+                           long long seq_len, float* __restrict__ row_loss, float* __restrict__ row_valid,
+                           unsigned short* __restrict__ g16, long long ld_g, float* __restrict__ row_scale,
+                           float* __restrict__ max_scale) {
+    constexpr int NT = 1024, NW = 32;
+    __shared__ float sm[4][NW];
+    __shared__ float s_b[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float cta_max_scale = 0.f;
+    for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+        unsigned short* go = g16 + row * ld_g;
+        long long tgt = -1;
+        bool skip = seq_len > 0 && (row % seq_len) == seq_len - 1;
+        if (KIND == 1) {
+            tgt = targets[row];
+            skip = skip || tgt == ignore_index || tgt < 0 || tgt >= V;
+        }
+        if (skip) {                                                  // block-uniform
+            if (tid == 0) { row_loss[row] = 0.f; if (row_valid) row_valid[row] = 0.f; row_scale[row] = 3.0814879110195774e-33f; }   // 2^-108
+            for (long long i = tid; i < (ld_g >> 1); i += NT) reinterpret_cast<unsigned int*>(go)[i] = 0u;
+            cta_max_scale = fmaxf(cta_max_scale, 3.0814879110195774e-33f);
+            continue;
+        }
+        const float* ps_ = s_logits + row * ld_s;
+        const float* pt_ = KIND == 0 ? t_logits + row * ld_t : nullptr;
+        const bool vec = ((ld_s & 3) == 0) && aligned16_dev(s_logits) && (KIND == 1 || (((ld_t & 3) == 0) && aligned16_dev(t_logits)));
+        const long long v4 = vec ? (V >> 2) : 0;
+        // ---- pass 1 (HBM): online max / sum exp
+        MS a; a.m = -INFINITY; a.s = 0.f;
+        MS b; b.m = -INFINITY; b.s = 0.f;
+        for (long long i = tid; i < v4; i += NT) {
+            float4 x = ld_stream_f4(ps_ + 4 * i);
+            x.x *= inv_T; x.y *= inv_T; x.z *= inv_T; x.w *= inv_T;
+            float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+            if (mx > a.m) { a.s *= __expf(a.m - mx); a.m = mx; }
+            a.s += __expf(x.x - a.m) + __expf(x.y - a.m) + __expf(x.z - a.m) + __expf(x.w - a.m);
+            if (KIND == 0) {
+                float4 y = ld_stream_f4(pt_ + 4 * i);
+                y.x *= inv_T; y.y *= inv_T; y.z *= inv_T; y.w *= inv_T;
+                mx = fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w));
+                if (mx > b.m) { b.s *= __expf(b.m - mx); b.m = mx; }
+                b.s += __expf(y.x - b.m) + __expf(y.y - b.m) + __expf(y.z - b.m) + __expf(y.w - b.m);
+            }
+        }
+        for (long long i = 4 * v4 + tid; i < V; i += NT) {
+            push(a, __ldg(ps_ + i) * inv_T);
+            if (KIND == 0) push(b, __ldg(pt_ + i) * inv_T);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MS c; c.m = __shfl_xor_sync(0xffffffffu, a.m, o); c.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+            a = combine(a, c);
+            if (KIND == 0) {
+                c.m = __shfl_xor_sync(0xffffffffu, b.m, o); c.s = __shfl_xor_sync(0xffffffffu, b.s, o);
+                b = combine(b, c);
+            }
+        }
+        __syncthreads();                                             // previous row's readers of sm / s_b are done
+        if (lane == 0) { sm[0][warp] = a.m; sm[1][warp] = a.s; sm[2][warp] = b.m; sm[3][warp] = b.s; }
+        __syncthreads();
+        if (warp == 0) {
+            MS x; x.m = sm[0][lane]; x.s = sm[1][lane];
+            MS y; y.m = sm[2][lane]; y.s = sm[3][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                MS c; c.m = __shfl_xor_sync(0xffffffffu, x.m, o); c.s = __shfl_xor_sync(0xffffffffu, x.s, o);
+                x = combine(x, c);
+                c.m = __shfl_xor_sync(0xffffffffu, y.m, o); c.s = __shfl_xor_sync(0xffffffffu, y.s, o);
+                y = combine(y, c);
+            }
+            if (lane == 0) { s_b[0] = x.m + logf(x.s); s_b[1] = (KIND == 0) ? y.m + logf(y.s) : 0.f; }
+        }
+        __syncthreads();
+        const float lse_s = s_b[0], lse_t = s_b[1];
+        // ---- pass 2 (L2): loss terms and max |d|
+        float acc = 0.f, dmax = 0.f;
+        auto dval = [&](float sv, float tv, long long idx) -> float {
+            const float ls = fmaf(sv, inv_T, -lse_s);
+            if (KIND == 0) {
+                const float lt = fmaf(tv, inv_T, -lse_t);
+                const float pt = __expf(lt);
+                acc = fmaf(pt, lt - ls, acc);
+                return __expf(ls) - pt;
+            }
+            return __expf(ls) - (idx == tgt ? 1.0f : 0.0f);
+        };
+        for (long long i = tid; i < v4; i += NT) {
+            const float4 x = *reinterpret_cast<const float4*>(ps_ + 4 * i);
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (KIND == 0) y = *reinterpret_cast<const float4*>(pt_ + 4 * i);
+            const float d0 = dval(x.x, y.x, 4 * i), d1 = dval(x.y, y.y, 4 * i + 1), d2 = dval(x.z, y.z, 4 * i + 2), d3 = dval(x.w, y.w, 4 * i + 3);
+            dmax = fmaxf(dmax, fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))));
+        }
+        for (long long i = 4 * v4 + tid; i < V; i += NT)
+            dmax = fmaxf(dmax, fabsf(dval(__ldg(ps_ + i), KIND == 0 ? __ldg(pt_ + i) : 0.f, i)));
+        acc = warp_sum(acc);
+        dmax = warp_fmax(dmax);
+        __syncthreads();
+        if (lane == 0) { sm[0][warp] = acc; sm[1][warp] = dmax; }
+        __syncthreads();
+        if (warp == 0) {
+            float t0 = warp_sum(sm[0][lane]);
+            float t1 = warp_fmax(sm[1][lane]);
+            if (lane == 0) { s_b[2] = t0; s_b[3] = t1; }
+        }
+        __syncthreads();
+        const float amax = s_b[3];
+        int E = 0;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;
+        E = E < -100 ? -100 : E;
+        const float down = exp2f(static_cast<float>(8 - E));
+        const float up = exp2f(static_cast<float>(E - 8));
+        if (tid == 0) {
+            row_loss[row] = (KIND == 0) ? s_b[2] : (lse_s - __ldg(ps_ + tgt) * inv_T);
+            if (row_valid) row_valid[row] = 1.f;
+            row_scale[row] = up;
+        }
+        cta_max_scale = fmaxf(cta_max_scale, up);
+        // ---- pass 3 (L2): the scaled fp16 operand
+        auto dq = [&](float sv, float tv, long long idx) -> float {
+            const float ls = fmaf(sv, inv_T, -lse_s);
+            float d;
+            if (KIND == 0) d = __expf(ls) - __expf(fmaf(tv, inv_T, -lse_t));
+            else d = __expf(ls) - (idx == tgt ? 1.0f : 0.0f);
+            return d * down;
+        };
+        const bool gvec = (ld_g & 3) == 0 && (reinterpret_cast<uintptr_t>(g16) & 7u) == 0;
+        if (gvec) {
+            for (long long i = tid; i < v4; i += NT) {
+                const float4 x = *reinterpret_cast<const float4*>(ps_ + 4 * i);
+                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (KIND == 0) y = *reinterpret_cast<const float4*>(pt_ + 4 * i);
+                *reinterpret_cast<uint2*>(go + 4 * i) = make_uint2(pack_h2(dq(x.x, y.x, 4 * i), dq(x.y, y.y, 4 * i + 1)),
+                                                                  pack_h2(dq(x.z, y.z, 4 * i + 2), dq(x.w, y.w, 4 * i + 3)));
+            }
+            for (long long i = 4 * v4 + tid; i < ld_g; i += NT)
+                go[i] = i < V ? f2h_sat(dq(__ldg(ps_ + i), KIND == 0 ? __ldg(pt_ + i) : 0.f, i)) : static_cast<unsigned short>(0);
+        } else {
+            for (long long i = tid; i < ld_g; i += NT)
+                go[i] = i < V ? f2h_sat(dq(__ldg(ps_ + i), KIND == 0 ? __ldg(pt_ + i) : 0.f, i)) : static_cast<unsigned short>(0);
+        }
+    }
+    if (tid == 0 && max_scale) atomicMax(reinterpret_cast<int*>(max_scale), __float_as_int(cta_max_scale));
+}
+
 }  // namespace loss
 }  // namespace spq
 
@@ -220,6 +381,32 @@ extern "C" int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* 
     if (ctas > M) ctas = M;
     loss::distill_kl_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(
         s_logits, ld_s, t_logits, ld_t, M, V, 1.0f / temperature, seq_len, grad_scale / temperature, row_loss, grad);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_softmax_loss_grad16(int kind, const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t,
+                                       const int64_t* targets, int64_t ignore_index, int64_t M, int64_t V, float temperature,
+                                       int64_t seq_len, float* row_loss, float* row_valid, spq_half_t* g16, int64_t ld_g,
+                                       float* row_scale, float* max_scale, spq_stream_t stream) {
+    SPQ_REQUIRE(s_logits && row_loss && g16 && row_scale && max_scale && M > 0 && V > 0 && ld_s >= V && ld_g >= V && (ld_g % 2) == 0,
+                "spq_softmax_loss_grad16: bad arguments");
+    SPQ_REQUIRE((reinterpret_cast<uintptr_t>(g16) & 3u) == 0, "spq_softmax_loss_grad16: g16 must be 4-byte aligned");
+    SPQ_REQUIRE(kind == 0 || kind == 1, "spq_softmax_loss_grad16: kind must be 0 (distillation KL) or 1 (cross-entropy)");
+    SPQ_REQUIRE(kind == 1 || (t_logits && ld_t >= V && temperature > 0.f), "spq_softmax_loss_grad16: KL needs teacher logits and T > 0");
+    SPQ_REQUIRE(kind == 0 || targets, "spq_softmax_loss_grad16: cross-entropy needs targets");
+    cudaStream_t st = as_stream(stream);
+    SPQ_CUDA_OK(cudaMemsetAsync(max_scale, 0, sizeof(float), st));
+    long long ctas = sm_count() > 0 ? sm_count() : 148;
+    if (ctas > M) ctas = M;
+    if (kind == 0)
+        loss::softmax_loss_grad16_kernel<0><<<static_cast<unsigned>(ctas), 1024, 0, st>>>(
+            s_logits, ld_s, t_logits, ld_t, nullptr, ignore_index, M, V, 1.0f / temperature, seq_len, row_loss, row_valid, g16, ld_g,
+            row_scale, max_scale);
+    else
+        loss::softmax_loss_grad16_kernel<1><<<static_cast<unsigned>(ctas), 1024, 0, st>>>(
+            s_logits, ld_s, nullptr, 0, reinterpret_cast<const long long*>(targets), ignore_index, M, V, 1.0f, seq_len, row_loss,
+            row_valid, g16, ld_g, row_scale, max_scale);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

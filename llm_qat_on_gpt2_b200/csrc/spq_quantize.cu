@@ -295,6 +295,7 @@ struct ActArgs {
     unsigned short* a_raw;
     float* raw_row_scale;       // row-scaled variant only
     const float* raw_col_mul;   // elementwise variant: per-column multiplier of the raw operand
+    float* max_scale;           // row-scaled variant: optional device scalar, max over rows of the row scale
 };
 
 // Row-scaled raw operand (no quantiser): one CTA of G threads owns a row at a time, the row stays in
@@ -306,6 +307,7 @@ rowscale_kernel(ActArgs a) {
     const int G = blockDim.x;
     const int tid = threadIdx.x;
     __shared__ float s_red[8];
+    float cta_max_scale = 0.f;
     for (long long row = blockIdx.x; row < a.M; row += gridDim.x) {
         const XT* px = static_cast<const XT*>(a.x) + row * a.K;
         float4 v[NV];
@@ -332,7 +334,9 @@ rowscale_kernel(ActArgs a) {
         if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;
         E = E < -100 ? -100 : E;
         const float down = exp2f(static_cast<float>(8 - E));
-        if (tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = exp2f(static_cast<float>(E - 8));
+        const float up = exp2f(static_cast<float>(E - 8));
+        if (tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = up;
+        cta_max_scale = fmaxf(cta_max_scale, up);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const long long c = (static_cast<long long>(i) * G + tid) * 4;
@@ -341,6 +345,8 @@ rowscale_kernel(ActArgs a) {
                     make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
         }
     }
+    // scales are positive floats: their bit patterns order like integers
+    if (tid == 0 && a.max_scale) atomicMax(reinterpret_cast<int*>(a.max_scale), __float_as_int(cta_max_scale));
 }
 
 // Fused activation-side kernel (calibrated quantiser): purely elementwise.  Thread = 4 consecutive
@@ -427,9 +433,10 @@ quantize_act_kernel(ActArgs a) {
 // one CTA per row, two passes (the second pass hits L2), output rows `ld_out` apart.
 __global__ void __launch_bounds__(256)
 rowscale_wide_kernel(const float* __restrict__ x, long long M, long long K, unsigned short* __restrict__ out,
-                     long long ld_out, float* __restrict__ row_scale) {
+                     long long ld_out, float* __restrict__ row_scale, float* __restrict__ max_scale) {
     __shared__ float s_red[8];
     const int tid = threadIdx.x;
+    float cta_max_scale = 0.f;
     for (long long row = blockIdx.x; row < M; row += gridDim.x) {
         const float* p = x + row * K;
         float amax = 0.f;
@@ -446,6 +453,7 @@ rowscale_wide_kernel(const float* __restrict__ x, long long M, long long K, unsi
         E = E < -100 ? -100 : E;
         const float down = exp2f(static_cast<float>(8 - E));
         if (tid == 0 && row_scale) row_scale[row] = exp2f(static_cast<float>(E - 8));
+        cta_max_scale = fmaxf(cta_max_scale, exp2f(static_cast<float>(E - 8)));
         unsigned short* o = out + row * ld_out;
         for (long long c = 2 * tid; c < K; c += 512) {
             const float a = __ldg(p + c) * down;
@@ -453,6 +461,7 @@ rowscale_wide_kernel(const float* __restrict__ x, long long M, long long K, unsi
             else o[c] = f2h_sat(a);
         }
     }
+    if (tid == 0 && max_scale) atomicMax(reinterpret_cast<int*>(max_scale), __float_as_int(cta_max_scale));
 }
 
 __global__ void __launch_bounds__(256) ste_backward_kernel(const float* __restrict__ g, long long n, int clampit, float* __restrict__ out) {
@@ -601,30 +610,94 @@ extern "C" int spq_quantize_act(const void* x, int x_is_half, int64_t M, int64_t
     a.x = x; a.x_half = x_is_half ? 1 : 0; a.M = M; a.K = K; a.scale = scale; a.zp = zero_point; a.bcast = bcast;
     a.qp = make_qparams(bits, symmetric);
     a.operand_kind = operand_kind; a.col_mul = col_mul; a.mul = mul;
-    a.a_q = a_q; a.a_raw = a_raw; a.raw_row_scale = nullptr; a.raw_col_mul = raw_col_mul;
+    a.a_q = a_q; a.a_raw = a_raw; a.raw_row_scale = nullptr; a.raw_col_mul = raw_col_mul; a.max_scale = nullptr;
     cudaStream_t st = as_stream(stream);
     if (qtype == SPQ_MINMAX) return launch_act<SPQ_MINMAX>(a, st);
     return launch_act<SPQ_LOG>(a, st);
 }
 
-extern "C" int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
-                                float* row_scale, spq_stream_t stream) {
+static int rowscale_impl(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
+                         float* row_scale, float* max_scale, spq_stream_t stream) {
     SPQ_REQUIRE(g && out && M > 0 && N > 0, "spq_rowscale_f16: bad arguments");
     if (ld_out <= 0) ld_out = N;
     SPQ_REQUIRE(ld_out >= N, "spq_rowscale_f16: ld_out < N");
+    if (max_scale) SPQ_CUDA_OK(cudaMemsetAsync(max_scale, 0, sizeof(float), as_stream(stream)));
     if (ld_out == N && (N % 4) == 0 && N <= 8192 && aligned16(g)) {
         ActArgs a;
         a.x = g; a.x_half = g_is_half ? 1 : 0; a.M = M; a.K = N; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
         a.qp = make_qparams(8, 1);
         a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
-        a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr;
+        a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr; a.max_scale = max_scale;
         return launch_rowscale(a, as_stream(stream));
     }
     SPQ_REQUIRE(!g_is_half, "spq_rowscale_f16: float16 input needs dense rows (ld_out == N), N %% 4 == 0, N <= 8192, 16-byte alignment");
     SPQ_REQUIRE((ld_out % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0, "spq_rowscale_f16: ld_out must be even");
     long long ctas = static_cast<long long>(sm_count()) * 8;
     if (ctas > M) ctas = M;
-    rowscale_wide_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(static_cast<const float*>(g), M, N, out, ld_out, row_scale);
+    rowscale_wide_kernel<<<static_cast<unsigned>(ctas), 256, 0, as_stream(stream)>>>(static_cast<const float*>(g), M, N, out, ld_out,
+                                                                                    row_scale, max_scale);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
+                                float* row_scale, spq_stream_t stream) {
+    return rowscale_impl(g, g_is_half, M, N, out, ld_out, row_scale, nullptr, stream);
+}
+
+extern "C" int spq_rowscale_f16_max(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
+                                    float* row_scale, float* max_scale, spq_stream_t stream) {
+    SPQ_REQUIRE(max_scale, "spq_rowscale_f16_max: null max_scale");
+    return rowscale_impl(g, g_is_half, M, N, out, ld_out, row_scale, max_scale, stream);
+}
+
+// Operands of the LoRA gradient GEMMs from the down-projected gradient (SURVEY section 8 a13 backward):
+//   dt16[m,j] = fp16(dtn[m,j] * dt_mul)                     -> dX += dt q(A)^T      (token scale eg[m] in the epilogue)
+//   dt2 [m,j] = fp16(dtn[m,j] * dt_mul * eg[m] / gmax)      -> dA  = x^T dt         (token scale folded: reduction over m)
+//   t2  [m,j] = fp16(t16[m,j] * eg[m] / gmax)               -> dB  = t^T dY
+// eg[m] are the power-of-two row scales of the fp16 gradient operand and gmax their maximum (both from
+// spq_rowscale_f16_max), so eg / gmax <= 1 is a power of two and the products are exact up to fp16 underflow.
+__global__ void __launch_bounds__(256)
+lora_bwd_prep_kernel(const float* __restrict__ dtn, const unsigned short* __restrict__ t16, long long ld_t,
+                     const float* __restrict__ eg, const float* __restrict__ gmax, long long M, int r, float dt_mul,
+                     unsigned short* __restrict__ dt16, unsigned short* __restrict__ dt2, unsigned short* __restrict__ t2) {
+    const float inv_gmax = 1.0f / __ldg(gmax);
+    const int per_row = r >> 2;                                  // float4 groups per row
+    const long long total = M * per_row;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long m = i / per_row;
+        const int c = static_cast<int>(i - m * per_row) * 4;
+        const float e = __ldg(eg + m) * inv_gmax;
+        if (dtn) {
+            const float4 v = ld_stream_f4(dtn + m * r + c);
+            const float a0 = v.x * dt_mul, a1 = v.y * dt_mul, a2 = v.z * dt_mul, a3 = v.w * dt_mul;
+            if (dt16) *reinterpret_cast<uint2*>(dt16 + m * r + c) = make_uint2(pack_h2(a0, a1), pack_h2(a2, a3));
+            if (dt2) *reinterpret_cast<uint2*>(dt2 + m * r + c) = make_uint2(pack_h2(a0 * e, a1 * e), pack_h2(a2 * e, a3 * e));
+        }
+        if (t16 && t2) {
+            const uint2 h = *reinterpret_cast<const uint2*>(t16 + m * ld_t + c);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+            *reinterpret_cast<uint2*>(t2 + m * r + c) = make_uint2(pack_h2(lo.x * e, lo.y * e), pack_h2(hi.x * e, hi.y * e));
+        }
+    }
+}
+
+extern "C" int spq_lora_bwd_prep(const float* dtn, const spq_half_t* t16, int64_t ld_t16, const float* row_scale,
+                                 const float* max_scale, int64_t M, int64_t r, float dt_mul, spq_half_t* dt16, spq_half_t* dt2,
+                                 spq_half_t* t2, spq_stream_t stream) {
+    SPQ_REQUIRE(row_scale && max_scale && M > 0 && r > 0 && (r % 4) == 0, "spq_lora_bwd_prep: bad arguments (rank must be a multiple of 4)");
+    SPQ_REQUIRE((!dt16 || (reinterpret_cast<uintptr_t>(dt16) & 7u) == 0) && (!dt2 || (reinterpret_cast<uintptr_t>(dt2) & 7u) == 0) && (!t2 || (reinterpret_cast<uintptr_t>(t2) & 7u) == 0) && (!t16 || (reinterpret_cast<uintptr_t>(t16) & 7u) == 0), "spq_lora_bwd_prep: operands must be 8-byte aligned");
+    SPQ_REQUIRE((dtn && (dt16 || dt2)) || (t16 && t2), "spq_lora_bwd_prep: nothing to do");
+    SPQ_REQUIRE(!dtn || aligned16(dtn), "spq_lora_bwd_prep: dtn must be 16-byte aligned");
+    SPQ_REQUIRE(!t16 || ((ld_t16 % 4) == 0 && ld_t16 >= r), "spq_lora_bwd_prep: bad t16 leading dimension");
+    const long long total = M * (r / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    lora_bwd_prep_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(dtn, t16, ld_t16, row_scale, max_scale, M,
+                                                                                     static_cast<int>(r), dt_mul, dt16, dt2, t2);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

@@ -322,18 +322,13 @@ class _SPLinearFn(torch.autograd.Function):
         y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
         res2d = None if residual is None else residual.reshape(M, N)
-        t = None
+        t16 = None
         if use_lora:
             r = lo['rank']
-            if grad_mode and any(ctx.needs_input_grad[:5]):
-                t = torch.empty((M, r), dtype=torch.float32, device=x.device)     # kept for dB
-                _lib.qgemm(a_raw, lo['A_op'], M, r, K, t, col_scale=lo['pa'])
-                t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
-            else:
-                # nothing to save: the down-projection stores its fp16 operand directly (pa and tau are
-                # powers of two, so fp16(acc * (pa tau)) is the same value as the two-step form)
-                t16 = _lib.empty_f16_padded(M, r, x.device)
-                _lib.qgemm(a_raw, lo['A_op'], M, r, K, t16, col_scale=lo['pa_tmul'])
+            # the down-projection stores its fp16 operand directly (pa and tau are powers of two, so
+            # fp16(acc * (pa tau)) is the value the GEMM consumes); the same tensor is what dB = t^T dY needs later
+            t16 = _lib.empty_f16_padded(M, r, x.device)
+            _lib.qgemm(a_raw, lo['A_op'], M, r, K, t16, col_scale=lo['pa_tmul'])
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f,
                        activation=activation, C=res2d)
         else:
@@ -346,54 +341,52 @@ class _SPLinearFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         ctx.mod, ctx.bits = mod, bits       # backward operands are built (and cached) when backward first runs
         ctx.weight_qtype = mod.quantizers_weight[f'{bits}bit'].quantizer_type
-        ctx.save_for_backward(a_q if need[1] else None, a_raw, t)
+        keep_t = grad_mode and use_lora and need[4]
+        ctx.save_for_backward(a_q if need[1] else None, a_raw if (grad_mode and use_lora and need[3]) else None,
+                              t16 if keep_t else None)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gy):
-        a_q, a_raw, t = ctx.saved_tensors
+        a_q, a_raw, t16 = ctx.saved_tensors
         base, lo = ctx.base, ctx.lo
         bw = ctx.mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
         g2d = _as_2d_f32(gy, N)
         dev = gy.device
         act = base['act']
-        g16, eg = _rowscaled_f16(g2d)                 # dY = g16 * eg[:,None]
-        gx = gw = gb = gA = gB = None
         need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
+        # dY = g16 * eg[:,None]; gmax1 = max eg (all-zero rows -- positions without a loss -- carry the smallest scale)
+        g16 = _lib.empty_f16_padded(M, N, dev)
+        eg = torch.empty(M, dtype=torch.float32, device=dev)
+        gmax1 = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.rowscale_f16_max(g2d, g16, eg, gmax1)
+        gx = gw = gb = gA = gB = None
         clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
-        gmax = egn = gmax1 = None
-        if need_w or (ctx.use_lora and (need_A or need_B)):
-            gmax = eg.max()
-            gmax1 = gmax.reshape(1)
-            egn = eg / gmax                                  # token scales relative to the largest one (<= 1)
 
         dt16 = None
         if ctx.use_lora and (need_x or need_A or need_B):
             lb = bw['lora']
             r = lo['rank']
+            dtn = None
             if need_x or need_A:
                 # dtn[m,r] = dt[m,r] / eg[m],  dt = scaling * dY q(B)^T
                 dtn = torch.empty((M, r), dtype=torch.float32, device=dev)
                 _lib.qgemm(g16, lb['B_rn_op'], M, r, N, dtn, col_scale=lb['pb'])
-                if need_x:
-                    dt16 = _to_f16_operand(dtn, mul=lb['dt_mul'])
-                if need_A:
-                    # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; token scale eg folded into dt
-                    dt2 = _to_f16_operand(dtn, row_mul=egn, mul=lb['dt_mul'])
-                    gA = torch.empty((K, r), dtype=torch.float32, device=dev)
-                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1,
-                                 i_scale=act['inv_raw_mul'])
-                    if lo['qtype_A'] == 'log':
-                        gA = _lib.ste_backward(gA, _lib.LOG)
+            # one pass builds every fp16 operand of the three LoRA gradient GEMMs (token scales relative to the
+            # largest one folded into the operands of the two token reductions)
+            dt16, dt2, t2 = _lib.lora_bwd_prep(dtn, t16 if need_B else None, eg, gmax1, lb['dt_mul'],
+                                               want_dt16=need_x, want_dt2=need_A, want_t2=need_B)
+            if need_A:
+                # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; log STE clamp in the reduce pass
+                gA = torch.empty((K, r), dtype=torch.float32, device=dev)
+                _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['inv_raw_mul'],
+                             clamp_abs=10.0 if lo['qtype_A'] == 'log' else 0.0)
             if need_B:
-                # dB[r,n] = scaling * sum_m t[m,r] dY[m,n]; token scales folded into t
-                t2 = _to_f16_operand(t, row_mul=egn, col_mul=lo['tmul_vec'])
+                # dB[r,n] = scaling * sum_m t[m,r] dY[m,n],  t[m,r] = t16[m,r] / tau[r]
                 gB = torch.empty((r, N), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1,
-                             j_scale=lo['inv_tmul_vec'], transposed_out=True)
-                if lo['qtype_B'] == 'log':
-                    gB = _lib.ste_backward(gB, _lib.LOG)
+                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
+                             transposed_out=True, clamp_abs=10.0 if lo['qtype_B'] == 'log' else 0.0)
 
         if need_x:
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)
@@ -410,12 +403,11 @@ class _SPLinearFn(torch.autograd.Function):
                 _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in)
             gx = gx.view(ctx.x_shape).to(ctx.x_dtype)
         if need_w:
-            # dW[n,k] = sum_m dY[m,n] q(x)[m,k];  q(x)[m,k] = a_q[m,k] * absorb[k]
-            gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax).expand(M).contiguous())
+            # dW[n,k] = sum_m dY[m,n] q(x)[m,k];  q(x)[m,k] = a_q[m,k] * absorb[k]; gG = dY / gmax, |gG| <= 256
+            gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax1).expand(M).contiguous())
             gw = torch.empty((N, K), dtype=torch.float32, device=dev)
-            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax1, j_scale=act['absorb'])
-            if ctx.weight_qtype == 'log':
-                gw = _lib.ste_backward(gw, _lib.LOG)
+            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax1, j_scale=act['absorb'],
+                         clamp_abs=10.0 if ctx.weight_qtype == 'log' else 0.0)
         if ctx.has_bias and need_b:
             gb = g2d.sum(dim=0)
         return gx, gw, gb, gA, gB, None, None, None, None, None, None

@@ -74,11 +74,11 @@ class LoRARefresher:
         for m, _ in self.active:
             m._restamp_lora_keys(self.bits, self.with_bwd)
 
-    def refresh(self) -> None:
-        """Recalibrate the active LoRA quantisers on the current LoRA weights and rebuild every operand that
-        depends on them, for all linears."""
+    def replay(self):
+        """The device part of `refresh()` as one graph replay (captured on first use / when an address or a static
+        cache level changed); returns the deferred host part (`finish(redo=...)`, one device->host flag read)."""
         if not self.active:
-            return
+            return lambda redo=True: 0
         with torch.no_grad():
             sig = self._signature()
             if self.graph is None or sig != self._sig:
@@ -92,14 +92,21 @@ class LoRARefresher:
                     fin = self.body()
                 self.graph, self.finish, self._sig = g, fin, self._signature()
             self.graph.replay()
-            redone = self.finish()
-            if redone:
-                # a log quantiser without data (fresh all-zero lora_B) went through the reference's default-shape
-                # path on the host side: its scales are not the ones the replay used -- rebuild eagerly this once
+            self.restamp()
+        return self.finish
+
+    def refresh(self) -> None:
+        """Recalibrate the active LoRA quantisers on the current LoRA weights and rebuild every operand that
+        depends on them, for all linears."""
+        if not self.active:
+            return
+        redone = self.replay()()
+        if redone:
+            # a log quantiser without data (fresh all-zero lora_B) went through the reference's default-shape
+            # path on the host side: its scales are not the ones the replay used -- rebuild eagerly this once
+            with torch.no_grad():
                 self._build_all()
-                self._sig = None
-            else:
-                self.restamp()
+            self._sig = None
 
 
 class _DistillKL(torch.autograd.Function):
@@ -160,6 +167,79 @@ def distillation_loss(student_outputs, teacher_outputs, temperature: float = 3.0
                 l = (rng or random).choice(layers)
                 feature = F.mse_loss(hs[l], ht[l], reduction='mean')
     return alpha_kl * kl if feature is None else alpha_kl * kl + alpha_feature * feature
+
+
+class _LMHeadLossFn(torch.autograd.Function):
+    """loss(lm_head(hidden)) with the LM-head backward fed by the loss kernel's fp16 gradient operand: the float32
+    [B, T, V] dlogits matrix, its row-scaling pass and torch's softmax passes never exist."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, cache, kind, other, temperature):
+        from . import _lib
+        from .lora import _as_2d_act, _rowscaled_f16
+        V, C = weight.shape
+        B, T = hidden.shape[0], hidden.shape[1]
+        x2d = _as_2d_act(hidden, C, max_cols=8192)
+        M = x2d.shape[0]
+        x16, rs = _rowscaled_f16(x2d)
+        w16, pw = cache.get(weight, transposed=False)
+        ld = (V + 31) // 32 * 32
+        logits = torch.empty((M, ld), dtype=torch.float32, device=hidden.device)
+        s2d = logits[:, :V]
+        _lib.qgemm(x16, w16, M, V, C, s2d, row_scale=rs, col_scale=pw)
+        if kind == 'kl':
+            t = other
+            if t.dtype != torch.float32:
+                t = t.float()
+            if t.stride(-1) == 1 and t.stride(0) == T * t.stride(1):
+                t2d = t.as_strided((M, V), (t.stride(1), 1))              # the row-padded view the LM head returns
+            else:
+                t2d = t.reshape(M, V).contiguous()
+            row_loss, _, g16, eg, _ = _lib.softmax_loss_grad16(s2d, 'kl', t2d=t2d, temperature=temperature, seq_len=T)
+            rows = B * (T - 1)
+            loss = row_loss.sum() * (temperature * temperature / rows)
+            factor = torch.full((1,), temperature / rows, dtype=torch.float32, device=hidden.device)
+        else:
+            labels = other
+            targets = torch.full_like(labels, -100)
+            targets[..., :-1] = labels[..., 1:]                             # position t is scored against token t+1
+            row_loss, row_valid, g16, eg, _ = _lib.softmax_loss_grad16(s2d, 'ce', targets=targets)
+            factor = (1.0 / row_valid.sum()).reshape(1)
+            loss = row_loss.sum() * factor[0]
+        ctx.cache, ctx.x_shape, ctx.dims = cache, hidden.shape, (M, V, C)
+        ctx.save_for_backward(g16, eg, factor, weight)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import _lib
+        g16, eg, factor, weight = ctx.saved_tensors
+        M, V, C = ctx.dims
+        gx = None
+        if ctx.needs_input_grad[0]:
+            wt16, pk = ctx.cache.get(weight, transposed=True)
+            gx = torch.empty((M, C), dtype=torch.float32, device=g16.device)
+            _lib.qgemm(g16, wt16, M, C, V, gx, row_scale=eg * (gout * factor), col_scale=pk)
+            gx = gx.view(ctx.x_shape)
+        return gx, None, None, None, None, None
+
+
+def lm_head_loss(model, hidden, *, labels=None, teacher_logits=None, temperature: float = 3.0):
+    """Loss of the tied LM head on the final hidden states [B, T, C] of an SPLMHeadModel:
+      labels given          -> the next-token cross-entropy of SPLMHeadModel.forward (p1/models_sp.py:441-449);
+      teacher_logits given  -> KL(T) * T^2 of DistillationManager.compute_distillation_loss (p1/distillation_manager.py:64-80).
+    Same values as `F.cross_entropy` / `distillation_kl_loss` on `model.lm_head(hidden)`; gradient flows to `hidden`
+    only (the tied embedding is frozen on this path)."""
+    if (labels is None) == (teacher_logits is None):
+        raise ValueError("lm_head_loss: give either labels or teacher_logits")
+    if not hidden.is_cuda:
+        raise RuntimeError("lm_head_loss runs on the CUDA kernels only (no CPU fallback)")
+    w = model.lm_head.weight
+    if torch.is_grad_enabled() and w.requires_grad:
+        raise RuntimeError("lm_head_loss does not produce a gradient for the (tied) LM-head weight; freeze it or use model(...)")
+    if labels is not None:
+        return _LMHeadLossFn.apply(hidden, w, model._lm_head_cache, 'ce', labels, 1.0)
+    return _LMHeadLossFn.apply(hidden, w, model._lm_head_cache, 'kl', teacher_logits, float(temperature))
 
 
 class GraphedNoGradForward:
@@ -373,8 +453,8 @@ class SPTrainer:
         m = self.model
         m.set_precision(self.teacher_bits)
         self._mark_inner('teacher_forward')
-        out = m(self.ids, labels=self.ids, output_hidden_states=True, return_dict=True)
-        loss = out['loss'] / self.G
+        hidden, _ = m.transformer(self.ids, output_hidden_states=True)
+        loss = lm_head_loss(m, hidden, labels=self.ids) / self.G           # outputs['loss'] of model(ids, labels=ids)
         self._mark_inner('teacher_backward')
         loss.backward()
         self._mark_inner('teacher_cache_forward')
@@ -386,20 +466,26 @@ class SPTrainer:
         import torch.nn.functional as F
         m = self.model
         m.set_precision(bits)
-        self._mark_inner('lora_recalibration')
-        fin = self.refreshers[bits].body()                                  # calibrate_lora_only(bits)
         self._mark_inner('student_forward')
-        out = m(self.ids, output_hidden_states=True, return_dict=True)
+        hidden, hs = m.transformer(self.ids, output_hidden_states=True)
         tch = self.outs[self.teacher_bits]
         self._mark_inner('distillation_loss')
-        kl = distillation_kl_loss(out['logits'], tch['logits'], self.T)
+        kl = lm_head_loss(m, hidden, teacher_logits=tch['logits'], temperature=self.T)
         with torch.no_grad():
-            hs, ht = out['hidden_states'], tch['hidden']
+            ht = tch['hidden']
             n = min(len(hs), len(ht))
             feats = torch.stack([F.mse_loss(hs[l], ht[l], reduction='mean') for l in range(n)])
         self._mark_inner('student_backward')
         ((self.alpha_kl / self.G) * kl).backward()          # the feature term carries no gradient (detached copies)
-        return {'kl': kl.detach().reshape(1), 'feats': feats, 'finish': fin}
+        return {'kl': kl.detach().reshape(1), 'feats': feats}
+
+    def _refresh(self, bits):
+        """calibrate_lora_only(bits) (p1/train_sp.py:125-163, 362-364).  Upstream repeats it before every student
+        micro-step; the LoRA weights only change at the optimizer step, so it runs before the FIRST micro-step of each
+        width in an optimizer step -- the repeats would reproduce the same numbers bit for bit (cached, like q(W))."""
+        self._mark_inner('lora_recalibration')
+        r = self.refreshers[bits]
+        self.finishers[bits] = r.replay() if self.use_graphs else r.body()
 
     def _body(self, bits):
         return self._teacher_body() if bits == self.teacher_bits else self._student_body(bits)
@@ -420,12 +506,12 @@ class SPTrainer:
         sig = self._signature(bits)
         if bits in self.graphs and self.sigs.get(bits) == sig:
             return
-        # warm-up on the eager path: operand caches, cuDNN plans, workspaces, the calibration job tables
+        if bits != self.teacher_bits:
+            self._refresh(bits)            # (captures the refresher's own graph on first use; its outputs are static)
+        # warm-up on the eager path: operand caches, cuDNN plans, workspaces
         for _ in range(2):
             self.outs[bits] = self._body(bits)
         torch.cuda.synchronize()
-        if bits != self.teacher_bits:
-            self.refreshers[bits].invalidate()
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
@@ -440,8 +526,6 @@ class SPTrainer:
     def _run(self, bits):
         if self.use_graphs:
             self.graphs[bits].replay()
-            if bits != self.teacher_bits:
-                self.refreshers[bits].restamp()
         else:
             self.outs[bits] = self._body(bits)
         return self.outs[bits]
@@ -492,7 +576,13 @@ class SPTrainer:
         self._mark('zero_grad')
         st.zero_grad()
         works = []
+        refreshed = set()
         for i, bits in enumerate(sched):
+            if bits != self.teacher_bits and bits not in refreshed:
+                self._mark(f'lora_recalibration_{bits}')
+                if bits not in self.finishers:          # (_ensure already refreshed a width it just captured)
+                    self._refresh(bits)
+                refreshed.add(bits)
             self._mark(f'micro_step_{bits}')
             out = self._run(bits)
             if bits == self.teacher_bits:
@@ -501,7 +591,6 @@ class SPTrainer:
             else:
                 self.loss_buf[i, 0:1].copy_(out['kl'])
                 self.loss_buf[i, 1:2].copy_(out['feats'][layers[i]:layers[i] + 1])
-                self.finishers[bits] = out['finish']
             if self.world > 1 and last_use[bits] == i:
                 # this segment is final: its all-reduce runs on NCCL's stream under the remaining micro-steps
                 works.append(dist.all_reduce(st.seg_grad(bits), op=dist.ReduceOp.SUM, group=self.group, async_op=True))

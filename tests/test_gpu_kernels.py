@@ -273,6 +273,70 @@ def test_gemm_tn_matches_fp64(lib, Mred, I, J, transposed):
     if transposed:
         ref = ref.t()
     assert ((out.double() - ref).norm() / ref.norm()) <= 1e-5
+    # deterministic (fixed-order fold of the split planes, no atomics) and the fused STE clamp
+    out2 = torch.empty_like(out)
+    lib.gemm_tn(P, Q, out2, alpha=2.0, alpha_dev=adev, i_scale=isc, j_scale=jsc, transposed_out=transposed)
+    assert torch.equal(out, out2)
+    c = float(ref.abs().median())
+    lib.gemm_tn(P, Q, out2, alpha=2.0, alpha_dev=adev, i_scale=isc, j_scale=jsc, transposed_out=transposed, clamp_abs=c)
+    assert torch.equal(out2, out.clamp(-c, c))
+
+
+def test_rowscale_max_and_lora_bwd_prep(lib):
+    torch.manual_seed(3)
+    M, N, r = 777, 2304, 64
+    g = torch.randn(M, N, device="cuda") * torch.exp(2 * torch.randn(M, 1, device="cuda")) * 1e-4
+    g[5] = 0.0; g[M - 1] = 0.0
+    g16 = lib.empty_f16_padded(M, N, "cuda"); eg = torch.empty(M, device="cuda"); gmax = torch.empty(1, device="cuda")
+    lib.rowscale_f16_max(g, g16, eg, gmax)
+    g16b = lib.empty_f16_padded(M, N, "cuda"); egb = torch.empty(M, device="cuda")
+    lib.rowscale_f16(g, g16b, egb)
+    assert torch.equal(g16, g16b) and torch.equal(eg, egb) and float(gmax) == float(eg.max())
+    assert float(eg[5]) == 2.0 ** -108 and float(gmax) > 2.0 ** -60
+    dtn = torch.randn(M, r, device="cuda") * 37.0
+    t16 = (torch.randn(M, r, device="cuda") * 5.0).half()
+    dt_mul = 2.0 ** -5
+    dt16, dt2, t2 = lib.lora_bwd_prep(dtn, t16, eg, gmax, dt_mul)
+    e = (eg / gmax).unsqueeze(1)
+    assert torch.equal(dt16, (dtn * dt_mul).half())
+    assert torch.equal(dt2, (dtn * dt_mul * e).half())
+    assert torch.equal(t2, (t16.float() * e).half())
+    assert float(dt2[5].abs().max()) == 0.0 and float(t2[5].abs().max()) == 0.0
+    a, b, c = lib.lora_bwd_prep(None, t16, eg, gmax, dt_mul)
+    assert a is None and b is None and torch.equal(c, t2)
+
+
+@pytest.mark.parametrize("kind", ["kl", "ce"])
+@pytest.mark.parametrize("M,V,T", [(96, 50257, 32), (40, 1000, 8), (33, 211, 11)])
+def test_softmax_loss_grad16(lib, kind, M, V, T):
+    """Loss value and the fp16 gradient operand (g16 * row_scale) against torch float64."""
+    torch.manual_seed(V + M)
+    ld = (V + 31) // 32 * 32
+    sbuf = torch.randn(M, ld, device="cuda") * 3; tbuf = sbuf + 0.3 * torch.randn(M, ld, device="cuda")
+    s, t = sbuf[:, :V], tbuf[:, :V]
+    sd = s.double().clone().requires_grad_(True)
+    if kind == "kl":
+        Tm = 3.0
+        row_loss, valid, g16, rs, mx = lib.softmax_loss_grad16(s, "kl", t2d=t, temperature=Tm, seq_len=T)
+        keep = (torch.arange(M, device="cuda") % T) != T - 1
+        ls = torch.log_softmax(sd / Tm, -1); lt = torch.log_softmax(t.double() / Tm, -1)
+        ref_rows = (lt.exp() * (lt - ls)).sum(-1) * keep
+        ref_rows.sum().backward()
+        ref_grad = sd.grad * Tm                                    # kernel emits d = ps - pt; d(row)/ds = d / T
+    else:
+        tg = torch.randint(0, V, (M,), device="cuda"); tg[::7] = -100
+        row_loss, valid, g16, rs, mx = lib.softmax_loss_grad16(s, "ce", targets=tg)
+        keep = tg >= 0
+        ref_rows = torch.nn.functional.cross_entropy(sd, tg.clamp_min(0), reduction="none") * keep
+        ref_rows.sum().backward()
+        ref_grad = sd.grad
+        assert torch.equal(valid, keep.float())
+    assert ((row_loss.double() - ref_rows).abs().max() <= 1e-5 * max(1.0, float(ref_rows.abs().max())))
+    got = g16.double() * rs.double()[:, None]
+    assert (got - ref_grad).norm() / ref_grad.norm() <= 6e-4             # fp16 rounding of a row-normalised operand
+    assert float(got[~keep].abs().max()) == 0.0 and bool((rs[~keep] == 2.0 ** -108).all())
+    assert float(mx) == float(rs.max()) and float(g16.float().abs().max()) <= 256.0
+    assert g16.stride(0) % 8 == 0
 
 
 # --------------------------------------------------------------------------- LayerNorm

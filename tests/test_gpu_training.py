@@ -81,6 +81,37 @@ def _calibrate(model, bits_list, batches):
                 m.quantizers_input[key].finish_calibration()
 
 
+def test_lm_head_loss_matches_torch():
+    """training.lm_head_loss (LM-head GEMM + softmax-loss kernel + backward GEMM fed by the fp16 gradient operand)
+    against F.cross_entropy / kl_div on float64 logits: value and d loss / d hidden."""
+    import torch.nn.functional as F
+    from llm_qat_on_gpt2_b200.training import lm_head_loss
+    model, cfg = _tiny_model((8, 32))
+    for p in model.parameters():
+        p.requires_grad_(False)
+    B, T, C, V = 2, 48, 768, 50257
+    torch.manual_seed(1)
+    hidden = torch.randn(B, T, C, device="cuda")
+    labels = torch.randint(0, V, (B, T), device="cuda")
+    W = model.lm_head.weight.double()
+    t_logits = (hidden.double() + 0.1 * torch.randn(B, T, C, device="cuda").double()) @ W.t()
+    for kind in ("ce", "kl"):
+        h = hidden.clone().requires_grad_(True)
+        hd = hidden.double().clone().requires_grad_(True)
+        logits = hd @ W.t()
+        if kind == "ce":
+            loss = lm_head_loss(model, h, labels=labels)
+            ref = F.cross_entropy(logits[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1))
+        else:
+            loss = lm_head_loss(model, h, teacher_logits=t_logits.float(), temperature=3.0)
+            ref = F.kl_div(F.log_softmax(logits[:, :-1] / 3.0, -1).reshape(-1, V), F.log_softmax(t_logits[:, :-1] / 3.0, -1).reshape(-1, V),
+                           reduction="batchmean", log_target=True) * 9.0
+        (loss * 0.125).backward()
+        (ref * 0.125).backward()
+        assert abs(float(loss) - float(ref)) <= 1e-3 * abs(float(ref)), (kind, float(loss), float(ref))
+        assert rel(h.grad, hd.grad) <= 1e-3, (kind, rel(h.grad, hd.grad))
+
+
 def test_flat_state_views_and_segments():
     from llm_qat_on_gpt2_b200.training import FlatTrainState
     model, cfg = _tiny_model((4, 8, 32))
