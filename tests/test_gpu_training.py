@@ -94,7 +94,9 @@ def test_lm_head_loss_matches_torch():
     hidden = torch.randn(B, T, C, device="cuda")
     labels = torch.randint(0, V, (B, T), device="cuda")
     W = model.lm_head.weight.double()
-    t_logits = (hidden.double() + 0.1 * torch.randn(B, T, C, device="cuda").double()) @ W.t()
+    # a teacher well away from the student: d = softmax(s) - softmax(t) is then not a difference of nearly equal
+    # numbers, and the comparison measures the kernels rather than the conditioning of the loss
+    t_logits = (0.5 * hidden.double() + torch.randn(B, T, C, device="cuda").double()) @ W.t()
     for kind in ("ce", "kl"):
         h = hidden.clone().requires_grad_(True)
         hd = hidden.double().clone().requires_grad_(True)
@@ -202,6 +204,7 @@ def test_trainer_accumulated_gradients_vs_upstream_components():
     for n, p in ref.named_parameters():
         p.requires_grad_("lora_A" in n or "lora_B" in n or ".weights." in n or ".biases." in n)
     tcfg = make_config(grad_accum=4)
+    init_params = {n: p.detach().clone() for n, p in ref.named_parameters()}
     random.seed(11)
     total_ref, used_ref, g_ref = UpstreamTrainStep(ref, bw, tcfg, lr=1e-4, total_lr_steps=40).step(ids)
     ours.train()
@@ -234,6 +237,16 @@ def test_trainer_accumulated_gradients_vs_upstream_components():
     bad = {k: v for k, v in errs.items() if not v <= 2e-3}
     assert not bad, bad
     assert float(np.median(list(errs.values()))) <= 1e-3
-    # the parameters moved like upstream's (AdamW, clip 1.0, cosine LR after G micro-steps)
-    moved = {n: rel(p.detach() , dict(ref.named_parameters())[n].detach()) for n, (p, _, _) in tr.state.slots.items() if n in g_ref}
-    assert max(moved.values()) <= 1e-3, max(moved.values())
+    # the parameters moved like upstream's (AdamW, clip 1.0, cosine LR after G micro-steps).  Adam's first step moves
+    # every element by ~lr * sign(g), so elements whose gradient is noise-level may go the other way: compare the
+    # whole vector, and the direction where the gradient is significant
+    refp = dict(ref.named_parameters())
+    names = [n for n in tr.state.slots if n in g_ref]
+    ours_vec = torch.cat([tr.state.slots[n][0].detach().reshape(-1) for n in names])
+    ref_vec = torch.cat([refp[n].detach().reshape(-1) for n in names])
+    assert rel(ours_vec, ref_vec) <= 1e-4, rel(ours_vec, ref_vec)
+    before = torch.cat([init_params[n].reshape(-1) for n in names])
+    gcat = torch.cat([g_ref[n].reshape(-1) for n in names])
+    big = gcat.abs() > 1e-2 * gcat.abs().max()
+    agree = (torch.sign(ours_vec - before)[big] == torch.sign(ref_vec - before)[big]).float().mean()
+    assert float(agree) >= 0.999 and int(big.sum()) > 100, (float(agree), int(big.sum()))
