@@ -914,7 +914,7 @@ struct TnReduce {
 };
 
 // D[e] = clamp(alpha * alpha_dev * is[i] * js[j] * sum_s part[s][e]): the splits are added in index order.
-__global__ void __launch_bounds__(256) tn_reduce_kernel(TnReduce a) {
+__global__ void __launch_bounds__(64) tn_reduce_kernel(TnReduce a) {
     const float al = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.0f);
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const bool vec = (a.plane & 3) == 0 && (reinterpret_cast<uintptr_t>(a.part) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.D) & 15u) == 0 &&
@@ -922,8 +922,16 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(TnReduce a) {
     if (vec) {
         for (long long e4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e4 < (a.plane >> 2); e4 += stride) {
             const long long e = e4 << 2;
-            float4 acc = *reinterpret_cast<const float4*>(a.part + e);
-            for (int s = 1; s < a.splits; ++s) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int s = 0;
+            for (; s + 8 <= a.splits; s += 8) {           // eight independent loads in flight, added in index order
+                float4 p[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p[u] = *reinterpret_cast<const float4*>(a.part + static_cast<long long>(s + u) * a.plane + e);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { acc.x += p[u].x; acc.y += p[u].y; acc.z += p[u].z; acc.w += p[u].w; }
+            }
+            for (; s < a.splits; ++s) {
                 const float4 p = *reinterpret_cast<const float4*>(a.part + static_cast<long long>(s) * a.plane + e);
                 acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
             }
@@ -960,7 +968,7 @@ static void tn_splits(int64_t Mred, int64_t I, int64_t J, int bj, int& splits, i
     tiles = i_tiles * j_tiles;
     const int kb_total = static_cast<int>((Mred + 63) / 64);
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    splits = (2 * sms + tiles - 1) / tiles;
+    splits = (sms + tiles - 1) / tiles;               // one wave of CTAs: every extra split is another plane to fold
     if (splits > kb_total) splits = kb_total;
     if (splits < 1) splits = 1;
     per = (kb_total + splits - 1) / splits;
@@ -1169,11 +1177,11 @@ extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q
     TnReduce ra;
     ra.part = ep.part; ra.splits = splits; ra.plane = ep.plane; ra.I = I; ra.J = J; ra.stride_i = d_stride_i; ra.stride_j = d_stride_j;
     ra.i_scale = i_scale; ra.j_scale = j_scale; ra.alpha_dev = alpha_dev; ra.alpha = alpha; ra.clamp_abs = clamp_abs; ra.D = D;
-    long long blocks = (ep.plane / 4 + 255) / 256;
-    const long long cap = static_cast<long long>(sm_count()) * 8;
+    long long blocks = (ep.plane / 4 + 63) / 64;
+    const long long cap = static_cast<long long>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    tn_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(ra);
+    tn_reduce_kernel<<<static_cast<unsigned>(blocks), 64, 0, st>>>(ra);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }

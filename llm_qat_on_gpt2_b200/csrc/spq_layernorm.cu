@@ -141,17 +141,27 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
 }
 
-// Fold the per-CTA partial column sums: 32 columns per block, 8 lanes share the `parts` rows of a column
-// (one thread walking ~600 dependent-latency loads per column made this as slow as the backward itself).
+// Fold the per-CTA partial column sums.  Block = 8 columns x 32 part-lanes: a warp row reads 8 consecutive floats
+// (one 32-byte sector) of 4 different partial rows, every thread keeps 4 independent loads in flight, and the grid
+// is C / 8 blocks (96 for C = 768; the first version's 24 blocks of 32 columns took as long as the backward itself).
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int parts, long long C,
                        float* __restrict__ out_a, float* __restrict__ out_b) {
-    __shared__ float fa[8][33], fb[8][33];
-    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const long long c = static_cast<long long>(blockIdx.x) * 32 + cl;
+    __shared__ float fa[32][9], fb[32][9];
+    const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;            // column in the block, part lane 0..31
+    const long long c = static_cast<long long>(blockIdx.x) * 8 + cl;
     float a = 0.f, b = 0.f;
     if (c < C) {
-        for (int p = sl; p < parts; p += 8) {
+        int p = sl;
+        for (; p + 96 < parts; p += 128) {
+            const float a0 = part_a[static_cast<long long>(p) * C + c], a1 = part_a[static_cast<long long>(p + 32) * C + c];
+            const float a2 = part_a[static_cast<long long>(p + 64) * C + c], a3 = part_a[static_cast<long long>(p + 96) * C + c];
+            const float b0 = part_b[static_cast<long long>(p) * C + c], b1 = part_b[static_cast<long long>(p + 32) * C + c];
+            const float b2 = part_b[static_cast<long long>(p + 64) * C + c], b3 = part_b[static_cast<long long>(p + 96) * C + c];
+            a += (a0 + a1) + (a2 + a3);
+            b += (b0 + b1) + (b2 + b3);
+        }
+        for (; p < parts; p += 32) {
             a += part_a[static_cast<long long>(p) * C + c];
             b += part_b[static_cast<long long>(p) * C + c];
         }
@@ -160,7 +170,7 @@ colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict
     __syncthreads();
     if (sl == 0 && c < C) {
 #pragma unroll
-        for (int w = 1; w < 8; ++w) { a += fa[w][cl]; b += fb[w][cl]; }
+        for (int w = 1; w < 32; ++w) { a += fa[w][cl]; b += fb[w][cl]; }
         if (out_a) out_a[c] = a;
         if (out_b) out_b[c] = b;
     }
@@ -216,7 +226,7 @@ extern "C" int spq_layernorm_fwd(const float* x, int64_t rows, int64_t cols, con
 
 extern "C" size_t spq_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cols) {
     Cfg c;
-    if (rows <= 0 || cols <= 0 || !pick(rows, cols, &c, 4)) return 0;
+    if (rows <= 0 || cols <= 0 || !pick(rows, cols, &c, 8)) return 0;
     return static_cast<size_t>(c.grid) * static_cast<size_t>(cols) * 2 * sizeof(float);
 }
 
@@ -227,7 +237,7 @@ extern "C" int spq_layernorm_bwd(const float* dy, const float* x, const float* w
     SPQ_REQUIRE((cols % 4) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(weight) && aligned16(workspace),
                 "spq_layernorm_bwd: alignment");
     Cfg c;
-    if (!pick(rows, cols, &c, 4)) {
+    if (!pick(rows, cols, &c, 8)) {          // 8 CTAs of G threads per SM: ~64 KB of loads in flight per SM
         set_error("spq_layernorm_bwd: normalized dim %lld > 8192 unsupported", (long long)cols);
         return SPQ_ERR_UNSUPPORTED;
     }
@@ -243,7 +253,7 @@ extern "C" int spq_layernorm_bwd(const float* dy, const float* x, const float* w
     }
     SPQ_LAUNCH_OK();
     if (dweight || dbias) {
-        colsum_finalize_kernel<<<static_cast<unsigned>((cols + 31) / 32), 256, 0, st>>>(pdw, pdb, static_cast<int>(c.grid), cols,
+        colsum_finalize_kernel<<<static_cast<unsigned>((cols + 7) / 8), 256, 0, st>>>(pdw, pdb, static_cast<int>(c.grid), cols,
                                                                                             dweight, dbias);
         SPQ_LAUNCH_OK();
     }

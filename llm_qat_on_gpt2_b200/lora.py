@@ -122,6 +122,12 @@ def _as_2d_act(x: torch.Tensor, last: int, max_cols: int = 1 << 30) -> torch.Ten
     return _as_2d_f32(x, last)
 
 
+def _as_2d_grad(gy: torch.Tensor, last: int) -> torch.Tensor:
+    """Incoming gradient as a contiguous 2-D matrix.  float16 gradients (the fp16 attention backward feeding c_attn)
+    go to the row-scaling kernel as they are -- it widens them exactly -- instead of through a float32 copy."""
+    return _as_2d_act(gy, last, max_cols=8192)
+
+
 # ----------------------------------------------------------------------------------------------
 # plain (unquantised) linear on the tcgen05 GEMM: 32-bit teacher path, calibration pass, LM head
 # ----------------------------------------------------------------------------------------------
@@ -188,7 +194,7 @@ class _LinearFpFn(torch.autograd.Function):
     def backward(ctx, gy):
         x16, rs, weight = ctx.saved_tensors
         N, K = weight.shape
-        g2d = _as_2d_f32(gy, N)
+        g2d = _as_2d_grad(gy, N)
         M = g2d.shape[0]
         g16, eg = _rowscaled_f16(g2d)
         gx = gw = gb = None
@@ -206,18 +212,19 @@ class _LinearFpFn(torch.autograd.Function):
             gw = torch.empty((N, K), dtype=torch.float32, device=gy.device)
             _lib.gemm_tn(g16, x2, gw, alpha=1.0, alpha_dev=(gmax * xmax).reshape(1).contiguous())
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2d.sum(dim=0)
-        return gx, gw, gb, None, None, None, None, None
+            gb = g2d.float().sum(dim=0)
+        # the residual added in the epilogue passes its gradient through unchanged
+        return gx, gw, gb, None, None, None, (gy if ctx.needs_input_grad[6] else None), None
 
 
 def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0, out_half: bool = False,
               residual=None, lse_out=None):
-    """`activation=1` fuses the exact-erf GELU into the GEMM epilogue, `out_half` stores float16 from the
-    epilogue, `residual` (float32, contiguous, output-shaped) is added in the epilogue, `lse_out` (a list) receives
-    the per-row log-sum-exp partials of the output for `_lib.cross_entropy_from_parts`; all no-grad fast paths."""
-    if (activation or out_half or residual is not None or lse_out is not None) and torch.is_grad_enabled() and \
-            (x.requires_grad or weight.requires_grad):
-        raise RuntimeError("fused activation / float16 output / residual epilogues are no-grad fast paths")
+    """`out_half` stores float16 from the epilogue and `residual` (float32, contiguous, output-shaped) is added in
+    the epilogue -- both differentiable (the backward takes float16 gradients; the residual's gradient is the output
+    gradient).  `activation=1` fuses the exact-erf GELU into the epilogue and `lse_out` (a list) receives the per-row
+    log-sum-exp partials of the output for `_lib.cross_entropy_from_parts`: no-grad fast paths."""
+    if (activation or lse_out is not None) and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        raise RuntimeError("the fused activation / log-sum-exp epilogues are no-grad fast paths")
     return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation, out_half,
                              residual, lse_out)
 
@@ -352,7 +359,7 @@ class _SPLinearFn(torch.autograd.Function):
         base, lo = ctx.base, ctx.lo
         bw = ctx.mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
-        g2d = _as_2d_f32(gy, N)
+        g2d = _as_2d_grad(gy, N)
         dev = gy.device
         act = base['act']
         need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
@@ -389,7 +396,8 @@ class _SPLinearFn(torch.autograd.Function):
                              transposed_out=True, clamp_abs=10.0 if lo['qtype_B'] == 'log' else 0.0)
 
         if need_x:
-            gx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            # the fp16 attention output feeding c_proj takes its gradient in fp16 straight from the epilogue
+            gx = torch.empty((M, K), dtype=torch.float16 if ctx.x_dtype == torch.float16 else torch.float32, device=dev)
             if dt16 is not None and clamp_in == 0.0:
                 # identity STE: base and LoRA input-gradients share one accumulator
                 _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, A2=dt16, B2=bw['lora']['A_kr_op'], K2=lo['rank'],
@@ -404,13 +412,13 @@ class _SPLinearFn(torch.autograd.Function):
             gx = gx.view(ctx.x_shape).to(ctx.x_dtype)
         if need_w:
             # dW[n,k] = sum_m dY[m,n] q(x)[m,k];  q(x)[m,k] = a_q[m,k] * absorb[k]; gG = dY / gmax, |gG| <= 256
-            gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax1).expand(M).contiguous())
+            gG = _to_f16_operand(g2d.float(), row_mul=(1.0 / gmax1).expand(M).contiguous())
             gw = torch.empty((N, K), dtype=torch.float32, device=dev)
             _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax1, j_scale=act['absorb'],
                          clamp_abs=10.0 if ctx.weight_qtype == 'log' else 0.0)
         if ctx.has_bias and need_b:
-            gb = g2d.sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None, None, None, None, None
+            gb = g2d.float().sum(dim=0)
+        return gx, gw, gb, gA, gB, None, None, None, None, (gy if ctx.needs_input_grad[9] else None), None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -626,9 +634,10 @@ class SPLinearWithLoRA(nn.Module):
         wrapper: `out_half=True` (SPAttention with fp16 attention) stores fp16 from the GEMM epilogue
         instead of float32 followed by a cast; `fuse_gelu=True` (SPMLP under no_grad) applies the exact
         erf GELU in the epilogue instead of a separate elementwise pass; `residual` (SPBlock's residual
-        stream) returns residual + forward(x), the add done in the GEMM epilogue when autograd is off."""
+        stream) returns residual + forward(x), the add done in the GEMM epilogue (with autograd on, the residual's
+        gradient is the output gradient)."""
         if residual is not None:
-            fuse_res = (not torch.is_grad_enabled() and not out_half and not fuse_gelu and residual.is_cuda
+            fuse_res = (not out_half and not fuse_gelu and residual.is_cuda
                         and residual.dtype == torch.float32 and residual.is_contiguous()
                         and residual.shape == x.shape[:-1] + (self.linear.out_features,))
             if not fuse_res:
@@ -636,7 +645,7 @@ class SPLinearWithLoRA(nn.Module):
         act = 1 if (fuse_gelu and not torch.is_grad_enabled()) else 0
         post_gelu = fuse_gelu and not act
         if self.current_bits >= 32:
-            half_here = out_half and not post_gelu and not torch.is_grad_enabled()
+            half_here = out_half and not post_gelu
             y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act, out_half=half_here,
                           residual=residual)
             if post_gelu:

@@ -215,14 +215,17 @@ class SPModel(nn.Module):
             position_ids = torch.arange(0, T, dtype=torch.long, device=input_ids.device).unsqueeze(0)
             hidden_states = self.drop(self.wte(input_ids) + self.wpe(position_ids))
 
+        # upstream returns `hidden_states.clone().detach()` copies (:323); nothing on this path writes a hidden state
+        # in place (every block output is a fresh tensor), so the detached tensors themselves are returned and the
+        # 13 copies per forward are skipped
         all_hidden_states = [] if output_hidden_states else None
         for block in self.h:
             if output_hidden_states:
-                all_hidden_states.append(hidden_states.clone().detach())
+                all_hidden_states.append(hidden_states.detach())
             hidden_states = block(hidden_states, attention_mask, use_checkpoint)
         hidden_states = self.ln_f(hidden_states)
         if output_hidden_states:
-            all_hidden_states.append(hidden_states.clone().detach())
+            all_hidden_states.append(hidden_states.detach())
             return hidden_states, all_hidden_states
         return hidden_states
 
