@@ -681,7 +681,15 @@ def dp_parity_section(args, model, linears, dev, world, rank, group):
     d = (single.long() - mine.long()).abs()
     res["calibration"] = {"ranks_bit_identical": bool(same.item()), "vs_single_process_max_ulp": int(d.max()),
                           "vs_single_process_differing": int((d > 0).sum()), "parameters": int(d.numel())}
-    # ---- (2) gradients: lr = 0 keeps the replicas' parameters untouched
+    # ---- (2) gradients: lr = 0 keeps the replicas' parameters untouched.  The library attention between the hot-path
+    # linears (cuDNN fp16 flash SDPA) is not batch-invariant: its results for a sequence depend on how many sequences
+    # are in the call (measured: 2-4e-2 on these gradients between B = 4 and B = 8, tools/diag_dp.py), which would
+    # mask what is being checked.  The check therefore runs the exact fp32 attention path; every kernel of this repo
+    # is batch-invariant, so shard-average and global gradient then differ only by fp32 summation order.
+    att_modules = [m for m in model.modules() if hasattr(m, "attention_dtype")]
+    att_saved = [m.attention_dtype for m in att_modules]
+    for m in att_modules:
+        m.attention_dtype = "fp32"
     def grads(batch, data_parallel):
         tr = SPTrainer(model, BIT_WIDTHS, grad_accum=3, lr=0.0, weight_decay=0.0, group=group, rng=random.Random(3),
                        use_graphs=False)
@@ -695,9 +703,11 @@ def dp_parity_section(args, model, linears, dev, world, rank, group):
     g_single = grads(global_ids, False)
     rel = float((g_dp.double() - g_single.double()).norm() / g_single.double().norm())
     model.transformer.drop.p = p_drop
+    for m, a in zip(att_modules, att_saved):
+        m.attention_dtype = a
     res["gradient"] = {"rel_allreduced_vs_single_process": rel, "elements": int(g_dp.numel()),
-                       "per_rank_batch": Bp, "global_batch": Bp * world, "micro_steps": 3}
-    ok = res["calibration"]["ranks_bit_identical"] and res["calibration"]["vs_single_process_max_ulp"] == 0 and rel <= 1e-4
+                       "per_rank_batch": Bp, "global_batch": Bp * world, "micro_steps": 3, "attention": "fp32 (batch-invariant)"}
+    ok = res["calibration"]["ranks_bit_identical"] and res["calibration"]["vs_single_process_max_ulp"] == 0 and rel <= 1e-5
     res["ok"] = bool(ok)
     torch.cuda.empty_cache()
     return res
