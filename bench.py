@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--train-eager", action="store_true", help="run the micro-steps eagerly (no CUDA graphs): per-phase timing")
     ap.add_argument("--train-strong", type=int, default=1, help="also time the strong-scaling shapes (global 32x256, 32x1024)")
     ap.add_argument("--no-dp-parity", action="store_true")
+    ap.add_argument("--cpt-steps", type=int, default=10, help="timed steps of the GPT-2 medium CPT section (configs[3]; 0 = skip)")
+    ap.add_argument("--sweep-tokens", type=int, nargs="*", default=[4096, 8192, 16384, 32768, 65536],
+                    help="token counts of the QLinear sweep (configs[4]; none = skip; runs on rank 0 at N = 1 only)")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU sequences of the training step (p1/config_sp.py:46)")
     ap.add_argument("--train-seq", type=int, default=256, help="sequence length of the training step (p1/config_sp.py:47)")
     ap.add_argument("--profile-train-step", action="store_true",
@@ -416,9 +419,8 @@ def gpu_arm(args):
     import gc
     gc.collect()
     gc.disable()
-    # ---- timed region 1: inputs resident in HBM ("value")
+    # ---- timed region 1: inputs resident in HBM ("value"), nothing instrumented
     sampler.rows.clear()
-    patch(timed_qgemm)
     launches0 = _lib.launch_count()
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -429,6 +431,15 @@ def gpu_arm(args):
     barrier()
     ms_value = t0.elapsed_time(t1)
     launches = _lib.launch_count() - launches0
+    # ---- roofline pass (separate, untimed for `value`): the same steps with a CUDA-event pair around every GEMM launch
+    patch(timed_qgemm)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        step(dev_ids[args.warmup + i])
+    t1.record()
+    barrier()
+    ms_roofline_pass = t0.elapsed_time(t1)
     patch(orig_qgemm)
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_events)
     gemm_flops = sum(f for _, _, f, _ in gemm_events)
@@ -453,6 +464,19 @@ def gpu_arm(args):
     train = None
     if args.train_steps > 0:
         train = train_section(args, model, linears, key, dev, world, rank, group, barrier)
+    cpt = sweep = None
+    if args.cpt_steps > 0 or (args.sweep_tokens and world == 1):
+        # the GPT-2 small replica (and its graph pools) is not needed any more
+        del model, linears, input_q
+        gc.collect()
+        torch.cuda.empty_cache()
+        if args.cpt_steps > 0:
+            cpt = cpt_section(args, dev, world, rank, group, barrier)
+        if args.sweep_tokens and world == 1:
+            sweep = qlinear_sweep_section(args, dev)
+    wd = _lib.debug_status()
+    if wd != 0:
+        raise RuntimeError(f"GEMM pipeline watchdog flag {wd}: results of this run are invalid")
 
     if world > 1:
         t = torch.tensor([ms_value, ms_e2e], device=dev, dtype=torch.float64)
@@ -489,10 +513,16 @@ def gpu_arm(args):
                          "traffic_source": measured_traffic()[1],
                          "algorithmic_bytes_per_launch": gemm_bytes / max(n_gemm, 1),
                          "peak_source": peaks["source"] + ", bf16 dense sustained",
-                         "launches": n_gemm, "share_of_step": gemm_ms / ms_value if ms_value else None},
+                         "launches": n_gemm, "share_of_step": gemm_ms / ms_roofline_pass if ms_roofline_pass else None,
+                         "measured_in": "separate instrumented pass of the same steps (CUDA-event pair per launch), "
+                                        f"{ms_roofline_pass / args.steps:.2f} ms per step"},
         }
         if train is not None:
             line["train"] = train
+        if cpt is not None:
+            line["cpt_medium"] = cpt
+        if sweep is not None:
+            line["qlinear_sweep"] = sweep
         if world == 1 and not args.no_cpu_baseline:
             base, _, _ = run_cpu_baseline(args.cpu_sample_batch, args.seq, steps=1, warmup=0)
             line["cpu_baseline"] = base
@@ -711,6 +741,156 @@ def dp_parity_section(args, model, linears, dev, world, rank, group):
     res["ok"] = bool(ok)
     torch.cuda.empty_cache()
     return res
+
+
+def cpt_section(args, dev, world, rank, group, barrier):
+    """BASELINE.json configs[3]: CPTModel GPT-2 medium (n_embd 1024, 24 layers, 16 heads; shared LoRA r = 16, alpha = 32:
+    p2/config_cpt.py:11-12), every width 3..8 pre-calibrated (p2/calibration.py), the width cycling 3 -> 8 -> 3 PER
+    STEP along CyclicPrecisionScheduler's cosine (p2/cyclic_scheduler.py:24-43), one optimizer step per batch of
+    32 x 256 per GPU (p2/main_cpt.py:45-60: CE loss, backward, clip 1.0, AdamW), batch-sharded data parallel."""
+    import types
+    import torch
+    import torch.distributed as dist
+    from llm_qat_on_gpt2_b200.cpt import CPTModel, CyclicPrecisionScheduler, CalibrationManager, CPTTrainer
+    widths = [3, 4, 5, 6, 7, 8]
+    mc = types.SimpleNamespace(vocab_size=50257, n_positions=1024, n_embd=1024, n_layer=24, n_head=16, layer_norm_epsilon=1e-5,
+                               embd_pdrop=args.train_dropout, bit_widths=widths + [32], shared_lora_rank=16, shared_lora_alpha=32,
+                               quantizer_per_bit={**{b: "log" for b in widths}, 32: None}, gradient_bits=8)
+    cfg = {"model": mc, "training": types.SimpleNamespace(target_bits=5)}
+    torch.manual_seed(0)
+    model = CPTModel(cfg).to(dev)
+    with torch.no_grad():
+        for m in model.modules():
+            if m.__class__.__name__ == "LoRAAdapter" and m.lora_B is not None:
+                m.lora_B.normal_(0, 0.02)                      # non-trivial adapter (upstream starts at zero)
+    B, T, V = args.train_batch, args.train_seq, mc.vocab_size
+    gen = torch.Generator().manual_seed(555 + rank)
+    loader = [{"input_ids": torch.randint(0, V, (B, T), generator=gen)} for _ in range(2)]
+    mgr = CalibrationManager(model, loader, dev, data_parallel_group=group)
+    mgr.calibrate_gradient_quantizers()
+    for b in widths:
+        mgr.ensure_calibrated(b, num_batches=1)
+    model.train()
+    steps, warm = args.cpt_steps, 2 * len(widths)
+    sched = CyclicPrecisionScheduler(bit_widths=widths, schedule_type="cosine", total_epochs=2 * (len(widths) - 1) * 10,
+                                     total_cycles=10)            # 10 steps per cycle: 3 -> 8 -> 3
+    trainer = CPTTrainer(model, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0, total_lr_steps=10000, group=group,
+                         use_graphs=not args.train_eager)
+    hosts = [torch.randint(0, V, (B, T), generator=gen).pin_memory() for _ in range(4)]
+    devs = [h.to(dev) for h in hosts]
+    for w in widths:                                            # capture every width's graph (untimed)
+        trainer.train_step(devs[0], w, read_loss=False)
+    seq = [sched.get_precision_for_epoch(i) for i in range(warm + 2 * steps)]
+    for i in range(warm):
+        trainer.train_step(devs[i % 4], seq[i], read_loss=False)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        r = trainer.train_step(devs[i % 4], seq[warm + i], read_loss=False)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1) / steps
+    t0.record()
+    for i in range(steps):
+        r = trainer.train_step(hosts[i % 4], seq[warm + steps + i], read_loss=True)     # ids from pinned host, loss to host
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1) / steps
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+    tokens = B * T * world
+    # base GEMMs 603.98 + quantised LM head 2*1024*50257 = 102.93 MFLOP/token per pass; forward + dX; LoRA r = 16 adds
+    # 2*16*(K+N) per linear per pass (x3 with backward)
+    lora = 2 * 16 * (24 * ((1024 + 3072) + (1024 + 1024) + (1024 + 4096) + (4096 + 1024)) + (1024 + 50257)) / 1e6
+    flop = (2 * (603.98 + 102.93) + 3 * lora) * 1e6 * B * T
+    peak = measured_peaks()["tflops_sustained"]
+    out = {"metric": "GPT-2 medium CPT training tokens/s, width cycling 3->8 per step (p2 train_epoch_with_cpt step)",
+           "value": tokens / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warm, "per_gpu_batch": B, "seq_len": T,
+           "widths_timed": seq[warm:warm + steps], "loss": r["loss"], "scaling": "weak",
+           "e2e": {"value": tokens / (ms_e2e / 1e3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * T * 8, "d2h_bytes_per_step": 4},
+           "trainable_params": int(trainer.numel), "cuda_graphs": sorted(trainer.graphs),
+           "roofline": {"bound": "tensor", "kernel": "all GEMMs of the step (algorithmic FLOP / whole step time)",
+                        "achieved": flop / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flop / (ms / 1e3) / 1e12 / peak if peak else None}}
+    del trainer, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def qlinear_sweep_section(args, dev):
+    """BASELINE.json configs[4]: SPLinearWithLoRA over GPT-2 XL shapes (1600 -> 4800 / 6400, 6400 -> 1600), 4-bit min-max and
+    8-bit log, 4K-64K tokens, forward (no_grad) and forward + STE backward (LoRA A/B and dX), LoRA rank 64; x ~ N(0,1)
+    with x20 outlier channels, W ~ N(0, 0.02).  Reported per case: time, tokens/s, algorithmic
+    TFLOP/s of the whole call against the measured bf16 peak (forward 2*M*N*K + LoRA 2*M*r*(K+N); backward adds dX
+    2*M*N*K and 2x the LoRA work)."""
+    import torch
+    from llm_qat_on_gpt2_b200.lora import SPLinearWithLoRA
+    peak = measured_peaks()["tflops_sustained"]
+    R = 64
+    rows = []
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for K, N in ((1600, 4800), (1600, 6400), (6400, 1600)):
+        for bits, qt in ((4, "minmax"), (8, "log")):
+            torch.manual_seed(0)
+            m = SPLinearWithLoRA(K, N, [4, 8, 32], {4: R, 8: R, 32: 0}, {4: R, 8: R, 32: 0}, {4: "minmax", 8: "log", 32: None}).to(dev)
+            m.set_precision(bits)
+            key = f"{bits}bit"
+            lo = m.lora_adapters[key]
+            with torch.no_grad():
+                m.linear.weight.normal_(0, 0.02)
+                lo.lora_B.normal_(0, 0.02)
+                q = m.quantizers_weight[key]; q.start_calibration(); q(m.linear.weight.data); q.finish_calibration()
+                for qq, w in ((lo.quantize_A, lo.lora_A), (lo.quantize_B, lo.lora_B)):
+                    qq.start_calibration(); qq(w.data); qq.finish_calibration()
+            m.linear.weight.requires_grad_(False); m.linear.bias.requires_grad_(False)
+            for tokens in args.sweep_tokens:
+                x = torch.randn(tokens, K, device=dev)
+                x[:, 7::97] *= 20.0
+                gy = torch.randn(tokens, N, device=dev) * 1e-3
+                with torch.no_grad():
+                    m.calibration_mode = True
+                    iq = m.quantizers_input[key]; iq.start_calibration(); m(x); iq.finish_calibration()
+                    m.calibration_mode = False
+                reps = max(3, min(20, int(2.0e11 / (tokens * N * K))))
+
+                def fwd():
+                    with torch.no_grad():
+                        m(x)
+
+                xg = x.clone().requires_grad_(True)
+
+                def fwd_bwd():
+                    xg.grad = None; lo.lora_A.grad = None; lo.lora_B.grad = None
+                    m(xg).backward(gy)
+                t_f, t_fb = timed(fwd, reps), timed(fwd_bwd, reps)
+                f_fwd = 2.0 * tokens * N * K + 2.0 * tokens * R * (K + N)
+                f_fb = 2 * 2.0 * tokens * N * K + 3 * 2.0 * tokens * R * (K + N)
+                rows.append({"K": K, "N": N, "bits": bits, "quantizer": qt, "tokens": tokens, "fwd_ms": round(t_f, 4),
+                             "fwd_bwd_ms": round(t_fb, 4), "fwd_Mtok_s": round(tokens / t_f / 1e3, 2),
+                             "fwd_bwd_Mtok_s": round(tokens / t_fb / 1e3, 2),
+                             "fwd_frac_of_peak": round(f_fwd / (t_f / 1e3) / 1e12 / peak, 3),
+                             "fwd_bwd_frac_of_peak": round(f_fb / (t_fb / 1e3) / 1e12 / peak, 3)})
+                del x, gy, xg
+            del m
+            torch.cuda.empty_cache()
+    best = max(rows, key=lambda r: r["fwd_frac_of_peak"])
+    return {"metric": "SPLinearWithLoRA microbench, GPT-2 XL shapes (whole module call: quantise + LoRA + fused GEMM [+ STE backward])",
+            "peak_tflops": peak, "lora_rank": R, "rows": rows, "best_fwd_frac_of_peak": best["fwd_frac_of_peak"]}
 
 
 def main():

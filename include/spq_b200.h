@@ -182,12 +182,15 @@ SPQ_API int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
  * The reduction over Mred is split across CTAs; each split writes its partial tile to its own plane of
  * `workspace` (spq_gemm_tn_workspace_bytes) and a second kernel folds the planes in a fixed order, so the
  * result is bitwise reproducible (no atomics).  clamp_abs > 0 applies the log quantiser's STE clamp
- * (p1/quantization_methods.py:82-90) to the finished gradient.  alpha_dev (device scalar), i_scale, j_scale
+ * (p1/quantization_methods.py:82-90) to the finished gradient.  gq_scale_i (nullable, [I]) fuses the CPT variant's
+ * GradientQuantizer (p2/quantization.py:14-26) in front of that clamp: symmetric gq_bits-bit min-max fake
+ * quantisation of the gradient with one calibrated scale per row i.  alpha_dev (device scalar), i_scale, j_scale
  * are nullable.  Per-reduction-row scales cannot be applied here: fold them into P or Q. */
 SPQ_API size_t spq_gemm_tn_workspace_bytes(int64_t Mred, int64_t I, int64_t J);
 SPQ_API int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq,
                 int64_t Mred, int64_t I, int64_t J, float alpha, const float* alpha_dev,
                 const float* i_scale, const float* j_scale, float clamp_abs,
+                const float* gq_scale_i, int gq_bits,
                 float* D, int64_t d_stride_i, int64_t d_stride_j, void* workspace, size_t workspace_bytes,
                 spq_stream_t stream);
 

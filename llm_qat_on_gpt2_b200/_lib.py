@@ -51,7 +51,7 @@ SIGNATURES = {
                           c_void_p, c_int64, c_int, c_int, c_void_p]),
     "spq_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
-                            c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+                            c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "spq_rowscale_f16_max": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_lora_bwd_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
@@ -262,14 +262,16 @@ def qgemm(A, B, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None,
     return out
 
 
-def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, transposed_out=False, clamp_abs=0.0):
+def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, transposed_out=False, clamp_abs=0.0,
+            gq_scale_i=None, gq_bits=8):
     """out[I,J] (or out[J,I] when transposed_out) = clamp(alpha * P[Mred,I]^T Q[Mred,J]); fp16 in, fp32 out.
     Deterministic (split reduction folded in a fixed order); clamp_abs > 0 applies the log STE clamp."""
     lib = load_library()
-    _req_cuda(P, Q, out, alpha_dev, i_scale, j_scale)
+    _req_cuda(P, Q, out, alpha_dev, i_scale, j_scale, gq_scale_i)
     assert P.dtype == torch.float16 and Q.dtype == torch.float16 and out.dtype == torch.float32
     assert P.stride(-1) == 1 and Q.stride(-1) == 1 and out.is_contiguous()
     Mred, I = P.shape
+    assert gq_scale_i is None or (gq_scale_i.numel() == I and gq_scale_i.dtype == torch.float32 and gq_scale_i.is_contiguous())
     J = Q.shape[1]
     assert Q.shape[0] == Mred
     if transposed_out:
@@ -280,7 +282,8 @@ def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, tr
         si, sj = J, 1
     ws = _workspace(lib.spq_gemm_tn_workspace_bytes(Mred, I, J), out.device, "gemm_tn")
     _check(lib.spq_gemm_tn(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), Mred, I, J, float(alpha),
-                           _ptr(alpha_dev), _ptr(i_scale), _ptr(j_scale), float(clamp_abs), out.data_ptr(), si, sj,
+                           _ptr(alpha_dev), _ptr(i_scale), _ptr(j_scale), float(clamp_abs), _ptr(gq_scale_i), int(gq_bits),
+                           out.data_ptr(), si, sj,
                            ws.data_ptr(), ws.numel(), _stream()), "spq_gemm_tn")
     return out
 

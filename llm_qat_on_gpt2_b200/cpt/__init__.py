@@ -8,6 +8,8 @@ from .quantization import GradientQuantizer, LearnableFakeQuantize
 from .cpt_model import LoRAAdapter, CPTLinear, CPTSelfAttention, CPTMLP, CPTBlock, CPTModel
 
 from .cyclic_scheduler import CyclicPrecisionScheduler, PrecisionRangeTest
+from .calibration import CalibrationManager
+from .training import CPTTrainer
 
-__all__ = ["CyclicPrecisionScheduler", "PrecisionRangeTest", "GradientQuantizer", "LearnableFakeQuantize", "LoRAAdapter", "CPTLinear", "CPTSelfAttention",
+__all__ = ["CyclicPrecisionScheduler", "PrecisionRangeTest", "CalibrationManager", "CPTTrainer", "GradientQuantizer", "LearnableFakeQuantize", "LoRAAdapter", "CPTLinear", "CPTSelfAttention",
            "CPTMLP", "CPTBlock", "CPTModel"]

@@ -23,8 +23,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..lora import (_FpWeightCache, _act_config, _as_2d_f32, _dequant, _norm_pow2, _quantized_operand, _rowscaled_f16,
-                    _to_f16_operand, linear_fp)
+from ..lora import (_FpWeightCache, _act_config, _as_2d_f32, _as_2d_grad, _dequant, _norm_pow2, _quantized_operand,
+                    _rowscaled_f16, _to_f16_operand, linear_fp)
 from ..quantization import pow2_ceil
 from .quantization import GradientQuantizer, LearnableFakeQuantize
 
@@ -60,6 +60,19 @@ def _grad_quantize(q: Optional[LearnableFakeQuantize], g: torch.Tensor) -> torch
     return g
 
 
+def _grad_quantizer_scale(q: Optional[LearnableFakeQuantize], rows: int):
+    """(per-row scale for the fused epilogue or None, whether the whole GradientQuantizer + STE tail is fused).
+    Fusable: no gradient quantiser / not active (identity), or calibrated symmetric min-max with one scale per row."""
+    if q is None or not (q.collecting_stats or q.num_bits in q.calibrated_bits):
+        return None, True
+    if q.collecting_stats or q.quantizer_type != 'minmax' or not q.symmetric or q.num_bits >= 32:
+        return None, False
+    sc = q.scales[q.num_bits]
+    if sc.numel() != rows:
+        return None, False
+    return sc.detach().float().reshape(-1).contiguous(), True
+
+
 class _CPTLinearFn(torch.autograd.Function):
     """Fused forward / backward of CPTLinear at a quantised width."""
 
@@ -76,12 +89,12 @@ class _CPTLinearFn(torch.autograd.Function):
                           act['kind'], act['col_mul'], act['mul'], a_q, None, None)
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
-        t = None
+        t16 = None
         if use_lora:
             r = lo['rank']
-            t = torch.empty((M, r), dtype=torch.float32, device=x.device)
-            _lib.qgemm(a_q, lo['A_op'], M, r, K, t, col_scale=lo['pa'])            # t = q(x) q(A)
-            t16 = _to_f16_operand(t, col_mul=lo['tmul_vec'])
+            # t = q(x) q(A), stored as the fp16 operand of the up-projection (pa and tau are powers of two)
+            t16 = _lib.empty_f16_padded(M, r, x.device)
+            _lib.qgemm(a_q, lo['A_op'], M, r, K, t16, col_scale=lo['pa_tmul'])
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f)
         else:
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f)
@@ -91,50 +104,61 @@ class _CPTLinearFn(torch.autograd.Function):
         ctx.bits = bits                     # backward operands are built (and cached) when backward first runs
         ctx.weight_qtype = mod.quantizer_weight.quantizer_type
         keep_aq = need[1] or (use_lora and need[3])
-        ctx.save_for_backward(a_q if keep_aq else None, t)
+        ctx.save_for_backward(a_q if keep_aq else None, t16 if (use_lora and need[4]) else None)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gy):
-        a_q, t = ctx.saved_tensors
+        a_q, t16 = ctx.saved_tensors
         base, lo, mod = ctx.base, ctx.lo, ctx.mod
         bw = mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
-        g2d = _as_2d_f32(gy, N)
+        g2d = _as_2d_grad(gy, N)
         dev = gy.device
         act = base['act']
-        g16, eg = _rowscaled_f16(g2d)
+        g16 = _lib.empty_f16_padded(M, N, dev)
+        eg = torch.empty(M, dtype=torch.float32, device=dev)
+        gmax1 = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.rowscale_f16_max(g2d, g16, eg, gmax1)           # dY = g16 * eg[:,None], gmax1 = max eg
         gx = gw = gb = gA = gB = None
         need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
         clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
-        gmax = eg.max() if (need_w or (ctx.use_lora and (need_A or need_B))) else None
         dt16 = None
         if ctx.use_lora and (need_x or need_A or need_B):
             lb = bw['lora']
             r = lo['rank']
+            clamp_w = 10.0 if lo['qtype'] == 'log' else 0.0
+            dtn = None
             if need_x or need_A:
                 dtn = torch.empty((M, r), dtype=torch.float32, device=dev)       # dt / eg,  dt = scaling * dY q(B)
                 _lib.qgemm(g16, lb['B_rn_op'], M, r, N, dtn, col_scale=lb['pb'])
-                if need_x:
-                    dt16 = _to_f16_operand(dtn, mul=lb['dt_mul'])
-                if need_A:
-                    # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
-                    dt2 = _to_f16_operand(dtn, row_mul=(eg / gmax).contiguous(), mul=lb['dt_mul'])
-                    gA = torch.empty((K, r), dtype=torch.float32, device=dev)
-                    _lib.gemm_tn(a_q, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax.reshape(1).contiguous(),
-                                 i_scale=act['absorb'])
-                    gA = _grad_quantize(mod.shared_lora.grad_quantizer_A, gA)
-                    if lo['qtype'] == 'log':
+            dt16, dt2, t2 = _lib.lora_bwd_prep(dtn, t16 if need_B else None, eg, gmax1, lb['dt_mul'],
+                                               want_dt16=need_x, want_dt2=need_A, want_t2=need_B)
+            # GradientQuantizer (p2/quantization.py:14-26): calibrated -> fused into the gradient GEMM's fold pass in
+            # front of the weight quantiser's STE clamp; collecting statistics -> the module call records them
+            sl = mod.shared_lora
+            if need_A:
+                # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
+                gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_A, K)
+                gA = torch.empty((K, r), dtype=torch.float32, device=dev)
+                _lib.gemm_tn(a_q, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['absorb'],
+                             clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
+                             gq_bits=sl.grad_quantizer_A.num_bits if gqs is not None else 8)
+                if not fused:
+                    gA = _grad_quantize(sl.grad_quantizer_A, gA)
+                    if clamp_w:
                         gA = _lib.ste_backward(gA, _lib.LOG)
             if need_B:
-                # dB[n,j] = scaling * sum_m dY[m,n] t[m,j]
-                t2 = _to_f16_operand(t, row_mul=(eg / gmax).contiguous(), col_mul=lo['tmul_vec'])
+                # dB[n,j] = scaling * sum_m dY[m,n] t[m,j],  t[m,j] = t16[m,j] / tau
+                gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_B, N)
                 gB = torch.empty((N, r), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax.reshape(1).contiguous(),
-                             j_scale=lo['inv_tmul_vec'])
-                gB = _grad_quantize(mod.shared_lora.grad_quantizer_B, gB)
-                if lo['qtype'] == 'log':
-                    gB = _lib.ste_backward(gB, _lib.LOG)
+                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
+                             clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
+                             gq_bits=sl.grad_quantizer_B.num_bits if gqs is not None else 8)
+                if not fused:
+                    gB = _grad_quantize(sl.grad_quantizer_B, gB)
+                    if clamp_w:
+                        gB = _lib.ste_backward(gB, _lib.LOG)
         if need_x:
             # both terms flow through q_in(x) here, so the STE clamp applies to their sum
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)
@@ -145,13 +169,12 @@ class _CPTLinearFn(torch.autograd.Function):
                 _lib.qgemm(g16, bw['WT_op'], M, K, N, gx, row_scale=eg, col_scale=bw['pk'], clamp_abs=clamp_in)
             gx = gx.view(ctx.x_shape)
         if need_w:
-            gG = _to_f16_operand(g2d, row_mul=(1.0 / gmax).expand(M).contiguous())
+            gG = _to_f16_operand(g2d.float(), row_mul=(1.0 / gmax1).expand(M).contiguous())
             gw = torch.empty((N, K), dtype=torch.float32, device=dev)
-            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax.reshape(1).contiguous(), j_scale=act['absorb'])
-            if ctx.weight_qtype == 'log':
-                gw = _lib.ste_backward(gw, _lib.LOG)
+            _lib.gemm_tn(gG, a_q, gw, alpha=1.0, alpha_dev=gmax1, j_scale=act['absorb'],
+                         clamp_abs=10.0 if ctx.weight_qtype == 'log' else 0.0)
         if ctx.has_bias and need_b:
-            gb = g2d.sum(dim=0)
+            gb = g2d.float().sum(dim=0)
         return gx, gw, gb, gA, gB, None, None
 
 
@@ -225,7 +248,8 @@ class CPTLinear(nn.Module):
                 tmul_vec = tmul.expand(r).contiguous()
                 Bl_op = _quantized_operand(lq, sl.lora_B, row_mul=1.0 / base['pw'],
                                            col_mul=(sl.scaling / tmul).expand(r).contiguous())                      # [N, r]
-            lora = ent['lora'] = dict(key=lkey, rank=r, A_op=A_op, pa=pa, Bl_op=Bl_op, tmul_vec=tmul_vec,
+            lora = ent['lora'] = dict(key=lkey, rank=r, A_op=A_op, pa=pa, pa_tmul=(pa * tmul_vec).contiguous(), Bl_op=Bl_op,
+                                      tmul_vec=tmul_vec,
                                       inv_tmul_vec=(1.0 / tmul_vec).contiguous(), scaling=float(sl.scaling),
                                       qtype=lq.quantizer_type)
             ent['bwd'] = None

@@ -910,8 +910,21 @@ struct TnReduce {
     const float* j_scale;
     const float* alpha_dev;
     float alpha, clamp_abs;
+    const float* gq_scale_i;     // optional: min-max fake quantisation of the result, scale per row i (GradientQuantizer)
+    float gq_levels;             // 2^(b-1) - 1
     float* D;
 };
+
+// p2/quantization.py:14-26 GradientQuantizer.backward on the finished LoRA gradient: symmetric min-max fake quantisation
+// with a per-row scale (true division, round-half-even, clamp to +-levels), then the weight quantiser's STE clamp
+__device__ __forceinline__ float tn_finish(const TnReduce& a, float v, long long i) {
+    if (a.gq_scale_i) {
+        const float sc = __ldg(a.gq_scale_i + i);
+        v = fminf(fmaxf(rintf(__fdiv_rn(v, sc)), -a.gq_levels), a.gq_levels) * sc;
+    }
+    if (a.clamp_abs > 0.f) v = fminf(fmaxf(v, -a.clamp_abs), a.clamp_abs);
+    return v;
+}
 
 // D[e] = clamp(alpha * alpha_dev * is[i] * js[j] * sum_s part[s][e]): the splits are added in index order.
 __global__ void __launch_bounds__(64) tn_reduce_kernel(TnReduce a) {
@@ -941,9 +954,7 @@ __global__ void __launch_bounds__(64) tn_reduce_kernel(TnReduce a) {
                 long long i, j;
                 if (a.stride_j == 1) { i = (e + u) / a.J; j = (e + u) - i * a.J; }
                 else { j = (e + u) / a.I; i = (e + u) - j * a.I; }
-                float v = o[u] * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f);
-                if (a.clamp_abs > 0.f) v = fminf(fmaxf(v, -a.clamp_abs), a.clamp_abs);
-                o[u] = v;
+                o[u] = tn_finish(a, o[u] * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f), i);
             }
             *reinterpret_cast<float4*>(a.D + e) = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -954,9 +965,7 @@ __global__ void __launch_bounds__(64) tn_reduce_kernel(TnReduce a) {
             long long i, j;
             if (a.stride_j == 1) { i = e / a.J; j = e - i * a.J; }
             else { j = e / a.I; i = e - j * a.I; }
-            float v = acc * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f);
-            if (a.clamp_abs > 0.f) v = fminf(fmaxf(v, -a.clamp_abs), a.clamp_abs);
-            a.D[e] = v;
+            a.D[e] = tn_finish(a, acc * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f), i);
         }
     }
 }
@@ -1145,8 +1154,10 @@ extern "C" size_t spq_gemm_tn_workspace_bytes(int64_t Mred, int64_t I, int64_t J
 
 extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq, int64_t Mred, int64_t I, int64_t J,
                            float alpha, const float* alpha_dev, const float* i_scale, const float* j_scale, float clamp_abs,
+                           const float* gq_scale_i, int gq_bits,
                            float* D, int64_t d_stride_i, int64_t d_stride_j, void* workspace, size_t workspace_bytes,
                            spq_stream_t stream) {
+    SPQ_REQUIRE(!gq_scale_i || (gq_bits >= 2 && gq_bits <= 24), "spq_gemm_tn: gradient quantiser bits %d", gq_bits);
     SPQ_REQUIRE(P && Q && D && workspace, "spq_gemm_tn: null operand");
     SPQ_REQUIRE(Mred > 0 && I > 0 && J > 0 && Mred < (1ll << 31) && I < (1ll << 31) && J < (1ll << 31), "spq_gemm_tn: bad shape");
     SPQ_REQUIRE((ldp % 8) == 0 && (ldq % 8) == 0 && ldp >= I && ldq >= J && aligned16(P) && aligned16(Q),
@@ -1177,6 +1188,7 @@ extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q
     TnReduce ra;
     ra.part = ep.part; ra.splits = splits; ra.plane = ep.plane; ra.I = I; ra.J = J; ra.stride_i = d_stride_i; ra.stride_j = d_stride_j;
     ra.i_scale = i_scale; ra.j_scale = j_scale; ra.alpha_dev = alpha_dev; ra.alpha = alpha; ra.clamp_abs = clamp_abs; ra.D = D;
+    ra.gq_scale_i = gq_scale_i; ra.gq_levels = gq_scale_i ? static_cast<float>((1 << (gq_bits - 1)) - 1) : 0.f;
     long long blocks = (ep.plane / 4 + 63) / 64;
     const long long cap = static_cast<long long>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
