@@ -158,11 +158,32 @@ def load_model_for_evaluation(checkpoint_path, config=None, target_bits=None, de
     return model.to(device).eval()
 
 
-def export_integer_weights(model, bits):
+def pack_int4(codes: torch.Tensor) -> torch.Tensor:
+    """[..., K] integer codes in [-8, 7] (or [0, 15]) -> uint8 [..., ceil(K / 2)]: element 2i in the low nibble, 2i+1 in
+    the high nibble, two's complement; an odd K is padded with a zero nibble."""
+    c = codes.to(torch.int16)
+    if c.shape[-1] % 2:
+        c = torch.nn.functional.pad(c, (0, 1))
+    lo, hi = c[..., 0::2] & 0xF, c[..., 1::2] & 0xF
+    return (lo | (hi << 4)).to(torch.uint8)
+
+
+def unpack_int4(packed: torch.Tensor, K: int, signed: bool = True) -> torch.Tensor:
+    """Inverse of pack_int4: uint8 [..., ceil(K / 2)] -> int8 [..., K]."""
+    p = packed.to(torch.int16)
+    both = torch.stack((p & 0xF, (p >> 4) & 0xF), dim=-1).reshape(*packed.shape[:-1], -1)[..., :K]
+    if signed:
+        both = torch.where(both >= 8, both - 16, both)
+    return both.to(torch.int8)
+
+
+def export_integer_weights(model, bits, packed: bool = False):
     """True integer weights of every SPLinearWithLoRA at `bits`: the codes the calibrated weight quantiser assigns
     (int8 when they fit, else int32; log quantisers: level index + int8 sign) with its scale / zero-point --
     `codes` from the same kernel the forward uses, so `dequant == (codes - zero_point) * scale` exactly for
-    min-max quantisers.  CUDA only."""
+    min-max quantisers.  `packed=True`: widths <= 4 store two codes per byte (`codes_packed`, see pack_int4;
+    `codes_shape` keeps [N, K]) -- the packed int4 container upstream's `convert_to_int8` (p1/deploy.py:5-30) lacks.
+    CUDA only."""
     from .quantization_methods import quantize_codes
     out = {}
     key = f"{bits}bit"
@@ -177,7 +198,13 @@ def export_integer_weights(model, bits):
                                              q.quantizer_type)
             small = int(codes.abs().max()) <= 127
             prefix = f"{name}." if name else ""
-            out[prefix + "codes"] = codes.to(torch.int8 if small else torch.int32).cpu()
+            lo, hi = int(codes.min()), int(codes.max())
+            if packed and q.num_bits <= 4 and ((lo >= -8 and hi <= 7) or (lo >= 0 and hi <= 15)):
+                out[prefix + "codes_packed"] = pack_int4(codes).cpu()
+                out[prefix + "codes_shape"] = tuple(codes.shape)
+                out[prefix + "codes_signed"] = lo < 0 or hi <= 7
+            else:
+                out[prefix + "codes"] = codes.to(torch.int8 if small else torch.int32).cpu()
             if sign is not None:
                 out[prefix + "sign"] = sign.cpu()
             out[prefix + "scale"] = q.scale.detach().cpu()

@@ -64,3 +64,17 @@ def test_sp_checkpoints_roundtrip(tmp_path):
     ck = save_int8_checkpoint(model, str(tmp_path / "m_int8.pth"), model_config=mc, target_bits=8)
     assert ck["model_info"]["target_bits"] == 8 and ck["model_info"]["compression_ratio"] > 1.0
     assert any(k.endswith("weight_int8") for k in ck["int8_state_dict"])
+
+
+def test_pack_unpack_int4_roundtrip():
+    import torch
+    from llm_qat_on_gpt2_b200.deploy import pack_int4, unpack_int4
+    g = torch.Generator().manual_seed(0)
+    for K in (8, 7, 1):
+        c = torch.randint(-7, 8, (5, K), generator=g)
+        p = pack_int4(c)
+        assert p.dtype == torch.uint8 and p.shape == (5, (K + 1) // 2)
+        assert torch.equal(unpack_int4(p, K).to(torch.int64), c)
+        u = torch.randint(0, 16, (3, K), generator=g)
+        assert torch.equal(unpack_int4(pack_int4(u), K, signed=False).to(torch.int64), u)
+    assert int(pack_int4(torch.tensor([[-1, 7]]))[0, 0]) == 0x7F

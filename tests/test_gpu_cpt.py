@@ -173,3 +173,91 @@ def test_cpt_model_forward_backward_smoke():
         else:
             ref32 = out.logits
     assert ref32.shape == (2, 32, 211)
+
+
+def _tiny_cpt(widths=(4, 6, 8), vocab=211, n_embd=64, n_layer=2):
+    from types import SimpleNamespace
+    from llm_qat_on_gpt2_b200.cpt import CPTModel
+    mc = SimpleNamespace(vocab_size=vocab, n_positions=64, n_embd=n_embd, n_layer=n_layer, n_head=4, embd_pdrop=0.0,
+                         layer_norm_epsilon=1e-5, bit_widths=list(widths) + [32],
+                         quantizer_per_bit={**{b: "log" for b in widths}, 32: None}, gradient_bits=8, shared_lora_rank=8,
+                         shared_lora_alpha=16)
+    torch.manual_seed(0)
+    model = CPTModel({"model": mc, "training": SimpleNamespace(target_bits=widths[-1])}).cuda()
+    with torch.no_grad():
+        for mod in model.modules():
+            if mod.__class__.__name__ == "LoRAAdapter" and mod.lora_B is not None:
+                mod.lora_B.normal_(0, 0.02)
+    return model
+
+
+def test_cpt_calibration_manager_and_fused_gradient_quantizer():
+    """cpt.CalibrationManager follows upstream's order; with the gradient quantisers calibrated (on real LoRA gradients
+    at a quantised width) the GradientQuantizer + log STE clamp fused into the gradient GEMM's fold pass gives the same
+    LoRA gradients as the unfused tail (separate fake-quant and clamp launches)."""
+    from llm_qat_on_gpt2_b200.cpt import CalibrationManager, cpt_model
+    model = _tiny_cpt()
+    g = torch.Generator().manual_seed(0)
+    loader = [{"input_ids": torch.randint(0, 211, (2, 32), generator=g)} for _ in range(2)]
+    mgr = CalibrationManager(model, loader, torch.device("cuda"))
+    mgr.calibrate_gradient_quantizers()                      # upstream: at 32 bits -> nothing collected, identity
+    gqs = [q for m in model.modules() if m.__class__.__name__ == "LoRAAdapter" for q in (m.grad_quantizer_A, m.grad_quantizer_B)]
+    assert all(8 not in q.calibrated_bits for q in gqs)
+    for b in (4, 6, 8):
+        mgr.ensure_calibrated(b, num_batches=2)
+    assert mgr.calibrated_bits == {4, 6, 8} == mgr.lora_calibrated_bits
+    mgr.calibrate_gradient_quantizers(precision=8)           # extension: statistics from real LoRA gradients
+    assert all(8 in q.calibrated_bits for q in gqs)
+    model.train()
+    ids = loader[0]["input_ids"].cuda()
+
+    def lora_grads(fused):
+        orig = cpt_model._grad_quantizer_scale
+        if not fused:
+            cpt_model._grad_quantizer_scale = lambda q, rows: (None, q is None or not (q.collecting_stats or q.num_bits in q.calibrated_bits))
+        try:
+            model.zero_grad(set_to_none=True)
+            model.set_precision(6)
+            model(ids, labels=ids).loss.backward()
+        finally:
+            cpt_model._grad_quantizer_scale = orig
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None and "shared_lora" in n}
+    a, b = lora_grads(True), lora_grads(False)
+    assert a.keys() == b.keys() and len(a) == 2 * 9
+    for n in a:
+        assert torch.equal(a[n], b[n]), n
+        # the quantised gradient sits on the 8-bit grid of its row scale
+    sl = model.h[0].attn.c_attn.shared_lora
+    gA = a["h.0.attn.c_attn.shared_lora.lora_A"]
+    sc = sl.grad_quantizer_A.scales[8].reshape(-1, 1)
+    codes = gA / sc
+    assert torch.allclose(codes, codes.round(), atol=1e-3) and float(codes.abs().max()) <= 127.0
+
+
+def test_cpt_trainer_graphs_match_eager_and_cycle():
+    """CPTTrainer: per-width CUDA graphs (LoRA-level operand rebuild + forward + loss + backward) reproduce the eager
+    steps while the width cycles per step along CyclicPrecisionScheduler; parameters move; losses agree."""
+    from llm_qat_on_gpt2_b200.cpt import CalibrationManager, CPTTrainer, CyclicPrecisionScheduler
+    g = torch.Generator().manual_seed(1)
+    loader = [{"input_ids": torch.randint(0, 211, (2, 32), generator=g)} for _ in range(2)]
+    batches = [torch.randint(0, 211, (2, 32), generator=g).cuda() for _ in range(6)]
+    sched = CyclicPrecisionScheduler(bit_widths=[4, 6, 8], schedule_type="cosine", total_epochs=12, total_cycles=3)
+    seq = [sched.get_precision_for_epoch(i) for i in range(6)]
+    assert set(seq) == {4, 6, 8}
+    res = []
+    for use_graphs in (False, True):
+        model = _tiny_cpt()
+        mgr = CalibrationManager(model, loader, torch.device("cuda"))
+        for b in (4, 6, 8):
+            mgr.ensure_calibrated(b, num_batches=2)
+        model.train()
+        tr = CPTTrainer(model, lr=1e-3, total_lr_steps=100, use_graphs=use_graphs)
+        p0 = tr.flat_param.clone()
+        losses = [tr.train_step(x, b)["loss"] for x, b in zip(batches, seq)]
+        res.append((losses, tr.flat_param.clone(), p0, tr))
+    (l_e, p_e, p0, _), (l_g, p_g, _, tg) = res
+    assert sorted(tg.graphs) == [4, 6, 8]
+    for a, b in zip(l_e, l_g):
+        assert abs(a - b) <= 1e-4 * abs(a), (l_e, l_g)
+    assert float((p_e - p0).abs().max()) > 1e-4
+    assert float((p_g.double() - p_e.double()).norm() / (p_e.double() - p0.double()).norm()) <= 2e-2

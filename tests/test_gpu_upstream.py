@@ -345,3 +345,43 @@ def test_all_linears_teacher_forced_backward():
                                             "median_rel": float(np.median(list(errs.values()))), "checks": len(errs)})
         bad = {k: v for k, v in errs.items() if not v <= TOL}
         assert not bad, (bits, bad)
+
+
+def test_exported_integer_weights_equal_upstream_quantised_weights():
+    """deploy.export_integer_weights against the UNMODIFIED upstream weight quantiser on torch-CPU (not against this
+    repo's own dequant): 4-bit min-max codes * scale reproduce upstream's q_w(W) bit for bit, packed int4 included;
+    8-bit log levels + signs reproduce upstream's level indices."""
+    from llm_qat_on_gpt2_b200.deploy import export_integer_weights, unpack_int4
+    ref, ours, cfg = _make_pair(2, (4, 8), seed=9)
+    refm = dict(ref.named_modules())
+    for bits in (4, 8):
+        # calibrate the weight quantisers with this repo's kernels (true IEEE division = torch-CPU semantics; the pair
+        # was calibrated by upstream on torch-CUDA, whose scale is 1 ulp off its own CPU result)
+        with torch.no_grad():
+            for m in ours.modules():
+                if m.__class__.__name__ == "SPLinearWithLoRA":
+                    qw = m.quantizers_weight[f"{bits}bit"]
+                    qw.start_calibration(); qw(m.linear.weight.data); qw.finish_calibration()
+        exp = export_integer_weights(ours, bits, packed=True)
+        names = [n for n, m in ours.named_modules() if m.__class__.__name__ == "SPLinearWithLoRA"]
+        assert len(names) == 8
+        for n in names:
+            rm = refm[n]
+            W = rm.linear.weight.detach().cpu()
+            UQ = up.p1("quantization").LearnableFakeQuantize
+            q = UQ(bits, channel_dim=0, quantizer_type=cfg.quantizer_per_bit[bits])
+            with up.quiet(), torch.no_grad():
+                q.start_calibration(); q(W); q.finish_calibration()
+                store = []
+                with record_round(store):
+                    wq = q(W)
+            nmax = 2 ** (bits - 1) - 1
+            ref_codes = torch.clamp(store[-1], -nmax, nmax).to(torch.int32)
+            if bits == 4:
+                codes = unpack_int4(exp[f"{n}.codes_packed"], W.shape[1]).to(torch.int32)
+                assert exp[f"{n}.codes_shape"] == tuple(W.shape)
+                assert torch.equal(codes, ref_codes)
+                assert torch.equal(codes.float() * exp[f"{n}.scale"], wq)            # upstream's fake-quantised weight, exactly
+            else:
+                assert torch.equal(exp[f"{n}.codes"].to(torch.int32), ref_codes)
+                assert torch.equal(exp[f"{n}.sign"].float(), torch.sign(wq) * (W.abs() >= 1e-5))
