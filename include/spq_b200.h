@@ -42,7 +42,9 @@ enum { SPQ_MINMAX = 0, SPQ_LOG = 1 };
 /* what the GEMM-operand output of a quantise kernel holds */
 enum { SPQ_OPERAND_CODE = 0,     /* (q - zero_point): the integer code, exact in fp16 for <= 11 bits */
        SPQ_OPERAND_DEQUANT = 1,  /* the dequantised value */
-       SPQ_OPERAND_RAW = 2 };    /* the unquantised input (32-bit path) */
+       SPQ_OPERAND_RAW = 2,      /* the unquantised input (32-bit path) */
+       SPQ_OPERAND_CODE_E4M3 = 3 };  /* the integer code as ONE e4m3 byte (exact for |code| <= 16: <= 4-bit min-max);
+                                        the operand pointer is a byte buffer, leading dimensions in bytes */
 
 SPQ_API int spq_abi_version(void);
 SPQ_API const char* spq_last_error(void);
@@ -172,6 +174,17 @@ SPQ_API int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
               float alpha, const float* row_scale, const float* col_scale, const float* bias,
               float clamp_abs, const float* C, int64_t ldc,
               void* D, int64_t ldd, int d_is_half, int activation, spq_stream_t stream);
+
+/* The same fused GEMM on e4m3 integer-code operands (north_star (b)/(c): "codes held in e4m3 where they fit",
+ * tcgen05.mma.kind::f8f6f4 at twice the fp16 rate): A [M, K] and B [N, K] are e4m3 BYTES (SPQ_OPERAND_CODE_E4M3;
+ * lda / ldb in bytes, multiples of 16), exact for the <= 4-bit min-max codes of the per-tensor-scale evaluation
+ * configurations (p1/deploy.py:210,238; part3_eval_sp/main_sp_eval.py:60): with K * 7^2 < 2^24 the fp32 accumulator holds
+ * the integer dot product exactly, and the scales s_x * s_w[n] arrive through col_scale.  The optional second K
+ * segment (A2, B2: the fp16 LoRA operands) is accumulated with kind::f16 into the same TMEM tile.  No residual. */
+SPQ_API int spq_qgemm_f8(const uint8_t* A, int64_t lda, const uint8_t* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                 const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2, float alpha,
+                 const float* row_scale, const float* col_scale, const float* bias, void* D, int64_t ldd,
+                 int d_is_half, int activation, spq_stream_t stream);
 
 /* Transposed-operand GEMM for the weight-gradient shaped products of the STE backward
  * (dA = x^T dT, dB = t^T dY, optional dW = dY^T q(x); torch autograd of p1/lora.py:51-52, 144):

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libspq_b200.so")
 
 PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
 MINMAX, LOG = 0, 1
-OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW = 0, 1, 2
+OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW, OPERAND_CODE_E4M3 = 0, 1, 2, 3
 QTYPE = {"minmax": MINMAX, "log": LOG}
 ABI_VERSION = 2
 
@@ -49,6 +49,9 @@ SIGNATURES = {
                           c_void_p, c_int64, c_void_p, c_int64, c_int64,
                           c_float, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64,
                           c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "spq_qgemm_f8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                             c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                             c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "spq_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
                             c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
@@ -207,6 +210,7 @@ def fake_quantize(x2d, scale, zp, bcast, qtype, bits, symmetric, dequant=None, c
     assert scale.numel() == need and zp.numel() == need, (scale.shape, zp.shape, bcast, x2d.shape)
     assert row_mul is None or row_mul.numel() == rows
     assert col_mul is None or col_mul.numel() == cols
+    assert operand is None or (operand.dtype == torch.uint8) == (operand_kind == OPERAND_CODE_E4M3)
     _check(load_library().spq_fake_quantize(x2d.data_ptr(), rows, cols, scale.data_ptr(), zp.data_ptr(), bcast, qtype,
                                             bits, int(symmetric), _ptr(dequant), _ptr(codes), _ptr(sign),
                                             _ptr(operand), operand_kind, _ptr(row_mul), _ptr(col_mul), float(mul),
@@ -259,6 +263,19 @@ def qgemm(A, B, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None,
                                     _ptr(col_scale), _ptr(bias), float(clamp_abs), _ptr(C),
                                     0 if C is None else C.stride(0), out.data_ptr(), out.stride(0), int(d_half),
                                     int(activation), _stream()), "spq_qgemm")
+    return out
+
+
+def qgemm_f8(A8, B8, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=None, col_scale=None, bias=None, activation=0):
+    """out[M,N] = epi(A8[M,K] B8[N,K]^T + A2[M,K2] B2[N,K2]^T): A8 / B8 e4m3 integer codes (uint8 storage, row strides
+    multiples of 16 bytes) on tcgen05.mma.kind::f8f6f4, the optional second segment fp16; out fp32 or fp16."""
+    _req_cuda(A8, B8, out, A2, B2, row_scale, col_scale, bias)
+    assert A8.dtype == torch.uint8 and B8.dtype == torch.uint8 and A8.stride(-1) == 1 and B8.stride(-1) == 1
+    assert out.stride(-1) == 1 and out.dtype in (torch.float32, torch.float16)
+    _check(load_library().spq_qgemm_f8(A8.data_ptr(), A8.stride(0), B8.data_ptr(), B8.stride(0), M, N, K,
+                                       _ptr(A2), 0 if A2 is None else A2.stride(0), _ptr(B2), 0 if B2 is None else B2.stride(0),
+                                       K2, float(alpha), _ptr(row_scale), _ptr(col_scale), _ptr(bias), out.data_ptr(),
+                                       out.stride(0), int(out.dtype == torch.float16), int(activation), _stream()), "spq_qgemm_f8")
     return out
 
 

@@ -134,6 +134,25 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// e4m3 x e4m3 -> fp32 (kind::f8f6f4, K = 32 per instruction): the operands of a <= 4-bit integer-code GEMM
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -252,7 +271,10 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
 // pair per column half-tile -- the log-sum-exp of the LM head's logits without a second pass over them
 // CTA2: launched as clusters of two CTAs; the pair computes 256 x BN tiles with tcgen05.mma.cta_group::2 (issued
 // by the even CTA), each CTA owning 128 rows of A, half of B in shared memory and its 128 rows of the accumulator.
-template <int BN, bool OUT_HALF, bool PRE_C, bool LSE = false, bool CTA2 = false>
+// F8: the first K segment (A, B) holds e4m3 bytes -- 128 of them per 128-byte swizzle row, tcgen05.mma.kind::f8f6f4
+// (instruction-descriptor format code 0 = E4M3, the same bits as F16 under kind::f16); the second segment (the fp16
+// LoRA operands) keeps kind::f16 and lands in the same fp32 accumulator.
+template <int BN, bool OUT_HALF, bool PRE_C, bool LSE = false, bool CTA2 = false, bool F8 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -343,8 +365,8 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
                         if (kb < kb1) {
-                            tma_load_2d_pair(sa, &tmA, lead_bar, kb * BK, m0);
-                            tma_load_2d_pair(sb, &tmB, lead_bar, kb * BK, n0);
+                            tma_load_2d_pair(sa, &tmA, lead_bar, kb * (F8 ? 2 * BK : BK), m0);
+                            tma_load_2d_pair(sb, &tmB, lead_bar, kb * (F8 ? 2 * BK : BK), n0);
                         } else {
                             tma_load_2d_pair(sa, &tmA2, lead_bar, (kb - kb1) * BK, m0);
                             tma_load_2d_pair(sb, &tmB2, lead_bar, (kb - kb1) * BK, n0);
@@ -352,8 +374,8 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                         if (kb < kb1) {
-                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-                            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                            tma_load_2d(sa, &tmA, &full_bar[stage], kb * (F8 ? 2 * BK : BK), m0);
+                            tma_load_2d(sb, &tmB, &full_bar[stage], kb * (F8 ? 2 * BK : BK), n0);
                         } else {
                             tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - kb1) * BK, m0);
                             tma_load_2d(sb, &tmB2, &full_bar[stage], (kb - kb1) * BK, n0);
@@ -385,12 +407,15 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         if (ep.debug & 2) break;
                         // +32 B per UMMA_K inside the 128 B swizzle span: +2 in the (addr >> 4) field
-                        if constexpr (CTA2)
-                            umma_f16_pair(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                                          (kb | k) != 0 ? 1u : 0u);
-                        else
-                            umma_f16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                        const uint64_t ad = adesc + static_cast<uint64_t>(2 * k), bd = bdesc + static_cast<uint64_t>(2 * k);
+                        const uint32_t acc_on = (kb | k) != 0 ? 1u : 0u;
+                        if (F8 && kb < kb1) {
+                            if constexpr (CTA2) umma_f8_pair(tmem_d, ad, bd, idesc, acc_on);
+                            else umma_f8(tmem_d, ad, bd, idesc, acc_on);
+                        } else {
+                            if constexpr (CTA2) umma_f16_pair(tmem_d, ad, bd, idesc, acc_on);
+                            else umma_f16(tmem_d, ad, bd, idesc, acc_on);
+                        }
                     }
                     if constexpr (CTA2) {
                         umma_commit_pair(&empty_bar[stage]);     // frees the slot in both CTAs
@@ -686,6 +711,28 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
     return SPQ_OK;
 }
 
+// e4m3 row-major [rows, cols] bytes with leading dimension ld (bytes); box = 128 columns (one swizzle row) x box_rows.
+static int make_tmap_u8(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return SPQ_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(2 * BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (e4m3) failed (%d) for [%lld x %lld] ld %lld box %d", static_cast<int>(r),
+                  static_cast<long long>(rows), static_cast<long long>(cols), static_cast<long long>(ld), box_rows);
+        return SPQ_ERR_CUDA;
+    }
+    return SPQ_OK;
+}
+
 // row-major D [M, N], leading dimension ldd (elements): box = 32 columns x 32 rows; fp32 rows of the box are
 // 128 B (128B swizzle), fp16 rows 64 B (64B swizzle) -- the swizzle keeps the per-row smem writes conflict-free
 static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, bool is_half) {
@@ -709,29 +756,29 @@ static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t rows, int64_
     return SPQ_OK;
 }
 
-template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false>
+template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false, bool F8 = false>
 static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
                      const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
     using L = SmemLayout<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SPQ_CUDA_OK(cudaFuncSetAttribute(qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE, false, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
+    qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE, false, F8><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
 
 
 // CTA-pair launch: clusters of two CTAs, 256 x BN tiles, one cluster per SM pair
-template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false>
+template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false, bool F8 = false>
 static int launch_nt_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
                           const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
     using L = SmemLayout<BN, true>;
-    auto kern = qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE, true>;
+    auto kern = qgemm_nt_kernel<BN, OUT_HALF, PRE_C, LSE, true, F8>;
     static bool attr_set = false;
     if (!attr_set) {
         SPQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -1034,15 +1081,16 @@ static int pick_bn(int64_t M, int64_t N, int sms) {
     return 64;
 }
 
-static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,
+static int qgemm_impl(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
                       int64_t K, const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2,
                       float alpha, const float* row_scale, const float* col_scale, const float* bias, float clamp_abs,
                       const float* C, int64_t ldc, void* D, int64_t ldd, int d_is_half, int activation,
-                      float* lse_part, int64_t lse_ld, spq_stream_t stream) {
+                      float* lse_part, int64_t lse_ld, spq_stream_t stream, bool f8 = false) {
     SPQ_REQUIRE(A && B && D, "spq_qgemm: null operand");
     SPQ_REQUIRE(M > 0 && N > 0 && K > 0, "spq_qgemm: empty problem %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
     SPQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "spq_qgemm: dimension overflow");
-    SPQ_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0 && lda >= K && ldb >= K, "spq_qgemm: lda/ldb must be multiples of 8 and >= K");
+    SPQ_REQUIRE((lda % (f8 ? 16 : 8)) == 0 && (ldb % (f8 ? 16 : 8)) == 0 && lda >= K && ldb >= K,
+                "spq_qgemm: lda/ldb must be multiples of 16 bytes and >= K");
     SPQ_REQUIRE(aligned16(A) && aligned16(B), "spq_qgemm: operands must be 16-byte aligned");
     SPQ_REQUIRE(K2 == 0 || (A2 && B2 && (lda2 % 8) == 0 && (ldb2 % 8) == 0 && aligned16(A2) && aligned16(B2)),
                 "spq_qgemm: bad second K segment");
@@ -1062,8 +1110,13 @@ static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
     const int b_rows = pair ? bn / 2 : bn;                // rows of B each CTA stages per k-block
     CUtensorMap tA, tB, tA2, tB2;
     int rc;
-    if ((rc = make_tmap(&tA, A, M, K, lda, BM)) != SPQ_OK) return rc;
-    if ((rc = make_tmap(&tB, B, N, K, ldb, b_rows)) != SPQ_OK) return rc;
+    if (f8) {
+        if ((rc = make_tmap_u8(&tA, A, M, K, lda, BM)) != SPQ_OK) return rc;
+        if ((rc = make_tmap_u8(&tB, B, N, K, ldb, b_rows)) != SPQ_OK) return rc;
+    } else {
+        if ((rc = make_tmap(&tA, A, M, K, lda, BM)) != SPQ_OK) return rc;
+        if ((rc = make_tmap(&tB, B, N, K, ldb, b_rows)) != SPQ_OK) return rc;
+    }
     if (K2 > 0) {
         if ((rc = make_tmap(&tA2, A2, M, K2, lda2, BM)) != SPQ_OK) return rc;
         if ((rc = make_tmap(&tB2, B2, N, K2, ldb2, b_rows)) != SPQ_OK) return rc;
@@ -1081,7 +1134,7 @@ static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
         if (dbg < 0) { const char* e = getenv("SPQ_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
         ep.debug = dbg;
     }
-    const int kb1 = static_cast<int>((K + BK - 1) / BK);
+    const int kb1 = static_cast<int>(f8 ? (K + 2 * BK - 1) / (2 * BK) : (K + BK - 1) / BK);
     const int kb2 = static_cast<int>((K2 + BK - 1) / BK);
     cudaStream_t st = as_stream(stream);
     const int m = static_cast<int>(M), n = static_cast<int>(N);
@@ -1100,6 +1153,22 @@ static int qgemm_impl(const spq_half_t* A, int64_t lda, const spq_half_t* B, int
         if (bn == 256) return launch_nt<256, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 128) return launch_nt<128, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         return launch_nt<64, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+    }
+    if (f8) {
+        // e4m3 code GEMM (eval configurations: <= 4-bit, per-tensor input scale): float32 or fp16 output, no residual
+        SPQ_REQUIRE(!C && !lse_part, "spq_qgemm_f8: no residual / log-sum-exp epilogue");
+        if (pair) {
+            if (d_is_half) return launch_nt_pair<256, true, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+            return launch_nt_pair<256, false, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        }
+        if (d_is_half) {
+            if (bn == 256) return launch_nt<256, true, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+            if (bn == 128) return launch_nt<128, true, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+            return launch_nt<64, true, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        }
+        if (bn == 256) return launch_nt<256, false, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        if (bn == 128) return launch_nt<128, false, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
+        return launch_nt<64, false, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
     }
     if (pair) {
         if (d_is_half) return launch_nt_pair<256, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
@@ -1128,6 +1197,14 @@ extern "C" int spq_qgemm(const spq_half_t* A, int64_t lda, const spq_half_t* B, 
                          spq_stream_t stream) {
     return qgemm_impl(A, lda, B, ldb, M, N, K, A2, lda2, B2, ldb2, K2, alpha, row_scale, col_scale, bias, clamp_abs, C, ldc,
                       D, ldd, d_is_half, activation, nullptr, 0, stream);
+}
+
+extern "C" int spq_qgemm_f8(const uint8_t* A, int64_t lda, const uint8_t* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                            const spq_half_t* A2, int64_t lda2, const spq_half_t* B2, int64_t ldb2, int64_t K2, float alpha,
+                            const float* row_scale, const float* col_scale, const float* bias, void* D, int64_t ldd,
+                            int d_is_half, int activation, spq_stream_t stream) {
+    return qgemm_impl(A, lda, B, ldb, M, N, K, A2, lda2, B2, ldb2, K2, alpha, row_scale, col_scale, bias, 0.f, nullptr, 0, D, ldd,
+                      d_is_half, activation, nullptr, 0, stream, true);
 }
 
 extern "C" int64_t spq_qgemm_lse_parts(int64_t M, int64_t N) {

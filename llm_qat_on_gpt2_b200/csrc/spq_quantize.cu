@@ -12,6 +12,7 @@
 // so the level index is exact everywhere while the double-precision unit is touched by < 0.1 %
 // of the elements at 8 bits.
 #include <stdlib.h>
+#include <cuda_fp8.h>
 
 #include "spq_common.cuh"
 
@@ -19,6 +20,16 @@ namespace spq {
 namespace quant {
 
 constexpr float LOG_EPS = 1e-5f;   // p1/quantization_methods.py:35 (hard-coded)
+
+// four floats -> four e4m3 bytes (saturating).  Integer codes |c| <= 16 are exact in e4m3 (3 mantissa bits).
+__device__ __forceinline__ unsigned int pack_e4m3x4(float a, float b, float c, float d) {
+    const unsigned int lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const unsigned int hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+__device__ __forceinline__ unsigned char to_e4m3(float a) {
+    return static_cast<unsigned char>(__nv_cvt_float_to_fp8(a, __NV_SATFINITE, __NV_E4M3));
+}
 
 struct QParams {
     int bits;
@@ -251,7 +262,8 @@ fake_quantize_kernel(FqArgs a) {
                 const LogOut o = log_elem(xv[j], make_logcol(zj, sj, a.qp), a.qp);
                 dq[j] = o.dq; code[j] = o.level; centered = o.level; sg[j] = o.sign;
             }
-            const float base = (a.operand_kind == SPQ_OPERAND_CODE) ? centered : (a.operand_kind == SPQ_OPERAND_DEQUANT ? dq[j] : xv[j]);
+            const float base = (a.operand_kind == SPQ_OPERAND_CODE || a.operand_kind == SPQ_OPERAND_CODE_E4M3)
+                                   ? centered : (a.operand_kind == SPQ_OPERAND_DEQUANT ? dq[j] : xv[j]);
             opv[j] = base * rm * cm[j];
         }
         const long long off = r * a.cols + c0;
@@ -259,7 +271,15 @@ fake_quantize_kernel(FqArgs a) {
             if (a.dequant) *reinterpret_cast<float4*>(a.dequant + off) = make_float4(dq[0], dq[1], dq[2], dq[3]);
             if (a.codes) *reinterpret_cast<int4*>(a.codes + off) = make_int4((int)code[0], (int)code[1], (int)code[2], (int)code[3]);
             if (a.sign) *reinterpret_cast<char4*>(a.sign + off) = make_char4((signed char)sg[0], (signed char)sg[1], (signed char)sg[2], (signed char)sg[3]);
-            if (a.operand) {
+            if (a.operand && a.operand_kind == SPQ_OPERAND_CODE_E4M3) {
+                unsigned char* o8 = reinterpret_cast<unsigned char*>(a.operand);      // op_ld in bytes
+                if (!a.transposed) {
+                    *reinterpret_cast<unsigned int*>(o8 + r * a.op_ld + c0) = pack_e4m3x4(opv[0], opv[1], opv[2], opv[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o8[(c0 + j) * a.op_ld + r] = to_e4m3(opv[j]);
+                }
+            } else if (a.operand) {
                 if (!a.transposed) {
                     *reinterpret_cast<uint2*>(a.operand + r * a.op_ld + c0) = make_uint2(pack_h2(opv[0], opv[1]), pack_h2(opv[2], opv[3]));
                 } else {
@@ -271,7 +291,9 @@ fake_quantize_kernel(FqArgs a) {
             if (a.dequant) a.dequant[off] = dq[0];
             if (a.codes) a.codes[off] = (int)code[0];
             if (a.sign) a.sign[off] = (signed char)sg[0];
-            if (a.operand) a.operand[a.transposed ? (c0 * a.op_ld + r) : (r * a.op_ld + c0)] = f2h_sat(opv[0]);
+            if (a.operand && a.operand_kind == SPQ_OPERAND_CODE_E4M3)
+                reinterpret_cast<unsigned char*>(a.operand)[a.transposed ? (c0 * a.op_ld + r) : (r * a.op_ld + c0)] = to_e4m3(opv[0]);
+            else if (a.operand) a.operand[a.transposed ? (c0 * a.op_ld + r) : (r * a.op_ld + c0)] = f2h_sat(opv[0]);
         }
     }
 }
@@ -405,7 +427,7 @@ quantize_act_kernel(ActArgs a) {
             float base;
             if constexpr (QTYPE == SPQ_MINMAX) {
                 const float cen = minmax_centered(q[j], mm[j], qp);
-                base = (kind == SPQ_OPERAND_CODE) ? cen : __fmul_rn(cen, mm[j].s);
+                base = (kind == SPQ_OPERAND_CODE || kind == SPQ_OPERAND_CODE_E4M3) ? cen : __fmul_rn(cen, mm[j].s);
             } else {
                 // q is already in range: the fast path rounds v = sat(.) * 2n - n (or sat(.) * n), the exact path clamps
                 const float lvl = q[j];
@@ -413,7 +435,10 @@ quantize_act_kernel(ActArgs a) {
             }
             o[j] = base * cm[j];
         }
-        *reinterpret_cast<uint2*>(a.a_q + r * a.K + c0) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
+        if (kind == SPQ_OPERAND_CODE_E4M3)           // one byte per code (a_q is an e4m3 buffer, rows K bytes apart)
+            *reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(a.a_q) + r * a.K + c0) = pack_e4m3x4(o[0], o[1], o[2], o[3]);
+        else
+            *reinterpret_cast<uint2*>(a.a_q + r * a.K + c0) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
         if (a.a_raw)
             *reinterpret_cast<uint2*>(a.a_raw + r * a.K + c0) =
                 make_uint2(pack_h2(xv[0] * rm[0], xv[1] * rm[1]), pack_h2(xv[2] * rm[2], xv[3] * rm[3]));

@@ -322,10 +322,13 @@ class _SPLinearFn(torch.autograd.Function):
         N, K = weight.shape
         x2d = _as_2d_act(x, K)
         M = x2d.shape[0]
-        a_q = torch.empty((M, K), dtype=torch.float16, device=x.device)
+        need_wgrad = grad_mode and ctx.needs_input_grad[1]
+        f8 = base.get('f8') if (residual is None and not need_wgrad) else None
+        a_q = torch.empty((M, K), dtype=torch.uint8 if f8 is not None else torch.float16, device=x.device)
         a_raw = torch.empty((M, K), dtype=torch.float16, device=x.device) if use_lora else None
         _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
-                          act['kind'], act['col_mul'], act['mul'], a_q, a_raw, act['raw_mul'] if use_lora else None)
+                          _lib.OPERAND_CODE_E4M3 if f8 is not None else act['kind'], act['col_mul'], act['mul'], a_q, a_raw,
+                          act['raw_mul'] if use_lora else None)
         y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
         res2d = None if residual is None else residual.reshape(M, N)
@@ -336,8 +339,15 @@ class _SPLinearFn(torch.autograd.Function):
             # fp16(acc * (pa tau)) is the value the GEMM consumes); the same tensor is what dB = t^T dY needs later
             t16 = _lib.empty_f16_padded(M, r, x.device)
             _lib.qgemm(a_raw, lo['A_op'], M, r, K, t16, col_scale=lo['pa_tmul'])
-            _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f,
-                       activation=activation, C=res2d)
+            if f8 is not None:
+                # integer codes x integer codes on the fp8 tensor pipe; the scales s_x * s_w[n] in the epilogue
+                _lib.qgemm_f8(a_q, f8['B8'], M, N, K, y, A2=t16, B2=lo['Bl_op8'], K2=r, col_scale=f8['cs'], bias=bias_f,
+                              activation=activation)
+            else:
+                _lib.qgemm(a_q, base['B_op'], M, N, K, y, A2=t16, B2=lo['Bl_op'], K2=r, col_scale=base['pw'], bias=bias_f,
+                           activation=activation, C=res2d)
+        elif f8 is not None:
+            _lib.qgemm_f8(a_q, f8['B8'], M, N, K, y, col_scale=f8['cs'], bias=bias_f, activation=activation)
         else:
             _lib.qgemm(a_q, base['B_op'], M, N, K, y, col_scale=base['pw'], bias=bias_f, activation=activation, C=res2d)
         ctx.use_lora = use_lora
@@ -572,6 +582,7 @@ class SPLinearWithLoRA(nn.Module):
                            bits=qi.num_bits, symmetric=qi.symmetric, input_qtype=qi.quantizer_type)
                 base = dict(key=bkey, act=act, pw=pw, inv_pw=inv_pw,
                             B_op=_to_f16_operand(wl['wq'], row_mul=inv_pw, col_mul=absorb))      # the big one: [N, K]
+                base['f8'] = self._f8_level(bits, sc, qi)
             if ll is not None:
                 if want_pb:
                     ll['pb'], ll['inv_pb'] = lora_vec[5 * r:6 * r].clone(), lora_vec[6 * r:7 * r].clone()
@@ -579,12 +590,42 @@ class SPLinearWithLoRA(nn.Module):
                 pa, inv_pa = lora_vec[3 * r:4 * r], lora_vec[4 * r:5 * r]
                 # A operand of the down-projection: q(A)[k,j] / (raw_mul[k] pa[j]), stored [r, K]
                 A_op = _to_f16_operand(ll['aq'], row_mul=base['act']['inv_raw_mul'], col_mul=inv_pa, transposed=True)
-                lora = dict(key=lkey, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
+                Bl_op8 = None
+                if base.get('f8') is not None:
+                    # the epilogue multiplies by cs[n] = s_x * s_w[n] (not a power of two): the LoRA operand carries its inverse
+                    b8 = (ll['bq'].t() * ll['scaling']) / (tmul_vec[None, :] * base['f8']['cs'][:, None])
+                    Bl_op8 = _lib.empty_f16_padded(N, r, dev)
+                    Bl_op8.copy_(b8.clamp(-65504.0, 65504.0))
+                lora = dict(key=lkey, rank=r, A_op=A_op, pa=pa, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec, Bl_op8=Bl_op8,
                             Bl_op=_to_f16_operand(ll['bq'], row_mul=bl_rowmul, col_mul=base['inv_pw'], transposed=True),   # [N, r]
                             scaling=ll['scaling'], qtype_A=ll['qtype_A'], qtype_B=ll['qtype_B'],
                             pb=ll['pb'], inv_pb=ll['inv_pb'], pa_tmul=lora_vec[7 * r:])
         ent['input'] = dict(base=base, lora=lora if ll is not None else (il['lora'] if il is not None and base is il['base'] else None))
         return base, (lora if ll is not None else None)
+
+    def _f8_level(self, bits, in_scale, qi):
+        """e4m3 operands of the integer-code GEMM, when the configuration allows one (north_star (b)/(c); the reference's
+        evaluation loaders force per-tensor scales: p1/deploy.py:210,238, part3_eval_sp/main_sp_eval.py:60): symmetric
+        min-max quantisers of <= 4 bits on both sides (codes in [-7, 7], exact in e4m3) and ONE input scale, so that
+        q(x)[m,k] q(W)[n,k] = (s_x s_w[n]) * cx[m,k] cw[n,k] and the scales can wait for the epilogue.  K * 49 < 2^24 keeps
+        the fp32 accumulation of the integer dot product exact.  `SPQ_FP8=0` disables the path (A/B switch)."""
+        import os
+        qw = self.quantizers_weight[f'{bits}bit']
+        K, N = self.in_features, self.out_features
+        ok = (qi.quantizer_type == 'minmax' and qw.quantizer_type == 'minmax' and qi.symmetric and qw.symmetric
+              and qi.num_bits <= 4 and qw.num_bits <= 4 and in_scale.numel() == 1 and K % 16 == 0 and K * 49 < (1 << 24)
+              and qw.scale.numel() in (1, N) and os.environ.get('SPQ_FP8', '1') != '0')
+        if not ok:
+            return None
+        W = self.linear.weight.detach().float().contiguous()
+        sw = qw.scale.detach().float().reshape(-1)
+        zw = qw.zero_point.detach().float().reshape(-1)
+        if zw.numel() != sw.numel():
+            zw = zw.expand_as(sw)
+        B8 = torch.empty((N, K), dtype=torch.uint8, device=W.device)
+        _lib.fake_quantize(W, sw.contiguous(), zw.contiguous(), _lib.PER_TENSOR if sw.numel() == 1 else _lib.PER_ROW, _lib.MINMAX,
+                           qw.num_bits, True, operand=B8, operand_kind=_lib.OPERAND_CODE_E4M3)
+        return dict(B8=B8, cs=(in_scale.reshape(1) * sw).expand(N).contiguous())
 
     def _backward_operands_for(self, bits, want_lora):
         wb = self._weight_level_bwd(bits)

@@ -569,3 +569,35 @@ def test_qgemm_lse_and_cross_entropy_from_parts(M, V, K):
     lse = mm + torch.log((s_ * torch.exp(m - mm[:, None])).sum(dim=1))
     assert float((lse.double() - torch.logsumexp(logits.double(), dim=1)).abs().max()) <= 1e-4
     assert lib.debug_status() == 0
+
+
+# --------------------------------------------------------------------------- fp8 (e4m3) integer-code GEMM
+@pytest.mark.parametrize("M,N,K,K2", [(300, 200, 256, 0), (4096, 2304, 768, 64), (1000, 768, 3072, 64), (129, 4800, 1600, 0)])
+def test_qgemm_f8_integer_codes_exact(lib, M, N, K, K2):
+    """tcgen05.mma.kind::f8f6f4 on e4m3 integer codes in [-7, 7]: the fp32 accumulator holds the integer dot product
+    exactly (K * 49 < 2^24), so the result equals the int64 matmul bit for bit; with the fp16 LoRA segment riding in
+    the same accumulator (kind::f16) it matches float64 to fp32 rounding."""
+    torch.manual_seed(M + K)
+    ca = torch.randint(-7, 8, (M, K), device="cuda")
+    cb = torch.randint(-7, 8, (N, K), device="cuda")
+    A8 = ca.float().to(torch.float8_e4m3fn).view(torch.uint8)
+    B8 = cb.float().to(torch.float8_e4m3fn).view(torch.uint8)
+    exact = (ca.double() @ cb.double().t())
+    out = torch.empty(M, N, device="cuda")
+    lib.qgemm_f8(A8, B8, M, N, K, out)
+    assert lib.debug_status() == 0
+    assert torch.equal(out.double(), exact)
+    cs = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    if K2:
+        A2 = torch.randn(M, K2, device="cuda").half(); B2 = (torch.randn(N, K2, device="cuda") * 3).half()
+        lib.qgemm_f8(A8, B8, M, N, K, out, A2=A2, B2=B2, K2=K2, col_scale=cs, bias=bias)
+        ref = (exact + A2.double() @ B2.double().t()) * cs.double()[None, :] + bias.double()[None, :]
+    else:
+        lib.qgemm_f8(A8, B8, M, N, K, out, col_scale=cs, bias=bias)
+        ref = exact * cs.double()[None, :] + bias.double()[None, :]
+    assert ((out.double() - ref).norm() / ref.norm()) <= 2e-7
+    outh = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    lib.qgemm_f8(A8, B8, M, N, K, outh, col_scale=cs * 1e-2)
+    assert ((outh.double() - exact * cs.double()[None, :] * 1e-2).norm() / (exact * 1e-2).norm()) <= 1e-3
+    assert lib.debug_status() == 0

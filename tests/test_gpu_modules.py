@@ -634,3 +634,52 @@ def test_graphed_no_grad_forward_equals_eager():
         assert torch.equal(got["logits"], want["logits"]), step
         assert all(torch.equal(a, b) for a, b in zip(got["hidden_states"], want["hidden_states"]))
     assert teacher.graph is not None
+
+
+def test_sp_linear_fp8_path_per_tensor_4bit(monkeypatch):
+    """The evaluation configuration (per_channel=False, 4-bit min-max: p1/deploy.py:210,238): SPLinearWithLoRA takes the
+    e4m3 integer-code GEMM.  With the LoRA branch off the output is the exact product of the codes times s_x s_w (fp32
+    rounding only); with it on the result agrees with float64 to the fp16 LoRA-operand rounding; SPQ_FP8=0 gives the
+    fp16-operand path, which agrees to 1e-3."""
+    from llm_qat_on_gpt2_b200 import SPLinearWithLoRA, quantize_codes
+    K, N, r, bits, M = 768, 2304, 64, 4, 1000
+
+    def build():
+        torch.manual_seed(4)
+        m = SPLinearWithLoRA(K, N, bit_widths=[bits, 32], lora_rank_per_bit={bits: r, 32: 0}, lora_alpha_per_bit={bits: r, 32: 0},
+                             quantizer_per_bit={bits: "minmax", 32: None}, per_channel=False).cuda()
+        with torch.no_grad():
+            m.linear.weight.normal_(0, 0.02); m.lora_adapters[f"{bits}bit"].lora_B.normal_(0, 0.02)
+        x = torch.randn(M, K, device="cuda") * 2
+        _calibrate_linear(m, bits, [x[None]])
+        return m, x
+    m, x = build()
+    key = f"{bits}bit"
+    qi, qw, lo = m.quantizers_input[key], m.quantizers_weight[key], m.lora_adapters[key]
+    assert qi.scale.numel() == 1 and qw.scale.numel() == 1
+    with torch.no_grad():
+        y = m(x[None])[0]
+        base, lora = m._operands_for(bits, True)
+        assert base["f8"] is not None and base["f8"]["B8"].dtype == torch.uint8 and lora["Bl_op8"] is not None
+        m.calibration_mode = True
+        y_base = m(x[None])[0]
+        m.calibration_mode = False
+        _, cx, _ = quantize_codes(x, qi.scale, qi.zero_point, bits, True, "minmax")
+        _, cw, _ = quantize_codes(m.linear.weight.data, qw.scale, qw.zero_point, bits, True, "minmax")
+        exact = (cx.double() @ cw.double().t()) * float(qi.scale) * float(qw.scale) + m.linear.bias.double()
+        assert ((y_base.double() - exact).norm() / exact.norm()) <= 3e-7
+        aq = lo.quantize_A(lo.lora_A).double(); bq = lo.quantize_B(lo.lora_B).double()
+        full = exact + (x.double() @ aq @ bq) * lo.scaling
+        assert ((y.double() - full).norm() / full.norm()) <= 5e-4
+    monkeypatch.setenv("SPQ_FP8", "0")
+    m2, x2 = build()
+    with torch.no_grad():
+        y2 = m2(x2[None])[0]
+        assert m2._operands_for(bits, True)[0]["f8"] is None
+    assert ((y2.double() - full).norm() / full.norm()) <= 1e-3
+    # the backward is the fp16-operand STE path either way
+    monkeypatch.setenv("SPQ_FP8", "1")
+    m.linear.weight.requires_grad_(False); m.linear.bias.requires_grad_(False)
+    xg = x.clone().requires_grad_(True)
+    out = m(xg[None]); out.backward(torch.randn_like(out) * 1e-2)
+    assert torch.isfinite(xg.grad).all() and lo.lora_A.grad is not None and lo.lora_B.grad is not None
