@@ -231,7 +231,7 @@ def test_cpt_calibration_manager_and_fused_gradient_quantizer():
     gA = a["h.0.attn.c_attn.shared_lora.lora_A"]
     sc = sl.grad_quantizer_A.scales[8].reshape(-1, 1)
     codes = gA / sc
-    assert torch.allclose(codes, codes.round(), atol=1e-3) and float(codes.abs().max()) <= 127.0
+    assert torch.allclose(codes, codes.round(), atol=1e-3) and float(codes.abs().max()) <= 127.001
 
 
 def test_cpt_trainer_graphs_match_eager_and_cycle():
