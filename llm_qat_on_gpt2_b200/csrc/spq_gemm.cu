@@ -29,6 +29,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 constexpr int STG_TILE_BYTES = 32 * 32 * 4;   // per-epilogue-warp 32 x 32 fp32 staging tile, 128B-XOR-swizzled
+constexpr int STG_BUFS = 2;                   // two tiles per warp: chunk i+1 is computed while the TMA engine still reads chunk i
 
 __device__ int g_abort = 0;    // watchdog: set when a pipeline wait timed out
 
@@ -233,9 +234,10 @@ template <int BN, bool CTA2 = false>
 struct SmemLayout {
     static constexpr int B_TILE_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;      // CTA pair: each CTA stages half of the B tile
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
     static constexpr int EPI_BYTES = 2 * BN * 4;      // col_scale + bias of the tile
-    static constexpr int STG_BYTES = EPI_WARPS * STG_TILE_BYTES;
+    static constexpr int STG_BYTES = EPI_WARPS * STG_BUFS * STG_TILE_BYTES;
+    static constexpr int RING_BYTES = 232448 - STG_BYTES - EPI_BYTES - 256;       // what is left for the operand ring
+    static constexpr int STAGES = (RING_BYTES / STAGE_BYTES) > 8 ? 8 : (RING_BYTES / STAGE_BYTES);
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     // order: [stages][staging tiles][col_scale|bias][barriers]; the dynamic smem base must be 1024 B aligned
     // (checked at run time) -- there is no room for alignment slack at BN = 256
@@ -436,8 +438,11 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int epi_tid = threadIdx.x - 64;         // 0..255
         constexpr int CHUNKS = (BN / 2) / 32 > 0 ? (BN / 2) / 32 : 1;   // 32-column chunks per warp
         constexpr int COLS_PER_HALF = BN / 2 >= 32 ? BN / 2 : 32;
-        float* stg = reinterpret_cast<float*>(stg_all + (warp - 2) * STG_TILE_BYTES);
-        const uint32_t stg_u32 = smem_u32(stg);
+        float* const stg_base = reinterpret_cast<float*>(stg_all + (warp - 2) * STG_BUFS * STG_TILE_BYTES);
+        float* stg = stg_base;
+        uint32_t stg_u32 = smem_u32(stg);
+        int stg_buf = 0;
+        int stores_in_flight = 0;                     // TMA store groups this warp has committed and not yet waited for
         int acc = 0;
         uint32_t acc_phase = 0;
         bool store_pending = false;
@@ -499,10 +504,16 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if constexpr (PRE_C) c_next();
                         continue;
                     }
-                    if (store_pending) {                            // the previous TMA store must have read the tile
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __syncwarp();
-                        store_pending = false;
+                    if (ep.tma_store) {
+                        // staging tile `stg_buf` was last handed to the TMA engine two chunks ago: at most ONE younger
+                        // store group may still be reading (the other tile) when this one is overwritten
+                        if (stores_in_flight >= STG_BUFS) {
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            __syncwarp();
+                            stores_in_flight = STG_BUFS - 1;
+                        }
+                        stg = stg_base + stg_buf * (STG_TILE_BYTES / 4);
+                        stg_u32 = smem_u32(stg);
                     }
                     if (ep.tma_store) {
                         if constexpr (PRE_C) {
@@ -570,6 +581,8 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                         store_pending = true;
+                        ++stores_in_flight;
+                        stg_buf ^= 1;
                     } else {
                         // general path (fp16 output, residual input, unaligned D): row scale before the transpose,
                         // column scale / clamp / bias / residual after it, coalesced stores from the swizzled tile

@@ -162,11 +162,15 @@ class _LinearFpFn(torch.autograd.Function):
     """y = x W^T + b with fp16 operands / fp32 accumulation on spq_qgemm."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False, residual=None, lse_out=None):
+    def forward(ctx, x, weight, bias, cache, activation=0, out_half=False, residual=None, lse_out=None, pre=None):
         N, K = weight.shape
-        x2d = _as_2d_act(x, K, max_cols=8192)
-        M = x2d.shape[0]
-        x16, rs = _rowscaled_f16(x2d)
+        if pre is not None:
+            x16, rs = pre                     # (row-scaled fp16 x, row scales) already built by the caller's pass over x
+            M = x16.shape[0]
+        else:
+            x2d = _as_2d_act(x, K, max_cols=8192)
+            M = x2d.shape[0]
+            x16, rs = _rowscaled_f16(x2d)
         w16, pw = cache.get(weight, transposed=False)
         # odd widths (N = 50257): rows padded to 128 bytes -- the GEMM then stores through TMA, and every 32 x 32
         # block it stores covers whole 32-byte sectors (rows merely 16-byte aligned made L2 fetch the other
@@ -214,11 +218,11 @@ class _LinearFpFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2d.float().sum(dim=0)
         # the residual added in the epilogue passes its gradient through unchanged
-        return gx, gw, gb, None, None, None, (gy if ctx.needs_input_grad[6] else None), None
+        return gx, gw, gb, None, None, None, (gy if ctx.needs_input_grad[6] else None), None, None
 
 
 def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: int = 0, out_half: bool = False,
-              residual=None, lse_out=None):
+              residual=None, lse_out=None, pre=None):
     """`out_half` stores float16 from the epilogue and `residual` (float32, contiguous, output-shaped) is added in
     the epilogue -- both differentiable (the backward takes float16 gradients; the residual's gradient is the output
     gradient).  `activation=1` fuses the exact-erf GELU into the epilogue and `lse_out` (a list) receives the per-row
@@ -226,7 +230,7 @@ def linear_fp(x, weight, bias=None, cache: _FpWeightCache = None, activation: in
     if (activation or lse_out is not None) and torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
         raise RuntimeError("the fused activation / log-sum-exp epilogues are no-grad fast paths")
     return _LinearFpFn.apply(x, weight, bias, cache if cache is not None else _FpWeightCache(), activation, out_half,
-                             residual, lse_out)
+                             residual, lse_out, pre)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -710,7 +714,9 @@ class SPLinearWithLoRA(nn.Module):
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
         # reference, module by module (this is the calibration pass; errors surface as upstream).
-        x_quantized = input_quantizer(x)                       # collecting: records stats, returns x
+        # collecting: the statistics and the fp16 operand of this pass's GEMM come from one read of x
+        pre = input_quantizer.collect_and_rowscale(x) if (input_quantizer.collecting_stats and not torch.is_grad_enabled()) else None
+        x_quantized = x if pre is not None else input_quantizer(x)      # collecting: records stats, returns x
         if torch.is_grad_enabled() and self.linear.weight.requires_grad and not weight_quantizer.collecting_stats:
             weight_quantized, cache = weight_quantizer(self.linear.weight), None
         else:
@@ -720,7 +726,7 @@ class SPLinearWithLoRA(nn.Module):
                      and not torch.is_grad_enabled())
         res_here = residual if self.calibration_mode else None      # otherwise after the LoRA add, as upstream
         base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0,
-                                out_half=half_here, residual=res_here)
+                                out_half=half_here, residual=res_here, pre=pre)
         if not self.calibration_mode:
             base_output = base_output + active_lora(x)
             if residual is not None:
