@@ -229,7 +229,7 @@ SPQ_API int spq_rowscale_f16_max(const void* g, int g_is_half, int64_t M, int64_
 /* The calibration pass in ONE read of x (p1/quantization.py:174-209 + the operand of the pass's own GEMM): the
  * row-scaled fp16 operand of spq_rowscale_f16 AND the input quantiser's statistics of spq_minmax_stats (per column, or
  * per tensor when per_tensor != 0; log_mode, eps, accumulate, state as there; bit-identical results).  x [M, K] float32
- * or float16, K % 4 == 0, K <= 8192; workspace from spq_rowscale_stats_workspace_bytes. */
+ * or float16, K % 4 == 0, K <= 4096; workspace from spq_rowscale_stats_workspace_bytes. */
 SPQ_API size_t spq_rowscale_stats_workspace_bytes(int64_t M, int64_t K);
 SPQ_API int spq_rowscale_stats(const void* x, int x_is_half, int64_t M, int64_t K, spq_half_t* out, float* row_scale,
                        int per_tensor, int log_mode, float eps, float* stat_min, float* stat_max, int accumulate,

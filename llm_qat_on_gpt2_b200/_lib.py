@@ -91,6 +91,8 @@ def load_library(path: str = LIB_PATH):
     global _lib
     if _lib is not None:
         return _lib
+    if path == LIB_PATH and os.environ.get("SPQ_LIB"):
+        path = os.environ["SPQ_LIB"]             # same-box A/B of two builds (tools/ab.sh)
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -m llm_qat_on_gpt2_b200.build` "

@@ -29,7 +29,10 @@ constexpr int EPI_WARPS = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 constexpr int STG_TILE_BYTES = 32 * 32 * 4;   // per-epilogue-warp 32 x 32 fp32 staging tile, 128B-XOR-swizzled
-constexpr int STG_BUFS = 2;                   // two tiles per warp: chunk i+1 is computed while the TMA engine still reads chunk i
+#ifndef SPQ_STG_BUFS
+#define SPQ_STG_BUFS 2
+#endif
+constexpr int STG_BUFS = SPQ_STG_BUFS;        // two tiles per warp: chunk i+1 is computed while the TMA engine still reads chunk i
 
 __device__ int g_abort = 0;    // watchdog: set when a pipeline wait timed out
 
@@ -508,7 +511,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // staging tile `stg_buf` was last handed to the TMA engine two chunks ago: at most ONE younger
                         // store group may still be reading (the other tile) when this one is overwritten
                         if (stores_in_flight >= STG_BUFS) {
-                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(STG_BUFS - 1) : "memory");
                             __syncwarp();
                             stores_in_flight = STG_BUFS - 1;
                         }
@@ -582,7 +585,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                         store_pending = true;
                         ++stores_in_flight;
-                        stg_buf ^= 1;
+                        stg_buf = (stg_buf + 1) % STG_BUFS;
                     } else {
                         // general path (fp16 output, residual input, unaligned D): row scale before the transpose,
                         // column scale / clamp / bias / residual after it, coalesced stores from the swizzled tile

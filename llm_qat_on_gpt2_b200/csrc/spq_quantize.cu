@@ -330,26 +330,13 @@ struct ActArgs {
 // Row-scaled raw operand (no quantiser): one CTA of G threads owns a row at a time, the row stays in
 // registers (NV float4 per thread), its absmax gives the power-of-two scale.  Used where no calibrated
 // bound exists: calibration pass, 32-bit path, LM head, gradients.
-// STATS: the same pass also keeps, per thread, the running min / max of the columns it owns (a column belongs to
-// exactly one thread of the CTA) -- the calibration statistics of the input quantiser, which the reference collects on
-// the very tensor whose fp16 operand this kernel builds for the calibration-pass GEMM (p1/quantization.py:174-209).
-template <int NV, typename XT, bool STATS = false>
+template <int NV, typename XT>
 __global__ void __launch_bounds__(256)
 rowscale_kernel(ActArgs a) {
     const int G = blockDim.x;
     const int tid = threadIdx.x;
     __shared__ float s_red[8];
     float cta_max_scale = 0.f;
-    float4 smn[STATS ? NV : 1], smx[STATS ? NV : 1];
-    unsigned s_nan = 0;            // bit 4 i + j: column j of this thread's i-th float4 saw a NaN (torch.min / max keep it)
-    bool s_any = false;
-    if constexpr (STATS) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            smn[i] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-            smx[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        }
-    }
     for (long long row = blockIdx.x; row < a.M; row += gridDim.x) {
         const XT* px = static_cast<const XT*>(a.x) + row * a.K;
         float4 v[NV];
@@ -359,16 +346,6 @@ rowscale_kernel(ActArgs a) {
             const long long c = (static_cast<long long>(i) * G + tid) * 4;
             v[i] = (c < a.K) ? ld_stream_x4<XT>(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-            if constexpr (STATS) {
-                if (c < a.K) {
-                    float4 e = v[i];
-                    if (a.stat_log) e = make_float4(fabsf(e.x), fabsf(e.y), fabsf(e.z), fabsf(e.w));
-                    s_nan |= ((e.x != e.x ? 1u : 0u) | (e.y != e.y ? 2u : 0u) | (e.z != e.z ? 4u : 0u) | (e.w != e.w ? 8u : 0u)) << (4 * i);
-                    s_any |= (e.x > a.stat_eps) | (e.y > a.stat_eps) | (e.z > a.stat_eps) | (e.w > a.stat_eps);
-                    smn[i].x = fminf(smn[i].x, e.x); smn[i].y = fminf(smn[i].y, e.y); smn[i].z = fminf(smn[i].z, e.z); smn[i].w = fminf(smn[i].w, e.w);
-                    smx[i].x = fmaxf(smx[i].x, e.x); smx[i].y = fmaxf(smx[i].y, e.y); smx[i].z = fmaxf(smx[i].z, e.z); smx[i].w = fmaxf(smx[i].w, e.w);
-                }
-            }
         }
         amax = warp_fmax(amax);
         if (G > 32) {
@@ -399,23 +376,109 @@ rowscale_kernel(ActArgs a) {
     }
     // scales are positive floats: their bit patterns order like integers
     if (tid == 0 && a.max_scale) atomicMax(reinterpret_cast<int*>(a.max_scale), __float_as_int(cta_max_scale));
-    if constexpr (STATS) {
-        // torch.min / max propagate NaN; fminf / fmaxf drop it: the columns that saw one report NaN
+}
+
+// The same pass with the calibration statistics of the input quantiser -- which the reference collects on the very tensor
+// whose fp16 operand this kernel builds for the calibration-pass GEMM (p1/quantization.py:174-209).  Block = (G, RY): RY
+// row slots of G threads each (256 threads in all, so the CTA count -- = rows of partial statistics the fold kernel
+// reads -- can stay at 8 per SM with the SM fully occupied).  A thread owns the same columns in every row of its slot and
+// keeps their running min / max (of |x| in log mode) in registers; the slots then merge through shared memory and the
+// CTA writes ONE partial row.
+template <int NV, typename XT>
+__global__ void __launch_bounds__(256)
+rowscale_stats_kernel(ActArgs a) {
+    extern __shared__ float s_stat[];                  // [2][K]
+    const int G = blockDim.x, RY = blockDim.y;
+    const int tid = threadIdx.x, ty = threadIdx.y;
+    __shared__ float s_red[8][8];
+    float4 smn[NV], smx[NV];
+    unsigned s_nan = 0;            // bit 4 i + j: column j of this thread's i-th float4 saw a NaN (torch.min / max keep it)
+    bool s_any = false;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        smn[i] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        smx[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    for (long long base = static_cast<long long>(blockIdx.x) * RY; base < a.M; base += static_cast<long long>(gridDim.x) * RY) {
+        const long long row = base + ty;
+        const bool live = row < a.M;
+        const XT* px = static_cast<const XT*>(a.x) + row * a.K;
+        float4 v[NV];
+        float amax = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const long long c = (static_cast<long long>(i) * G + tid) * 4;
-            if (c < a.K) {
-                const unsigned nm = (s_nan >> (4 * i)) & 15u;
-                if (nm & 1u) { smn[i].x = NAN; smx[i].x = NAN; }
-                if (nm & 2u) { smn[i].y = NAN; smx[i].y = NAN; }
-                if (nm & 4u) { smn[i].z = NAN; smx[i].z = NAN; }
-                if (nm & 8u) { smn[i].w = NAN; smx[i].w = NAN; }
-                *reinterpret_cast<float4*>(a.stat_pmin + static_cast<long long>(blockIdx.x) * a.K + c) = smn[i];
-                *reinterpret_cast<float4*>(a.stat_pmax + static_cast<long long>(blockIdx.x) * a.K + c) = smx[i];
+            const bool ok = live && c < a.K;
+            v[i] = ok ? ld_stream_x4<XT>(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+            if (ok) {
+                float4 e = v[i];
+                if (a.stat_log) e = make_float4(fabsf(e.x), fabsf(e.y), fabsf(e.z), fabsf(e.w));
+                s_nan |= ((e.x != e.x ? 1u : 0u) | (e.y != e.y ? 2u : 0u) | (e.z != e.z ? 4u : 0u) | (e.w != e.w ? 8u : 0u)) << (4 * i);
+                s_any |= (e.x > a.stat_eps) | (e.y > a.stat_eps) | (e.z > a.stat_eps) | (e.w > a.stat_eps);
+                smn[i].x = fminf(smn[i].x, e.x); smn[i].y = fminf(smn[i].y, e.y); smn[i].z = fminf(smn[i].z, e.z); smn[i].w = fminf(smn[i].w, e.w);
+                smx[i].x = fmaxf(smx[i].x, e.x); smx[i].y = fmaxf(smx[i].y, e.y); smx[i].z = fmaxf(smx[i].z, e.z); smx[i].w = fmaxf(smx[i].w, e.w);
             }
         }
-        if (a.stat_log && s_any) atomicOr(a.stat_flags, 1);
+        amax = warp_fmax(amax);
+        if (G > 32) {
+            __syncthreads();                      // s_red reuse across rows (every slot runs the same trip count)
+            if ((tid & 31) == 0) s_red[ty][tid >> 5] = amax;
+            __syncthreads();
+            amax = s_red[ty][0];
+            for (int w = 1; w < (G >> 5); ++w) amax = fmaxf(amax, s_red[ty][w]);
+        }
+        int E = 0;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;   // see rowscale_kernel
+        E = E < -100 ? -100 : E;
+        const float down = exp2f(static_cast<float>(8 - E));
+        if (live && tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = exp2f(static_cast<float>(E - 8));
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const long long c = (static_cast<long long>(i) * G + tid) * 4;
+                if (c < a.K)
+                    *reinterpret_cast<uint2*>(a.a_raw + row * a.K + c) =
+                        make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
+            }
+        }
     }
+    // torch.min / max propagate NaN; fminf / fmaxf drop it: the columns that saw one report NaN
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const unsigned nm = (s_nan >> (4 * i)) & 15u;
+        if (nm & 1u) { smn[i].x = NAN; smx[i].x = NAN; }
+        if (nm & 2u) { smn[i].y = NAN; smx[i].y = NAN; }
+        if (nm & 4u) { smn[i].z = NAN; smx[i].z = NAN; }
+        if (nm & 8u) { smn[i].w = NAN; smx[i].w = NAN; }
+    }
+    float* s_mn = s_stat;
+    float* s_mx = s_stat + a.K;
+    for (int slot = 0; slot < RY; ++slot) {
+        if (ty == slot) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const long long c = (static_cast<long long>(i) * G + tid) * 4;
+                if (c < a.K) {
+                    float4 m = smn[i], x = smx[i];
+                    if (slot > 0) {
+                        const float4 pm = *reinterpret_cast<const float4*>(s_mn + c), px4 = *reinterpret_cast<const float4*>(s_mx + c);
+                        m = make_float4(nan_min(pm.x, m.x), nan_min(pm.y, m.y), nan_min(pm.z, m.z), nan_min(pm.w, m.w));
+                        x = make_float4(nan_max(px4.x, x.x), nan_max(px4.y, x.y), nan_max(px4.z, x.z), nan_max(px4.w, x.w));
+                    }
+                    if (slot == RY - 1) {
+                        *reinterpret_cast<float4*>(a.stat_pmin + static_cast<long long>(blockIdx.x) * a.K + c) = m;
+                        *reinterpret_cast<float4*>(a.stat_pmax + static_cast<long long>(blockIdx.x) * a.K + c) = x;
+                    } else {
+                        *reinterpret_cast<float4*>(s_mn + c) = m;
+                        *reinterpret_cast<float4*>(s_mx + c) = x;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (a.stat_log && s_any) atomicOr(a.stat_flags, 1);
 }
 
 // Fused activation-side kernel (calibrated quantiser): purely elementwise.  Thread = 4 consecutive
@@ -582,8 +645,12 @@ static void rowscale_cfg(long long K, int& G, int& NV) {
 }
 // CTAs of the statistics variant = rows of partials the fold kernel reads: 8 (4 for wide rows) per SM
 static long long rowscale_stats_ctas(long long M, long long K) {
+    int G, NV;
+    rowscale_cfg(K, G, NV);
+    const long long ry = 256 / G;
     long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * (K > 2048 ? 4 : 8);
-    return ctas > M ? M : ctas;
+    const long long need = (M + ry - 1) / ry;
+    return ctas > need ? need : ctas;
 }
 
 static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
@@ -591,19 +658,21 @@ static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
     rowscale_cfg(a.K, G, NV);
     if (a.stat_pmin) {
         const unsigned sgrid = static_cast<unsigned>(rowscale_stats_ctas(a.M, a.K));
+        const dim3 block(G, 256 / G);
+        const size_t smem = 2 * static_cast<size_t>(a.K) * sizeof(float);
         if (a.x_half) {
             switch (NV) {
-                case 1: rowscale_kernel<1, __half, true><<<sgrid, G, 0, st>>>(a); break;
-                case 2: rowscale_kernel<2, __half, true><<<sgrid, G, 0, st>>>(a); break;
-                case 4: rowscale_kernel<4, __half, true><<<sgrid, G, 0, st>>>(a); break;
-                default: rowscale_kernel<8, __half, true><<<sgrid, G, 0, st>>>(a); break;
+                case 1: rowscale_stats_kernel<1, __half><<<sgrid, block, smem, st>>>(a); break;
+                case 2: rowscale_stats_kernel<2, __half><<<sgrid, block, smem, st>>>(a); break;
+                case 4: rowscale_stats_kernel<4, __half><<<sgrid, block, smem, st>>>(a); break;
+                default: rowscale_stats_kernel<8, __half><<<sgrid, block, smem, st>>>(a); break;
             }
         } else {
             switch (NV) {
-                case 1: rowscale_kernel<1, float, true><<<sgrid, G, 0, st>>>(a); break;
-                case 2: rowscale_kernel<2, float, true><<<sgrid, G, 0, st>>>(a); break;
-                case 4: rowscale_kernel<4, float, true><<<sgrid, G, 0, st>>>(a); break;
-                default: rowscale_kernel<8, float, true><<<sgrid, G, 0, st>>>(a); break;
+                case 1: rowscale_stats_kernel<1, float><<<sgrid, block, smem, st>>>(a); break;
+                case 2: rowscale_stats_kernel<2, float><<<sgrid, block, smem, st>>>(a); break;
+                case 4: rowscale_stats_kernel<4, float><<<sgrid, block, smem, st>>>(a); break;
+                default: rowscale_stats_kernel<8, float><<<sgrid, block, smem, st>>>(a); break;
             }
         }
         SPQ_LAUNCH_OK();
@@ -763,7 +832,7 @@ extern "C" int spq_rowscale_stats(const void* x, int x_is_half, int64_t M, int64
                                   int per_tensor, int log_mode, float eps, float* stat_min, float* stat_max, int accumulate,
                                   int32_t* state, void* workspace, size_t workspace_bytes, spq_stream_t stream) {
     SPQ_REQUIRE(x && out && row_scale && stat_min && stat_max && workspace && M > 0 && K > 0, "spq_rowscale_stats: bad arguments");
-    SPQ_REQUIRE((K % 4) == 0 && K <= 8192 && aligned16(x) && aligned16(out), "spq_rowscale_stats: needs K %% 4 == 0, K <= 8192, 16-byte alignment");
+    SPQ_REQUIRE((K % 4) == 0 && K <= 4096 && aligned16(x) && aligned16(out), "spq_rowscale_stats: needs K %% 4 == 0, K <= 4096, 16-byte alignment");
     SPQ_REQUIRE(workspace_bytes >= spq_rowscale_stats_workspace_bytes(M, K) && aligned16(workspace), "spq_rowscale_stats: workspace too small");
     cudaStream_t st = as_stream(stream);
     int32_t* flags = reinterpret_cast<int32_t*>(workspace);

@@ -154,14 +154,16 @@ class LearnableFakeQuantize(nn.Module):
         """Collecting mode, fused with what the calibration pass does next: ONE read of x records this batch's
         statistics (exactly `_collect_statistics_batch`) and writes the row-scaled fp16 operand the pass's GEMM
         consumes.  Returns (x16 [M, K], row_scale [M]) or None when the layout is not the activation layout
-        (per-last-dim or per-tensor statistics of a float32 / float16 tensor with K % 4 == 0, K <= 8192)."""
+        (per-last-dim or per-tensor statistics of a float32 / float16 tensor with K % 4 == 0, K <= 4096)."""
         if not (self.collecting_stats and x.is_cuda and x.dim() >= 2 and x.dtype in (torch.float32, torch.float16)):
+            return None
+        if _FUSED_STATS_OFF:
             return None
         K = x.shape[-1]
         nd = x.dim()
         per_col = self.per_channel and self.channel_dim is not None and (self.channel_dim % nd) == nd - 1
         per_tensor = not (self.per_channel and self.channel_dim is not None)
-        if not (per_col or per_tensor) or K % 4 or K > 8192 or x.numel() == 0:
+        if not (per_col or per_tensor) or K % 4 or K > 4096 or x.numel() == 0:
             return None
         with torch.no_grad():
             xc = x.detach().contiguous()
@@ -271,6 +273,8 @@ class LearnableFakeQuantize(nn.Module):
 
 
 _calib_tables = {}
+import os as _os
+_FUSED_STATS_OFF = _os.environ.get('SPQ_FUSED_STATS', '1') == '0'        # A/B switch for tools/ab.sh
 
 
 def calibrate_many(quantizers, tensors, defer: bool = False):
