@@ -226,15 +226,6 @@ SPQ_API int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N,
 SPQ_API int spq_rowscale_f16_max(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                          float* row_scale, float* max_scale, spq_stream_t stream);
 
-/* The calibration pass in ONE read of x (p1/quantization.py:174-209 + the operand of the pass's own GEMM): the
- * row-scaled fp16 operand of spq_rowscale_f16 AND the input quantiser's statistics of spq_minmax_stats (per column, or
- * per tensor when per_tensor != 0; log_mode, eps, accumulate, state as there; bit-identical results).  x [M, K] float32
- * or float16, K % 4 == 0, K <= 4096; workspace from spq_rowscale_stats_workspace_bytes. */
-SPQ_API size_t spq_rowscale_stats_workspace_bytes(int64_t M, int64_t K);
-SPQ_API int spq_rowscale_stats(const void* x, int x_is_half, int64_t M, int64_t K, spq_half_t* out, float* row_scale,
-                       int per_tensor, int log_mode, float eps, float* stat_min, float* stat_max, int accumulate,
-                       int32_t* state, void* workspace, size_t workspace_bytes, spq_stream_t stream);
-
 /* fp16 operands of the LoRA gradient GEMMs in one pass (STE backward of p1/lora.py:45-54):
  *   dt16 = fp16(dtn * dt_mul)                       (dX += dT q(A)^T; token scale applied in that GEMM's epilogue)
  *   dt2  = fp16(dtn * dt_mul * row_scale / max)     (dA = x^T dT: reduction over tokens, scale folded in)

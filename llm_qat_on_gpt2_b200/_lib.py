@@ -56,9 +56,6 @@ SIGNATURES = {
     "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
                             c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "spq_rowscale_f16_max": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "spq_rowscale_stats_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "spq_rowscale_stats": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
-                                   c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "spq_lora_bwd_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "spq_softmax_loss_grad16": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float,
@@ -427,19 +424,6 @@ def rowscale_f16_max(g2d, out, row_scale, max_scale):
     assert out.stride(-1) == 1 and g2d.is_contiguous() and g2d.dtype in (torch.float32, torch.float16)
     _check(load_library().spq_rowscale_f16_max(g2d.data_ptr(), int(g2d.dtype == torch.float16), M, N, out.data_ptr(), out.stride(0),
                                                row_scale.data_ptr(), max_scale.data_ptr(), _stream()), "spq_rowscale_f16_max")
-
-
-def rowscale_stats(x2d, out, row_scale, per_tensor, log_mode, eps, stat_min, stat_max, accumulate, state):
-    """rowscale_f16 + minmax_stats (per column / per tensor) in one pass over x2d."""
-    lib = load_library()
-    _req_cuda(x2d, out, row_scale, stat_min, stat_max, state)
-    M, K = x2d.shape
-    assert x2d.is_contiguous() and x2d.dtype in (torch.float32, torch.float16) and out.is_contiguous()
-    assert stat_min.numel() == (1 if per_tensor else K) and stat_max.numel() == stat_min.numel()
-    ws = _workspace(lib.spq_rowscale_stats_workspace_bytes(M, K), x2d.device, "rowscale_stats")
-    _check(lib.spq_rowscale_stats(x2d.data_ptr(), int(x2d.dtype == torch.float16), M, K, out.data_ptr(), row_scale.data_ptr(),
-                                  int(per_tensor), int(log_mode), float(eps), stat_min.data_ptr(), stat_max.data_ptr(),
-                                  int(accumulate), _ptr(state), ws.data_ptr(), ws.numel(), _stream()), "spq_rowscale_stats")
 
 
 def lora_bwd_prep(dtn, t16, row_scale, max_scale, dt_mul, want_dt16=True, want_dt2=True, want_t2=True):

@@ -47,11 +47,6 @@ int sm_count();
 
 inline cudaStream_t as_stream(spq_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// cross-file launchers (spq_stats.cu): fold `chunks` per-channel partial minima / maxima into the (running) statistics
-namespace stats {
-int finalize_launch(const float* pmin, const float* pmax, long long C, int chunks, int collapse, int log_mode, float eps,
-                    int accumulate, const int32_t* flags, float* stat_min, float* stat_max, int32_t* state, cudaStream_t st);
-}
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 #ifdef __CUDACC__

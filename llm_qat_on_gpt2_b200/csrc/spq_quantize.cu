@@ -318,13 +318,6 @@ struct ActArgs {
     float* raw_row_scale;       // row-scaled variant only
     const float* raw_col_mul;   // elementwise variant: per-column multiplier of the raw operand
     float* max_scale;           // row-scaled variant: optional device scalar, max over rows of the row scale
-    // row-scaled variant with calibration statistics (STATS): per-CTA partial column minima / maxima of x (of |x| in
-    // log mode) [gridDim.x, K], and the any(|x| > eps) flag
-    float* stat_pmin;
-    float* stat_pmax;
-    int32_t* stat_flags;
-    int stat_log;
-    float stat_eps;
 };
 
 // Row-scaled raw operand (no quantiser): one CTA of G threads owns a row at a time, the row stays in
@@ -376,109 +369,6 @@ rowscale_kernel(ActArgs a) {
     }
     // scales are positive floats: their bit patterns order like integers
     if (tid == 0 && a.max_scale) atomicMax(reinterpret_cast<int*>(a.max_scale), __float_as_int(cta_max_scale));
-}
-
-// The same pass with the calibration statistics of the input quantiser -- which the reference collects on the very tensor
-// whose fp16 operand this kernel builds for the calibration-pass GEMM (p1/quantization.py:174-209).  Block = (G, RY): RY
-// row slots of G threads each (256 threads in all, so the CTA count -- = rows of partial statistics the fold kernel
-// reads -- can stay at 8 per SM with the SM fully occupied).  A thread owns the same columns in every row of its slot and
-// keeps their running min / max (of |x| in log mode) in registers; the slots then merge through shared memory and the
-// CTA writes ONE partial row.
-template <int NV, typename XT>
-__global__ void __launch_bounds__(256)
-rowscale_stats_kernel(ActArgs a) {
-    extern __shared__ float s_stat[];                  // [2][K]
-    const int G = blockDim.x, RY = blockDim.y;
-    const int tid = threadIdx.x, ty = threadIdx.y;
-    __shared__ float s_red[8][8];
-    float4 smn[NV], smx[NV];
-    unsigned s_nan = 0;            // bit 4 i + j: column j of this thread's i-th float4 saw a NaN (torch.min / max keep it)
-    bool s_any = false;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        smn[i] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
-        smx[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    }
-    for (long long base = static_cast<long long>(blockIdx.x) * RY; base < a.M; base += static_cast<long long>(gridDim.x) * RY) {
-        const long long row = base + ty;
-        const bool live = row < a.M;
-        const XT* px = static_cast<const XT*>(a.x) + row * a.K;
-        float4 v[NV];
-        float amax = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const long long c = (static_cast<long long>(i) * G + tid) * 4;
-            const bool ok = live && c < a.K;
-            v[i] = ok ? ld_stream_x4<XT>(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-            if (ok) {
-                float4 e = v[i];
-                if (a.stat_log) e = make_float4(fabsf(e.x), fabsf(e.y), fabsf(e.z), fabsf(e.w));
-                s_nan |= ((e.x != e.x ? 1u : 0u) | (e.y != e.y ? 2u : 0u) | (e.z != e.z ? 4u : 0u) | (e.w != e.w ? 8u : 0u)) << (4 * i);
-                s_any |= (e.x > a.stat_eps) | (e.y > a.stat_eps) | (e.z > a.stat_eps) | (e.w > a.stat_eps);
-                smn[i].x = fminf(smn[i].x, e.x); smn[i].y = fminf(smn[i].y, e.y); smn[i].z = fminf(smn[i].z, e.z); smn[i].w = fminf(smn[i].w, e.w);
-                smx[i].x = fmaxf(smx[i].x, e.x); smx[i].y = fmaxf(smx[i].y, e.y); smx[i].z = fmaxf(smx[i].z, e.z); smx[i].w = fmaxf(smx[i].w, e.w);
-            }
-        }
-        amax = warp_fmax(amax);
-        if (G > 32) {
-            __syncthreads();                      // s_red reuse across rows (every slot runs the same trip count)
-            if ((tid & 31) == 0) s_red[ty][tid >> 5] = amax;
-            __syncthreads();
-            amax = s_red[ty][0];
-            for (int w = 1; w < (G >> 5); ++w) amax = fmaxf(amax, s_red[ty][w]);
-        }
-        int E = 0;
-        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;   // see rowscale_kernel
-        E = E < -100 ? -100 : E;
-        const float down = exp2f(static_cast<float>(8 - E));
-        if (live && tid == 0 && a.raw_row_scale) a.raw_row_scale[row] = exp2f(static_cast<float>(E - 8));
-        if (live) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const long long c = (static_cast<long long>(i) * G + tid) * 4;
-                if (c < a.K)
-                    *reinterpret_cast<uint2*>(a.a_raw + row * a.K + c) =
-                        make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
-            }
-        }
-    }
-    // torch.min / max propagate NaN; fminf / fmaxf drop it: the columns that saw one report NaN
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const unsigned nm = (s_nan >> (4 * i)) & 15u;
-        if (nm & 1u) { smn[i].x = NAN; smx[i].x = NAN; }
-        if (nm & 2u) { smn[i].y = NAN; smx[i].y = NAN; }
-        if (nm & 4u) { smn[i].z = NAN; smx[i].z = NAN; }
-        if (nm & 8u) { smn[i].w = NAN; smx[i].w = NAN; }
-    }
-    float* s_mn = s_stat;
-    float* s_mx = s_stat + a.K;
-    for (int slot = 0; slot < RY; ++slot) {
-        if (ty == slot) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const long long c = (static_cast<long long>(i) * G + tid) * 4;
-                if (c < a.K) {
-                    float4 m = smn[i], x = smx[i];
-                    if (slot > 0) {
-                        const float4 pm = *reinterpret_cast<const float4*>(s_mn + c), px4 = *reinterpret_cast<const float4*>(s_mx + c);
-                        m = make_float4(nan_min(pm.x, m.x), nan_min(pm.y, m.y), nan_min(pm.z, m.z), nan_min(pm.w, m.w));
-                        x = make_float4(nan_max(px4.x, x.x), nan_max(px4.y, x.y), nan_max(px4.z, x.z), nan_max(px4.w, x.w));
-                    }
-                    if (slot == RY - 1) {
-                        *reinterpret_cast<float4*>(a.stat_pmin + static_cast<long long>(blockIdx.x) * a.K + c) = m;
-                        *reinterpret_cast<float4*>(a.stat_pmax + static_cast<long long>(blockIdx.x) * a.K + c) = x;
-                    } else {
-                        *reinterpret_cast<float4*>(s_mn + c) = m;
-                        *reinterpret_cast<float4*>(s_mx + c) = x;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (a.stat_log && s_any) atomicOr(a.stat_flags, 1);
 }
 
 // Fused activation-side kernel (calibrated quantiser): purely elementwise.  Thread = 4 consecutive
@@ -643,41 +533,9 @@ static void rowscale_cfg(long long K, int& G, int& NV) {
     else if (nvec <= 1024) { G = 256; NV = 4; }
     else { G = 256; NV = 8; }
 }
-// CTAs of the statistics variant = rows of partials the fold kernel reads: 8 (4 for wide rows) per SM
-static long long rowscale_stats_ctas(long long M, long long K) {
-    int G, NV;
-    rowscale_cfg(K, G, NV);
-    const long long ry = 256 / G;
-    long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * (K > 2048 ? 4 : 8);
-    const long long need = (M + ry - 1) / ry;
-    return ctas > need ? need : ctas;
-}
-
 static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
     int G, NV;
     rowscale_cfg(a.K, G, NV);
-    if (a.stat_pmin) {
-        const unsigned sgrid = static_cast<unsigned>(rowscale_stats_ctas(a.M, a.K));
-        const dim3 block(G, 256 / G);
-        const size_t smem = 2 * static_cast<size_t>(a.K) * sizeof(float);
-        if (a.x_half) {
-            switch (NV) {
-                case 1: rowscale_stats_kernel<1, __half><<<sgrid, block, smem, st>>>(a); break;
-                case 2: rowscale_stats_kernel<2, __half><<<sgrid, block, smem, st>>>(a); break;
-                case 4: rowscale_stats_kernel<4, __half><<<sgrid, block, smem, st>>>(a); break;
-                default: rowscale_stats_kernel<8, __half><<<sgrid, block, smem, st>>>(a); break;
-            }
-        } else {
-            switch (NV) {
-                case 1: rowscale_stats_kernel<1, float><<<sgrid, block, smem, st>>>(a); break;
-                case 2: rowscale_stats_kernel<2, float><<<sgrid, block, smem, st>>>(a); break;
-                case 4: rowscale_stats_kernel<4, float><<<sgrid, block, smem, st>>>(a); break;
-                default: rowscale_stats_kernel<8, float><<<sgrid, block, smem, st>>>(a); break;
-            }
-        }
-        SPQ_LAUNCH_OK();
-        return SPQ_OK;
-    }
     long long ctas = static_cast<long long>(sm_count()) * (2048 / G > 32 ? 32 : 2048 / G);
     if (NV == 8) ctas = static_cast<long long>(sm_count()) * 4;
     if (ctas > a.M) ctas = a.M;
@@ -781,7 +639,6 @@ extern "C" int spq_quantize_act(const void* x, int x_is_half, int64_t M, int64_t
     a.qp = make_qparams(bits, symmetric);
     a.operand_kind = operand_kind; a.col_mul = col_mul; a.mul = mul;
     a.a_q = a_q; a.a_raw = a_raw; a.raw_row_scale = nullptr; a.raw_col_mul = raw_col_mul; a.max_scale = nullptr;
-    a.stat_pmin = nullptr; a.stat_pmax = nullptr; a.stat_flags = nullptr; a.stat_log = 0; a.stat_eps = 0.f;
     cudaStream_t st = as_stream(stream);
     if (qtype == SPQ_MINMAX) return launch_act<SPQ_MINMAX>(a, st);
     return launch_act<SPQ_LOG>(a, st);
@@ -799,7 +656,6 @@ static int rowscale_impl(const void* g, int g_is_half, int64_t M, int64_t N, spq
         a.qp = make_qparams(8, 1);
         a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
         a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr; a.max_scale = max_scale;
-        a.stat_pmin = nullptr; a.stat_pmax = nullptr; a.stat_flags = nullptr; a.stat_log = 0; a.stat_eps = 0.f;
         return launch_rowscale(a, as_stream(stream));
     }
     SPQ_REQUIRE(!g_is_half, "spq_rowscale_f16: float16 input needs dense rows (ld_out == N), N %% 4 == 0, N <= 8192, 16-byte alignment");
@@ -821,35 +677,6 @@ extern "C" int spq_rowscale_f16_max(const void* g, int g_is_half, int64_t M, int
                                     float* row_scale, float* max_scale, spq_stream_t stream) {
     SPQ_REQUIRE(max_scale, "spq_rowscale_f16_max: null max_scale");
     return rowscale_impl(g, g_is_half, M, N, out, ld_out, row_scale, max_scale, stream);
-}
-
-extern "C" size_t spq_rowscale_stats_workspace_bytes(int64_t M, int64_t K) {
-    if (M <= 0 || K <= 0) return 256;
-    return 256 + 2 * static_cast<size_t>(rowscale_stats_ctas(M, K)) * static_cast<size_t>(K) * sizeof(float);
-}
-
-extern "C" int spq_rowscale_stats(const void* x, int x_is_half, int64_t M, int64_t K, spq_half_t* out, float* row_scale,
-                                  int per_tensor, int log_mode, float eps, float* stat_min, float* stat_max, int accumulate,
-                                  int32_t* state, void* workspace, size_t workspace_bytes, spq_stream_t stream) {
-    SPQ_REQUIRE(x && out && row_scale && stat_min && stat_max && workspace && M > 0 && K > 0, "spq_rowscale_stats: bad arguments");
-    SPQ_REQUIRE((K % 4) == 0 && K <= 4096 && aligned16(x) && aligned16(out), "spq_rowscale_stats: needs K %% 4 == 0, K <= 4096, 16-byte alignment");
-    SPQ_REQUIRE(workspace_bytes >= spq_rowscale_stats_workspace_bytes(M, K) && aligned16(workspace), "spq_rowscale_stats: workspace too small");
-    cudaStream_t st = as_stream(stream);
-    int32_t* flags = reinterpret_cast<int32_t*>(workspace);
-    float* pmin = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
-    const long long parts = rowscale_stats_ctas(M, K);
-    float* pmax = pmin + parts * K;
-    SPQ_CUDA_OK(cudaMemsetAsync(flags, 0, 16, st));
-    ActArgs a;
-    a.x = x; a.x_half = x_is_half ? 1 : 0; a.M = M; a.K = K; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
-    a.qp = make_qparams(8, 1);
-    a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
-    a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr; a.max_scale = nullptr;
-    a.stat_pmin = pmin; a.stat_pmax = pmax; a.stat_flags = flags; a.stat_log = log_mode ? 1 : 0; a.stat_eps = eps;
-    int rc = launch_rowscale(a, st);
-    if (rc != SPQ_OK) return rc;
-    return spq::stats::finalize_launch(pmin, pmax, K, static_cast<int>(parts), per_tensor ? 1 : 0, log_mode, eps, accumulate, flags,
-                                       stat_min, stat_max, state, st);
 }
 
 // Operands of the LoRA gradient GEMMs from the down-projected gradient (SURVEY section 8 a13 backward):

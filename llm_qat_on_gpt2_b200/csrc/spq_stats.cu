@@ -346,22 +346,6 @@ calibrate_many_kernel(const SpqCalibJob* __restrict__ jobs, int32_t* __restrict_
 using namespace spq;
 using namespace spq::stats;
 
-namespace spq {
-namespace stats {
-int finalize_launch(const float* pmin, const float* pmax, long long C, int chunks, int collapse, int log_mode, float eps,
-                    int accumulate, const int32_t* flags, float* stat_min, float* stat_max, int32_t* state, cudaStream_t st) {
-    const unsigned fgrid = collapse ? 1u : static_cast<unsigned>((C + 31) / 32);
-    const unsigned fthreads = (!collapse && chunks > 64) ? 1024u : 256u;
-    if (log_mode)
-        stats_finalize_kernel<true><<<fgrid, fthreads, 0, st>>>(pmin, pmax, C, chunks, collapse, eps, accumulate, flags, stat_min, stat_max, state);
-    else
-        stats_finalize_kernel<false><<<fgrid, fthreads, 0, st>>>(pmin, pmax, C, chunks, collapse, eps, accumulate, flags, stat_min, stat_max, state);
-    SPQ_LAUNCH_OK();
-    return SPQ_OK;
-}
-}  // namespace stats
-}  // namespace spq
-
 extern "C" size_t spq_stats_workspace_bytes(int64_t rows, int64_t cols, int bcast) {
     if (rows <= 0 || cols <= 0) return 256;
     size_t n;

@@ -714,9 +714,7 @@ class SPLinearWithLoRA(nn.Module):
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
         # reference, module by module (this is the calibration pass; errors surface as upstream).
-        # collecting: the statistics and the fp16 operand of this pass's GEMM come from one read of x
-        pre = input_quantizer.collect_and_rowscale(x) if (input_quantizer.collecting_stats and not torch.is_grad_enabled()) else None
-        x_quantized = x if pre is not None else input_quantizer(x)      # collecting: records stats, returns x
+        x_quantized = input_quantizer(x)                       # collecting: records stats, returns x
         if torch.is_grad_enabled() and self.linear.weight.requires_grad and not weight_quantizer.collecting_stats:
             weight_quantized, cache = weight_quantizer(self.linear.weight), None
         else:
@@ -726,7 +724,7 @@ class SPLinearWithLoRA(nn.Module):
                      and not torch.is_grad_enabled())
         res_here = residual if self.calibration_mode else None      # otherwise after the LoRA add, as upstream
         base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0,
-                                out_half=half_here, residual=res_here, pre=pre)
+                                out_half=half_here, residual=res_here)
         if not self.calibration_mode:
             base_output = base_output + active_lora(x)
             if residual is not None:

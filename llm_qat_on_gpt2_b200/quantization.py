@@ -150,43 +150,6 @@ class LearnableFakeQuantize(nn.Module):
                               accumulate=not first, state=self._stat_state)
             self.num_batches_collected += 1
 
-    def collect_and_rowscale(self, x):
-        """Collecting mode, fused with what the calibration pass does next: ONE read of x records this batch's
-        statistics (exactly `_collect_statistics_batch`) and writes the row-scaled fp16 operand the pass's GEMM
-        consumes.  Returns (x16 [M, K], row_scale [M]) or None when the layout is not the activation layout
-        (per-last-dim or per-tensor statistics of a float32 / float16 tensor with K % 4 == 0, K <= 4096)."""
-        if not (self.collecting_stats and x.is_cuda and x.dim() >= 2 and x.dtype in (torch.float32, torch.float16)):
-            return None
-        if _FUSED_STATS_OFF:
-            return None
-        K = x.shape[-1]
-        nd = x.dim()
-        per_col = self.per_channel and self.channel_dim is not None and (self.channel_dim % nd) == nd - 1
-        per_tensor = not (self.per_channel and self.channel_dim is not None)
-        if not (per_col or per_tensor) or K % 4 or K > 4096 or x.numel() == 0:
-            return None
-        with torch.no_grad():
-            xc = x.detach().contiguous()
-            x2d = xc.reshape(-1, K)
-            if x2d.data_ptr() % 16:
-                return None
-            stat_shape = [1] * nd
-            if per_col:
-                stat_shape[-1] = K
-            if self._stat_state is None or self._stat_state.device != xc.device:
-                self._stat_state = torch.zeros(1, dtype=torch.int32, device=xc.device)
-            first = self.temp_min is None
-            if first:
-                self.temp_min = torch.empty(stat_shape, dtype=torch.float32, device=xc.device)
-                self.temp_max = torch.empty(stat_shape, dtype=torch.float32, device=xc.device)
-                self._first_shape = tuple(xc.shape)
-            x16 = torch.empty((x2d.shape[0], K), dtype=torch.float16, device=xc.device)
-            rs = torch.empty(x2d.shape[0], dtype=torch.float32, device=xc.device)
-            _lib.rowscale_stats(x2d, x16, rs, per_tensor, self.quantizer_type == 'log', self.eps, self.temp_min, self.temp_max,
-                                accumulate=not first, state=self._stat_state)
-            self.num_batches_collected += 1
-        return x16, rs
-
     def _log_default_shape(self):
         # reference :164-172: the CHANNEL dim is the one set to 1
         shape = list(self._first_shape)
@@ -273,8 +236,6 @@ class LearnableFakeQuantize(nn.Module):
 
 
 _calib_tables = {}
-import os as _os
-_FUSED_STATS_OFF = _os.environ.get('SPQ_FUSED_STATS', '1') == '0'        # A/B switch for tools/ab.sh
 
 
 def calibrate_many(quantizers, tensors, defer: bool = False):

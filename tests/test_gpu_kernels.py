@@ -601,35 +601,3 @@ def test_qgemm_f8_integer_codes_exact(lib, M, N, K, K2):
     lib.qgemm_f8(A8, B8, M, N, K, outh, col_scale=cs * 1e-2)
     assert ((outh.double() - exact * cs.double()[None, :] * 1e-2).norm() / (exact * 1e-2).norm()) <= 1e-3
     assert lib.debug_status() == 0
-
-
-@pytest.mark.parametrize("M,K", [(1000, 768), (333, 3072), (64, 96), (2048, 1600)])
-@pytest.mark.parametrize("log_mode", [False, True])
-def test_rowscale_stats_equals_the_two_kernels(lib, M, K, log_mode):
-    """spq_rowscale_stats (one read of x) == spq_rowscale_f16 + spq_minmax_stats, bit for bit: per-column and per-tensor
-    statistics, first batch and accumulation, a NaN column, float16 input."""
-    torch.manual_seed(M + K)
-    x = torch.randn(M, K, device="cuda") * torch.exp(torch.randn(M, K, device="cuda"))
-    x[::7, 3] = 0.0
-    x2 = torch.randn(M, K, device="cuda") * 3
-    x2[5, 11] = float("nan")
-    for per_tensor in (False, True):
-        n = 1 if per_tensor else K
-        bc = lib.PER_TENSOR if per_tensor else lib.PER_COL
-        for xin in (x, x.half()):
-            a_min, a_max = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
-            b_min, b_max = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
-            st_a = torch.zeros(1, dtype=torch.int32, device="cuda"); st_b = torch.zeros(1, dtype=torch.int32, device="cuda")
-            o_a = torch.empty(M, K, dtype=torch.float16, device="cuda"); rs_a = torch.empty(M, device="cuda")
-            o_b = torch.empty(M, K, dtype=torch.float16, device="cuda"); rs_b = torch.empty(M, device="cuda")
-            lib.rowscale_stats(xin, o_a, rs_a, per_tensor, log_mode, 1e-5, a_min, a_max, False, st_a)
-            lib.rowscale_f16(xin, o_b, rs_b)
-            lib.minmax_stats(xin, bc, log_mode, 1e-5, b_min, b_max, accumulate=False, state=st_b)
-            assert torch.equal(o_a, o_b) and torch.equal(rs_a, rs_b)
-            assert torch.equal(a_min, b_min) and torch.equal(a_max, b_max) and torch.equal(st_a, st_b)
-            # second batch accumulates; its NaN poisons exactly one column (or the tensor statistic)
-            lib.rowscale_stats(x2, o_a, rs_a, per_tensor, log_mode, 1e-5, a_min, a_max, True, st_a)
-            lib.minmax_stats(x2, bc, log_mode, 1e-5, b_min, b_max, accumulate=True, state=st_b)
-            assert torch.equal(a_min.isnan(), b_min.isnan()) and int(a_min.isnan().sum()) == 1
-            ok = ~a_min.isnan()
-            assert torch.equal(a_min[ok], b_min[ok]) and torch.equal(a_max[ok], b_max[ok])
