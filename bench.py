@@ -889,8 +889,68 @@ def qlinear_sweep_section(args, dev):
             del m
             torch.cuda.empty_cache()
     best = max(rows, key=lambda r: r["fwd_frac_of_peak"])
-    return {"metric": "SPLinearWithLoRA microbench, GPT-2 XL shapes (whole module call: quantise + LoRA + fused GEMM [+ STE backward])",
-            "peak_tflops": peak, "lora_rank": R, "rows": rows, "best_fwd_frac_of_peak": best["fwd_frac_of_peak"]}
+    out = {"metric": "SPLinearWithLoRA microbench, GPT-2 XL shapes (whole module call: quantise + LoRA + fused GEMM [+ STE backward])",
+           "peak_tflops": peak, "lora_rank": R, "rows": rows, "best_fwd_frac_of_peak": best["fwd_frac_of_peak"]}
+    out["fp8"] = fp8_section(args, dev, timed)
+    return out
+
+
+def fp8_section(args, dev, timed):
+    """The e4m3 integer-code path (tcgen05.mma.kind::f8f6f4): 4-bit min-max with per-tensor scales, the reference's evaluation
+    configuration (p1/deploy.py:210,238).  In-repo fp8 peak = torch._scaled_mm (cuBLASLt e4m3, 8192^3) on this GPU; GEMM-only
+    time of spq_qgemm_f8 with the LoRA segment, and the whole SPLinearWithLoRA.forward."""
+    import torch
+    from llm_qat_on_gpt2_b200 import _lib
+    from llm_qat_on_gpt2_b200.lora import SPLinearWithLoRA
+    res = {"peak_fp8_tflops": None, "rows": []}
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev).to(torch.float8_e4m3fn)
+        b = torch.randn(n, n, device=dev).to(torch.float8_e4m3fn).t()
+        one = torch.ones((), device=dev)
+        t = timed(lambda: torch._scaled_mm(a, b, scale_a=one, scale_b=one, out_dtype=torch.bfloat16), 20)
+        res["peak_fp8_tflops"] = 2.0 * n ** 3 / (t / 1e3) / 1e12
+        res["peak_fp8_source"] = "torch._scaled_mm e4m3 x e4m3 -> bf16, 8192^3, CUDA events, this run"
+        del a, b
+    except Exception as e:                                  # library fp8 GEMM unavailable: report against the bf16 peak only
+        res["peak_fp8_source"] = f"unavailable ({type(e).__name__})"
+    R = 64
+    for K, N in ((1600, 6400), (6400, 1600), (768, 2304)):
+        torch.manual_seed(0)
+        m = SPLinearWithLoRA(K, N, [4, 32], {4: R, 32: 0}, {4: R, 32: 0}, {4: "minmax", 32: None}, per_channel=False).to(dev)
+        m.set_precision(4)
+        lo = m.lora_adapters["4bit"]
+        with torch.no_grad():
+            m.linear.weight.normal_(0, 0.02); lo.lora_B.normal_(0, 0.02)
+            q = m.quantizers_weight["4bit"]; q.start_calibration(); q(m.linear.weight.data); q.finish_calibration()
+            for qq, w in ((lo.quantize_A, lo.lora_A), (lo.quantize_B, lo.lora_B)):
+                qq.start_calibration(); qq(w.data); qq.finish_calibration()
+        for tokens in (args.sweep_tokens[0], args.sweep_tokens[-1]):
+            x = torch.randn(tokens, K, device=dev)
+            with torch.no_grad():
+                m.calibration_mode = True
+                iq = m.quantizers_input["4bit"]; iq.start_calibration(); m(x); iq.finish_calibration()
+                m.calibration_mode = False
+                base, lora = m._operands_for(4, True)
+                if base.get("f8") is None:
+                    continue
+                reps = max(3, min(20, int(2.0e11 / (tokens * N * K))))
+                t_mod = timed(lambda: m(x), reps)
+                a8 = torch.randint(-7, 8, (tokens, K), device=dev).float().to(torch.float8_e4m3fn).view(torch.uint8)
+                t16 = torch.randn(tokens, R, device=dev).half()
+                y = torch.empty(tokens, N, device=dev)
+                t_g = timed(lambda: _lib.qgemm_f8(a8, base["f8"]["B8"], tokens, N, K, y, A2=t16, B2=lora["Bl_op8"], K2=R,
+                                                  col_scale=base["f8"]["cs"], bias=m.linear.bias.detach()), reps)
+            fl = 2.0 * tokens * N * (K + R)
+            tf = fl / (t_g / 1e3) / 1e12
+            res["rows"].append({"K": K, "N": N, "tokens": tokens, "module_fwd_ms": round(t_mod, 4), "gemm_ms": round(t_g, 4),
+                                "gemm_tflops": round(tf, 1),
+                                "gemm_frac_of_fp8_peak": round(tf / res["peak_fp8_tflops"], 3) if res["peak_fp8_tflops"] else None,
+                                "gemm_frac_of_bf16_peak": round(tf / measured_peaks()["tflops_sustained"], 3)})
+            del x
+        del m
+        torch.cuda.empty_cache()
+    return res
 
 
 def main():
