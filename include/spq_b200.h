@@ -198,12 +198,13 @@ SPQ_API int spq_qgemm_f8(const uint8_t* A, int64_t lda, const uint8_t* B, int64_
  * (p1/quantization_methods.py:82-90) to the finished gradient.  gq_scale_i (nullable, [I]) fuses the CPT variant's
  * GradientQuantizer (p2/quantization.py:14-26) in front of that clamp: symmetric gq_bits-bit min-max fake
  * quantisation of the gradient with one calibrated scale per row i.  alpha_dev (device scalar), i_scale, j_scale
- * are nullable.  Per-reduction-row scales cannot be applied here: fold them into P or Q. */
+ * are nullable.  accumulate != 0: D += result (the gradient lands in an existing .grad buffer, e.g. a slice of the flat
+ * gradient buffer of the training step).  Per-reduction-row scales cannot be applied here: fold them into P or Q. */
 SPQ_API size_t spq_gemm_tn_workspace_bytes(int64_t Mred, int64_t I, int64_t J);
 SPQ_API int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq,
                 int64_t Mred, int64_t I, int64_t J, float alpha, const float* alpha_dev,
                 const float* i_scale, const float* j_scale, float clamp_abs,
-                const float* gq_scale_i, int gq_bits,
+                const float* gq_scale_i, int gq_bits, int accumulate,
                 float* D, int64_t d_stride_i, int64_t d_stride_j, void* workspace, size_t workspace_bytes,
                 spq_stream_t stream);
 
@@ -211,9 +212,10 @@ SPQ_API int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, i
 SPQ_API int spq_layernorm_fwd(const float* x, int64_t rows, int64_t cols, const float* weight, const float* bias,
                       float eps, float* y, float* mean, float* rstd, spq_stream_t stream);
 SPQ_API size_t spq_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cols);
+/* accumulate_params != 0: dweight / dbias += the column sums (gradient accumulation in place) */
 SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean,
                       const float* rstd, int64_t rows, int64_t cols, float* dx, float* dweight,
-                      float* dbias, void* workspace, size_t workspace_bytes, spq_stream_t stream);
+                      float* dbias, int accumulate_params, void* workspace, size_t workspace_bytes, spq_stream_t stream);
 
 /* ---- gradient-side operand: out[m, 0:N] = fp16(g[m,n] * 2^-e[m]), e from the row's absmax,
  * row_scale[m] = 2^e[m] (an all-zero row reports the smallest scale, 2^-108, so that `max over rows` and

@@ -54,7 +54,8 @@ SIGNATURES = {
                              c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "spq_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "spq_gemm_tn": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
-                            c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+                            c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t,
+                            c_void_p]),
     "spq_rowscale_f16_max": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_lora_bwd_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
@@ -64,7 +65,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "spq_qgemm_lse_parts": (c_int64, [c_int64, c_int64]),
     "spq_qgemm_lse": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
@@ -282,7 +283,7 @@ def qgemm_f8(A8, B8, M, N, K, out, A2=None, B2=None, K2=0, alpha=1.0, row_scale=
 
 
 def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, transposed_out=False, clamp_abs=0.0,
-            gq_scale_i=None, gq_bits=8):
+            gq_scale_i=None, gq_bits=8, accumulate=False):
     """out[I,J] (or out[J,I] when transposed_out) = clamp(alpha * P[Mred,I]^T Q[Mred,J]); fp16 in, fp32 out.
     Deterministic (split reduction folded in a fixed order); clamp_abs > 0 applies the log STE clamp."""
     lib = load_library()
@@ -302,7 +303,7 @@ def gemm_tn(P, Q, out, alpha=1.0, alpha_dev=None, i_scale=None, j_scale=None, tr
     ws = _workspace(lib.spq_gemm_tn_workspace_bytes(Mred, I, J), out.device, "gemm_tn")
     _check(lib.spq_gemm_tn(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), Mred, I, J, float(alpha),
                            _ptr(alpha_dev), _ptr(i_scale), _ptr(j_scale), float(clamp_abs), _ptr(gq_scale_i), int(gq_bits),
-                           out.data_ptr(), si, sj,
+                           int(accumulate), out.data_ptr(), si, sj,
                            ws.data_ptr(), ws.numel(), _stream()), "spq_gemm_tn")
     return out
 
@@ -314,14 +315,14 @@ def layernorm_fwd(x2d, weight, bias, eps, y, mean, rstd):
                                             y.data_ptr(), _ptr(mean), _ptr(rstd), _stream()), "spq_layernorm_fwd")
 
 
-def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias):
+def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias, accumulate_params=False):
     lib = load_library()
     _req_cuda(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias)
     rows, cols = x2d.shape
     nbytes = lib.spq_layernorm_bwd_workspace_bytes(rows, cols)
     ws = _workspace(nbytes, x2d.device, "ln_bwd")
     _check(lib.spq_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                 rows, cols, dx.data_ptr(), _ptr(dweight), _ptr(dbias), ws.data_ptr(), ws.numel(),
+                                 rows, cols, dx.data_ptr(), _ptr(dweight), _ptr(dbias), int(accumulate_params), ws.data_ptr(), ws.numel(),
                                  _stream()), "spq_layernorm_bwd")
 
 

@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..lora import (_FpWeightCache, _act_config, _as_2d_f32, _as_2d_grad, _dequant, _norm_pow2, _quantized_operand,
+from ..lora import (_FpWeightCache, _act_config, _as_2d_f32, _as_2d_grad, _dequant, _grad_sink, _norm_pow2, _quantized_operand,
                     _rowscaled_f16, _to_f16_operand, linear_fp)
 from ..quantization import pow2_ceil
 from .quantization import GradientQuantizer, LearnableFakeQuantize
@@ -140,22 +140,28 @@ class _CPTLinearFn(torch.autograd.Function):
             if need_A:
                 # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
                 gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_A, K)
-                gA = torch.empty((K, r), dtype=torch.float32, device=dev)
+                sink = _grad_sink(sl.lora_A, (K, r)) if fused else None
+                gA = sink if sink is not None else torch.empty((K, r), dtype=torch.float32, device=dev)
                 _lib.gemm_tn(a_q, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['absorb'],
                              clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
-                             gq_bits=sl.grad_quantizer_A.num_bits if gqs is not None else 8)
-                if not fused:
+                             gq_bits=sl.grad_quantizer_A.num_bits if gqs is not None else 8, accumulate=sink is not None)
+                if sink is not None:
+                    gA = None
+                elif not fused:
                     gA = _grad_quantize(sl.grad_quantizer_A, gA)
                     if clamp_w:
                         gA = _lib.ste_backward(gA, _lib.LOG)
             if need_B:
                 # dB[n,j] = scaling * sum_m dY[m,n] t[m,j],  t[m,j] = t16[m,j] / tau
                 gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_B, N)
-                gB = torch.empty((N, r), dtype=torch.float32, device=dev)
+                sink = _grad_sink(sl.lora_B, (N, r)) if fused else None
+                gB = sink if sink is not None else torch.empty((N, r), dtype=torch.float32, device=dev)
                 _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
                              clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
-                             gq_bits=sl.grad_quantizer_B.num_bits if gqs is not None else 8)
-                if not fused:
+                             gq_bits=sl.grad_quantizer_B.num_bits if gqs is not None else 8, accumulate=sink is not None)
+                if sink is not None:
+                    gB = None
+                elif not fused:
                     gB = _grad_quantize(sl.grad_quantizer_B, gB)
                     if clamp_w:
                         gB = _lib.ste_backward(gB, _lib.LOG)

@@ -55,6 +55,7 @@ class CPTTrainer:
                 p.data = view
                 p.requires_grad_(True)
                 p.grad = self.flat_grad[off:off + cnt].view_as(p)
+                p._spq_accumulate_in_place = True      # the gradient GEMM's fold pass adds into p.grad (lora._grad_sink)
         self.params = [p for p, _, _ in self.slots.values()]
         self.linears = [m for m in model.modules() if m.__class__.__name__ == 'CPTLinear']
         self.dev = dev

@@ -975,6 +975,7 @@ struct TnReduce {
     float alpha, clamp_abs;
     const float* gq_scale_i;     // optional: min-max fake quantisation of the result, scale per row i (GradientQuantizer)
     float gq_levels;             // 2^(b-1) - 1
+    int accumulate;              // D += result (gradient accumulation straight into a .grad buffer)
     float* D;
 };
 
@@ -1019,6 +1020,10 @@ __global__ void __launch_bounds__(64) tn_reduce_kernel(TnReduce a) {
                 else { j = (e + u) / a.I; i = (e + u) - j * a.I; }
                 o[u] = tn_finish(a, o[u] * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f), i);
             }
+            if (a.accumulate) {
+                const float4 d = *reinterpret_cast<const float4*>(a.D + e);
+                o[0] += d.x; o[1] += d.y; o[2] += d.z; o[3] += d.w;
+            }
             *reinterpret_cast<float4*>(a.D + e) = make_float4(o[0], o[1], o[2], o[3]);
         }
     } else {
@@ -1028,7 +1033,8 @@ __global__ void __launch_bounds__(64) tn_reduce_kernel(TnReduce a) {
             long long i, j;
             if (a.stride_j == 1) { i = e / a.J; j = e - i * a.J; }
             else { j = e / a.I; i = e - j * a.I; }
-            a.D[e] = tn_finish(a, acc * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f), i);
+            const float v = tn_finish(a, acc * al * (a.i_scale ? __ldg(a.i_scale + i) : 1.0f) * (a.j_scale ? __ldg(a.j_scale + j) : 1.0f), i);
+            a.D[e] = a.accumulate ? a.D[e] + v : v;
         }
     }
 }
@@ -1247,7 +1253,7 @@ extern "C" size_t spq_gemm_tn_workspace_bytes(int64_t Mred, int64_t I, int64_t J
 
 extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q, int64_t ldq, int64_t Mred, int64_t I, int64_t J,
                            float alpha, const float* alpha_dev, const float* i_scale, const float* j_scale, float clamp_abs,
-                           const float* gq_scale_i, int gq_bits,
+                           const float* gq_scale_i, int gq_bits, int accumulate,
                            float* D, int64_t d_stride_i, int64_t d_stride_j, void* workspace, size_t workspace_bytes,
                            spq_stream_t stream) {
     SPQ_REQUIRE(!gq_scale_i || (gq_bits >= 2 && gq_bits <= 24), "spq_gemm_tn: gradient quantiser bits %d", gq_bits);
@@ -1282,6 +1288,7 @@ extern "C" int spq_gemm_tn(const spq_half_t* P, int64_t ldp, const spq_half_t* Q
     ra.part = ep.part; ra.splits = splits; ra.plane = ep.plane; ra.I = I; ra.J = J; ra.stride_i = d_stride_i; ra.stride_j = d_stride_j;
     ra.i_scale = i_scale; ra.j_scale = j_scale; ra.alpha_dev = alpha_dev; ra.alpha = alpha; ra.clamp_abs = clamp_abs; ra.D = D;
     ra.gq_scale_i = gq_scale_i; ra.gq_levels = gq_scale_i ? static_cast<float>((1 << (gq_bits - 1)) - 1) : 0.f;
+    ra.accumulate = accumulate ? 1 : 0;
     long long blocks = (ep.plane / 4 + 63) / 64;
     const long long cap = static_cast<long long>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;

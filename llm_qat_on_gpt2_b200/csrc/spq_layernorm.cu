@@ -146,7 +146,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // is C / 8 blocks (96 for C = 768; the first version's 24 blocks of 32 columns took as long as the backward itself).
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict__ part_b, int parts, long long C,
-                       float* __restrict__ out_a, float* __restrict__ out_b) {
+                       float* __restrict__ out_a, float* __restrict__ out_b, int accumulate) {
     __shared__ float fa[32][9], fb[32][9];
     const int cl = threadIdx.x & 7, sl = threadIdx.x >> 3;            // column in the block, part lane 0..31
     const long long c = static_cast<long long>(blockIdx.x) * 8 + cl;
@@ -171,8 +171,8 @@ colsum_finalize_kernel(const float* __restrict__ part_a, const float* __restrict
     if (sl == 0 && c < C) {
 #pragma unroll
         for (int w = 1; w < 32; ++w) { a += fa[w][cl]; b += fb[w][cl]; }
-        if (out_a) out_a[c] = a;
-        if (out_b) out_b[c] = b;
+        if (out_a) out_a[c] = accumulate ? out_a[c] + a : a;
+        if (out_b) out_b[c] = accumulate ? out_b[c] + b : b;
     }
 }
 
@@ -231,8 +231,8 @@ extern "C" size_t spq_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cols) 
 }
 
 extern "C" int spq_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean, const float* rstd,
-                                 int64_t rows, int64_t cols, float* dx, float* dweight, float* dbias, void* workspace,
-                                 size_t workspace_bytes, spq_stream_t stream) {
+                                 int64_t rows, int64_t cols, float* dx, float* dweight, float* dbias, int accumulate_params,
+                                 void* workspace, size_t workspace_bytes, spq_stream_t stream) {
     SPQ_REQUIRE(dy && x && weight && mean && rstd && dx && workspace && rows > 0 && cols > 0, "spq_layernorm_bwd: bad arguments");
     SPQ_REQUIRE((cols % 4) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(weight) && aligned16(workspace),
                 "spq_layernorm_bwd: alignment");
@@ -254,7 +254,7 @@ extern "C" int spq_layernorm_bwd(const float* dy, const float* x, const float* w
     SPQ_LAUNCH_OK();
     if (dweight || dbias) {
         colsum_finalize_kernel<<<static_cast<unsigned>((cols + 7) / 8), 256, 0, st>>>(pdw, pdb, static_cast<int>(c.grid), cols,
-                                                                                            dweight, dbias);
+                                                                                            dweight, dbias, accumulate_params ? 1 : 0);
         SPQ_LAUNCH_OK();
     }
     return SPQ_OK;

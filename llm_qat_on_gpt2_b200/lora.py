@@ -122,6 +122,19 @@ def _as_2d_act(x: torch.Tensor, last: int, max_cols: int = 1 << 30) -> torch.Ten
     return _as_2d_f32(x, last)
 
 
+def _grad_sink(param, shape):
+    """The tensor a backward kernel may accumulate this parameter's gradient INTO, or None.  A training driver that owns
+    the .grad buffers (training.FlatTrainState: slices of one flat float32 buffer, zeroed once per optimizer step) marks
+    its parameters `_spq_accumulate_in_place`; the gradient GEMM's fold pass then adds straight into p.grad and the
+    autograd node returns None for it -- the AccumulateGrad add (one small launch per parameter per micro-step) is gone."""
+    if not getattr(param, '_spq_accumulate_in_place', False):
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or tuple(g.shape) != tuple(shape):
+        return None
+    return g
+
+
 def _as_2d_grad(gy: torch.Tensor, last: int) -> torch.Tensor:
     """Incoming gradient as a contiguous 2-D matrix.  float16 gradients (the fp16 attention backward feeding c_attn)
     go to the row-scaling kernel as they are -- it widens them exactly -- instead of through a float32 copy."""
@@ -398,16 +411,23 @@ class _SPLinearFn(torch.autograd.Function):
             # largest one folded into the operands of the two token reductions)
             dt16, dt2, t2 = _lib.lora_bwd_prep(dtn, t16 if need_B else None, eg, gmax1, lb['dt_mul'],
                                                want_dt16=need_x, want_dt2=need_A, want_t2=need_B)
+            adapter = ctx.mod.lora_adapters[f'{ctx.bits}bit']
             if need_A:
                 # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; log STE clamp in the reduce pass
-                gA = torch.empty((K, r), dtype=torch.float32, device=dev)
+                sink = _grad_sink(adapter.lora_A, (K, r))
+                gA = sink if sink is not None else torch.empty((K, r), dtype=torch.float32, device=dev)
                 _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['inv_raw_mul'],
-                             clamp_abs=10.0 if lo['qtype_A'] == 'log' else 0.0)
+                             clamp_abs=10.0 if lo['qtype_A'] == 'log' else 0.0, accumulate=sink is not None)
+                if sink is not None:
+                    gA = None
             if need_B:
                 # dB[r,n] = scaling * sum_m t[m,r] dY[m,n],  t[m,r] = t16[m,r] / tau[r]
-                gB = torch.empty((r, N), dtype=torch.float32, device=dev)
+                sink = _grad_sink(adapter.lora_B, (r, N))
+                gB = sink if sink is not None else torch.empty((r, N), dtype=torch.float32, device=dev)
                 _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
-                             transposed_out=True, clamp_abs=10.0 if lo['qtype_B'] == 'log' else 0.0)
+                             transposed_out=True, clamp_abs=10.0 if lo['qtype_B'] == 'log' else 0.0, accumulate=sink is not None)
+                if sink is not None:
+                    gB = None
 
         if need_x:
             # the fp16 attention output feeding c_proj takes its gradient in fp16 straight from the epilogue

@@ -35,6 +35,7 @@ class _LayerNormFn(torch.autograd.Function):
             _lib.layernorm_fwd(x2d, w, b, eps, y, mean, rstd)
         ctx.save_for_backward(x2d, w, mean, rstd)
         ctx.x_shape, ctx.w_shape = x.shape, weight.shape
+        ctx.params = (weight, bias)
         return y.view(x.shape)
 
     @staticmethod
@@ -47,6 +48,14 @@ class _LayerNormFn(torch.autograd.Function):
         g2d = g2d.contiguous()
         dx = torch.empty_like(x2d)
         need_p = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        from .lora import _grad_sink
+        wp, bp = ctx.params
+        sw = _grad_sink(wp, ctx.w_shape) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else None
+        sb = _grad_sink(bp, ctx.w_shape) if sw is not None else None
+        if sw is not None and sb is not None:
+            # the training driver owns the .grad buffers: the column sums are added straight into them
+            _lib.layernorm_bwd(g2d, x2d, w, mean, rstd, dx, sw.view(-1), sb.view(-1), accumulate_params=True)
+            return (dx.view(ctx.x_shape) if ctx.needs_input_grad[0] else None, None, None, None, None)
         dw = torch.empty(cols, dtype=torch.float32, device=gy.device) if need_p else None
         db = torch.empty(cols, dtype=torch.float32, device=gy.device) if need_p else None
         _lib.layernorm_bwd(g2d, x2d, w, mean, rstd, dx, dw, db)

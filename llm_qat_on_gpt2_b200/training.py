@@ -376,6 +376,7 @@ class FlatTrainState:
                 p.data = view
                 p.requires_grad_(True)
                 p.grad = self.flat_grad[off:off + n].view_as(p)
+                p._spq_accumulate_in_place = True      # backward kernels add into p.grad themselves (lora._grad_sink)
         self.params = [p for p, _, _ in self.slots.values()]
 
     def seg_grad(self, key):
