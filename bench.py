@@ -755,7 +755,8 @@ def cpt_section(args, dev, world, rank, group, barrier):
     widths = [3, 4, 5, 6, 7, 8]
     mc = types.SimpleNamespace(vocab_size=50257, n_positions=1024, n_embd=1024, n_layer=24, n_head=16, layer_norm_epsilon=1e-5,
                                embd_pdrop=args.train_dropout, bit_widths=widths + [32], shared_lora_rank=16, shared_lora_alpha=32,
-                               quantizer_per_bit={**{b: "log" for b in widths}, 32: None}, gradient_bits=8)
+                               quantizer_per_bit={**{b: "log" for b in widths}, 32: None}, gradient_bits=8,
+                               attention_dtype="fp16")        # library flash attention between the hot-path linears, as in the SP arm
     cfg = {"model": mc, "training": types.SimpleNamespace(target_bits=5)}
     torch.manual_seed(0)
     model = CPTModel(cfg).to(dev)

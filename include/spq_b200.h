@@ -152,6 +152,13 @@ SPQ_API int spq_prep_linear_scales(const float* in_scale, const float* in_zero_p
                            float lora_scaling, float* absorb, float* act_mul, float* raw_mul,
                            float* inv_raw_mul, float* pw, float* inv_pw, float* lora_vec, spq_stream_t stream);
 
+/* CPT variant (p2/cpt_model.py:92-114): the scale vectors of one CPTLinear's shared-LoRA level in one launch.
+ * aq [K, r] = q(A), bq [N, r] = q(B) (dequantised, row-major), absorb [K] = per-K factor of the quantised activation operand,
+ * xbound [K] = calibrated bound of |q(x)|; out [8 r] = pa | 1/pa | tau | 1/tau | pa tau | scaling/tau | pb | 1/pb (all powers
+ * of two except scaling/tau): see csrc/spq_prep.cu.  r must divide 1024. */
+SPQ_API int spq_cpt_lora_scales(const float* aq, const float* bq, const float* absorb, const float* xbound, int64_t K, int64_t N,
+                        int64_t r, float scaling, float* out, spq_stream_t stream);
+
 /* STE backward (p1/quantization_methods.py:25-28, 82-90): identity (min-max) or clamp to
  * [-10, 10] (log).  out may alias grad. */
 SPQ_API int spq_ste_backward(const float* grad, int64_t n, int qtype, float* out, spq_stream_t stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "spq_prep_linear_scales": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int64,
                                        c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
+    "spq_cpt_lora_scales": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "spq_ste_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "spq_qgemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                           c_void_p, c_int64, c_void_p, c_int64, c_int64,
@@ -238,6 +239,17 @@ def prep_linear_scales(in_scale, in_zp, qtype, bits, symmetric, K, w_rowmax, N, 
                                                  float(lora_scaling), absorb.data_ptr(), act_mul.data_ptr(),
                                                  raw_mul.data_ptr(), inv_raw_mul.data_ptr(), pw.data_ptr(),
                                                  inv_pw.data_ptr(), _ptr(lora_vec), _stream()), "spq_prep_linear_scales")
+
+
+def cpt_lora_scales(aq, bq, absorb, xbound, scaling, out):
+    """Scale vectors of a CPTLinear's shared-LoRA level (see include/spq_b200.h): aq [K, r], bq [N, r] -> out [8 r]."""
+    _req_cuda(aq, bq, absorb, xbound, out)
+    K, r = aq.shape
+    N = bq.shape[0]
+    assert bq.shape[1] == r and absorb.numel() == K and xbound.numel() == K and out.numel() == 8 * r
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (aq, bq, absorb, xbound, out))
+    _check(load_library().spq_cpt_lora_scales(aq.data_ptr(), bq.data_ptr(), absorb.data_ptr(), xbound.data_ptr(), K, N, r,
+                                              float(scaling), out.data_ptr(), _stream()), "spq_cpt_lora_scales")
 
 
 def ste_backward(grad, qtype: int):

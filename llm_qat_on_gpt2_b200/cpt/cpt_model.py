@@ -222,6 +222,10 @@ class CPTLinear(nn.Module):
 
     # ---------------------------------------------------------------- operand caches (see lora.py)
     def _operands_for(self, bits, want_lora):
+        """Three cache levels, as in lora.py: the base level (weight + both calibrations of this width) survives the
+        per-step precision cycling and the optimizer steps; the shared-LoRA level is rebuilt whenever the adapter or
+        the width's LoRA quantiser changed -- 2 dequantise launches, ONE scale kernel (spq_cpt_lora_scales) and 4
+        operand builds, forward and backward operands together (the first version spent ~85 eager launches on it)."""
         qi, qw = self.quantizer_input, self.quantizer_weight
         W = self.linear.weight
         ent = self._op_cache.setdefault(bits, {'base': None, 'lora': None, 'bwd': None})
@@ -233,7 +237,10 @@ class CPTLinear(nn.Module):
                 wq = _dequant(qw, W)
                 pw = _norm_pow2((wq.abs() * act['absorb']).amax(dim=1))
                 B_op = _quantized_operand(qw, W, row_mul=1.0 / pw, col_mul=act['absorb'])
-            base = ent['base'] = dict(key=base_key, act=act, wq=wq, pw=pw, B_op=B_op)
+                xb = qi.abs_bound().detach().float().reshape(-1).expand(self.in_features).contiguous()
+                pk = _norm_pow2(wq.abs().amax(dim=0))
+            base = ent['base'] = dict(key=base_key, act=act, wq=wq, pw=pw, inv_pw=(1.0 / pw).contiguous(), B_op=B_op, xb=xb,
+                                      pk=pk, inv_pk=(1.0 / pk).contiguous(), WT_op=None)
             ent['lora'] = ent['bwd'] = None
         if not want_lora:
             return base, None
@@ -244,47 +251,42 @@ class CPTLinear(nn.Module):
         if lora is None or lora['key'] != lkey:
             with torch.no_grad():
                 K, r = sl.lora_A.shape
+                N = self.out_features
                 act = base['act']
                 aq = _dequant(lq, sl.lora_A)                                   # [K, r]
-                pa = _norm_pow2((aq.abs() * act['absorb'][:, None]).amax(dim=0), 0)
-                A_op = _quantized_operand(lq, sl.lora_A, row_mul=act['absorb'], col_mul=1.0 / pa, transposed=True)   # [r, K]
-                xb = qi.abs_bound().detach().float().reshape(-1).expand(K)
-                tmax = (xb[:, None] * aq.abs()).sum(dim=0).max()
-                tmul = torch.where(tmax > 0, (2.0 ** 14) / pow2_ceil(tmax), torch.ones_like(tmax))
-                tmul_vec = tmul.expand(r).contiguous()
-                Bl_op = _quantized_operand(lq, sl.lora_B, row_mul=1.0 / base['pw'],
-                                           col_mul=(sl.scaling / tmul).expand(r).contiguous())                      # [N, r]
-            lora = ent['lora'] = dict(key=lkey, rank=r, A_op=A_op, pa=pa, pa_tmul=(pa * tmul_vec).contiguous(), Bl_op=Bl_op,
-                                      tmul_vec=tmul_vec,
-                                      inv_tmul_vec=(1.0 / tmul_vec).contiguous(), scaling=float(sl.scaling),
-                                      qtype=lq.quantizer_type)
+                bq = _dequant(lq, sl.lora_B)                                   # [N, r]
+                if 1024 % r == 0:
+                    vec = torch.empty(8 * r, dtype=torch.float32, device=aq.device)
+                    _lib.cpt_lora_scales(aq, bq, act['absorb'], base['xb'], float(sl.scaling), vec)
+                    pa, inv_pa, tmul_vec, inv_tmul_vec = vec[:r], vec[r:2 * r], vec[2 * r:3 * r], vec[3 * r:4 * r]
+                    pa_tmul, bl_colmul, pb, inv_pb = vec[4 * r:5 * r], vec[5 * r:6 * r], vec[6 * r:7 * r], vec[7 * r:]
+                else:                                                          # ranks that do not divide 1024: torch ops
+                    pa = _norm_pow2((aq.abs() * act['absorb'][:, None]).amax(dim=0), 0)
+                    tmax = (base['xb'][:, None] * aq.abs()).sum(dim=0).max()
+                    tmul = torch.where(tmax > 0, (2.0 ** 14) / pow2_ceil(tmax), torch.ones_like(tmax))
+                    tmul_vec = tmul.expand(r).contiguous()
+                    inv_pa, inv_tmul_vec = (1.0 / pa).contiguous(), (1.0 / tmul_vec).contiguous()
+                    pa_tmul, bl_colmul = (pa * tmul_vec).contiguous(), (sl.scaling / tmul_vec).contiguous()
+                    pb = _norm_pow2(bq.abs().amax(dim=0) * abs(sl.scaling), 0)
+                    inv_pb = (1.0 / pb).contiguous()
+                dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
+                lora = ent['lora'] = dict(
+                    key=lkey, rank=r, pa=pa, pa_tmul=pa_tmul, tmul_vec=tmul_vec, inv_tmul_vec=inv_tmul_vec,
+                    scaling=float(sl.scaling), qtype=lq.quantizer_type,
+                    A_op=_to_f16_operand(aq, row_mul=act['absorb'], col_mul=inv_pa, transposed=True),        # [r, K]
+                    Bl_op=_to_f16_operand(bq, row_mul=base['inv_pw'], col_mul=bl_colmul),                     # [N, r]
+                    bwd=dict(pb=pb, dt_mul=dt_mul,
+                             B_rn_op=_to_f16_operand(bq, col_mul=inv_pb, mul=float(sl.scaling), transposed=True),   # [r, N]
+                             A_kr_op=_to_f16_operand(aq, row_mul=base['inv_pk'], mul=1.0 / dt_mul)))              # [K, r]
             ent['bwd'] = None
         return base, lora
 
     def _backward_operands_for(self, bits, want_lora):
         base, lora = self._operands_for(bits, want_lora)
-        ent = self._op_cache[bits]
-        bkey = (base['key'], None if lora is None else lora['key'])
-        bw = ent['bwd']
-        if bw is not None and bw['key'] == bkey:
-            return bw
-        qw, sl = self.quantizer_weight, self.shared_lora
-        W = self.linear.weight
-        with torch.no_grad():
-            pk = _norm_pow2(base['wq'].abs().amax(dim=0))
-            bw = dict(key=bkey, pk=pk, WT_op=_quantized_operand(qw, W, col_mul=1.0 / pk, transposed=True), lora=None)
-            if lora is not None:
-                lq = self.lora_weight_quantizers[f'{bits}bit']
-                N = self.out_features
-                dt_mul = 2.0 ** -max(0, math.ceil(math.log2(max(N, 2))) - 7)
-                bq = _dequant(lq, sl.lora_B)                                    # [N, r]
-                pb = _norm_pow2(bq.abs().amax(dim=0) * abs(sl.scaling), 0)      # [r]
-                bw['lora'] = dict(
-                    pb=pb, dt_mul=dt_mul,
-                    B_rn_op=_quantized_operand(lq, sl.lora_B, col_mul=1.0 / pb, mul=sl.scaling, transposed=True),  # [r, N]
-                    A_kr_op=_quantized_operand(lq, sl.lora_A, row_mul=1.0 / pk, mul=1.0 / dt_mul))                  # [K, r]
-        ent['bwd'] = bw
-        return bw
+        if base['WT_op'] is None:
+            with torch.no_grad():
+                base['WT_op'] = _quantized_operand(self.quantizer_weight, self.linear.weight, col_mul=base['inv_pk'], transposed=True)
+        return dict(pk=base['pk'], WT_op=base['WT_op'], lora=None if lora is None else lora['bwd'])
 
     # ---------------------------------------------------------------- forward (p2/cpt_model.py:92-114)
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -322,6 +324,9 @@ class CPTSelfAttention(nn.Module):
         self.c_proj = CPTLinear(self.n_embd, self.n_embd, bit_widths, quantizer_per_bit, gradient_bits, **kw)
         self.attn_dropout = nn.Dropout(config.embd_pdrop)
         self.resid_dropout = nn.Dropout(config.embd_pdrop)
+        # 'fp32': float32 q/k/v through torch SDPA (upstream computes the attention in float32); 'fp16': fused flash
+        # attention on fp16 q/k/v (a library call either way: between two hot-path linears)
+        self.attention_dtype = getattr(config, 'attention_dtype', 'fp32')
 
     def set_precision(self, num_bits: int):
         self.c_attn.set_precision(num_bits)
@@ -339,6 +344,9 @@ class CPTSelfAttention(nn.Module):
         present = (k, v)
         S = k.size(2)
         p_drop = self.attn_dropout.p if self.training else 0.0
+        half = self.attention_dtype == 'fp16' and q.dtype == torch.float32
+        if half:
+            q, k, v = q.half(), k.half(), v.half()
         if attention_mask is None and S == T:
             o = F.scaled_dot_product_attention(q, k, v, is_causal=True, dropout_p=p_drop)
         else:
@@ -347,6 +355,8 @@ class CPTSelfAttention(nn.Module):
             if attention_mask is not None:
                 bias = bias + attention_mask
             o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=p_drop)
+        if half:
+            o = o.float()
         o = o.transpose(1, 2).contiguous().view(B, T, self.n_embd)
         return self.resid_dropout(self.c_proj(o)), present
 
@@ -354,12 +364,23 @@ class CPTSelfAttention(nn.Module):
 CPTMLP = nn.ModuleDict          # the reference keeps the MLP as a ModuleDict {'fc_in', 'fc_out'} (:177-180)
 
 
+class CPTLayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (upstream's class: same parameters, same state_dict keys) whose forward / backward run on this repo's
+    row-resident LayerNorm kernels (csrc/spq_layernorm.cu) when the input is a CUDA tensor."""
+
+    def forward(self, x):
+        if not x.is_cuda or self.weight is None or self.bias is None:
+            return super().forward(x)
+        from ..switchable_batchnorm import _LayerNormFn
+        return _LayerNormFn.apply(x, self.weight, self.bias, self.eps, int(self.normalized_shape[-1]))
+
+
 class CPTBlock(nn.Module):
     def __init__(self, config, bit_widths: list, quantizer_per_bit: dict = None, gradient_bits: int = 8,
                  shared_lora_rank: int = 16, shared_lora_alpha: int = 32):
         super().__init__()
-        self.ln_1 = nn.LayerNorm(config.n_embd, eps=config.layer_norm_epsilon)
-        self.ln_2 = nn.LayerNorm(config.n_embd, eps=config.layer_norm_epsilon)
+        self.ln_1 = CPTLayerNorm(config.n_embd, eps=config.layer_norm_epsilon)
+        self.ln_2 = CPTLayerNorm(config.n_embd, eps=config.layer_norm_epsilon)
         self.bit_widths = bit_widths
         kw = dict(shared_lora_rank=shared_lora_rank, shared_lora_alpha=shared_lora_alpha)
         self.attn = CPTSelfAttention(config, bit_widths, quantizer_per_bit, gradient_bits, shared_lora_rank, shared_lora_alpha)
@@ -391,7 +412,7 @@ class CPTModel(nn.Module):
         self.h = nn.ModuleList([
             CPTBlock(mc, mc.bit_widths, mc.quantizer_per_bit, mc.gradient_bits, mc.shared_lora_rank, mc.shared_lora_alpha)
             for _ in range(mc.n_layer)])
-        self.ln_f = nn.LayerNorm(mc.n_embd, eps=mc.layer_norm_epsilon)
+        self.ln_f = CPTLayerNorm(mc.n_embd, eps=mc.layer_norm_epsilon)
         self.lm_head = CPTLinear(mc.n_embd, mc.vocab_size, mc.bit_widths, mc.quantizer_per_bit, mc.gradient_bits,
                                  bias=False, shared_lora_rank=mc.shared_lora_rank, shared_lora_alpha=mc.shared_lora_alpha)
         self.apply(self._init_weights)

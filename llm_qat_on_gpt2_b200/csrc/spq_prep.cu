@@ -216,6 +216,61 @@ __global__ void __launch_bounds__(1024) prep_linear_scales_kernel(PrepArgs a) {
     }
 }
 
+
+// CPT variant (p2/cpt_model.py:92-114): every scale vector of the shared-LoRA level of one CPTLinear in ONE launch.  The
+// adapter reads the QUANTISED input (its per-K factor `absorb` goes into the A operand) and B is stored [N, r].
+//   out[0r:1r] pa[j]      power-of-two normaliser of column j of q(A)[k,j] * absorb[k]   (operand values in (1/2, 1])
+//   out[1r:2r] 1 / pa
+//   out[2r:3r] tau        2^14 / pow2ceil(max_j sum_k xbound[k] |q(A)[k,j]|): multiplier of the fp16 down-projection
+//   out[3r:4r] 1 / tau
+//   out[4r:5r] pa * tau   epilogue scale of the down-projection GEMM
+//   out[5r:6r] scaling / tau   column multiplier of the up-projection operand
+//   out[6r:7r] pb[j]      power-of-two normaliser of column j of scaling * q(B)[n,j]     (operand of dT = dY q(B))
+//   out[7r:8r] 1 / pb
+// The shared adapter changes at every optimizer step and the width at every step (configs[3]): this replaces ~85
+// eager launches per linear per step (abs / amax / where / log2 / ceil / exp2 / ... on [K, r] and [N, r]).
+__global__ void __launch_bounds__(1024)
+cpt_lora_scales_kernel(const float* __restrict__ aq, const float* __restrict__ bq, const float* __restrict__ absorb,
+                       const float* __restrict__ xbound, long long K, long long N, int r, float scaling, float* __restrict__ out) {
+    __shared__ float s_a[1024], s_b[1024], s_red[32];
+    const int tid = threadIdx.x;
+    const int j = tid % r, lane0 = tid / r, lanes = 1024 / r;      // r divides 1024
+    float amx = 0.f, tsum = 0.f, bmx = 0.f;
+    for (long long k = lane0; k < K; k += lanes) {
+        const float av = fabsf(__ldg(aq + k * r + j));
+        amx = fmaxf(amx, av * __ldg(absorb + k));
+        tsum = fmaf(__ldg(xbound + k), av, tsum);
+    }
+    for (long long n = lane0; n < N; n += lanes) bmx = fmaxf(bmx, fabsf(__ldg(bq + n * r + j)));
+    s_a[tid] = amx; s_b[tid] = tsum;
+    __syncthreads();
+    float pa = 1.f, tj = 0.f;
+    if (tid < r) {
+        float m = 0.f, t = 0.f;
+        for (int q = tid; q < 1024; q += r) { m = fmaxf(m, s_a[q]); t += s_b[q]; }
+        pa = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
+        tj = t;
+    }
+    __syncthreads();
+    s_a[tid] = bmx;
+    __syncthreads();
+    float pb = 1.f;
+    if (tid < r) {
+        float m = 0.f;
+        for (int q = tid; q < 1024; q += r) m = fmaxf(m, s_a[q]);
+        m *= fabsf(scaling);
+        pb = (m > 0.f && m < INFINITY) ? pow2_ceil(m) : 1.0f;
+    }
+    const float tmax = block_max(tid < r ? tj : 0.f, s_red);
+    const float tau = (tmax > 0.f && tmax < INFINITY) ? 16384.0f / pow2_ceil(tmax) : 1.0f;
+    if (tid < r) {
+        out[tid] = pa;               out[r + tid] = 1.0f / pa;
+        out[2 * r + tid] = tau;      out[3 * r + tid] = 1.0f / tau;
+        out[4 * r + tid] = pa * tau; out[5 * r + tid] = scaling / tau;
+        out[6 * r + tid] = pb;       out[7 * r + tid] = 1.0f / pb;
+    }
+}
+
 }  // namespace prep
 }  // namespace spq
 
@@ -237,6 +292,15 @@ extern "C" int spq_prep_linear_scales(const float* in_scale, const float* in_zer
     a.absorb = absorb; a.act_mul = act_mul; a.raw_mul = raw_mul; a.inv_raw_mul = inv_raw_mul;
     a.pw = pw; a.inv_pw = inv_pw; a.lora = lora_vec;
     prep::prep_linear_scales_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_cpt_lora_scales(const float* aq, const float* bq, const float* absorb, const float* xbound, int64_t K, int64_t N,
+                                   int64_t r, float scaling, float* out, spq_stream_t stream) {
+    SPQ_REQUIRE(aq && bq && absorb && xbound && out && K > 0 && N > 0, "spq_cpt_lora_scales: bad arguments");
+    SPQ_REQUIRE(r > 0 && r <= 1024 && (1024 % r) == 0, "spq_cpt_lora_scales: rank must divide 1024");
+    prep::cpt_lora_scales_kernel<<<1, 1024, 0, as_stream(stream)>>>(aq, bq, absorb, xbound, K, N, static_cast<int>(r), scaling, out);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
