@@ -274,7 +274,8 @@ SPQ_API int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* t_l
  *   kind 1: next-token cross-entropy of p1/models_sp.py:441-449 (targets already shifted; rows whose target is
  *           ignore_index or out of range are not scored);                              d = softmax(s) - onehot(target)
  * row_loss[m] as spq_distill_kl / spq_cross_entropy_fwd, row_valid[m] (nullable) 1 for scored rows;
- * g16[m, 0:V] = fp16(d * 2^(8-E[m])), row_scale[m] = 2^(E[m]-8) (unscored rows: zeros, scale 2^-108),
+ * g16[m, 0:V] = fp16(d * 2^(8-E[m])), row_scale[m] = 2^(E[m]-8), E[m] from an analytic upper bound of max_v |d| (the row maxima
+ * of the softmaxes: |g16| <= 256 always, >= 64 for cross-entropy) (unscored rows: zeros, scale 2^-108),
  * max_scale[0] = max_m row_scale[m]; g16 rows are ld_g (even, >= V) elements apart, the padding is zeroed.
  * The caller's scalar factor (T/rows for kind 0, 1/scored-rows for kind 1) multiplies row_scale. */
 SPQ_API int spq_softmax_loss_grad16(int kind, const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t,

@@ -6,6 +6,8 @@
 // 32 x 1024 tokens.  Here each row is read once: online max / sum-of-exponentials per thread,
 // block combine, loss_row = log(sum) + max - logit[target].  Forward only (no-grad evaluation /
 // calibration); training keeps torch's differentiable implementation.
+#include <stdlib.h>
+
 #include "spq_common.cuh"
 
 namespace spq {
@@ -187,21 +189,21 @@ distill_kl_kernel(const float* __restrict__ s_logits, long long ld_s, const floa
 //           d[v] = softmax(s/T)[v] - softmax(t/T)[v]        (caller scale: T^2/rows * 1/T)
 //   KIND 1 (next-token cross-entropy, p1/models_sp.py:441-449): row_loss = logsumexp(s) - s[target],
 //           d[v] = softmax(s)[v] - [v == target]            (caller scale: 1 / number of scored rows)
-// Output: g16[m, v] = fp16(d[v] * 2^(8-E[m])), row_scale[m] = 2^(E[m]-8) with 2^(E-1) <= max_v |d| < 2^E (rows that are
+// Output: g16[m, v] = fp16(d[v] * 2^(8-E[m])), row_scale[m] = 2^(E[m]-8) with 2^E an upper bound of max_v |d| (rows that are
 // not scored -- the last position of each sequence, ignored targets -- are zero with the smallest scale 2^-108, the
 // convention of spq_rowscale_f16), max_scale[0] = max_m row_scale[m].
-// One 1024-thread CTA per row and ONE CTA per SM: 148 rows x 2 x 201 KB stay in L2, so of the three passes (online
-// max / sum-exp; loss + max|d|; scaled store) only the first reads HBM.  Algorithmic bytes: 4 (8 for KIND 0) read +
+// One 1024-thread CTA per row and ONE CTA per SM: 148 rows x 2 x 201 KB stay in L2, so of the two passes (online
+// max / sum-exp; loss + scaled store, the row scale from an analytic bound on |d|) only the first reads HBM.  Algorithmic bytes: 4 (8 for KIND 0) read +
 // 2 written per logit.
-template <int KIND>
-__global__ void __launch_bounds__(1024, 1)
+template <int KIND, int NT>
+__global__ void __launch_bounds__(NT, 2048 / NT > 2 ? 2 : 2048 / NT)
 softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, const float* __restrict__ t_logits, long long ld_t,
                            const long long* __restrict__ targets, long long ignore_index, long long M, long long V, float inv_T,
                            long long seq_len, float* __restrict__ row_loss, float* __restrict__ row_valid,
                            unsigned short* __restrict__ g16, long long ld_g, float* __restrict__ row_scale,
                            float* __restrict__ max_scale) {
-    constexpr int NT = 1024, NW = 32;
-    __shared__ float sm[4][NW];
+    constexpr int NW = NT / 32;
+    __shared__ float sm[4][32];
     __shared__ float s_b[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float cta_max_scale = 0.f;
@@ -226,18 +228,31 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
         // ---- pass 1 (HBM): online max / sum exp
         MS a; a.m = -INFINITY; a.s = 0.f;
         MS b; b.m = -INFINITY; b.s = 0.f;
-        for (long long i = tid; i < v4; i += NT) {
-            float4 x = ld_stream_f4(ps_ + 4 * i);
+        auto fold4 = [&](MS& acc, float4 x) {
             x.x *= inv_T; x.y *= inv_T; x.z *= inv_T; x.w *= inv_T;
-            float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-            if (mx > a.m) { a.s *= __expf(a.m - mx); a.m = mx; }
-            a.s += __expf(x.x - a.m) + __expf(x.y - a.m) + __expf(x.z - a.m) + __expf(x.w - a.m);
-            if (KIND == 0) {
-                float4 y = ld_stream_f4(pt_ + 4 * i);
-                y.x *= inv_T; y.y *= inv_T; y.z *= inv_T; y.w *= inv_T;
-                mx = fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w));
-                if (mx > b.m) { b.s *= __expf(b.m - mx); b.m = mx; }
-                b.s += __expf(y.x - b.m) + __expf(y.y - b.m) + __expf(y.z - b.m) + __expf(y.w - b.m);
+            const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+            if (mx > acc.m) { acc.s *= __expf(acc.m - mx); acc.m = mx; }
+            acc.s += __expf(x.x - acc.m) + __expf(x.y - acc.m) + __expf(x.z - acc.m) + __expf(x.w - acc.m);
+        };
+        {
+            // four 16-byte loads per matrix in flight per thread (the pass streams from HBM)
+            long long i = tid;
+            for (; i + 3 * NT < v4; i += 4 * NT) {
+                float4 xs[4], ys[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    xs[u] = ld_stream_f4(ps_ + 4 * (i + u * NT));
+                    if (KIND == 0) ys[u] = ld_stream_f4(pt_ + 4 * (i + u * NT));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    fold4(a, xs[u]);
+                    if (KIND == 0) fold4(b, ys[u]);
+                }
+            }
+            for (; i < v4; i += NT) {
+                fold4(a, ld_stream_f4(ps_ + 4 * i));
+                if (KIND == 0) fold4(b, ld_stream_f4(pt_ + 4 * i));
             }
         }
         for (long long i = 4 * v4 + tid; i < V; i += NT) {
@@ -257,8 +272,8 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
         if (lane == 0) { sm[0][warp] = a.m; sm[1][warp] = a.s; sm[2][warp] = b.m; sm[3][warp] = b.s; }
         __syncthreads();
         if (warp == 0) {
-            MS x; x.m = sm[0][lane]; x.s = sm[1][lane];
-            MS y; y.m = sm[2][lane]; y.s = sm[3][lane];
+            MS x; x.m = lane < NW ? sm[0][lane] : -INFINITY; x.s = lane < NW ? sm[1][lane] : 0.f;
+            MS y; y.m = lane < NW ? sm[2][lane] : -INFINITY; y.s = lane < NW ? sm[3][lane] : 0.f;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 MS c; c.m = __shfl_xor_sync(0xffffffffu, x.m, o); c.s = __shfl_xor_sync(0xffffffffu, x.s, o);
@@ -266,76 +281,87 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
                 c.m = __shfl_xor_sync(0xffffffffu, y.m, o); c.s = __shfl_xor_sync(0xffffffffu, y.s, o);
                 y = combine(y, c);
             }
-            if (lane == 0) { s_b[0] = x.m + logf(x.s); s_b[1] = (KIND == 0) ? y.m + logf(y.s) : 0.f; }
+            if (lane == 0) { s_b[0] = x.m + logf(x.s); s_b[1] = (KIND == 0) ? y.m + logf(y.s) : 0.f; s_b[2] = x.m; s_b[3] = y.m; }
         }
         __syncthreads();
         const float lse_s = s_b[0], lse_t = s_b[1];
-        // ---- pass 2 (L2): loss terms and max |d|
-        float acc = 0.f, dmax = 0.f;
-        auto dval = [&](float sv, float tv, long long idx) -> float {
-            const float ls = fmaf(sv, inv_T, -lse_s);
-            if (KIND == 0) {
-                const float lt = fmaf(tv, inv_T, -lse_t);
-                const float pt = __expf(lt);
-                acc = fmaf(pt, lt - ls, acc);
-                return __expf(ls) - pt;
+        // while passes 2 and 3 run out of L2, pull the NEXT row of this CTA towards L2 (its pass 1 then starts warm)
+        {
+            const long long nrow = row + gridDim.x;
+            if (nrow < M) {
+                const char* ns = reinterpret_cast<const char*>(s_logits + nrow * ld_s);
+                const long long bytes = V * 4;
+                for (long long o = static_cast<long long>(tid) * 128; o < bytes; o += static_cast<long long>(NT) * 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ns + o));
+                    if (KIND == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(t_logits + nrow * ld_t) + o));
+                }
             }
-            return __expf(ls) - (idx == tgt ? 1.0f : 0.0f);
-        };
-        for (long long i = tid; i < v4; i += NT) {
-            const float4 x = *reinterpret_cast<const float4*>(ps_ + 4 * i);
-            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (KIND == 0) y = *reinterpret_cast<const float4*>(pt_ + 4 * i);
-            const float d0 = dval(x.x, y.x, 4 * i), d1 = dval(x.y, y.y, 4 * i + 1), d2 = dval(x.z, y.z, 4 * i + 2), d3 = dval(x.w, y.w, 4 * i + 3);
-            dmax = fmaxf(dmax, fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))));
         }
-        for (long long i = 4 * v4 + tid; i < V; i += NT)
-            dmax = fmaxf(dmax, fabsf(dval(__ldg(ps_ + i), KIND == 0 ? __ldg(pt_ + i) : 0.f, i)));
-        acc = warp_sum(acc);
-        dmax = warp_fmax(dmax);
-        __syncthreads();
-        if (lane == 0) { sm[0][warp] = acc; sm[1][warp] = dmax; }
-        __syncthreads();
-        if (warp == 0) {
-            float t0 = warp_sum(sm[0][lane]);
-            float t1 = warp_fmax(sm[1][lane]);
-            if (lane == 0) { s_b[2] = t0; s_b[3] = t1; }
-        }
-        __syncthreads();
-        const float amax = s_b[3];
+        // The row scale comes from an analytic bound instead of a pass over d: |d[v]| <= max(max_v p_s, max_v p_t) (KL) resp.
+        // max(1 - p_s[target], max_v p_s) (CE), and the row maxima are known from pass 1.  The bound is within a factor 2 of
+        // max |d| for CE; for KL it can be far above it when student and teacher agree, which only moves the operand down
+        // inside fp16's normal range (elements more than 2^-22 below the bound are negligible either way).
+        float amax;
+        if (KIND == 0) amax = fmaxf(__expf(s_b[2] - lse_s), __expf(s_b[3] - lse_t));
+        else amax = fmaxf(1.0f - __expf(fmaf(__ldg(ps_ + tgt), inv_T, -lse_s)), __expf(s_b[2] - lse_s));
         int E = 0;
         if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;
         E = E < -100 ? -100 : E;
         const float down = exp2f(static_cast<float>(8 - E));
         const float up = exp2f(static_cast<float>(E - 8));
-        if (tid == 0) {
-            row_loss[row] = (KIND == 0) ? s_b[2] : (lse_s - __ldg(ps_ + tgt) * inv_T);
-            if (row_valid) row_valid[row] = 1.f;
-            row_scale[row] = up;
-        }
         cta_max_scale = fmaxf(cta_max_scale, up);
-        // ---- pass 3 (L2): the scaled fp16 operand
+        // ---- pass 2 (L2): loss terms and the scaled fp16 operand
+        float acc = 0.f;
         auto dq = [&](float sv, float tv, long long idx) -> float {
             const float ls = fmaf(sv, inv_T, -lse_s);
             float d;
-            if (KIND == 0) d = __expf(ls) - __expf(fmaf(tv, inv_T, -lse_t));
-            else d = __expf(ls) - (idx == tgt ? 1.0f : 0.0f);
+            if (KIND == 0) {
+                const float lt = fmaf(tv, inv_T, -lse_t);
+                const float pt = __expf(lt);
+                acc = fmaf(pt, lt - ls, acc);
+                d = __expf(ls) - pt;
+            } else {
+                d = __expf(ls) - (idx == tgt ? 1.0f : 0.0f);
+            }
             return d * down;
         };
         const bool gvec = (ld_g & 3) == 0 && (reinterpret_cast<uintptr_t>(g16) & 7u) == 0;
         if (gvec) {
-            for (long long i = tid; i < v4; i += NT) {
-                const float4 x = *reinterpret_cast<const float4*>(ps_ + 4 * i);
-                float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (KIND == 0) y = *reinterpret_cast<const float4*>(pt_ + 4 * i);
+            auto put = [&](long long i, const float4& x, const float4& y) {
                 *reinterpret_cast<uint2*>(go + 4 * i) = make_uint2(pack_h2(dq(x.x, y.x, 4 * i), dq(x.y, y.y, 4 * i + 1)),
                                                                   pack_h2(dq(x.z, y.z, 4 * i + 2), dq(x.w, y.w, 4 * i + 3)));
+            };
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            long long i = tid;
+            for (; i + 3 * NT < v4; i += 4 * NT) {
+                float4 xs[4], ys[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    xs[u] = *reinterpret_cast<const float4*>(ps_ + 4 * (i + u * NT));
+                    ys[u] = (KIND == 0) ? *reinterpret_cast<const float4*>(pt_ + 4 * (i + u * NT)) : z4;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) put(i + u * NT, xs[u], ys[u]);
             }
-            for (long long i = 4 * v4 + tid; i < ld_g; i += NT)
-                go[i] = i < V ? f2h_sat(dq(__ldg(ps_ + i), KIND == 0 ? __ldg(pt_ + i) : 0.f, i)) : static_cast<unsigned short>(0);
+            for (; i < v4; i += NT)
+                put(i, *reinterpret_cast<const float4*>(ps_ + 4 * i), (KIND == 0) ? *reinterpret_cast<const float4*>(pt_ + 4 * i) : z4);
+            for (long long j = 4 * v4 + tid; j < ld_g; j += NT)
+                go[j] = j < V ? f2h_sat(dq(__ldg(ps_ + j), KIND == 0 ? __ldg(pt_ + j) : 0.f, j)) : static_cast<unsigned short>(0);
         } else {
-            for (long long i = tid; i < ld_g; i += NT)
-                go[i] = i < V ? f2h_sat(dq(__ldg(ps_ + i), KIND == 0 ? __ldg(pt_ + i) : 0.f, i)) : static_cast<unsigned short>(0);
+            for (long long j = tid; j < ld_g; j += NT)
+                go[j] = j < V ? f2h_sat(dq(__ldg(ps_ + j), KIND == 0 ? __ldg(pt_ + j) : 0.f, j)) : static_cast<unsigned short>(0);
+        }
+        acc = warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) sm[0][warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            const float t0 = warp_sum(lane < NW ? sm[0][lane] : 0.f);
+            if (lane == 0) {
+                row_loss[row] = (KIND == 0) ? t0 : (lse_s - __ldg(ps_ + tgt) * inv_T);
+                if (row_valid) row_valid[row] = 1.f;
+                row_scale[row] = up;
+            }
         }
     }
     if (tid == 0 && max_scale) atomicMax(reinterpret_cast<int*>(max_scale), __float_as_int(cta_max_scale));
@@ -397,16 +423,25 @@ extern "C" int spq_softmax_loss_grad16(int kind, const float* s_logits, int64_t 
     SPQ_REQUIRE(kind == 0 || targets, "spq_softmax_loss_grad16: cross-entropy needs targets");
     cudaStream_t st = as_stream(stream);
     SPQ_CUDA_OK(cudaMemsetAsync(max_scale, 0, sizeof(float), st));
-    long long ctas = sm_count() > 0 ? sm_count() : 148;
+    static int variant = -1;                    // SPQ_LOSS_THREADS=512: two 512-thread CTAs per SM (A/B switch)
+    if (variant < 0) { const char* e = getenv("SPQ_LOSS_THREADS"); variant = e ? atoi(e) : 1024; }
+    const int nt = variant == 512 ? 512 : 1024;
+    long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * (nt == 512 ? 2 : 1);
     if (ctas > M) ctas = M;
-    if (kind == 0)
-        loss::softmax_loss_grad16_kernel<0><<<static_cast<unsigned>(ctas), 1024, 0, st>>>(
-            s_logits, ld_s, t_logits, ld_t, nullptr, ignore_index, M, V, 1.0f / temperature, seq_len, row_loss, row_valid, g16, ld_g,
-            row_scale, max_scale);
+    const unsigned grid = static_cast<unsigned>(ctas);
+    const long long* tg = reinterpret_cast<const long long*>(targets);
+    if (kind == 0 && nt == 1024)
+        loss::softmax_loss_grad16_kernel<0, 1024><<<grid, 1024, 0, st>>>(s_logits, ld_s, t_logits, ld_t, nullptr, ignore_index, M, V,
+            1.0f / temperature, seq_len, row_loss, row_valid, g16, ld_g, row_scale, max_scale);
+    else if (kind == 0)
+        loss::softmax_loss_grad16_kernel<0, 512><<<grid, 512, 0, st>>>(s_logits, ld_s, t_logits, ld_t, nullptr, ignore_index, M, V,
+            1.0f / temperature, seq_len, row_loss, row_valid, g16, ld_g, row_scale, max_scale);
+    else if (nt == 1024)
+        loss::softmax_loss_grad16_kernel<1, 1024><<<grid, 1024, 0, st>>>(s_logits, ld_s, nullptr, 0, tg, ignore_index, M, V, 1.0f, seq_len,
+            row_loss, row_valid, g16, ld_g, row_scale, max_scale);
     else
-        loss::softmax_loss_grad16_kernel<1><<<static_cast<unsigned>(ctas), 1024, 0, st>>>(
-            s_logits, ld_s, nullptr, 0, reinterpret_cast<const long long*>(targets), ignore_index, M, V, 1.0f, seq_len, row_loss,
-            row_valid, g16, ld_g, row_scale, max_scale);
+        loss::softmax_loss_grad16_kernel<1, 512><<<grid, 512, 0, st>>>(s_logits, ld_s, nullptr, 0, tg, ignore_index, M, V, 1.0f, seq_len,
+            row_loss, row_valid, g16, ld_g, row_scale, max_scale);
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
