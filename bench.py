@@ -210,6 +210,8 @@ class ClockSampler:
 
     def start(self):
         try:
+            if os.environ.get("SPQ_CLOCKS") == "smi":      # A/B: sample from a child process instead of in-process NVML
+                raise RuntimeError("nvidia-smi child requested")
             import pynvml
             pynvml.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
