@@ -210,7 +210,10 @@ class ClockSampler:
 
     def start(self):
         try:
-            if os.environ.get("SPQ_CLOCKS") == "smi":      # A/B: sample from a child process instead of in-process NVML
+            # default: the recipe's own sampler, `nvidia-smi -lms 200` in a CHILD process (no driver calls from a second
+            # thread of the measuring process: the in-process NVML poll coincided with single +50 ms steps in the
+            # end-to-end region of some runs); SPQ_CLOCKS=nvml selects the in-process poll
+            if os.environ.get("SPQ_CLOCKS", "smi") != "nvml":
                 raise RuntimeError("nvidia-smi child requested")
             import pynvml
             pynvml.nvmlInit()
@@ -224,8 +227,10 @@ class ClockSampler:
         except Exception:
             self.nvml = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[0].isdigit() else self.index
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(phys), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -284,7 +289,7 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvml (100 ms poll)" if self.nvml is not None else "nvidia-smi -lms 100",
+                "source": "nvml (100 ms poll)" if self.nvml is not None else "nvidia-smi -lms 200 (child process)",
                 "max_query_ms": [round(v, 2) for v in self.query_ms]}
 
 
