@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--train-seq", type=int, default=256, help="sequence length of the training step (p1/config_sp.py:47)")
     ap.add_argument("--profile-train-step", action="store_true",
                     help="for ncu launch lists: run the training section with one NVTX-ranged step")
+    ap.add_argument("--eager-step", action="store_true",
+                    help="run the headline step eagerly (one launch per kernel) instead of as CUDA-graph replays")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="for ncu launch lists: warm up, run exactly one un-instrumented step, print nothing else")
     return ap.parse_args()
@@ -348,7 +350,7 @@ def gpu_arm(args):
     host_ids = [torch.randint(0, MODEL["vocab_size"], (B, T), generator=gen).pin_memory() for _ in range(n_batches)]
     dev_ids = [h.to(dev) for h in host_ids]
 
-    def step(ids):
+    def step_eager(ids):
         with torch.no_grad():
             for q in input_q:
                 q.start_calibration()
@@ -358,6 +360,17 @@ def gpu_arm(args):
             dp.finish_calibration_many(input_q, group)   # one MIN/MAX exchange + one flag read
             out = model(ids, labels=ids)
         return out["loss"]
+
+    # the same step as two CUDA-graph replays (statistics pass | finish_calibration + operand rebuild + quantised
+    # forward + loss) with the statistics exchange in between and the flag read deferred: `--eager-step` is the A/B
+    # switch; the roofline pass (an event pair around every GEMM launch) and --profile-one-step run it eagerly
+    from llm_qat_on_gpt2_b200.training import GraphedCalibratedForward
+    graphed = None if (args.eager_step or args.profile_one_step) else GraphedCalibratedForward(model, group)
+
+    def step(ids):
+        if graphed is None:
+            return step_eager(ids.to(dev, non_blocking=True) if not ids.is_cuda else ids)
+        return graphed(ids)["loss"]
 
     def barrier():
         if world > 1:
@@ -438,12 +451,15 @@ def gpu_arm(args):
     barrier()
     ms_value = t0.elapsed_time(t1)
     launches = _lib.launch_count() - launches0
+    if graphed is not None:
+        # kernels of this library inside the replays (counted while they were captured) + eager launches, if any
+        launches += graphed.kernels_per_replay * args.steps
     # ---- roofline pass (separate, untimed for `value`): the same steps with a CUDA-event pair around every GEMM launch
     patch(timed_qgemm)
     barrier()
     t0.record()
     for i in range(args.steps):
-        step(dev_ids[args.warmup + i])
+        step_eager(dev_ids[args.warmup + i])
     t1.record()
     barrier()
     ms_roofline_pass = t0.elapsed_time(t1)
@@ -459,8 +475,8 @@ def gpu_arm(args):
     t0.record()
     for i in range(args.steps):
         w0 = time.perf_counter()
-        ids = host_ids[args.warmup + i].to(dev, non_blocking=True)
-        loss_host = float(step(ids).item())
+        # pinned host ids -> device (asynchronous copy into the step's input buffer), loss read back
+        loss_host = float(step(host_ids[args.warmup + i]).item())
         e2e_step_ms.append(round((time.perf_counter() - w0) * 1e3, 2))
     t1.record()
     barrier()
@@ -481,6 +497,7 @@ def gpu_arm(args):
             cpt = cpt_section(args, dev, world, rank, group, barrier)
         if args.sweep_tokens and world == 1:
             sweep = qlinear_sweep_section(args, dev)
+    nodata = graphed.nodata_count() if graphed is not None else 0
     wd = _lib.debug_status()
     if wd != 0:
         raise RuntimeError(f"GEMM pipeline watchdog flag {wd}: results of this run are invalid")
@@ -507,7 +524,10 @@ def gpu_arm(args):
                        "parallelism": f"dp{world} (replicas, batch-sharded; MIN/MAX all-reduce of calibration statistics)",
                        "l2": "per-step working set (~10 GB of activations + 6.6 GB of logits) >> 126 MB L2; fresh token ids every step",
                        "attention": "torch SDPA fp16 (outside the hot path)",
-                       "extra_untimed_warmup_steps": extra_warmup},
+                       "extra_untimed_warmup_steps": extra_warmup,
+                       "launch_mode": ("eager (one launch per kernel, one device->host flag read per step)" if graphed is None else
+                                       f"2 CUDA-graph replays per step ({graphed.kernels_per_replay} kernels of this library "
+                                       f"captured); quantiser calibrations without data: {nodata}")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * T * 8, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "loss": loss_host, "step_wall_ms": e2e_step_ms},
             "gpu_launches": launches,

@@ -46,36 +46,45 @@ def needs_build():
         return fh.read().strip() != _digest()
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """out / extra_flags: a side build for same-box A/B runs (e.g. out="libspq_epi8.so", extra_flags=["-DSPQ_EPI_WARPS=8"],
+    selected at run time with SPQ_LIB=<path>); the default build is the one every import loads."""
+    side = out is not None
+    if not side and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", os.path.basename(out)[:-3]) if side else os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"== {os.path.basename(src)}\n{out}\n")
+            sys.stderr.write(f"== {os.path.basename(src)}\n{log}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libspq_b200.so")
-    link = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    target = os.path.join(HERE, out) if side else LIB
+    link = [nvcc, "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link of libspq_b200.so failed")
+    if side:
+        return target
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else None,
+                 extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")])
     print(path)

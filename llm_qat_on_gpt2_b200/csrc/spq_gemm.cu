@@ -24,15 +24,27 @@ namespace gemm {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // 64 fp16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;     // 2 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
+// Epilogue warps: 4 per TMEM lane quadrant, each owning BN / 4 columns of its 32 rows.  With 8 warps (2 per SM
+// sub-partition) ncu showed the epilogue latency-bound -- issue slots 32 % (LM head) / 47 % (GELU) busy, stall_wait +
+// short_scoreboard on the dependent FP / MUFU chains, 15-20 k cycles per tile against a 6-9 k cycle main loop; 16
+// warps give every sub-partition four instruction streams to interleave (SPQ_EPI_WARPS=8 rebuilds the old layout).
+#ifndef SPQ_EPI_WARPS
+#define SPQ_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = SPQ_EPI_WARPS;
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int NPART = EPI_WARPS / 4;               // column parts of a tile (one per warp of a lane quadrant)
+constexpr int NUM_THREADS = 64 + EPI_THREADS;      // 2 control warps + the epilogue warps
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 constexpr int STG_TILE_BYTES = 32 * 32 * 4;   // per-epilogue-warp 32 x 32 fp32 staging tile, 128B-XOR-swizzled
 #ifndef SPQ_STG_BUFS
-#define SPQ_STG_BUFS 2
+#define SPQ_STG_BUFS (SPQ_EPI_WARPS >= 16 ? 1 : 2)
 #endif
-constexpr int STG_BUFS = SPQ_STG_BUFS;        // two tiles per warp: chunk i+1 is computed while the TMA engine still reads chunk i
+// 8 warps: two tiles per warp (chunk i+1 is computed while the TMA engine still reads chunk i); 16 warps: one tile
+// per warp (the same 64 KB in total) -- the other three warps of the sub-partition cover the wait
+constexpr int STG_BUFS = SPQ_STG_BUFS;
 
 __device__ int g_abort = 0;    // watchdog: set when a pipeline wait timed out
 
@@ -200,6 +212,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int umma_m, int umma_n, in
 // on the output), arranged as 12 FMUL/FFMA + MUFU.RCP + MUFU.EX2: erff() costs ~30 instructions and the IEEE
 // reciprocal / denormal-guarded exp another ~10, which shows in an epilogue that has ~18 issue slots per element.
 //   gelu(v) = v/2 + |v|/2 * erf(|v|/sqrt 2),   erf(x) = 1 - (a1 t + ... + a5 t^5) exp(-x^2),  t = 1/(1 + p x)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gelu_erf(float v) {
     const float x = fabsf(v) * 0.70710678118654752f;
     float t, ex;
@@ -229,6 +246,7 @@ struct EpiParams {
                               // 4 disable the TMA-store path, 8 skip the TMA store instruction, 16 skip the staging writes
     int tma_store;            // 1: D is written with TMA bulk tensor stores (16 B aligned rows; residual prefetched per lane)
     int act;                  // 0: none, 1: exact (erf) GELU applied after the bias
+    int store_hint;           // 1: TMA stores carry an L2 evict-first policy (outputs much larger than L2)
     float2* lse_part;         // LSE kernels: [M, lse_ld] (max, sum of exp(v - max)) of each row over each column half-tile
     long long lse_ld;
 };
@@ -437,10 +455,10 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else {
         // ===================================================== epilogue (warps 2..9)
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;             // which half of the tile's columns
-        const int epi_tid = threadIdx.x - 64;         // 0..255
-        constexpr int CHUNKS = (BN / 2) / 32 > 0 ? (BN / 2) / 32 : 1;   // 32-column chunks per warp
-        constexpr int COLS_PER_HALF = BN / 2 >= 32 ? BN / 2 : 32;
+        const int part = (warp - 2) >> 2;             // which part of the tile's columns
+        const int epi_tid = threadIdx.x - 64;         // 0..EPI_THREADS-1
+        constexpr int COLS_PER_PART = BN / NPART >= 32 ? BN / NPART : 32;
+        constexpr int CHUNKS = COLS_PER_PART / 32;    // 32-column chunks per warp
         float* const stg_base = reinterpret_cast<float*>(stg_all + (warp - 2) * STG_BUFS * STG_TILE_BYTES);
         float* stg = stg_base;
         uint32_t stg_u32 = smem_u32(stg);
@@ -450,7 +468,9 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t acc_phase = 0;
         bool store_pending = false;
         const float alpha = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f);
-        const bool active = (BN >= 64) || (half == 0);   // BN = 32 would leave the second half idle (not instantiated)
+        const bool active = part * COLS_PER_PART < BN;   // narrow tiles (BN = 64 with four parts) leave the upper parts idle
+        uint64_t store_policy = 0;
+        if (ep.store_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
         // residual C on the TMA-store path: the warp reads the NEXT chunk's 32 x 32 block of C coalesced (8 lanes
         // per 128 B row segment) into registers as soon as the current block has been parked in the staging tile;
         // the block goes through the same swizzled tile, so every lane then finds its own row next to its
@@ -460,7 +480,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int m_blk, n_blk;
             tile_coords(tt, m_tiles, n_tiles, m_blk, n_blk);
             const int rb = m_blk * TILE_M + row_off + quad * 32 + (lane >> 3);
-            const int ncol = n_blk * BN + half * COLS_PER_HALF + cc * 32 + (lane & 7) * 4;
+            const int ncol = n_blk * BN + part * COLS_PER_PART + cc * 32 + (lane & 7) * 4;
             const float* pc = ep.C + static_cast<long long>(rb) * ep.ldc + ncol;
 #pragma unroll
             for (int i = 0; i < (PRE_C ? 8 : 1); ++i)
@@ -474,13 +494,13 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int m0 = m_blk * TILE_M + row_off;
             const int n0 = n_blk * BN;
             // stage this tile's per-column parameters (previous tile's readers are done: barrier 1)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int j = epi_tid; j < BN; j += 256) {
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            for (int j = epi_tid; j < BN; j += EPI_THREADS) {
                 const int n = n0 + j;
                 epi_cs[j] = (ep.col_scale && n < N) ? __ldg(ep.col_scale + n) : 1.0f;
                 epi_bias[j] = (ep.bias && n < N) ? __ldg(ep.bias + n) : 0.0f;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
@@ -488,7 +508,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int row = rbase + lane;
             const float rs = alpha * ((ep.row_scale && row < M) ? __ldg(ep.row_scale + row) : 1.0f);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN + half * COLS_PER_HALF);
+                                   static_cast<uint32_t>(acc * BN + part * COLS_PER_PART);
             const int sw = lane & 7;                                // 128B swizzle: 16 B chunk index ^ (row % 8)
             float lse_m = -INFINITY, lse_s = 0.f;                   // LSE: this row over this warp's columns of the tile
             if (active) {
@@ -497,7 +517,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
                     tmem_ld_wait();
-                    const int cl = half * COLS_PER_HALF + c * 32;   // first column of the chunk inside the tile
+                    const int cl = part * COLS_PER_PART + c * 32;   // first column of the chunk inside the tile
                     const int nc = n0 + cl;
                     auto c_next = [&]() {                           // issue the next chunk's residual loads
                         if (c + 1 < CHUNKS) c_load(t, c + 1);
@@ -549,14 +569,9 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                             if (ep.act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                             if constexpr (LSE) {
-                                // columns >= N (ragged last tile) do not take part
-                                const float e0 = (nc + j < N) ? o.x : -INFINITY, e1 = (nc + j + 1 < N) ? o.y : -INFINITY;
-                                const float e2 = (nc + j + 2 < N) ? o.z : -INFINITY, e3 = (nc + j + 3 < N) ? o.w : -INFINITY;
-                                const float mn = fmaxf(fmaxf(lse_m, fmaxf(e0, e1)), fmaxf(e2, e3));
-                                if (mn > -INFINITY) {
-                                    lse_s = lse_s * __expf(lse_m - mn) + __expf(e0 - mn) + __expf(e1 - mn) + __expf(e2 - mn) + __expf(e3 - mn);
-                                    lse_m = mn;
-                                }
+                                // the finished values stay in v[] for the chunk-level log-sum-exp below
+                                v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y);
+                                v[j + 2] = __float_as_uint(o.z); v[j + 3] = __float_as_uint(o.w);
                             }
                             if constexpr (OUT_HALF) {
                                 // 64 B rows, 64B swizzle: 16-byte chunk index ^ ((row / 2) % 4); one 16-byte store
@@ -577,15 +592,54 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0 && !(ep.debug & 8)) {
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                             reinterpret_cast<uint64_t>(&tmD)),
-                                         "r"(stg_u32), "r"(nc), "r"(rbase)
-                                         : "memory");
+                            if (ep.store_hint) {
+                                // streaming output (>> L2, nobody reads it back soon): evict-first keeps the operand
+                                // tiles of the tiles in flight resident while the store stream passes through L2
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&tmD)),
+                                             "r"(stg_u32), "r"(nc), "r"(rbase), "l"(store_policy)
+                                             : "memory");
+                            } else {
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&tmD)),
+                                             "r"(stg_u32), "r"(nc), "r"(rbase)
+                                             : "memory");
+                            }
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                         store_pending = true;
                         ++stores_in_flight;
                         stg_buf = (stg_buf + 1) % STG_BUFS;
+                        if constexpr (LSE) {
+                            // running (max, sum exp) of this row over the chunk: ONE rescale per 32 values -- max of the
+                            // chunk first (FMNMX3), then exp2((v - max) log2 e) per value: 3.5 instructions per value
+                            // where the per-quad online update (five guarded __expf) cost ~13.  Columns >= N (ragged last
+                            // tile) do not take part.
+                            constexpr float LOG2E = 1.4426950408889634f;
+                            const bool ragged = nc + 32 > N;            // warp-uniform
+                            float cm = -INFINITY;
+                            if (!ragged) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (nc + j < N) ? __uint_as_float(v[j]) : -INFINITY);
+                            }
+                            if (cm > -INFINITY) {
+                                const float mn = fmaxf(lse_m, cm);
+                                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                                if (!ragged) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_ftz((__uint_as_float(v[j]) - mn) * LOG2E);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        s4[j & 3] += (nc + j < N) ? ex2_ftz((__uint_as_float(v[j]) - mn) * LOG2E) : 0.f;
+                                }
+                                lse_s = lse_s * ex2_ftz((lse_m - mn) * LOG2E) + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+                                lse_m = mn;
+                            }
+                        }
                     } else {
                         // general path (fp16 output, residual input, unaligned D): row scale before the transpose,
                         // column scale / clamp / bias / residual after it, coalesced stores from the swizzled tile
@@ -661,7 +715,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
             if constexpr (LSE) {
-                if (row < M) ep.lse_part[static_cast<long long>(row) * ep.lse_ld + n_blk * 2 + half] = make_float2(lse_m, lse_s);
+                if (row < M) ep.lse_part[static_cast<long long>(row) * ep.lse_ld + n_blk * NPART + part] = make_float2(lse_m, lse_s);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -1150,6 +1204,13 @@ static int qgemm_impl(const void* A, int64_t lda, const void* B, int64_t ldb, in
     ep.row_scale = row_scale; ep.col_scale = col_scale; ep.bias = bias; ep.C = C; ep.alpha_dev = nullptr;
     ep.D = D; ep.ldc = ldc; ep.ldd = ldd; ep.d_stride_n = 1; ep.alpha = alpha; ep.clamp_abs = clamp_abs;
     ep.act = activation;
+    {
+        // SPQ_GEMM_STORE_HINT: 0 never, 1 always, unset: outputs of at least 1 GB (the LM head's logits)
+        static int hint_env = -2;
+        if (hint_env == -2) { const char* e = getenv("SPQ_GEMM_STORE_HINT"); hint_env = e ? atoi(e) : -1; }
+        const double out_bytes = static_cast<double>(M) * static_cast<double>(N) * (d_is_half ? 2.0 : 4.0);
+        ep.store_hint = hint_env >= 0 ? (hint_env != 0) : (out_bytes >= 1073741824.0);
+    }
     ep.lse_part = reinterpret_cast<float2*>(lse_part); ep.lse_ld = lse_ld;
     {
         static int dbg = -1;
@@ -1170,7 +1231,7 @@ static int qgemm_impl(const void* A, int64_t lda, const void* B, int64_t ldb, in
     if (ep.tma_store && (rc = make_tmap_out(&tD, D, M, N, ldd, d_is_half != 0)) != SPQ_OK) return rc;
     if (lse_part) {
         SPQ_REQUIRE(ep.tma_store && !d_is_half && !C, "spq_qgemm_lse: needs float32 output with 16-byte aligned, padded rows and no residual");
-        SPQ_REQUIRE(lse_ld >= 2 * ((N + bn - 1) / bn) && (reinterpret_cast<uintptr_t>(lse_part) & 7u) == 0, "spq_qgemm_lse: partials buffer too narrow");
+        SPQ_REQUIRE(lse_ld >= NPART * ((N + bn - 1) / bn) && (reinterpret_cast<uintptr_t>(lse_part) & 7u) == 0, "spq_qgemm_lse: partials buffer too narrow");
         if (pair) return launch_nt_pair<256, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 256) return launch_nt<256, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
         if (bn == 128) return launch_nt<128, false, false, true>(tA, tB, tA2, tB2, tD, m, n, kb1, kb2, ep, st);
@@ -1233,7 +1294,7 @@ extern "C" int64_t spq_qgemm_lse_parts(int64_t M, int64_t N) {
     const int sms = sm_count();
     if (M <= 0 || N <= 0 || sms <= 0) return 0;
     const int bn = pick_bn(M, N, sms);
-    return 2 * ((N + bn - 1) / bn);
+    return NPART * ((N + bn - 1) / bn);
 }
 
 extern "C" int spq_qgemm_lse(const spq_half_t* A, int64_t lda, const spq_half_t* B, int64_t ldb, int64_t M, int64_t N,

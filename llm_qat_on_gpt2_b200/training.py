@@ -317,6 +317,170 @@ class GraphedNoGradForward:
         return self.out
 
 
+class GraphedCalibratedForward:
+    """BASELINE configs[1] as two CUDA-graph replays: the calibration pass of upstream's CalibrationManager
+    (p1/train_sp.py:47-83 -- start_calibration() on every input quantiser, LoRA disabled, one forward of the
+    transformer body on the batch, finish_calibration()) followed by `model(ids, labels=ids)` at the same width.
+
+    Eagerly that step is ~630 launches of 5-200 us kernels with one device->host read in the middle (the log
+    quantisers' any(|x| > eps) flags), after which the host has to refill an empty launch queue.  Here:
+
+      graph 1   statistics pass: every input quantiser's min / max (log2 domain for log quantisers) into static
+                buffers, plus the packed MIN / MAX / flag buckets when data parallel
+      (eager)   world > 1 only: three NCCL all-reduces on the packed buckets -- no host synchronisation
+      graph 2   unpack, finish_calibration of every quantiser, the operand rebuild that depends on the new input
+                scales (prep_linear_scales, W / LoRA operands), the quantised forward, the LM head and the loss
+
+    The flag read is deferred: a log quantiser whose input had nothing above eps keeps what the statistics kernel
+    wrote (log2(eps), zero range, per-channel layout -- the same dequantised VALUES as upstream's default-shape
+    path, p1/quantization.py:164-172, 194-197); `nodata_count()` reports how many quantiser calibrations took that
+    path since construction (one device->host read, outside the step).
+
+    Returned tensors are static buffers, overwritten by the next call.  The capture hard-wires parameter / buffer
+    addresses and the weight- and LoRA-level operand caches: the signature covers (data_ptr, _version) of every
+    parameter the forward reads and the generation of every weight / LoRA quantiser; a change recaptures."""
+
+    def __init__(self, model, group=None, with_labels: bool = True):
+        self.model, self.group, self.with_labels = model, group, with_labels
+        self.linears = [m for m in model.modules() if m.__class__.__name__ == 'SPLinearWithLoRA']
+        self.world = torch.distributed.get_world_size(group) if (torch.distributed.is_available()
+                                                                  and torch.distributed.is_initialized()) else 1
+        self.g1 = self.g2 = None
+        self.ids = None
+        self.out = None
+        self._sig = None
+        self._keep = None
+        self._buckets = None
+        self._nodata = None
+        self._temps = None
+        self.kernels_per_replay = 0
+        self._helper = GraphedNoGradForward(model)        # parameter bookkeeping shared with the teacher graph
+
+    def _input_quantizers(self, bits):
+        return [m.quantizers_input[f'{bits}bit'] for m in self.linears]
+
+    def _signature(self, ids):
+        bits = self.model.get_current_precision()
+        key = f'{bits}bit'
+        tensors = tuple((t.data_ptr(), t._version) for t in self._helper._read_params(bits))
+        gens = []
+        for m in self.linears:
+            lo = m.lora_adapters[key]
+            qi = m.quantizers_input[key]
+            gens.append((m.quantizers_weight[key].generation, lo.quantize_A.generation, lo.quantize_B.generation,
+                         lo.enabled, qi.scale.data_ptr(), qi.zero_point.data_ptr(), qi.running_min.data_ptr(),
+                         qi.running_max.data_ptr(), tuple(qi.scale.shape)))
+        return (tuple(ids.shape), ids.dtype, self.model.training, bits, tensors, tuple(gens))
+
+    # -------------------------------------------------------------------------------- the two bodies
+    def _stats_body(self, qs):
+        m = self.model
+        for q in qs:
+            q.start_calibration()
+        m.disable_lora_for_calibration()
+        try:
+            m.transformer(self.ids)                          # statistics only need the transformer body
+        finally:
+            m.enable_lora_after_calibration()
+        live = [q for q in qs if q.temp_min is not None]
+        self._temps = [(q.temp_min, q.temp_max) for q in live]       # finish_calibration drops the quantisers' references
+        flags = [q._stat_state for q in live if q.quantizer_type == 'log' and q._stat_state is not None]
+        fl = torch.cat(flags) if flags else None
+        if self.world > 1:
+            mins = torch.cat([q.temp_min.reshape(-1) for q in live])
+            maxs = torch.cat([q.temp_max.reshape(-1) for q in live])
+        else:
+            mins = maxs = None
+        return live, mins, maxs, fl
+
+    def _forward_body(self, qs, live, mins, maxs, fl):
+        if self.world > 1:
+            off = 0
+            for q in live:
+                n = q.temp_min.numel()
+                q.temp_min.copy_(mins[off:off + n].view_as(q.temp_min))
+                q.temp_max.copy_(maxs[off:off + n].view_as(q.temp_max))
+                off += n
+        if fl is not None:
+            self._nodata += (fl == 0).sum()
+        for q in qs:
+            hook, q.stats_sync_hook = q.stats_sync_hook, None
+            q._stat_flag_host = 1                            # deferred (class docstring)
+            try:
+                q.finish_calibration()
+            finally:
+                q.stats_sync_hook = hook
+                q._stat_flag_host = None
+        if self.with_labels:
+            return self.model(self.ids, labels=self.ids)
+        return self.model(self.ids)
+
+    def _exchange(self, mins, maxs, fl):
+        import torch.distributed as dist
+        dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=self.group)
+        if fl is not None:
+            dist.all_reduce(fl, op=dist.ReduceOp.MAX, group=self.group)
+
+    def _eager(self, qs):
+        live, mins, maxs, fl = self._stats_body(qs)
+        if self.world > 1:
+            self._exchange(mins, maxs, fl)
+        return self._forward_body(qs, live, mins, maxs, fl)
+
+    # -------------------------------------------------------------------------------- call
+    def __call__(self, ids):
+        from . import _lib
+        sig = self._signature(ids)
+        if self.g1 is None or sig != self._sig:
+            bits = self.model.get_current_precision()
+            if bits >= 32:
+                raise RuntimeError("GraphedCalibratedForward: set a quantised precision first (nothing to calibrate at 32 bits)")
+            qs = self._input_quantizers(bits)
+            if self.world > 1:
+                # every rank must bring the same quantisers (checked once per capture, dp.sync_calibration_stats
+                # checks it on every call)
+                import torch.distributed as dist
+                mine = torch.tensor([len(qs), sum(q.scale.numel() for q in qs)], dtype=torch.int64,
+                                    device=next(self.model.parameters()).device)
+                lo, hi = mine.clone(), mine.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+                if not torch.equal(lo, hi):
+                    raise RuntimeError("GraphedCalibratedForward: ranks disagree on the input quantisers")
+            dev = next(self.model.parameters()).device
+            self.ids = torch.empty(ids.shape, dtype=ids.dtype, device=dev)      # `ids` may live in pinned host memory
+            self.ids.copy_(ids)
+            if self._nodata is None:
+                self._nodata = torch.zeros((), dtype=torch.int64, device=dev)
+            with torch.no_grad():
+                for _ in range(2):                           # warm-up: operand caches, cuDNN plans, workspaces, shapes
+                    self._eager(qs)
+                torch.cuda.synchronize()
+                self._nodata.zero_()
+                pool = torch.cuda.graph_pool_handle()
+                n0 = _lib.launch_count()
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, pool=pool):
+                    live, mins, maxs, fl = self._stats_body(qs)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=pool):
+                    self.out = self._forward_body(qs, live, mins, maxs, fl)
+                self.kernels_per_replay = _lib.launch_count() - n0
+            self.g1, self.g2, self._buckets = g1, g2, (mins, maxs, fl)
+            self._keep = (self._helper._cached_operands(), live, self._temps)
+            self._sig = self._signature(ids)
+        self.ids.copy_(ids, non_blocking=True)
+        self.g1.replay()
+        if self.world > 1:
+            self._exchange(*self._buckets)
+        self.g2.replay()
+        return self.out
+
+    def nodata_count(self) -> int:
+        return 0 if self._nodata is None else int(self._nodata.item())
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # The switchable-precision training step (BASELINE.json configs[2]; p1/train_sp.py:341-397)
 # ----------------------------------------------------------------------------------------------------------------

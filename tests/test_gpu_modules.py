@@ -636,6 +636,54 @@ def test_graphed_no_grad_forward_equals_eager():
     assert teacher.graph is not None
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [8, 4])
+def test_graphed_calibrated_forward_equals_eager(bits):
+    """training.GraphedCalibratedForward (the headline step of bench.py: calibration pass of the input quantisers on the
+    batch + quantised forward + CE as two CUDA-graph replays) against the eager module calls of upstream's
+    CalibrationManager sequence (p1/train_sp.py:47-83) on the same ids: calibrated statistics, scale / zero-point,
+    logits and loss bit for bit, for new token ids on every call; eager calls may be interleaved."""
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel
+    from llm_qat_on_gpt2_b200.training import GraphedCalibratedForward
+    torch.manual_seed(5)
+    model = SPLMHeadModel(_tiny_config()).cuda().eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("lora_B"):
+                p.normal_(0, 0.02)
+    _calibrate_model(model, bits, [torch.randint(0, 211, (2, 32), device="cuda")])
+    key = f"{bits}bit"
+    mods = [m for m in model.modules() if m.__class__.__name__ == "SPLinearWithLoRA"]
+    qs = [m.quantizers_input[key] for m in mods]
+    step = GraphedCalibratedForward(model)
+
+    def eager(ids):
+        with torch.no_grad():
+            for q in qs:
+                q.start_calibration()
+            model.disable_lora_for_calibration()
+            model.transformer(ids)
+            model.enable_lora_after_calibration()
+            for q in qs:
+                q.finish_calibration()
+            out = model(ids, labels=ids)
+        return out, [(q.running_min.clone(), q.running_max.clone(), q.scale.clone(), q.zero_point.clone()) for q in qs]
+
+    for it in range(4):
+        ids = torch.randint(0, 211, (2, 32), device="cuda")
+        got = step(ids)
+        got_logits, got_loss = got["logits"].clone(), got["loss"].clone()
+        got_stats = [(q.running_min.clone(), q.running_max.clone(), q.scale.clone(), q.zero_point.clone()) for q in qs]
+        if it % 2 == 0:                     # an eager call in between must not disturb the next replay
+            want, want_stats = eager(ids)
+            for a, b in zip(got_stats, want_stats):
+                assert all(torch.equal(x, y) for x, y in zip(a, b)), it
+            assert torch.equal(got_logits, want["logits"]), it
+            assert torch.equal(got_loss.reshape(()), want["loss"].reshape(())), it
+    assert step.g1 is not None and step.kernels_per_replay > 0
+    assert step.nodata_count() == 0
+
+
 def test_sp_linear_fp8_path_per_tensor_4bit(monkeypatch):
     """The evaluation configuration (per_channel=False, 4-bit min-max: p1/deploy.py:210,238): SPLinearWithLoRA takes the
     e4m3 integer-code GEMM.  With the LoRA branch off the output is the exact product of the codes times s_x s_w (fp32
