@@ -24,12 +24,12 @@ namespace gemm {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 64;         // 64 fp16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-// Epilogue warps: 4 per TMEM lane quadrant, each owning BN / 4 columns of its 32 rows.  With 8 warps (2 per SM
-// sub-partition) ncu showed the epilogue latency-bound -- issue slots 32 % (LM head) / 47 % (GELU) busy, stall_wait +
-// short_scoreboard on the dependent FP / MUFU chains, 15-20 k cycles per tile against a 6-9 k cycle main loop; 16
-// warps give every sub-partition four instruction streams to interleave (SPQ_EPI_WARPS=8 rebuilds the old layout).
+// Epilogue warps: EPI_WARPS / 4 per TMEM lane quadrant, each owning BN / NPART columns of its 32 rows.  8 is the
+// default.  -DSPQ_EPI_WARPS=16 (four instruction streams per SM sub-partition, one staging tile per warp) was measured
+// on the same box and is no faster (c_fc +GELU 179.8 vs 177.9 us, fp32 store 160 vs 152 us): the kernel is bound by the
+// bytes that cross the L2 <-> SM fabric (operand tiles in, output tiles out), not by epilogue latency.
 #ifndef SPQ_EPI_WARPS
-#define SPQ_EPI_WARPS 16
+#define SPQ_EPI_WARPS 8
 #endif
 constexpr int EPI_WARPS = SPQ_EPI_WARPS;
 static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
@@ -102,6 +102,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {   // same offset, in CTA `cta_rank`
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
@@ -118,6 +123,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+// Multicast variant (clusters of two CTA pairs): the box lands at the same CTA-relative offset in every CTA of
+// `cta_mask`, and each destination signals the barrier at the CTA-relative offset of `bar_local` in the LEADER of its own
+// pair (cta_group::2 honours the peer bit of the barrier address: bit 24 of the shared-window address, cleared here).
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_local, int c0, int c1,
+                                                    uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_local & 0xFEFFFFFFu), "h"(cta_mask),
+          "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n"
@@ -128,9 +145,9 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
         : "memory");
 }
 // arrives on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
@@ -316,12 +333,22 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr int TILE_M = CTA2 ? 2 * BM : BM;                     // rows per tile (per CTA pair in CTA2 mode)
-    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
-    const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-    const int row_off = static_cast<int>(cta_rank) * BM;           // this CTA's rows inside the tile
+    // CTA2 kernels run as clusters of ONE pair (2 CTAs) or TWO pairs (4 CTAs, "quad"): in a quad the pairs work on
+    // vertically adjacent 256-row tiles of the same column block, so they need the same B tile -- every CTA fetches a
+    // QUARTER of it and multicasts the box into the CTA at its position in the other pair: the B bytes cross the
+    // L2 -> SM fabric once per quad instead of once per pair (the kernel is bound by that traffic)
+    const uint32_t cluster_rank = CTA2 ? cluster_ctarank() : 0u;
+    const bool quad_cluster = CTA2 && cluster_nctarank() == 4u;
+    const uint32_t cta_rank = cluster_rank & 1u;                   // rank inside the CTA pair
+    const uint32_t pair_id = cluster_rank >> 1;                    // which pair of the cluster (0 unless quad)
+    const uint32_t lead_rank = pair_id << 1;                       // cluster rank of this pair's leader (it issues the MMAs)
+    const int cpc = CTA2 ? (quad_cluster ? 4 : 2) : 1;             // CTAs per cluster
+    const int tile_first = static_cast<int>(blockIdx.x) / cpc;
+    const int tile_step = static_cast<int>(gridDim.x) / cpc;
+    const int tile_rows = quad_cluster ? 2 * TILE_M : TILE_M;      // rows one cluster covers per scheduled tile
+    const int row_off = static_cast<int>(pair_id) * TILE_M + static_cast<int>(cta_rank) * BM;   // this CTA's rows inside it
     const int n_tiles = (N + BN - 1) / BN;
-    const int m_tiles = (M + TILE_M - 1) / TILE_M;
+    const int m_tiles = (M + tile_rows - 1) / tile_rows;
     const int num_tiles = n_tiles * m_tiles;
     const int kb_total = kb1 + kb2;
 
@@ -341,7 +368,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (ep.tma_store) tma_prefetch_desc(&tmD);
         for (int s = 0; s < L::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], quad_cluster ? 2 : 1);     // quad: both pairs' MMAs must have retired before a slot is rewritten
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -377,7 +404,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int t = tile_first; t < num_tiles; t += tile_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
-                const int m0 = m_blk * TILE_M + row_off;
+                const int m0 = m_blk * tile_rows + row_off;
                 const int n0 = n_blk * BN + (CTA2 ? static_cast<int>(cta_rank) * (BN / 2) : 0);   // this CTA's half of B
                 for (int kb = 0; kb < kb_total; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -385,14 +412,20 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* sb = sa + A_TILE_BYTES;
                     if constexpr (CTA2) {
                         // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
-                        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), lead_rank);
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-                        if (kb < kb1) {
-                            tma_load_2d_pair(sa, &tmA, lead_bar, kb * (F8 ? 2 * BK : BK), m0);
-                            tma_load_2d_pair(sb, &tmB, lead_bar, kb * (F8 ? 2 * BK : BK), n0);
+                        const CUtensorMap* ta = kb < kb1 ? &tmA : &tmA2;
+                        const CUtensorMap* tb = kb < kb1 ? &tmB : &tmB2;
+                        const int kc = kb < kb1 ? kb * (F8 ? 2 * BK : BK) : (kb - kb1) * BK;
+                        tma_load_2d_pair(sa, ta, lead_bar, kc, m0);
+                        if (!quad_cluster) {
+                            tma_load_2d_pair(sb, tb, lead_bar, kc, n0);
                         } else {
-                            tma_load_2d_pair(sa, &tmA2, lead_bar, (kb - kb1) * BK, m0);
-                            tma_load_2d_pair(sb, &tmB2, lead_bar, (kb - kb1) * BK, n0);
+                            // this CTA's quarter of the B tile (BN / 4 rows), into its own half-tile AND into the half-tile
+                            // of the CTA at the same position in the other pair; the other quarter arrives from there
+                            tma_load_2d_pair_mc(sb + pair_id * (L::B_TILE_BYTES / 2), tb, smem_u32(&full_bar[stage]), kc,
+                                                n0 + static_cast<int>(pair_id) * (BN / 4),
+                                                static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2))));
                         }
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -441,8 +474,9 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     if constexpr (CTA2) {
-                        umma_commit_pair(&empty_bar[stage]);     // frees the slot in both CTAs
-                        if (kb == kb_total - 1) umma_commit_pair(&tmem_full[acc]);
+                        // frees the slot in every CTA that writes into it (quad: both pairs); the accumulator is the pair's
+                        umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(quad_cluster ? 0xF : 0x3));
+                        if (kb == kb_total - 1) umma_commit_pair(&tmem_full[acc], static_cast<uint16_t>(0x3u << lead_rank));
                     } else {
                         umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
                         if (kb == kb_total - 1) umma_commit(&tmem_full[acc]);
@@ -479,7 +513,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         auto c_load = [&](int tt, int cc) {
             int m_blk, n_blk;
             tile_coords(tt, m_tiles, n_tiles, m_blk, n_blk);
-            const int rb = m_blk * TILE_M + row_off + quad * 32 + (lane >> 3);
+            const int rb = m_blk * tile_rows + row_off + quad * 32 + (lane >> 3);
             const int ncol = n_blk * BN + part * COLS_PER_PART + cc * 32 + (lane & 7) * 4;
             const float* pc = ep.C + static_cast<long long>(rb) * ep.ldc + ncol;
 #pragma unroll
@@ -491,7 +525,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int t = tile_first; t < num_tiles; t += tile_step) {
             int m_blk, n_blk;
             tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
-            const int m0 = m_blk * TILE_M + row_off;
+            const int m0 = m_blk * tile_rows + row_off;
             const int n0 = n_blk * BN;
             // stage this tile's per-column parameters (previous tile's readers are done: barrier 1)
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -720,7 +754,7 @@ qgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));   // the leader's barrier
+                if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), lead_rank));   // the pair leader's barrier
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -843,7 +877,23 @@ static int launch_nt(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
 }
 
 
-// CTA-pair launch: clusters of two CTAs, 256 x BN tiles, one cluster per SM pair
+// cluster size of a CTA-pair launch: 2 (one pair) or 4 (two pairs sharing the B tile by multicast).  Set by qgemm_impl
+// before it builds the B tensor maps (a quad stages BN / 4 rows of B per CTA and k-block).
+static thread_local int g_pair_cluster = 2;
+
+// how many clusters of `csize` CTAs of this kernel can be co-resident (cached per kernel and size)
+template <typename K>
+static int max_active_clusters(K kern, cudaLaunchConfig_t cfg, int csize, int* cache) {
+    if (cache[csize] < 0) {
+        int n = 0;
+        cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / csize * csize));
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+        cache[csize] = n > 0 ? n : 0;
+    }
+    return cache[csize];
+}
+
+// CTA-pair launch: clusters of two (or four) CTAs, 256 x BN tiles per pair, persistent: as many clusters as fit
 template <int BN, bool OUT_HALF, bool PRE_C = false, bool LSE = false, bool F8 = false>
 static int launch_nt_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tA2, const CUtensorMap& tB2,
                           const CUtensorMap& tD, int M, int N, int kb1, int kb2, const EpiParams& ep, cudaStream_t stream) {
@@ -854,26 +904,25 @@ static int launch_nt_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CU
         SPQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    const int csize = g_pair_cluster;
+    const int rows_per_cluster = BM * csize;
+    const int tiles = ((M + rows_per_cluster - 1) / rows_per_cluster) * ((N + BN - 1) / BN);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(sm_count() & ~1));
+    cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / csize * csize));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(csize); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // persistent clusters: exactly as many as can be co-resident (a TPC with one SM fused off cannot host a pair)
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-        int n = 0;
-        SPQ_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-        max_clusters = n > 0 ? n : 1;
-    }
+    static int cache[5] = {-1, -1, -1, -1, -1};
+    int max_clusters = max_active_clusters(kern, cfg, csize, cache);
+    if (max_clusters < 1) max_clusters = 1;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+    cfg.gridDim = dim3(static_cast<unsigned>(csize * clusters));
     SPQ_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tA, tB, tA2, tB2, tD, M, N, kb1, kb2, ep));
     spq::count_launch();
     return SPQ_OK;
@@ -1183,7 +1232,16 @@ static int qgemm_impl(const void* A, int64_t lda, const void* B, int64_t ldb, in
     if (pair_env < 0) { const char* e = getenv("SPQ_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }      // SPQ_GEMM_PAIR=0: A/B switch
     const bool pair = pair_env != 0 && bn == 256 &&
                       ((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn) >= sms / 2;
-    const int b_rows = pair ? bn / 2 : bn;                // rows of B each CTA stages per k-block
+    // Two pairs per cluster with the B tile multicast (SPQ_GEMM_CLUSTER4=1).  OFF by default: measured on the same box it
+    // is ~10 % slower (c_attn 114.0 vs 106.7 us, c_fc + GELU 197 vs 178 us, main loop alone 123 vs 110 us).  Multicast
+    // halves the B bytes REQUESTED from L2 but every SM still RECEIVES its half tile, and quads fit 128 of the 148 SMs:
+    // the kernel is bound by the bytes that enter and leave each SM (~43 B/clk/SM, the rate cuBLAS also stops at), not
+    // by L2 slice bandwidth.  Kept because it is bit-identical (tests/test_gpu_gemm_cluster.py) and documents the bound.
+    static int quad_env = -2;
+    if (quad_env == -2) { const char* e = getenv("SPQ_GEMM_CLUSTER4"); quad_env = e ? atoi(e) : 0; }
+    const bool quad = pair && quad_env > 0;
+    g_pair_cluster = quad ? 4 : 2;
+    const int b_rows = pair ? (quad ? bn / 4 : bn / 2) : bn;      // rows of B each CTA fetches per k-block
     CUtensorMap tA, tB, tA2, tB2;
     int rc;
     if (f8) {
