@@ -365,7 +365,9 @@ def gpu_arm(args):
     # forward + loss) with the statistics exchange in between and the flag read deferred: `--eager-step` is the A/B
     # switch; the roofline pass (an event pair around every GEMM launch) and --profile-one-step run it eagerly
     from llm_qat_on_gpt2_b200.training import GraphedCalibratedForward
-    graphed = None if (args.eager_step or args.profile_one_step) else GraphedCalibratedForward(model, group)
+    graphed = None if (args.eager_step or args.profile_one_step) else GraphedCalibratedForward(
+        model, group, n_side=int(os.environ.get("SPQ_STEP_SIDE_STREAMS", "8")),
+        overlap_stats=os.environ.get("SPQ_STEP_OVERLAP_STATS", "1") != "0")
 
     def step(ids):
         if graphed is None:

@@ -751,4 +751,5 @@ class SPLinearWithLoRA(nn.Module):
                 base_output = residual + base_output
         if fuse_gelu and not fuse_here:
             base_output = torch.nn.functional.gelu(base_output)
+        input_quantizer.join_stats()          # a statistics pass issued on a side stream reads x: join before x can go
         return base_output.half() if (out_half and not half_here) else base_output

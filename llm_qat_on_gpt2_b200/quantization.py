@@ -54,6 +54,8 @@ class LearnableFakeQuantize(nn.Module):
         # data-parallel driver can MIN/MAX all-reduce the statistics (see dp.py)
         self.stats_sync_hook = None
         self._stat_flag_host = None    # set by dp.finish_calibration_many to avoid a per-quantiser host read
+        self.stats_stream = None       # optional torch.cuda.Stream for the statistics pass (training.GraphedCalibratedForward)
+        self._stats_x = None
 
     # ---------------------------------------------------------------- checkpoint loading
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
@@ -146,9 +148,26 @@ class LearnableFakeQuantize(nn.Module):
                 self.temp_min = torch.empty(stat_shape, dtype=torch.float32, device=xc.device)
                 self.temp_max = torch.empty(stat_shape, dtype=torch.float32, device=xc.device)
                 self._first_shape = tuple(xc.shape)
-            _lib.minmax_stats(x2d, bcast, self.quantizer_type == 'log', self.eps, self.temp_min, self.temp_max,
-                              accumulate=not first, state=self._stat_state)
+            side = self.stats_stream
+            if side is None:
+                _lib.minmax_stats(x2d, bcast, self.quantizer_type == 'log', self.eps, self.temp_min, self.temp_max,
+                                  accumulate=not first, state=self._stat_state)
+            else:
+                # the statistics pass runs beside the caller's own pass over x (the row-scaling of the calibration
+                # GEMM's operand): two streaming readers of the same tensor at the same time, the second one is served
+                # by L2.  The caller joins with `join_stats()` before x can be released (SPLinearWithLoRA.forward)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    _lib.minmax_stats(x2d, bcast, self.quantizer_type == 'log', self.eps, self.temp_min, self.temp_max,
+                                      accumulate=not first, state=self._stat_state)
+                self._stats_x = x2d                      # keeps the (possibly converted) input alive until the join
             self.num_batches_collected += 1
+
+    def join_stats(self):
+        """Make the current stream wait for a statistics pass issued on `stats_stream` (no-op otherwise)."""
+        if self._stats_x is not None:
+            torch.cuda.current_stream().wait_stream(self.stats_stream)
+            self._stats_x = None
 
     def _log_default_shape(self):
         # reference :164-172: the CHANNEL dim is the one set to 1

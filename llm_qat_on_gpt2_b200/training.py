@@ -340,7 +340,7 @@ class GraphedCalibratedForward:
     addresses and the weight- and LoRA-level operand caches: the signature covers (data_ptr, _version) of every
     parameter the forward reads and the generation of every weight / LoRA quantiser; a change recaptures."""
 
-    def __init__(self, model, group=None, with_labels: bool = True):
+    def __init__(self, model, group=None, with_labels: bool = True, n_side: int = 8, overlap_stats: bool = True):
         self.model, self.group, self.with_labels = model, group, with_labels
         self.linears = [m for m in model.modules() if m.__class__.__name__ == 'SPLinearWithLoRA']
         self.world = torch.distributed.get_world_size(group) if (torch.distributed.is_available()
@@ -353,6 +353,10 @@ class GraphedCalibratedForward:
         self._buckets = None
         self._nodata = None
         self._temps = None
+        self._side = None
+        self._stats_stream = None
+        self.n_side = n_side
+        self.overlap_stats = overlap_stats
         self.kernels_per_replay = 0
         self._helper = GraphedNoGradForward(model)        # parameter bookkeeping shared with the teacher graph
 
@@ -375,13 +379,19 @@ class GraphedCalibratedForward:
     # -------------------------------------------------------------------------------- the two bodies
     def _stats_body(self, qs):
         m = self.model
+        if self.overlap_stats and self._stats_stream is None:
+            self._stats_stream = torch.cuda.Stream()
         for q in qs:
             q.start_calibration()
+            q.stats_stream = self._stats_stream if self.overlap_stats else None
         m.disable_lora_for_calibration()
         try:
             m.transformer(self.ids)                          # statistics only need the transformer body
         finally:
             m.enable_lora_after_calibration()
+            for q in qs:
+                q.join_stats()
+                q.stats_stream = None
         live = [q for q in qs if q.temp_min is not None]
         self._temps = [(q.temp_min, q.temp_max) for q in live]       # finish_calibration drops the quantisers' references
         flags = [q._stat_state for q in live if q.quantizer_type == 'log' and q._stat_state is not None]
@@ -403,14 +413,32 @@ class GraphedCalibratedForward:
                 off += n
         if fl is not None:
             self._nodata += (fl == 0).sum()
-        for q in qs:
-            hook, q.stats_sync_hook = q.stats_sync_hook, None
-            q._stat_flag_host = 1                            # deferred (class docstring)
-            try:
-                q.finish_calibration()
-            finally:
-                q.stats_sync_hook = hook
-                q._stat_flag_host = None
+        # per linear: finish_calibration -> prep_linear_scales -> W / LoRA operand builds: five launches of one to a
+        # few CTAs each, independent across the 48 linears.  Issued round-robin on side streams they become parallel
+        # branches of the captured graph (~2 ms of serialised small kernels per step otherwise); the forward below
+        # finds every operand cache current
+        bits = self.model.get_current_precision()
+        key = f'{bits}bit'
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = [torch.cuda.Stream() for _ in range(self.n_side)]
+        lanes = self._side if self._side else [main]         # n_side = 0: everything in line (A/B switch)
+        for st in self._side:
+            st.wait_stream(main)
+        for i, (m, q) in enumerate(zip(self.linears, qs)):
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                hook, q.stats_sync_hook = q.stats_sync_hook, None
+                q._stat_flag_host = 1                        # deferred (class docstring)
+                try:
+                    q.finish_calibration()
+                finally:
+                    q.stats_sync_hook = hook
+                    q._stat_flag_host = None
+                lo = m.lora_adapters[key]
+                if q.ready() and m.quantizers_weight[key].ready():
+                    m._operands_for(bits, bool(lo.enabled and lo.scaling != 0))
+        for st in self._side:
+            main.wait_stream(st)
         if self.with_labels:
             return self.model(self.ids, labels=self.ids)
         return self.model(self.ids)
