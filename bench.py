@@ -320,6 +320,10 @@ def gpu_arm(args):
     cfg.quantizer_per_bit = QUANTIZER_PER_BIT
     cfg.per_channel_quantization = True
     cfg.attention_dtype = "fp16"       # stock torch SDPA (flash) between the hot-path linears
+    # SPQ_MLP_ACT=fp16: gelu(c_fc(.)) held in float16 between the two MLP linears, as under upstream's autocast
+    # (p1/train_sp.py:319).  Measured -0.3..-0.7 ms per step (profiles/r02b_*): not worth leaving upstream's fp32
+    # semantics for, so the headline keeps float32 there
+    cfg.mlp_activation_dtype = os.environ.get("SPQ_MLP_ACT", "fp32")
     torch.manual_seed(0)               # identical replicas on every rank
     model = SPLMHeadModel(cfg).to(dev).eval()
     with torch.no_grad():
@@ -526,6 +530,7 @@ def gpu_arm(args):
                        "parallelism": f"dp{world} (replicas, batch-sharded; MIN/MAX all-reduce of calibration statistics)",
                        "l2": "per-step working set (~10 GB of activations + 6.6 GB of logits) >> 126 MB L2; fresh token ids every step",
                        "attention": "torch SDPA fp16 (outside the hot path)",
+                       "mlp_activation": f"gelu(c_fc) stored as {cfg.mlp_activation_dtype} between the MLP linears",
                        "extra_untimed_warmup_steps": extra_warmup,
                        "launch_mode": ("eager (one launch per kernel, one device->host flag read per step)" if graphed is None else
                                        f"2 CUDA-graph replays per step ({graphed.kernels_per_replay} kernels of this library "

@@ -83,6 +83,10 @@ class SPMLP(nn.Module):
         self.c_fc = _sp_linear(config, config.n_embd, 4 * config.n_embd, bit_widths)
         self.c_proj = _sp_linear(config, 4 * config.n_embd, config.n_embd, bit_widths)
         self.act = nn.GELU()          # exact-erf GELU, as the reference (:114)
+        # 'fp32' (default): the GELU output is float32, as upstream's fp32 path.  'fp16': under no_grad the c_fc epilogue
+        # stores gelu(.) as float16 -- what upstream's AMP loop holds there (autocast runs F.linear and GELU in fp16,
+        # p1/train_sp.py:319) -- and c_proj's statistics / quantise kernels read 2 bytes per element instead of 4
+        self.activation_dtype = getattr(config, 'mlp_activation_dtype', 'fp32')
 
     def set_precision(self, bits) -> int:
         if bits not in self.bit_widths:
@@ -94,7 +98,8 @@ class SPMLP(nn.Module):
     def forward(self, hidden_states, residual=None):
         # exact-erf GELU: fused into c_fc's GEMM epilogue when autograd is off, a separate pass otherwise;
         # `residual` (SPBlock) is added to the projection output
-        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True), residual=residual)
+        half = self.activation_dtype == 'fp16' and not torch.is_grad_enabled()
+        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True, out_half=half), residual=residual)
 
 
 class SPBlock(nn.Module):

@@ -16,7 +16,7 @@ from .quantization import calibrate_many
 
 
 class LoRARefresher:
-    def __init__(self, linears: List[torch.nn.Module], bits: int, with_backward_operands: bool = True):
+    def __init__(self, linears: List[torch.nn.Module], bits: int, with_backward_operands: bool = True, n_side: int = 8):
         self.linears = [m for m in linears if m.__class__.__name__ == 'SPLinearWithLoRA']
         self.bits = bits
         self.key = f'{bits}bit'
@@ -24,6 +24,8 @@ class LoRARefresher:
         self.graph = None
         self.finish = None
         self._sig = None
+        self._side = None
+        self.n_side = n_side
         adapters = [m.lora_adapters[self.key] for m in self.linears]
         self.active = [(m, lo) for m, lo in zip(self.linears, adapters) if lo.enabled and lo.scaling != 0]
         self.quantizers = [q for _, lo in self.active for q in (lo.quantize_A, lo.quantize_B)]
@@ -41,10 +43,21 @@ class LoRARefresher:
         return tuple(sig)
 
     def _build_all(self):
-        for m, _ in self.active:
-            m._operands_for(self.bits, True)
-            if self.with_bwd:
-                m._backward_operands_for(self.bits, True)
+        # per linear: two dequantise launches, one scale-preparation launch, four operand builds -- a few CTAs each and
+        # independent across linears.  Round-robin on side streams: parallel branches when captured into a graph
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = [torch.cuda.Stream() for _ in range(self.n_side)]
+        lanes = self._side if self._side else [main]
+        for st in self._side:
+            st.wait_stream(main)
+        for i, (m, _) in enumerate(self.active):
+            with torch.cuda.stream(lanes[i % len(lanes)]):
+                m._operands_for(self.bits, True)
+                if self.with_bwd:
+                    m._backward_operands_for(self.bits, True)
+        for st in self._side:
+            main.wait_stream(st)
 
     def _eager(self):
         calibrate_many(self.quantizers, [w.data for w in self.weights])

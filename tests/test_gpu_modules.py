@@ -684,6 +684,40 @@ def test_graphed_calibrated_forward_equals_eager(bits):
     assert step.nodata_count() == 0
 
 
+@pytest.mark.gpu
+def test_mlp_activation_fp16_option():
+    """config.mlp_activation_dtype = 'fp16': under no_grad the c_fc epilogue stores gelu(.) as float16 and c_proj's
+    statistics / quantise kernels read it directly.  Against the float32 default on the same weights: 32-bit logits
+    within 1e-3 (one fp16 rounding of a 4C-wide intermediate per block), 8-bit logits in the same direction (code
+    flips), calibrated statistics of the c_proj inputs within one fp16 ulp; with autograd on the option is ignored."""
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel
+    outs = {}
+    for mode in ("fp32", "fp16"):
+        torch.manual_seed(6)
+        cfg = _tiny_config()
+        cfg.mlp_activation_dtype = mode
+        model = SPLMHeadModel(cfg).cuda().eval()
+        ids = torch.randint(0, 211, (2, 32), device="cuda")
+        with torch.no_grad():
+            model.set_precision(32)
+            l32 = model(ids).float()
+        _calibrate_model(model, 8, [ids])
+        with torch.no_grad():
+            l8 = model(ids).float()
+        q = model.transformer.h[0].mlp.c_proj.quantizers_input["8bit"]
+        model.set_precision(32)
+        xg = model.transformer.wte(ids).detach().requires_grad_(True)
+        out = model(inputs_embeds=xg)
+        (out["logits"] if isinstance(out, dict) else out).sum().backward()
+        outs[mode] = (l32, l8, q.running_max.clone(), xg.grad.clone())
+    a, b = outs["fp32"], outs["fp16"]
+    assert float((a[0] - b[0]).norm() / a[0].norm()) <= 1e-3
+    cos = float((a[1] * b[1]).sum() / a[1].norm() / b[1].norm())
+    assert cos >= 0.995, cos
+    assert float((a[2] - b[2]).abs().max()) <= 2e-3          # log2-domain statistics: one fp16 ulp of the value is 7e-4
+    assert torch.equal(a[3], b[3])                           # training path untouched
+
+
 def test_sp_linear_fp8_path_per_tensor_4bit(monkeypatch):
     """The evaluation configuration (per_channel=False, 4-bit min-max: p1/deploy.py:210,238): SPLinearWithLoRA takes the
     e4m3 integer-code GEMM.  With the LoRA branch off the output is the exact product of the codes times s_x s_w (fp32
