@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPQ_ABI_VERSION 2
+#define SPQ_ABI_VERSION 3
 #define SPQ_API __attribute__((visibility("default")))
 
 typedef void* spq_stream_t;          /* cudaStream_t */
@@ -223,6 +223,24 @@ SPQ_API size_t spq_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cols);
 SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean,
                       const float* rstd, int64_t rows, int64_t cols, float* dx, float* dweight,
                       float* dbias, int accumulate_params, void* workspace, size_t workspace_bytes, spq_stream_t stream);
+
+/* ---- SwitchableLayerNorm fused into its consumer's activation-side kernel (no float32 round trip of the normalised
+ * rows): ln_1 -> c_attn, ln_2 -> c_fc, ln_f -> LM head (p1/models_sp.py:139-147, 316-319; p1/lora.py:141-149).
+ * Normalised dim: a multiple of 4, <= 2048.  y_out (optional) receives the float32 normalised rows as well.
+ *
+ * spq_ln_quantize_act: a_q / a_raw exactly as spq_quantize_act would write them for layernorm(x) (same arguments). */
+SPQ_API int spq_ln_quantize_act(const float* x, int64_t M, int64_t K, const float* ln_weight, const float* ln_bias, float ln_eps,
+                        const float* scale, const float* zero_point, int bcast, int qtype, int bits, int symmetric,
+                        int operand_kind, const float* col_mul, float mul, spq_half_t* a_q, spq_half_t* a_raw,
+                        const float* raw_col_mul, float* y_out, spq_stream_t stream);
+/* spq_ln_rowscale_stats: out / row_scale as spq_rowscale_f16 on layernorm(x) (dense rows); stats_mode 1 / 2 also folds
+ * the per-column min / max of layernorm(x) (2: of |.|, log2 applied after the fold, `state` |= any(|.| > stat_eps)) into
+ * stat_min / stat_max [K] exactly as spq_minmax_stats (bcast = SPQ_PER_COL, log_mode = stats_mode == 2) would. */
+SPQ_API size_t spq_ln_rowscale_stats_workspace_bytes(int64_t M, int64_t K);
+SPQ_API int spq_ln_rowscale_stats(const float* x, int64_t M, int64_t K, const float* ln_weight, const float* ln_bias, float ln_eps,
+                          spq_half_t* out, float* row_scale, int stats_mode, float stat_eps, float* stat_min,
+                          float* stat_max, int accumulate, int32_t* state, float* y_out, void* workspace,
+                          size_t workspace_bytes, spq_stream_t stream);
 
 /* ---- gradient-side operand: out[m, 0:N] = fp16(g[m,n] * 2^-e[m]), e from the row's absmax,
  * row_scale[m] = 2^e[m] (an all-zero row reports the smallest scale, 2^-108, so that `max over rows` and

@@ -21,7 +21,7 @@ PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
 MINMAX, LOG = 0, 1
 OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW, OPERAND_CODE_E4M3 = 0, 1, 2, 3
 QTYPE = {"minmax": MINMAX, "log": LOG}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); must list every SPQ_API symbol of include/spq_b200.h
 SIGNATURES = {
@@ -64,6 +64,11 @@ SIGNATURES = {
                                         c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "spq_layernorm_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    "spq_ln_quantize_act": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "spq_ln_rowscale_stats_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "spq_ln_rowscale_stats": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_float,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
@@ -325,6 +330,40 @@ def layernorm_fwd(x2d, weight, bias, eps, y, mean, rstd):
     rows, cols = x2d.shape
     _check(load_library().spq_layernorm_fwd(x2d.data_ptr(), rows, cols, weight.data_ptr(), bias.data_ptr(), float(eps),
                                             y.data_ptr(), _ptr(mean), _ptr(rstd), _stream()), "spq_layernorm_fwd")
+
+
+def ln_quantize_act(x2d, ln_w, ln_b, ln_eps, scale, zp, bcast, qtype, bits, symmetric, operand_kind, col_mul, mul, a_q, a_raw,
+                    raw_col_mul, y_out=None):
+    """quantize_act(layernorm(x2d)) without the float32 round trip of the normalised rows."""
+    _req_cuda(x2d, ln_w, ln_b, scale, zp, col_mul, a_q, a_raw, raw_col_mul, y_out)
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    M, K = x2d.shape
+    assert ln_w.numel() == K and ln_b.numel() == K and ln_w.dtype == torch.float32 and ln_b.dtype == torch.float32
+    assert a_q.shape == (M, K) and a_q.is_contiguous() and (a_raw is None or (a_raw.shape == (M, K) and a_raw.is_contiguous()))
+    _check(load_library().spq_ln_quantize_act(x2d.data_ptr(), M, K, ln_w.data_ptr(), ln_b.data_ptr(), float(ln_eps), scale.data_ptr(),
+                                              zp.data_ptr(), bcast, qtype, bits, int(symmetric), operand_kind, _ptr(col_mul),
+                                              float(mul), a_q.data_ptr(), _ptr(a_raw), _ptr(raw_col_mul), _ptr(y_out), _stream()),
+           "spq_ln_quantize_act")
+
+
+def ln_rowscale_stats(x2d, ln_w, ln_b, ln_eps, out, row_scale, stats_mode=0, stat_eps=0.0, stat_min=None, stat_max=None,
+                      accumulate=False, state=None, y_out=None):
+    """rowscale_f16(layernorm(x2d)) and, with stats_mode 1 (min-max) / 2 (log), minmax_stats(layernorm(x2d), PER_COL) too."""
+    lib = load_library()
+    _req_cuda(x2d, ln_w, ln_b, out, row_scale, stat_min, stat_max, state, y_out)
+    assert x2d.dim() == 2 and x2d.is_contiguous() and x2d.dtype == torch.float32
+    M, K = x2d.shape
+    assert out.dtype == torch.float16 and out.shape == (M, K) and out.stride(0) == K and row_scale.numel() == M
+    ws = None
+    nbytes = 0
+    if stats_mode:
+        assert stat_min.numel() == K and stat_max.numel() == K and stat_min.is_contiguous() and stat_max.is_contiguous()
+        nbytes = lib.spq_ln_rowscale_stats_workspace_bytes(M, K)
+        ws = _workspace(nbytes, x2d.device, "ln_stats")
+    _check(lib.spq_ln_rowscale_stats(x2d.data_ptr(), M, K, ln_w.data_ptr(), ln_b.data_ptr(), float(ln_eps), out.data_ptr(),
+                                     row_scale.data_ptr(), int(stats_mode), float(stat_eps), _ptr(stat_min), _ptr(stat_max),
+                                     int(accumulate), _ptr(state), _ptr(y_out), _ptr(ws), ws.numel() if ws is not None else 0,
+                                     _stream()), "spq_ln_rowscale_stats")
 
 
 def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias, accumulate_params=False):

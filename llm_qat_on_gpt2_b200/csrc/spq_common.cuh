@@ -45,6 +45,12 @@ int sm_count();
         spq::count_launch();                                                           \
     } while (0)
 
+namespace stats {
+// spq_stats.cu: fold per-CTA column partials [chunks, C] into the running statistics (log2 applied after the fold)
+int finalize_partials(const float* pmin, const float* pmax, long long C, int chunks, int log_mode, float eps, int accumulate,
+                      const int32_t* flags, float* stat_min, float* stat_max, int32_t* state, cudaStream_t st);
+}
+
 inline cudaStream_t as_stream(spq_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

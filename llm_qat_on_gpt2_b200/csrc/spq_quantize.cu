@@ -559,6 +559,326 @@ static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
     return SPQ_OK;
 }
 
+// ---------------------------------------------------------------- LayerNorm-fused activation side
+// SwitchableLayerNorm feeds exactly one consumer on this path -- ln_1 -> c_attn, ln_2 -> c_fc, ln_f -> LM head
+// (p1/models_sp.py:139-147, 316-319) -- so its float32 output only exists to be read back by the consumer's
+// activation-side kernel.  The two kernels below normalise a row in registers (the arithmetic of
+// spq_layernorm.cu: mean, biased variance, w * ((x - mean) * rstd) + b) and hand the normalised values straight to
+//   (a) the calibrated quantiser: a_q / a_raw as spq_quantize_act would have written them   (quantised forward), or
+//   (b) the row-scaled fp16 operand of spq_rowscale_f16 plus the per-column statistics of spq_minmax_stats
+//       (calibration pass, 32-bit path),
+// 4 B read + 2..4 B written per element instead of 4 + 4 (LayerNorm) + 4 + 2..4 (consumer) [+ 4 (statistics)].
+// One CTA of G threads owns RPI rows at a time; a thread owns the same 4 * NV columns of every row, so the
+// per-column constants stay in registers.  The codes are those of spq_quantize_act on the SAME normalised values
+// (identical element arithmetic, including the exact tie path).
+struct LnArgs {
+    const float* x;
+    long long M, K;
+    const float* ln_w;
+    const float* ln_b;
+    float ln_eps;
+    float* y;                   // optional float32 copy of the normalised rows (null: not written)
+    // (a) quantiser
+    const float* scale;
+    const float* zp;
+    int bcast;
+    QParams qp;
+    int operand_kind;
+    const float* col_mul;
+    float mul;
+    unsigned short* a_q;
+    unsigned short* a_raw;
+    const float* raw_col_mul;
+    // (b) row-scaled operand + statistics
+    unsigned short* x16;
+    float* row_scale;
+    int stats_mode;             // 0 none, 1 min / max of y, 2 min / max of |y| + any(|y| > eps)   (log quantisers)
+    float stat_eps;
+    float* pmin;                // [gridDim.x, K] per-CTA partials
+    float* pmax;
+    int32_t* flags;
+};
+
+// Layout: ONE WARP PER ROW (8 rows per CTA in flight, no block barrier in the row loop): lane l owns the float4 column
+// groups (32 i + l), i < NV, so every load / store instruction of a warp covers 512 contiguous bytes and a thread has NV
+// independent 16-byte loads in flight.  (A first version with one CTA of K / 4 threads per row pair and block-wide
+// reductions ran at 1.5-2.1 TB/s -- slower than the kernels it replaced; profiles/r02b_ln_fused_*.)  Per-column
+// constants (LayerNorm weight / bias, quantiser constants, operand multipliers) sit in shared memory, filled once per
+// persistent CTA: a lane owns 4 NV columns, too many to keep their ~9 constants each in registers.
+constexpr int LN_WARPS = 8;
+
+template <int NV>
+__device__ __forceinline__ void ln_warp_normalise(const LnArgs& a, long long row, int lane, const float* s_w, const float* s_b,
+                                                  float4 (&v)[NV]) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        v[i] = (c < a.K) ? ld_stream_f4(a.x + row * a.K + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float inv_c = 1.0f / static_cast<float>(a.K);
+    const float mean = warp_sum(sum) * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < a.K) {
+            const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * inv_c + a.ln_eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 w4 = *reinterpret_cast<const float4*>(s_w + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_b + c);
+        float4 o;
+        o.x = w4.x * ((v[i].x - mean) * rstd) + b4.x;
+        o.y = w4.y * ((v[i].y - mean) * rstd) + b4.y;
+        o.z = w4.z * ((v[i].z - mean) * rstd) + b4.z;
+        o.w = w4.w * ((v[i].w - mean) * rstd) + b4.w;
+        v[i] = o;
+        if (a.y && c < a.K) *reinterpret_cast<float4*>(a.y + row * a.K + c) = o;
+    }
+}
+
+// (a) LayerNorm -> calibrated quantiser.  Shared table: 9 arrays of Kp = 128 NV floats:
+//   w, b, cm, rm, then min-max: s, inv_s, zp (2 unused) / log: inv, c0, band, log_range, log_min
+template <int QTYPE, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_quantize_act_kernel(LnArgs a) {
+    extern __shared__ __align__(16) float s_tab[];
+    constexpr int Kp = NV * 128;
+    float* s_w = s_tab;
+    float* s_b = s_tab + Kp;
+    float* s_cm = s_tab + 2 * Kp;
+    float* s_rm = s_tab + 3 * Kp;
+    float* s_q = s_tab + 4 * Kp;                 // 5 quantiser arrays
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    QParams qp = a.qp;
+    const int kind = a.operand_kind;
+    for (int c = tid; c < Kp; c += LN_WARPS * 32) {
+        const bool in = c < a.K;
+        const int cc = in ? c : 0;
+        s_w[c] = in ? __ldg(a.ln_w + cc) : 0.f;
+        s_b[c] = in ? __ldg(a.ln_b + cc) : 0.f;
+        s_cm[c] = (a.col_mul ? __ldg(a.col_mul + cc) : 1.f) * a.mul;
+        s_rm[c] = a.raw_col_mul ? __ldg(a.raw_col_mul + cc) : 1.f;
+        const float sc = bparam(a.scale, a.bcast, 0, cc);
+        const float zp = bparam(a.zp, a.bcast, 0, cc);
+        if constexpr (QTYPE == SPQ_MINMAX) {
+            const MmCol m = make_mmcol(sc, zp);
+            s_q[c] = m.s; s_q[Kp + c] = m.inv_s; s_q[2 * Kp + c] = m.zp;
+        } else {
+            const LogCol l = make_logcol(zp, sc, qp);
+            s_q[c] = l.inv; s_q[Kp + c] = l.c0; s_q[2 * Kp + c] = l.band; s_q[3 * Kp + c] = l.log_range; s_q[4 * Kp + c] = l.log_min;
+        }
+    }
+    __syncthreads();
+    const float nl_ = qp.symmetric ? qp.n_sym : qp.full;
+    const float inv_lev = __frcp_rn(qp.symmetric ? 2.f * nl_ : nl_);
+    const bool no_exact = (qp.debug & 1) != 0;
+    for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < a.M; row += static_cast<long long>(gridDim.x) * LN_WARPS) {
+        float4 v[NV];
+        ln_warp_normalise<NV>(a, row, lane, s_w, s_b, v);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c0 = (i * 32 + lane) * 4;
+            if (c0 >= a.K) continue;
+            const float xv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            MmCol mm[4];
+            LogCol lg[4];
+            {
+                const float4 q0 = *reinterpret_cast<const float4*>(s_q + c0);
+                const float4 q1 = *reinterpret_cast<const float4*>(s_q + Kp + c0);
+                const float4 q2 = *reinterpret_cast<const float4*>(s_q + 2 * Kp + c0);
+                const float f0[4] = {q0.x, q0.y, q0.z, q0.w}, f1[4] = {q1.x, q1.y, q1.z, q1.w}, f2[4] = {q2.x, q2.y, q2.z, q2.w};
+                if constexpr (QTYPE == SPQ_MINMAX) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { mm[j].s = f0[j]; mm[j].inv_s = f1[j]; mm[j].zp = f2[j]; }
+                } else {
+                    const float4 q3 = *reinterpret_cast<const float4*>(s_q + 3 * Kp + c0);
+                    const float4 q4 = *reinterpret_cast<const float4*>(s_q + 4 * Kp + c0);
+                    const float f3[4] = {q3.x, q3.y, q3.z, q3.w}, f4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        lg[j].inv = f0[j]; lg[j].c0 = f1[j]; lg[j].band = f2[j]; lg[j].log_range = f3[j]; lg[j].log_min = f4[j];
+                        lg[j].range_c = (f3[j] < LOG_EPS) ? LOG_EPS : f3[j];
+                        lg[j].out_add = 0.f; lg[j].e0 = f4[j];             // make_logcol: e0 = log_min + 0
+                    }
+                }
+            }
+            float q[4];
+            bool tie[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_fast(xv[j], mm[j], qp, tie[j]);
+                else q[j] = log_level_fast(xv[j], lg[j], qp, tie[j]);
+            }
+            if ((tie[0] | tie[1] | tie[2] | tie[3]) && !no_exact) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (tie[j]) {
+                        if constexpr (QTYPE == SPQ_MINMAX) q[j] = minmax_code_exact(xv[j], mm[j].s, mm[j].zp, qp.symmetric);
+                        else q[j] = log_level_exact(fmaxf(fabsf(xv[j]), LOG_EPS), lg[j].log_min, lg[j].range_c, qp.symmetric,
+                                                    qp.n_sym, qp.full);
+                    }
+                }
+            }
+            const float4 cm4 = *reinterpret_cast<const float4*>(s_cm + c0);
+            const float cmv[4] = {cm4.x, cm4.y, cm4.z, cm4.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float base;
+                if constexpr (QTYPE == SPQ_MINMAX) {
+                    const float cen = minmax_centered(q[j], mm[j], qp);
+                    base = (kind == SPQ_OPERAND_CODE || kind == SPQ_OPERAND_CODE_E4M3) ? cen : __fmul_rn(cen, mm[j].s);
+                } else {
+                    base = (kind == SPQ_OPERAND_CODE) ? q[j] : log_value(xv[j], q[j], lg[j], qp, inv_lev);
+                }
+                o[j] = base * cmv[j];
+            }
+            const long long off = row * a.K + c0;
+            if (kind == SPQ_OPERAND_CODE_E4M3)
+                *reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(a.a_q) + off) = pack_e4m3x4(o[0], o[1], o[2], o[3]);
+            else
+                *reinterpret_cast<uint2*>(a.a_q + off) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
+            if (a.a_raw) {
+                const float4 rm4 = *reinterpret_cast<const float4*>(s_rm + c0);
+                *reinterpret_cast<uint2*>(a.a_raw + off) =
+                    make_uint2(pack_h2(xv[0] * rm4.x, xv[1] * rm4.y), pack_h2(xv[2] * rm4.z, xv[3] * rm4.w));
+            }
+        }
+    }
+}
+
+// (b) LayerNorm -> row-scaled fp16 operand (+ per-column statistics partials).  Shared: w, b [Kp]; at the end the
+// eight warps fold their column statistics through 2 x [LN_WARPS][Kp] floats of the same buffer.
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_rowscale_stats_kernel(LnArgs a) {
+    extern __shared__ __align__(16) float s_tab[];
+    constexpr int Kp = NV * 128;
+    float* s_w = s_tab;
+    float* s_b = s_tab + Kp;
+    float* s_mn = s_tab + 2 * Kp;                // [LN_WARPS][Kp], statistics only
+    float* s_mx = s_mn + LN_WARPS * Kp;
+    __shared__ int s_any;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < Kp; c += LN_WARPS * 32) {
+        s_w[c] = (c < a.K) ? __ldg(a.ln_w + c) : 0.f;
+        s_b[c] = (c < a.K) ? __ldg(a.ln_b + c) : 0.f;
+    }
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    float mn[NV][4], mx[NV][4];
+    unsigned long long nan_cols = 0ull;   // bit (4 i + j): this lane's column saw a NaN (fminf / fmaxf drop it, torch keeps it)
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mn[i][j] = INFINITY; mx[i][j] = -INFINITY; }
+    }
+    const bool log_stats = a.stats_mode == 2;
+    for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < a.M; row += static_cast<long long>(gridDim.x) * LN_WARPS) {
+        float4 v[NV];
+        ln_warp_normalise<NV>(a, row, lane, s_w, s_b, v);
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c0 = (i * 32 + lane) * 4;
+            if (c0 >= a.K) continue;
+            const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(e[0]), fabsf(e[1])), fmaxf(fabsf(e[2]), fabsf(e[3]))));
+            if (a.stats_mode) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float s = log_stats ? fabsf(e[j]) : e[j];
+                    nan_cols |= (s != s) ? (1ull << (4 * i + j)) : 0ull;
+                    if (log_stats) any |= (s > a.stat_eps);
+                    mn[i][j] = fminf(mn[i][j], s);
+                    mx[i][j] = fmaxf(mx[i][j], s);
+                }
+            }
+        }
+        amax = warp_fmax(amax);
+        // the scale rule of rowscale_kernel: amax in [2^(E-1), 2^E) -> x * 2^(8-E); zero rows: smallest scale; inf / NaN: 1
+        int E = 0;
+        if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;
+        E = E < -100 ? -100 : E;
+        const float down = exp2f(static_cast<float>(8 - E));
+        if (lane == 0 && a.row_scale) a.row_scale[row] = exp2f(static_cast<float>(E - 8));
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c0 = (i * 32 + lane) * 4;
+            if (c0 < a.K)
+                *reinterpret_cast<uint2*>(a.x16 + row * a.K + c0) =
+                    make_uint2(pack_h2(v[i].x * down, v[i].y * down), pack_h2(v[i].z * down, v[i].w * down));
+        }
+    }
+    if (a.stats_mode) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c0 = (i * 32 + lane) * 4;
+            float lo[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool bad = (nan_cols >> (4 * i + j)) & 1ull;
+                lo[j] = bad ? NAN : mn[i][j];
+                hi[j] = bad ? NAN : mx[i][j];
+            }
+            *reinterpret_cast<float4*>(s_mn + warp * Kp + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(s_mx + warp * Kp + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        }
+        if (log_stats && any) s_any = 1;
+        __syncthreads();
+        for (int c = tid; c < a.K; c += LN_WARPS * 32) {
+            float lo = s_mn[c], hi = s_mx[c];
+#pragma unroll
+            for (int w = 1; w < LN_WARPS; ++w) { lo = nan_min(lo, s_mn[w * Kp + c]); hi = nan_max(hi, s_mx[w * Kp + c]); }
+            a.pmin[static_cast<long long>(blockIdx.x) * a.K + c] = lo;
+            a.pmax[static_cast<long long>(blockIdx.x) * a.K + c] = hi;
+        }
+        if (log_stats && tid == 0 && s_any) atomicOr(a.flags, 1);
+    }
+}
+
+// float4 column groups per lane: the smallest instantiated NV with 128 NV >= K
+static int ln_fused_nv(long long K) {
+    if ((K % 4) != 0 || K < 4) return 0;
+    const int opts[] = {2, 4, 6, 8, 13, 16};
+    for (int nv : opts)
+        if (128ll * nv >= K) return nv;
+    return 0;
+}
+static size_t ln_quant_smem(int NV) { return static_cast<size_t>(9) * NV * 128 * sizeof(float); }
+static size_t ln_stats_smem(int NV, bool stats) { return static_cast<size_t>(2 + (stats ? 2 * LN_WARPS : 0)) * NV * 128 * sizeof(float); }
+constexpr int LN_MAX_CTAS_PER_SM = 8;
+// persistent grid: as many CTAs as are co-resident (registers and the shared table decide), never more than the rows need
+template <typename Kern>
+static int ln_launch(Kern kern, size_t smem, LnArgs& a, cudaStream_t st, unsigned* grid_out) {
+    if (smem > 48 * 1024) SPQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    SPQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LN_WARPS * 32, smem));
+    static int cap_env = -1;                    // SPQ_LN_CTAS_PER_SM: tuning switch
+    if (cap_env < 0) { const char* e = getenv("SPQ_LN_CTAS_PER_SM"); cap_env = e ? atoi(e) : 0; }
+    if (cap_env > 0 && per_sm > cap_env) per_sm = cap_env;
+    if (per_sm > LN_MAX_CTAS_PER_SM) per_sm = LN_MAX_CTAS_PER_SM;
+    if (per_sm < 1) per_sm = 1;
+    long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * per_sm;
+    const long long need = (a.M + LN_WARPS - 1) / LN_WARPS;
+    if (ctas > need) ctas = need;
+    const unsigned grid = static_cast<unsigned>(ctas < 1 ? 1 : ctas);
+    if (a.pmin) a.pmax = a.pmin + static_cast<size_t>(grid) * a.K;       // partials are [grid, K]
+    kern<<<grid, LN_WARPS * 32, smem, st>>>(a);
+    SPQ_LAUNCH_OK();
+    if (grid_out) *grid_out = grid;
+    return SPQ_OK;
+}
+
 template <int QTYPE>
 static int launch_act(const ActArgs& a, cudaStream_t st) {
     const unsigned gx = static_cast<unsigned>((a.K / 4 + 31) / 32);
@@ -738,5 +1058,91 @@ extern "C" int spq_ste_backward(const float* grad, int64_t n, int qtype, float* 
     if (blocks < 1) blocks = 1;
     ste_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(grad, n, qtype == SPQ_LOG ? 1 : 0, out);
     SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
+extern "C" int spq_ln_quantize_act(const float* x, int64_t M, int64_t K, const float* ln_weight, const float* ln_bias, float ln_eps,
+                                   const float* scale, const float* zero_point, int bcast, int qtype, int bits, int symmetric,
+                                   int operand_kind, const float* col_mul, float mul, spq_half_t* a_q, spq_half_t* a_raw,
+                                   const float* raw_col_mul, float* y_out, spq_stream_t stream) {
+    SPQ_REQUIRE(x && ln_weight && ln_bias && M > 0 && K > 0, "spq_ln_quantize_act: bad input");
+    SPQ_REQUIRE(aligned16(x) && (!y_out || aligned16(y_out)), "spq_ln_quantize_act: x and y must be 16-byte aligned");
+    SPQ_REQUIRE(qtype == SPQ_MINMAX || qtype == SPQ_LOG, "spq_ln_quantize_act: unknown quantizer type %d", qtype);
+    SPQ_REQUIRE(scale && zero_point && a_q, "spq_ln_quantize_act: missing parameters or output");
+    SPQ_REQUIRE(bcast == SPQ_PER_COL || bcast == SPQ_PER_TENSOR, "spq_ln_quantize_act: per-row scales are not an activation layout");
+    SPQ_REQUIRE(bits >= 1 && bits < 32, "spq_ln_quantize_act: bits %d", bits);
+    SPQ_REQUIRE((reinterpret_cast<uintptr_t>(a_q) & 7u) == 0 && (!a_raw || (reinterpret_cast<uintptr_t>(a_raw) & 7u) == 0),
+                "spq_ln_quantize_act: operands must be 8-byte aligned");
+    const int NV = ln_fused_nv(K);
+    if (!NV) {
+        set_error("spq_ln_quantize_act: normalized dim %lld unsupported (multiple of 4, <= 2048)", (long long)K);
+        return SPQ_ERR_UNSUPPORTED;
+    }
+    LnArgs a = {};
+    a.x = x; a.M = M; a.K = K; a.ln_w = ln_weight; a.ln_b = ln_bias; a.ln_eps = ln_eps; a.y = y_out;
+    a.scale = scale; a.zp = zero_point; a.bcast = bcast; a.qp = make_qparams(bits, symmetric);
+    a.operand_kind = operand_kind; a.col_mul = col_mul; a.mul = mul; a.a_q = a_q; a.a_raw = a_raw; a.raw_col_mul = raw_col_mul;
+    const size_t smem = ln_quant_smem(NV);
+    cudaStream_t st = as_stream(stream);
+#define SPQ_LNQ(QT, N) return ln_launch(ln_quantize_act_kernel<QT, N>, smem, a, st, nullptr)
+    if (qtype == SPQ_MINMAX) {
+        switch (NV) { case 2: SPQ_LNQ(SPQ_MINMAX, 2); case 4: SPQ_LNQ(SPQ_MINMAX, 4); case 6: SPQ_LNQ(SPQ_MINMAX, 6);
+                      case 8: SPQ_LNQ(SPQ_MINMAX, 8); case 13: SPQ_LNQ(SPQ_MINMAX, 13); default: SPQ_LNQ(SPQ_MINMAX, 16); }
+    }
+    switch (NV) { case 2: SPQ_LNQ(SPQ_LOG, 2); case 4: SPQ_LNQ(SPQ_LOG, 4); case 6: SPQ_LNQ(SPQ_LOG, 6);
+                  case 8: SPQ_LNQ(SPQ_LOG, 8); case 13: SPQ_LNQ(SPQ_LOG, 13); default: SPQ_LNQ(SPQ_LOG, 16); }
+#undef SPQ_LNQ
+}
+
+extern "C" size_t spq_ln_rowscale_stats_workspace_bytes(int64_t M, int64_t K) {
+    const int NV = ln_fused_nv(K);
+    if (M <= 0 || K <= 0 || !NV) return 256;
+    // [grid, K] minima and maxima; the grid is decided at launch (occupancy), bounded by LN_MAX_CTAS_PER_SM CTAs per SM
+    long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * LN_MAX_CTAS_PER_SM;
+    const long long need = (M + LN_WARPS - 1) / LN_WARPS;
+    if (ctas > need) ctas = need;
+    return 256 + 2 * static_cast<size_t>(ctas) * static_cast<size_t>(K) * sizeof(float);
+}
+
+extern "C" int spq_ln_rowscale_stats(const float* x, int64_t M, int64_t K, const float* ln_weight, const float* ln_bias, float ln_eps,
+                                     spq_half_t* out, float* row_scale, int stats_mode, float stat_eps, float* stat_min,
+                                     float* stat_max, int accumulate, int32_t* state, float* y_out, void* workspace,
+                                     size_t workspace_bytes, spq_stream_t stream) {
+    SPQ_REQUIRE(x && ln_weight && ln_bias && out && row_scale && M > 0 && K > 0, "spq_ln_rowscale_stats: bad input");
+    SPQ_REQUIRE(aligned16(x) && (!y_out || aligned16(y_out)) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+                "spq_ln_rowscale_stats: alignment");
+    SPQ_REQUIRE(stats_mode >= 0 && stats_mode <= 2, "spq_ln_rowscale_stats: stats_mode %d", stats_mode);
+    SPQ_REQUIRE(!stats_mode || (stat_min && stat_max && workspace && aligned16(workspace) &&
+                                workspace_bytes >= spq_ln_rowscale_stats_workspace_bytes(M, K)),
+                "spq_ln_rowscale_stats: statistics need stat_min / stat_max and a workspace");
+    const int NV = ln_fused_nv(K);
+    if (!NV) {
+        set_error("spq_ln_rowscale_stats: normalized dim %lld unsupported (multiple of 4, <= 2048)", (long long)K);
+        return SPQ_ERR_UNSUPPORTED;
+    }
+    LnArgs a = {};
+    a.x = x; a.M = M; a.K = K; a.ln_w = ln_weight; a.ln_b = ln_bias; a.ln_eps = ln_eps; a.y = y_out;
+    a.x16 = out; a.row_scale = row_scale; a.stats_mode = stats_mode; a.stat_eps = stat_eps;
+    const size_t smem = ln_stats_smem(NV, stats_mode != 0);
+    cudaStream_t st = as_stream(stream);
+    if (stats_mode) {
+        a.flags = reinterpret_cast<int32_t*>(workspace);
+        a.pmin = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);      // pmax follows (set at launch)
+        SPQ_CUDA_OK(cudaMemsetAsync(a.flags, 0, 16, st));
+    }
+    unsigned grid = 0;
+    int rc;
+    switch (NV) {
+        case 2: rc = ln_launch(ln_rowscale_stats_kernel<2>, smem, a, st, &grid); break;
+        case 4: rc = ln_launch(ln_rowscale_stats_kernel<4>, smem, a, st, &grid); break;
+        case 6: rc = ln_launch(ln_rowscale_stats_kernel<6>, smem, a, st, &grid); break;
+        case 8: rc = ln_launch(ln_rowscale_stats_kernel<8>, smem, a, st, &grid); break;
+        case 13: rc = ln_launch(ln_rowscale_stats_kernel<13>, smem, a, st, &grid); break;
+        default: rc = ln_launch(ln_rowscale_stats_kernel<16>, smem, a, st, &grid); break;
+    }
+    if (rc != SPQ_OK) return rc;
+    if (stats_mode)
+        return spq::stats::finalize_partials(a.pmin, a.pmax, K, static_cast<int>(grid), stats_mode == 2, stat_eps, accumulate, a.flags,
+                                             stat_min, stat_max, state, st);
     return SPQ_OK;
 }

@@ -354,6 +354,21 @@ extern "C" size_t spq_stats_workspace_bytes(int64_t rows, int64_t cols, int bcas
     return 256 + 2 * n * sizeof(float);
 }
 
+// Fold [chunks, C] partials produced by another kernel of the library (the LayerNorm-fused statistics pass of
+// spq_quantize.cu) into the running statistics: the second half of spq_minmax_stats, per-column layout.
+int spq::stats::finalize_partials(const float* pmin, const float* pmax, long long C, int chunks, int log_mode, float eps,
+                                  int accumulate, const int32_t* flags, float* stat_min, float* stat_max, int32_t* state,
+                                  cudaStream_t st) {
+    const unsigned fgrid = static_cast<unsigned>((C + 31) / 32);
+    const unsigned fthreads = chunks > 64 ? 1024u : 256u;
+    if (log_mode)
+        stats_finalize_kernel<true><<<fgrid, fthreads, 0, st>>>(pmin, pmax, C, chunks, 0, eps, accumulate, flags, stat_min, stat_max, state);
+    else
+        stats_finalize_kernel<false><<<fgrid, fthreads, 0, st>>>(pmin, pmax, C, chunks, 0, eps, accumulate, flags, stat_min, stat_max, state);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+
 template <int VEC, typename XT>
 static void launch_colstats(dim3 grid, dim3 block, cudaStream_t st, int log_mode, const void* x, long long rows, long long cols,
                             float eps, long long rpc, float* pmin, float* pmax, int32_t* flags) {

@@ -21,6 +21,7 @@ fp32 reference to rel ~3e-4 (tolerance 1e-3, BASELINE.json).
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -99,6 +100,42 @@ def _rowscaled_f16(x2d: torch.Tensor):
     x16 = _lib.empty_f16_padded(M, K, x2d.device)
     rs = torch.empty(M, dtype=torch.float32, device=x2d.device)
     _lib.rowscale_f16(x2d, x16, rs)
+    return x16, rs
+
+
+# LayerNorm fused into the consumer's activation-side kernel (SPQ_FUSE_LN=0: A/B switch, read at import)
+_FUSE_LN = os.environ.get("SPQ_FUSE_LN", "1") != "0"
+
+
+def _ln_params(ln):
+    """(weight, bias, eps) of the active precision of a SwitchableLayerNorm, as flat float32 vectors."""
+    key = str(ln.current_precision)
+    return (ln.weights[key].detach().reshape(-1).float().contiguous(), ln.biases[key].detach().reshape(-1).float().contiguous(),
+            float(ln.eps))
+
+
+def _ln_fusable(x: torch.Tensor, ln, K: int) -> bool:
+    """The fused kernels take a float32, contiguous [..., K] input under no_grad, K a multiple of 4.  One warp holds a
+    row in registers: beyond 1024 columns (8 float4 per lane) occupancy drops to one CTA per SM and the separate
+    kernels are faster -- GPT-2 XL (1600) keeps the unfused path."""
+    return (_FUSE_LN and ln is not None and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+            and x.is_contiguous() and x.shape[-1] == K and K % 4 == 0 and K <= 1024 and x.numel() > 0
+            and ln.__class__.__name__ == 'SwitchableLayerNorm' and getattr(ln, '_ncols', None) == K
+            and x.data_ptr() % 16 == 0)
+
+
+def _ln_rowscaled_f16(x2d: torch.Tensor, ln, stats=None):
+    """(x16, row_scale) of layernorm(x2d), one pass; `stats` = (mode, eps, temp_min, temp_max, accumulate, state)."""
+    M, K = x2d.shape
+    w, b, eps = _ln_params(ln)
+    x16 = torch.empty((M, K), dtype=torch.float16, device=x2d.device)
+    rs = torch.empty(M, dtype=torch.float32, device=x2d.device)
+    if stats is None:
+        _lib.ln_rowscale_stats(x2d, w, b, eps, x16, rs)
+    else:
+        mode, seps, tmin, tmax, acc, state = stats
+        _lib.ln_rowscale_stats(x2d, w, b, eps, x16, rs, stats_mode=mode, stat_eps=seps, stat_min=tmin, stat_max=tmax,
+                               accumulate=acc, state=state)
     return x16, rs
 
 
@@ -331,7 +368,8 @@ class _SPLinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0, residual=None,
-                grad_mode=True):
+                grad_mode=True, ln=None):
+        # ln: a SwitchableLayerNorm to apply to x first, inside the activation-side kernel (no_grad only)
         # grad_mode: torch.is_grad_enabled() of the caller (always False inside Function.forward)
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
@@ -343,9 +381,15 @@ class _SPLinearFn(torch.autograd.Function):
         f8 = base.get('f8') if (residual is None and not need_wgrad) else None
         a_q = torch.empty((M, K), dtype=torch.uint8 if f8 is not None else torch.float16, device=x.device)
         a_raw = torch.empty((M, K), dtype=torch.float16, device=x.device) if use_lora else None
-        _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
-                          _lib.OPERAND_CODE_E4M3 if f8 is not None else act['kind'], act['col_mul'], act['mul'], a_q, a_raw,
-                          act['raw_mul'] if use_lora else None)
+        if ln is not None:
+            lw, lb, leps = _ln_params(ln)
+            _lib.ln_quantize_act(x2d, lw, lb, leps, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'],
+                                 act['symmetric'], _lib.OPERAND_CODE_E4M3 if f8 is not None else act['kind'], act['col_mul'],
+                                 act['mul'], a_q, a_raw, act['raw_mul'] if use_lora else None)
+        else:
+            _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
+                              _lib.OPERAND_CODE_E4M3 if f8 is not None else act['kind'], act['col_mul'], act['mul'], a_q, a_raw,
+                              act['raw_mul'] if use_lora else None)
         y = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=x.device)
         bias_f = None if bias is None else bias.detach().float().contiguous()
         res2d = None if residual is None else residual.reshape(M, N)
@@ -452,7 +496,7 @@ class _SPLinearFn(torch.autograd.Function):
                          clamp_abs=10.0 if ctx.weight_qtype == 'log' else 0.0)
         if ctx.has_bias and need_b:
             gb = g2d.float().sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None, None, None, (gy if ctx.needs_input_grad[9] else None), None
+        return gx, gw, gb, gA, gB, None, None, None, None, (gy if ctx.needs_input_grad[9] else None), None, None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -694,25 +738,31 @@ class SPLinearWithLoRA(nn.Module):
         return ent[1], ent[2]
 
     # ---------------------------------------------------------------- forward (reference :127-150)
-    def forward(self, x, out_half=False, fuse_gelu=False, residual=None):
+    def forward(self, x, out_half=False, fuse_gelu=False, residual=None, pre_norm=None):
         """Reference signature is forward(x) -> float32.  Two internal extensions used by the model
         wrapper: `out_half=True` (SPAttention with fp16 attention) stores fp16 from the GEMM epilogue
         instead of float32 followed by a cast; `fuse_gelu=True` (SPMLP under no_grad) applies the exact
         erf GELU in the epilogue instead of a separate elementwise pass; `residual` (SPBlock's residual
         stream) returns residual + forward(x), the add done in the GEMM epilogue (with autograd on, the residual's
         gradient is the output gradient)."""
+        # `pre_norm` (SPBlock: the SwitchableLayerNorm in front of c_attn / c_fc): forward(pre_norm(x)), with the
+        # normalisation done inside this layer's activation-side kernel whenever the fused kernels apply (no_grad,
+        # float32 contiguous input); otherwise it is simply applied first
+        if pre_norm is not None and not _ln_fusable(x, pre_norm, self.in_features):
+            x, pre_norm = pre_norm(x), None
         if residual is not None:
             fuse_res = (not out_half and not fuse_gelu and residual.is_cuda
                         and residual.dtype == torch.float32 and residual.is_contiguous()
                         and residual.shape == x.shape[:-1] + (self.linear.out_features,))
             if not fuse_res:
-                return residual + self.forward(x, out_half=out_half, fuse_gelu=fuse_gelu)
+                return residual + self.forward(x, out_half=out_half, fuse_gelu=fuse_gelu, pre_norm=pre_norm)
         act = 1 if (fuse_gelu and not torch.is_grad_enabled()) else 0
         post_gelu = fuse_gelu and not act
         if self.current_bits >= 32:
             half_here = out_half and not post_gelu
+            pre = _ln_rowscaled_f16(x.reshape(-1, self.in_features), pre_norm) if pre_norm is not None else None
             y = linear_fp(x, self.linear.weight, self.linear.bias, self._fp_cache, activation=act, out_half=half_here,
-                          residual=residual)
+                          residual=residual, pre=pre)
             if post_gelu:
                 y = torch.nn.functional.gelu(y)
             return y.half() if (out_half and not half_here) else y
@@ -729,12 +779,26 @@ class SPLinearWithLoRA(nn.Module):
             y = _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
                                   active_lora.lora_A if lora_on else None,
                                   active_lora.lora_B if lora_on else None, self, self.current_bits, out_half, act,
-                                  residual, torch.is_grad_enabled())
+                                  residual, torch.is_grad_enabled(), pre_norm)
             return torch.nn.functional.gelu(y) if post_gelu else y
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
         # reference, module by module (this is the calibration pass; errors surface as upstream).
-        x_quantized = input_quantizer(x)                       # collecting: records stats, returns x
+        pre = None
+        if pre_norm is not None:
+            # calibration pass behind a LayerNorm: ONE kernel normalises the rows, folds the input quantiser's per-column
+            # statistics and writes the fp16 operand of the GEMM below (the float32 normalised rows are never stored)
+            # (with LoRA enabled the adapter needs the normalised rows themselves: not fused)
+            tg = (input_quantizer._stats_targets_lastdim(tuple(x.shape), x.device)
+                  if (self.calibration_mode and input_quantizer.collecting_stats and input_quantizer.num_bits < 32
+                      and input_quantizer.quantizer_type in ('minmax', 'log')) else None)
+            if tg is None:
+                x, pre_norm = pre_norm(x), None
+            else:
+                mode = 2 if input_quantizer.quantizer_type == 'log' else 1
+                pre = _ln_rowscaled_f16(x.reshape(-1, self.in_features), pre_norm,
+                                        stats=(mode, input_quantizer.eps, tg[0], tg[1], tg[2], tg[3]))
+        x_quantized = input_quantizer(x) if pre is None else x   # collecting: records stats, returns x
         if torch.is_grad_enabled() and self.linear.weight.requires_grad and not weight_quantizer.collecting_stats:
             weight_quantized, cache = weight_quantizer(self.linear.weight), None
         else:
@@ -744,7 +808,7 @@ class SPLinearWithLoRA(nn.Module):
                      and not torch.is_grad_enabled())
         res_here = residual if self.calibration_mode else None      # otherwise after the LoRA add, as upstream
         base_output = linear_fp(x_quantized, weight_quantized, self.linear.bias, cache, activation=1 if fuse_here else 0,
-                                out_half=half_here, residual=res_here)
+                                out_half=half_here, residual=res_here, pre=pre)
         if not self.calibration_mode:
             base_output = base_output + active_lora(x)
             if residual is not None:

@@ -54,12 +54,13 @@ class SPAttention(nn.Module):
         self.c_proj.set_precision(bits)
         return self.current_bit_width
 
-    def forward(self, hidden_states, attention_mask=None, residual=None):
+    def forward(self, hidden_states, attention_mask=None, residual=None, pre_norm=None):
         # attention_mask is accepted and ignored, as in the reference (:58-76); `residual` (SPBlock) is added
-        # to the projection output (inside c_proj's GEMM epilogue when autograd is off)
+        # to the projection output (inside c_proj's GEMM epilogue when autograd is off); `pre_norm` (SPBlock: ln_1) is
+        # applied to hidden_states first, inside c_attn's activation-side kernel when autograd is off
         B, T, C = hidden_states.shape
         half = self.attention_dtype == 'fp16'
-        qkv = self.c_attn(hidden_states, out_half=True) if half else self.c_attn(hidden_states)
+        qkv = self.c_attn(hidden_states, out_half=half, pre_norm=pre_norm)
         q, k, v = qkv.split(self.n_embd, dim=2)
         q = q.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
         k = k.view(B, T, self.n_head, self.head_dim).transpose(1, 2)
@@ -95,11 +96,11 @@ class SPMLP(nn.Module):
         self.c_proj.set_precision(bits)
         return bits
 
-    def forward(self, hidden_states, residual=None):
+    def forward(self, hidden_states, residual=None, pre_norm=None):
         # exact-erf GELU: fused into c_fc's GEMM epilogue when autograd is off, a separate pass otherwise;
-        # `residual` (SPBlock) is added to the projection output
+        # `residual` (SPBlock) is added to the projection output, `pre_norm` (SPBlock: ln_2) applied to the input first
         half = self.activation_dtype == 'fp16' and not torch.is_grad_enabled()
-        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True, out_half=half), residual=residual)
+        return self.c_proj(self.c_fc(hidden_states, fuse_gelu=True, out_half=half, pre_norm=pre_norm), residual=residual)
 
 
 class SPBlock(nn.Module):
@@ -125,8 +126,14 @@ class SPBlock(nn.Module):
     def _forward(self, hidden_states, attention_mask=None):
         # residual stream (reference :139-147): x + attn(ln_1(x)), then x + mlp(ln_2(x)); the adds ride in the
         # c_proj epilogues when autograd is off
-        hidden_states = self.attn(self.ln_1(hidden_states), attention_mask, residual=hidden_states)
-        hidden_states = self.mlp(self.ln_2(hidden_states), residual=hidden_states)
+        if torch.is_grad_enabled():
+            hidden_states = self.attn(self.ln_1(hidden_states), attention_mask, residual=hidden_states)
+            hidden_states = self.mlp(self.ln_2(hidden_states), residual=hidden_states)
+            return hidden_states
+        # no_grad: each LayerNorm has exactly one consumer (c_attn / c_fc), which normalises the rows inside its own
+        # activation-side kernel -- the float32 LayerNorm output is never stored
+        hidden_states = self.attn(hidden_states, attention_mask, residual=hidden_states, pre_norm=self.ln_1)
+        hidden_states = self.mlp(hidden_states, residual=hidden_states, pre_norm=self.ln_2)
         return hidden_states
 
 

@@ -163,6 +163,28 @@ class LearnableFakeQuantize(nn.Module):
                 self._stats_x = x2d                      # keeps the (possibly converted) input alive until the join
             self.num_batches_collected += 1
 
+    def _stats_targets_lastdim(self, x_shape, device):
+        """Bookkeeping of `_collect_statistics_batch` for a producer that computes the statistics itself (the
+        LayerNorm-fused activation pass, lora.py): returns (temp_min, temp_max, accumulate, state) for a float32 input of
+        shape `x_shape` whose channel dim is the LAST one, or None when this quantiser's layout is a different one."""
+        nd = len(x_shape)
+        if not (self.per_channel and self.channel_dim is not None and nd > 1):
+            return None
+        cd = self.channel_dim if self.channel_dim >= 0 else nd + self.channel_dim
+        if cd != nd - 1:
+            return None
+        stat_shape = [1] * nd
+        stat_shape[cd] = x_shape[cd]
+        if self._stat_state is None or self._stat_state.device != device:
+            self._stat_state = torch.zeros(1, dtype=torch.int32, device=device)
+        first = self.temp_min is None
+        if first:
+            self.temp_min = torch.empty(stat_shape, dtype=torch.float32, device=device)
+            self.temp_max = torch.empty(stat_shape, dtype=torch.float32, device=device)
+            self._first_shape = tuple(x_shape)
+        self.num_batches_collected += 1
+        return self.temp_min, self.temp_max, (not first), self._stat_state
+
     def join_stats(self):
         """Make the current stream wait for a statistics pass issued on `stats_stream` (no-op otherwise)."""
         if self._stats_x is not None:

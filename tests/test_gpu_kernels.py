@@ -365,6 +365,66 @@ def test_layernorm_against_oracle(lib, rows, C):
         ln.set_precision(5)
 
 
+@pytest.mark.parametrize("rows,C", [(51, 96), (4097, 768), (300, 1024), (65, 1600), (33, 2048)])
+@pytest.mark.parametrize("qtype,bits", [("log", 8), ("minmax", 4)])
+def test_ln_quantize_act_fused(lib, rows, C, qtype, bits):
+    """spq_ln_quantize_act (SwitchableLayerNorm folded into the activation quantiser, p1/models_sp.py:139-147 +
+    p1/lora.py:141-149): the normalised rows it can emit agree with the oracle's LayerNorm to fp32 rounding, and the
+    operands are BIT-identical to spq_quantize_act applied to those rows -- so the codes are the reference quantiser's
+    codes of the kernel's own LayerNorm output."""
+    rng = np.random.default_rng(rows + C)
+    x = dev(heavy_tailed((rows, C), 2, zeros=False))
+    w = dev((1 + 0.2 * rng.standard_normal(C)).astype(np.float32)); b = dev((0.2 * rng.standard_normal(C)).astype(np.float32))
+    y_ref, _, _ = switchable_layernorm_forward(x.cpu().numpy(), w.cpu().numpy(), b.cpu().numpy(), 1e-5)
+    # calibrated parameters of an 8-bit log / 4-bit min-max per-column quantiser on the normalised rows
+    st = QuantizerState(num_bits=bits, quantizer_type=qtype, channel_dim=-1, per_channel=True, symmetric=True)
+    st.start_calibration(); collect_statistics(st, y_ref); finish_calibration(st)
+    sc = dev(np.asarray(st.scale, dtype=np.float32).reshape(-1)); zp = dev(np.broadcast_to(np.asarray(st.zero_point, dtype=np.float32).reshape(-1), sc.shape).copy())
+    QT = lib.QTYPE[qtype]
+    kind = lib.OPERAND_DEQUANT if qtype == "log" else lib.OPERAND_CODE
+    col_mul = dev(np.exp2(rng.integers(-3, 4, C)).astype(np.float32)) if qtype == "log" else None
+    raw_mul = dev(np.exp2(rng.integers(-2, 3, C)).astype(np.float32))
+    y = torch.empty_like(x)
+    a_q = torch.empty((rows, C), dtype=torch.float16, device="cuda"); a_raw = torch.empty_like(a_q)
+    lib.ln_quantize_act(x, w, b, 1e-5, sc, zp, lib.PER_COL, QT, bits, True, kind, col_mul, 1.0, a_q, a_raw, raw_mul, y_out=y)
+    assert rel_fro(y.cpu().numpy(), y_ref) <= 2e-6
+    want_q = torch.empty_like(a_q); want_raw = torch.empty_like(a_raw)
+    lib.quantize_act(y, sc, zp, lib.PER_COL, QT, bits, True, kind, col_mul, 1.0, want_q, want_raw, raw_mul)
+    assert torch.equal(a_q, want_q) and torch.equal(a_raw, want_raw)
+    # without the optional float32 copy, and without the raw (LoRA) operand
+    a_q2 = torch.empty_like(a_q)
+    lib.ln_quantize_act(x, w, b, 1e-5, sc, zp, lib.PER_COL, QT, bits, True, kind, col_mul, 1.0, a_q2, None, None)
+    assert torch.equal(a_q2, want_q)
+
+
+@pytest.mark.parametrize("rows,C", [(51, 96), (4097, 768), (300, 1024), (65, 1600)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_ln_rowscale_stats_fused(lib, rows, C, mode):
+    """spq_ln_rowscale_stats (calibration pass / 32-bit path behind a LayerNorm): operand and row scales BIT-identical to
+    spq_rowscale_f16, per-column statistics (mode 1: min-max quantisers, mode 2: log quantisers) BIT-identical to
+    spq_minmax_stats, both applied to the normalised rows the kernel can emit; first batch and accumulation."""
+    rng = np.random.default_rng(rows * 3 + C)
+    w = dev((1 + 0.2 * rng.standard_normal(C)).astype(np.float32)); b = dev((0.2 * rng.standard_normal(C)).astype(np.float32))
+    smin = torch.empty(C, device="cuda"); smax = torch.empty(C, device="cuda"); state = torch.zeros(1, dtype=torch.int32, device="cuda")
+    wmin = torch.empty(C, device="cuda"); wmax = torch.empty(C, device="cuda"); wstate = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for batch in range(2):
+        x = dev(heavy_tailed((rows, C), 5 + batch, zeros=False))
+        if batch == 1:
+            x[3].zero_()                                    # a constant row: LayerNorm output = bias
+        y = torch.empty_like(x)
+        x16 = torch.empty((rows, C), dtype=torch.float16, device="cuda"); rs = torch.empty(rows, device="cuda")
+        lib.ln_rowscale_stats(x, w, b, 1e-5, x16, rs, stats_mode=mode, stat_eps=1e-5, stat_min=smin if mode else None,
+                              stat_max=smax if mode else None, accumulate=batch > 0, state=state if mode else None, y_out=y)
+        y_ref, _, _ = switchable_layernorm_forward(x.cpu().numpy(), w.cpu().numpy(), b.cpu().numpy(), 1e-5)
+        assert rel_fro(y.cpu().numpy(), y_ref) <= 2e-6
+        want16 = torch.empty_like(x16); wrs = torch.empty_like(rs)
+        lib.rowscale_f16(y, want16, wrs)
+        assert torch.equal(x16, want16) and torch.equal(rs, wrs)
+        if mode:
+            lib.minmax_stats(y, lib.PER_COL, mode == 2, 1e-5, wmin, wmax, accumulate=batch > 0, state=wstate)
+            assert torch.equal(smin, wmin) and torch.equal(smax, wmax) and torch.equal(state, wstate)
+
+
 def test_layernorm_golden(lib):
     from llm_qat_on_gpt2_b200 import SwitchableLayerNorm
     g = np.load(os.path.join(GOLDEN, "layernorm.npz"))

@@ -718,6 +718,50 @@ def test_mlp_activation_fp16_option():
     assert torch.equal(a[3], b[3])                           # training path untouched
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [32, 8, 4])
+def test_layernorm_fused_into_consumer_matches_unfused(bits, monkeypatch):
+    """Under no_grad SPBlock hands ln_1 / ln_2 to c_attn / c_fc (`pre_norm`), which normalise inside their activation-side
+    kernel (spq_ln_quantize_act / spq_ln_rowscale_stats).  Against the unfused path (SPQ_FUSE_LN=0 semantics) on the same
+    weights: calibrated statistics of the LayerNorm-fed quantisers and the logits agree to fp32 rounding of the LayerNorm
+    (the two kernels reduce a row in a different order) -- 32-bit logits within 1e-5, quantised logits within the
+    code-flip bar of the tiny-model test; with autograd on nothing is fused."""
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel
+    import llm_qat_on_gpt2_b200.lora as lora_mod
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(lora_mod, "_FUSE_LN", fused)
+        torch.manual_seed(8)
+        model = SPLMHeadModel(_tiny_config()).cuda().eval()
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith("lora_B"):
+                    p.normal_(0, 0.02)
+                if ".weights." in n or ".biases." in n:
+                    p.add_(0.1 * torch.randn_like(p))
+        ids = torch.randint(0, 211, (2, 32), device="cuda")
+        if bits < 32:
+            _calibrate_model(model, bits, [ids])
+            q = model.transformer.h[1].attn.c_attn.quantizers_input[f"{bits}bit"]
+            stats = (q.running_min.clone(), q.running_max.clone())
+        else:
+            model.set_precision(32)
+            stats = None
+        n0 = lora_mod._lib.launch_count()
+        with torch.no_grad():
+            logits = model(ids).float()
+        outs[fused] = (logits, stats, lora_mod._lib.launch_count() - n0)
+    a, b = outs[True], outs[False]
+    assert a[2] < b[2]                                       # fewer launches: the LayerNorm kernels are gone
+    rel = float((a[0] - b[0]).norm() / b[0].norm())
+    if bits == 32:
+        assert rel <= 1e-5, rel
+    else:
+        assert float((a[1][0] - b[1][0]).abs().max()) <= 1e-4 and float((a[1][1] - b[1][1]).abs().max()) <= 1e-4
+        cos = float((a[0] * b[0]).sum() / a[0].norm() / b[0].norm())
+        assert cos >= 0.999, (rel, cos)
+
+
 def test_sp_linear_fp8_path_per_tensor_4bit(monkeypatch):
     """The evaluation configuration (per_channel=False, 4-bit min-max: p1/deploy.py:210,238): SPLinearWithLoRA takes the
     e4m3 integer-code GEMM.  With the LoRA branch off the output is the exact product of the codes times s_x s_w (fp32
