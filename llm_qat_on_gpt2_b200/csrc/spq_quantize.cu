@@ -889,6 +889,8 @@ static int launch_act(const ActArgs& a, cudaStream_t st) {
     if (gy > 65535) gy = 65535;
     const dim3 grid(gx, static_cast<unsigned>(gy)), block(32, 8);
     constexpr int HOT_KIND = (QTYPE == SPQ_MINMAX) ? SPQ_OPERAND_CODE : SPQ_OPERAND_DEQUANT;
+    // (a variant with the per-column constants in shared memory -- 64 registers, 8 warps per sub-partition instead of 6 --
+    // measured the same 50-51 us at 32768 x 768: the kernel is not occupancy-bound; profiles/r02b_quantize_act_smem_table.txt)
     if (a.qp.symmetric && a.operand_kind == HOT_KIND) {
         if (a.x_half) quantize_act_kernel<QTYPE, __half, 1, HOT_KIND><<<grid, block, 0, st>>>(a);
         else quantize_act_kernel<QTYPE, float, 1, HOT_KIND><<<grid, block, 0, st>>>(a);
