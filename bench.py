@@ -490,6 +490,27 @@ def gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     gc.enable()
 
+    # ---- untimed: the graph-replayed step against the eager module calls on the same ids -- calibrated scale /
+    # zero-point of all 48 input quantisers and the loss bit for bit, and (N > 1) identical on every rank
+    step_parity = None
+    if graphed is not None:
+        def snapshot():
+            return torch.cat([torch.cat([q.scale.reshape(-1), q.zero_point.reshape(-1)]) for q in input_q])
+        probe = dev_ids[0]
+        loss_g = graphed(probe)["loss"].clone()
+        snap_g = snapshot().clone()
+        loss_e = step_eager(probe).clone()
+        snap_e = snapshot()
+        same = bool(torch.equal(snap_g.view(torch.int32), snap_e.view(torch.int32)) and torch.equal(loss_g.reshape(()), loss_e.reshape(())))
+        ranks_same = True
+        if world > 1:
+            gathered = [torch.empty_like(snap_g) for _ in range(world)]
+            dist.all_gather(gathered, snap_g)
+            ranks_same = all(torch.equal(g.view(torch.int32), gathered[0].view(torch.int32)) for g in gathered)
+        step_parity = {"graph_vs_eager_bit_identical": same, "ranks_bit_identical": ranks_same, "parameters": int(snap_g.numel())}
+        if not (same and ranks_same):
+            raise RuntimeError(f"graph-replayed step differs from the eager step: {step_parity}")
+
     train = None
     if args.train_steps > 0:
         train = train_section(args, model, linears, key, dev, world, rank, group, barrier)
@@ -538,6 +559,7 @@ def gpu_arm(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * T * 8, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "loss": loss_host, "step_wall_ms": e2e_step_ms},
             "gpu_launches": launches,
+            "step_parity": step_parity,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "spq::gemm::qgemm_nt_kernel (all launches in the timed region)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
