@@ -82,14 +82,14 @@ def measured_peaks():
 
 def measured_traffic():
     """DRAM bytes per qgemm_nt launch from the committed ncu capture of one step (profiles/), or None."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_qgemm_dram_per_launch.csv")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02c_qgemm_dram_per_launch.csv")
     try:
         with open(path) as f:
             for line in f:
                 if line.startswith("TOTAL("):
                     n = int(line[len("TOTAL("):].split(" ")[0])
                     _, _, rd, wr = line.strip().split(",")
-                    return (float(rd) + float(wr)) * 1e6 / n, "profiles/r02_qgemm_dram_per_launch.csv (ncu, one step)"
+                    return (float(rd) + float(wr)) * 1e6 / n, "profiles/r02c_qgemm_dram_per_launch.csv (ncu, one step)"
     except Exception:
         pass
     return None, "no capture committed"
