@@ -719,8 +719,8 @@ def test_mlp_activation_fp16_option():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bits", [32, 8, 4])
-def test_layernorm_fused_into_consumer_matches_unfused(bits, monkeypatch):
+@pytest.mark.parametrize("bits,per_channel", [(32, True), (8, True), (4, True), (4, False)])
+def test_layernorm_fused_into_consumer_matches_unfused(bits, per_channel, monkeypatch):
     """Under no_grad SPBlock hands ln_1 / ln_2 to c_attn / c_fc (`pre_norm`), which normalise inside their activation-side
     kernel (spq_ln_quantize_act / spq_ln_rowscale_stats).  Against the unfused path (SPQ_FUSE_LN=0 semantics) on the same
     weights: calibrated statistics of the LayerNorm-fed quantisers and the logits agree to fp32 rounding of the LayerNorm
@@ -732,7 +732,11 @@ def test_layernorm_fused_into_consumer_matches_unfused(bits, monkeypatch):
     for fused in (True, False):
         monkeypatch.setattr(lora_mod, "_FUSE_LN", fused)
         torch.manual_seed(8)
-        model = SPLMHeadModel(_tiny_config()).cuda().eval()
+        cfg = _tiny_config()
+        # per_channel=False at 4 bits is upstream's evaluation configuration (p1/deploy.py:210,238): per-tensor scales,
+        # e4m3 integer-code operands -- the fused kernel then writes one byte per code
+        cfg.per_channel_quantization = per_channel
+        model = SPLMHeadModel(cfg).cuda().eval()
         with torch.no_grad():
             for n, p in model.named_parameters():
                 if n.endswith("lora_B"):
