@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPQ_ABI_VERSION 3
+#define SPQ_ABI_VERSION 4
 #define SPQ_API __attribute__((visibility("default")))
 
 typedef void* spq_stream_t;          /* cudaStream_t */
@@ -282,6 +282,14 @@ SPQ_API int spq_cross_entropy_from_parts(const float* parts, int64_t P, int64_t 
  * grad[m,v] = grad_scale / T * (softmax(s[m]/T)[v] - softmax(t[m]/T)[v])  (grad_scale = T^2 / rows for the
  * reference's batchmean * T^2).  Rows with m % seq_len == seq_len - 1 are ignored (seq_len = 0: none) -- the
  * reference scores positions 0..T-2.  Logits may have padded rows (ld_s, ld_t in elements). */
+/* Feature term of the distillation loss (p1/distillation_manager.py:82-116: F.mse_loss(student_hidden[l], teacher_hidden[l])
+ * for ONE layer l drawn per micro-step): out[0] = mean((a[l] - b[l])^2) with l = select[0] read on the DEVICE (clamped to
+ * [0, n_pairs)), so that a captured CUDA graph serves every draw.  a / b: host arrays of n_pairs (<= 32) device pointers to
+ * float32 tensors of numel elements, 16-byte aligned.  Deterministic (fixed-order fold). */
+SPQ_API size_t spq_mse_select_workspace_bytes(void);
+SPQ_API int spq_mse_select(const float* const* a, const float* const* b, int n_pairs, const int32_t* select, int64_t numel,
+                   float* out, void* workspace, size_t workspace_bytes, spq_stream_t stream);
+
 SPQ_API int spq_distill_kl(const float* s_logits, int64_t ld_s, const float* t_logits, int64_t ld_t, int64_t M, int64_t V,
                    float temperature, int64_t seq_len, float grad_scale, float* row_loss, float* grad,
                    spq_stream_t stream);

@@ -21,7 +21,7 @@ PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
 MINMAX, LOG = 0, 1
 OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW, OPERAND_CODE_E4M3 = 0, 1, 2, 3
 QTYPE = {"minmax": MINMAX, "log": LOG}
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); must list every SPQ_API symbol of include/spq_b200.h
 SIGNATURES = {
@@ -77,6 +77,8 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "spq_cross_entropy_from_parts": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                              c_void_p, c_void_p, c_void_p]),
+    "spq_mse_select_workspace_bytes": (c_size_t, []),
+    "spq_mse_select": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "spq_distill_kl": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float, c_int64, c_float, c_void_p,
                                c_void_p, c_void_p]),
     "spq_cross_entropy_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -422,6 +424,25 @@ def cross_entropy_from_parts(parts, logits2d, targets, ignore_index=-100):
            "spq_cross_entropy_from_parts")
     sums = out.sum(dim=1)
     return sums[0] / sums[1]
+
+
+def mse_select(a_list, b_list, select: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[0] = F.mse_loss(a_list[l], b_list[l]) with l = select[0] read on the device (int32 tensor of one element)."""
+    lib = load_library()
+    n = len(a_list)
+    assert n == len(b_list) and 0 < n <= 32 and select.dtype == torch.int32 and select.numel() == 1
+    _req_cuda(select, out, *a_list, *b_list)
+    numel = a_list[0].numel()
+    for t in list(a_list) + list(b_list):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == numel
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=select.device)
+    ws = _workspace(lib.spq_mse_select_workspace_bytes(), select.device, "mse")
+    pa = (c_void_p * n)(*[t.data_ptr() for t in a_list])
+    pb = (c_void_p * n)(*[t.data_ptr() for t in b_list])
+    _check(lib.spq_mse_select(pa, pb, n, select.data_ptr(), numel, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+           "spq_mse_select")
+    return out
 
 
 def distill_kl(s2d, t2d, temperature, seq_len, grad_scale, want_grad=True):

@@ -367,6 +367,53 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
     if (tid == 0 && max_scale) atomicMax(reinterpret_cast<int*>(max_scale), __float_as_int(cta_max_scale));
 }
 
+// Feature term of the distillation loss (p1/distillation_manager.py:82-116): mean squared error between ONE pair of
+// hidden-state tensors, the layer drawn at random per micro-step.  A captured micro-step cannot know the layer, so the
+// training driver used to evaluate all 13 pairs with torch (26 launches, 650 MB of reads per student micro-step) and pick
+// one on the host; here the candidate pairs are kernel arguments and the drawn index is read from device memory.
+constexpr int MSE_MAX_PAIRS = 32;
+struct MsePairs {
+    const float* a[MSE_MAX_PAIRS];
+    const float* b[MSE_MAX_PAIRS];
+};
+
+__global__ void __launch_bounds__(256)
+mse_select_partial_kernel(MsePairs p, int n_pairs, const int32_t* __restrict__ select, long long numel, float* __restrict__ partial) {
+    int sel = *select;
+    sel = sel < 0 ? 0 : (sel >= n_pairs ? n_pairs - 1 : sel);
+    const float* a = p.a[sel];
+    const float* b = p.b[sel];
+    const long long n4 = numel >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    float acc0 = 0.f, acc1 = 0.f;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x = ld_stream_f4(a + 4 * i), y = ld_stream_f4(b + 4 * i);
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        acc0 += d0 * d0 + d1 * d1;
+        acc1 += d2 * d2 + d3 * d3;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long long i = n4 << 2; i < numel; ++i) { const float d = a[i] - b[i]; acc0 += d * d; }
+    }
+    float acc = warp_sum(acc0 + acc1);
+    __shared__ float s_red[8];
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// fixed-order fold: the result is reproducible run to run
+__global__ void __launch_bounds__(32) mse_select_final_kernel(const float* __restrict__ partial, int n, long long numel, float* __restrict__ out) {
+    float t = 0.f;
+    for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t / static_cast<float>(numel);
+}
+
 }  // namespace loss
 }  // namespace spq
 
@@ -445,3 +492,31 @@ extern "C" int spq_softmax_loss_grad16(int kind, const float* s_logits, int64_t 
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
+
+extern "C" size_t spq_mse_select_workspace_bytes(void) {
+    return static_cast<size_t>((sm_count() > 0 ? sm_count() : 148) * 4) * sizeof(float);
+}
+
+extern "C" int spq_mse_select(const float* const* a, const float* const* b, int n_pairs, const int32_t* select, int64_t numel,
+                              float* out, void* workspace, size_t workspace_bytes, spq_stream_t stream) {
+    SPQ_REQUIRE(a && b && select && out && workspace && n_pairs > 0 && n_pairs <= loss::MSE_MAX_PAIRS && numel > 0,
+                "spq_mse_select: bad arguments (at most %d pairs)", loss::MSE_MAX_PAIRS);
+    SPQ_REQUIRE(workspace_bytes >= spq_mse_select_workspace_bytes(), "spq_mse_select: workspace too small");
+    loss::MsePairs p = {};
+    for (int i = 0; i < n_pairs; ++i) {
+        SPQ_REQUIRE(a[i] && b[i] && aligned16(a[i]) && aligned16(b[i]), "spq_mse_select: pair %d null or not 16-byte aligned", i);
+        p.a[i] = a[i];
+        p.b[i] = b[i];
+    }
+    long long blocks = (numel / 4 + 255) / 256;
+    const long long cap = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t st = as_stream(stream);
+    loss::mse_select_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p, n_pairs, select, numel, static_cast<float*>(workspace));
+    SPQ_LAUNCH_OK();
+    loss::mse_select_final_kernel<<<1, 32, 0, st>>>(static_cast<const float*>(workspace), static_cast<int>(blocks), numel, out);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+

@@ -646,6 +646,7 @@ class SPTrainer:
         self.dev = self.state.flat_param.device
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.loss_buf = torch.zeros(grad_accum, 2, dtype=torch.float32, device=self.dev)
+        self.layer_sel = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.ids = None
         self.graphs, self.outs, self.finishers, self.sigs = {}, {}, {}, {}
         self._frozen = None
@@ -669,7 +670,7 @@ class SPTrainer:
         return {'loss': loss.detach().reshape(1), 'logits': t['logits'], 'hidden': t['hidden_states']}
 
     def _student_body(self, bits):
-        import torch.nn.functional as F
+        from . import _lib
         m = self.model
         m.set_precision(bits)
         self._mark_inner('student_forward')
@@ -678,12 +679,15 @@ class SPTrainer:
         self._mark_inner('distillation_loss')
         kl = lm_head_loss(m, hidden, teacher_logits=tch['logits'], temperature=self.T)
         with torch.no_grad():
+            # F.mse_loss(student_hidden[l], teacher_hidden[l]) for the ONE layer drawn for this micro-step: the index is
+            # read on the device (self.layer_sel, set by train_step before the replay), so the captured graph serves
+            # every draw without evaluating all 13 pairs
             ht = tch['hidden']
             n = min(len(hs), len(ht))
-            feats = torch.stack([F.mse_loss(hs[l], ht[l], reduction='mean') for l in range(n)])
+            feat = _lib.mse_select([h.contiguous() for h in hs[:n]], [h.contiguous() for h in ht[:n]], self.layer_sel)
         self._mark_inner('student_backward')
         ((self.alpha_kl / self.G) * kl).backward()          # the feature term carries no gradient (detached copies)
-        return {'kl': kl.detach().reshape(1), 'feats': feats}
+        return {'kl': kl.detach().reshape(1), 'feat': feat}
 
     def _refresh(self, bits):
         """calibrate_lora_only(bits) (p1/train_sp.py:125-163, 362-364).  Upstream repeats it before every student
@@ -790,13 +794,15 @@ class SPTrainer:
                     self._refresh(bits)
                 refreshed.add(bits)
             self._mark(f'micro_step_{bits}')
+            if bits != self.teacher_bits:
+                self.layer_sel.fill_(layers[i])          # the feature layer of this micro-step (read by spq_mse_select)
             out = self._run(bits)
             if bits == self.teacher_bits:
                 self.loss_buf[i, 0:1].copy_(out['loss'])
                 self.loss_buf[i, 1].zero_()
             else:
                 self.loss_buf[i, 0:1].copy_(out['kl'])
-                self.loss_buf[i, 1:2].copy_(out['feats'][layers[i]:layers[i] + 1])
+                self.loss_buf[i, 1:2].copy_(out['feat'])
             if self.world > 1 and last_use[bits] == i:
                 # this segment is final: its all-reduce runs on NCCL's stream under the remaining micro-steps
                 works.append(dist.all_reduce(st.seg_grad(bits), op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -631,6 +631,26 @@ def test_qgemm_lse_and_cross_entropy_from_parts(M, V, K):
     assert lib.debug_status() == 0
 
 
+def test_mse_select_matches_torch(lib):
+    """spq_mse_select (feature term of the distillation loss, p1/distillation_manager.py:82-116): the pair is chosen by an
+    index read on the device; every index, an odd element count and out-of-range indices (clamped); run-to-run identical."""
+    torch.manual_seed(0)
+    for numel in (8 * 32 * 64, 4099):
+        a = [torch.randn(numel, device="cuda") for _ in range(13)]
+        b = [torch.randn(numel, device="cuda") * 0.5 for _ in range(13)]
+        if numel % 4:
+            a = [torch.randn(numel + 4, device="cuda")[:numel] for _ in range(13)]     # (still 16-byte aligned views)
+        sel = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for l in list(range(13)) + [-3, 99]:
+            sel.fill_(l)
+            got = lib.mse_select(a, b, sel)
+            ll = min(max(l, 0), 12)
+            want = torch.nn.functional.mse_loss(a[ll].double(), b[ll].double())
+            assert abs(got.item() - want.item()) <= 1e-6 * want.item(), (numel, l)
+            again = lib.mse_select(a, b, sel)
+            assert torch.equal(got, again)
+
+
 # --------------------------------------------------------------------------- fp8 (e4m3) integer-code GEMM
 @pytest.mark.parametrize("M,N,K,K2", [(300, 200, 256, 0), (4096, 2304, 768, 64), (1000, 768, 3072, 64), (129, 4800, 1600, 0)])
 def test_qgemm_f8_integer_codes_exact(lib, M, N, K, K2):
