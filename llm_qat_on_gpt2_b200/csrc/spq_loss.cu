@@ -13,6 +13,15 @@
 namespace spq {
 namespace loss {
 
+// exp(x) as ONE multiply + ex2.approx.ftz: `__expf` without -use_fast_math is the non-ftz ex2 (range test, two scaling
+// multiplies around the MUFU: ~5 instructions), which made the softmax passes issue-bound (the same finding as the LM
+// head's log-sum-exp epilogue).  Results below 2^-126 flush to zero: probabilities < 1e-38.
+__device__ __forceinline__ float fexp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 struct MS { float m, s; };                                   // running max and sum of exp(x - m)
 __device__ __forceinline__ MS combine(MS a, MS b) {
     if (b.m == -INFINITY) return a;
@@ -231,8 +240,8 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
         auto fold4 = [&](MS& acc, float4 x) {
             x.x *= inv_T; x.y *= inv_T; x.z *= inv_T; x.w *= inv_T;
             const float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-            if (mx > acc.m) { acc.s *= __expf(acc.m - mx); acc.m = mx; }
-            acc.s += __expf(x.x - acc.m) + __expf(x.y - acc.m) + __expf(x.z - acc.m) + __expf(x.w - acc.m);
+            if (mx > acc.m) { acc.s *= fexp(acc.m - mx); acc.m = mx; }
+            acc.s += fexp(x.x - acc.m) + fexp(x.y - acc.m) + fexp(x.z - acc.m) + fexp(x.w - acc.m);
         };
         {
             // four 16-byte loads per matrix in flight per thread (the pass streams from HBM)
@@ -302,8 +311,8 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
         // max |d| for CE; for KL it can be far above it when student and teacher agree, which only moves the operand down
         // inside fp16's normal range (elements more than 2^-22 below the bound are negligible either way).
         float amax;
-        if (KIND == 0) amax = fmaxf(__expf(s_b[2] - lse_s), __expf(s_b[3] - lse_t));
-        else amax = fmaxf(1.0f - __expf(fmaf(__ldg(ps_ + tgt), inv_T, -lse_s)), __expf(s_b[2] - lse_s));
+        if (KIND == 0) amax = fmaxf(fexp(s_b[2] - lse_s), fexp(s_b[3] - lse_t));
+        else amax = fmaxf(1.0f - fexp(fmaf(__ldg(ps_ + tgt), inv_T, -lse_s)), fexp(s_b[2] - lse_s));
         int E = 0;
         if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &E); else E = (amax == 0.f) ? -100 : 8;
         E = E < -100 ? -100 : E;
@@ -317,11 +326,11 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
             float d;
             if (KIND == 0) {
                 const float lt = fmaf(tv, inv_T, -lse_t);
-                const float pt = __expf(lt);
+                const float pt = fexp(lt);
                 acc = fmaf(pt, lt - ls, acc);
-                d = __expf(ls) - pt;
+                d = fexp(ls) - pt;
             } else {
-                d = __expf(ls) - (idx == tgt ? 1.0f : 0.0f);
+                d = fexp(ls) - (idx == tgt ? 1.0f : 0.0f);
             }
             return d * down;
         };
