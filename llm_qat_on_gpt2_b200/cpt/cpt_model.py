@@ -16,6 +16,7 @@ up-projection rides in the same TMEM accumulator as the base GEMM.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -77,7 +78,10 @@ class _CPTLinearFn(torch.autograd.Function):
     """Fused forward / backward of CPTLinear at a quantised width."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits):
+    def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, ce_targets=None):
+        # ce_targets (int64 [M], -100 = not scored): the LM head of CPTModel with labels.  The Function then returns
+        # (mean cross-entropy, logits): the loss kernel leaves the fp16 gradient operand of this layer's backward, so
+        # torch's log_softmax / nll passes, the float32 [M, V] dlogits and their row-scaling pass never exist
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
         act = base['act']
@@ -87,7 +91,11 @@ class _CPTLinearFn(torch.autograd.Function):
         a_q = torch.empty((M, K), dtype=torch.float16, device=x.device)
         _lib.quantize_act(x2d, act['scale'], act['zp'], act['bcast'], act['qtype'], act['bits'], act['symmetric'],
                           act['kind'], act['col_mul'], act['mul'], a_q, None, None)
-        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        # with the fused loss: odd widths (the vocabulary) get rows padded to 128 bytes so that the GEMM stores through
+        # TMA (as lora.linear_fp does); the plain call keeps the dense [.., N] tensor upstream's callers may .view()
+        ld = N if (N % 4 == 0 or ce_targets is None) else (N + 31) // 32 * 32
+        ybuf = torch.empty((M, ld), dtype=torch.float32, device=x.device)
+        y = ybuf[:, :N] if ld != N else ybuf
         bias_f = None if bias is None else bias.detach().float().contiguous()
         t16 = None
         if use_lora:
@@ -104,22 +112,39 @@ class _CPTLinearFn(torch.autograd.Function):
         ctx.bits = bits                     # backward operands are built (and cached) when backward first runs
         ctx.weight_qtype = mod.quantizer_weight.quantizer_type
         keep_aq = need[1] or (use_lora and need[3])
-        ctx.save_for_backward(a_q if keep_aq else None, t16 if (use_lora and need[4]) else None)
-        return y.view(*x.shape[:-1], N)
+        out = ybuf.view(*x.shape[:-1], ld)
+        out = out[..., :N] if ld != N else out
+        ctx.fused_ce = ce_targets is not None
+        if ce_targets is None:
+            ctx.save_for_backward(a_q if keep_aq else None, t16 if (use_lora and need[4]) else None)
+            return out
+        row_loss, row_valid, g16, eg, gmax1 = _lib.softmax_loss_grad16(y, 'ce', targets=ce_targets)
+        factor = (1.0 / row_valid.sum()).reshape(1)            # mean over the scored rows, as F.cross_entropy
+        loss = row_loss.sum() * factor[0]
+        ctx.save_for_backward(a_q if keep_aq else None, t16 if (use_lora and need[4]) else None, g16, eg, gmax1, factor)
+        ctx.mark_non_differentiable(out)
+        return loss, out
 
     @staticmethod
-    def backward(ctx, gy):
-        a_q, t16 = ctx.saved_tensors
+    def backward(ctx, gy, *unused):
         base, lo, mod = ctx.base, ctx.lo, ctx.mod
         bw = mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
-        g2d = _as_2d_grad(gy, N)
         dev = gy.device
         act = base['act']
-        g16 = _lib.empty_f16_padded(M, N, dev)
-        eg = torch.empty(M, dtype=torch.float32, device=dev)
-        gmax1 = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.rowscale_f16_max(g2d, g16, eg, gmax1)           # dY = g16 * eg[:,None], gmax1 = max eg
+        if ctx.fused_ce:
+            # gy = d(loss): dY = g16 * eg[:, None] * (gy / n_scored) -- the scalar goes into the row scales
+            a_q, t16, g16, eg, gmax1, factor = ctx.saved_tensors
+            scal = (gy.reshape(1).float() * factor)
+            eg, gmax1 = eg * scal, gmax1 * scal
+            g2d = None                                       # (weight / bias gradients are not taken on this path)
+        else:
+            a_q, t16 = ctx.saved_tensors
+            g2d = _as_2d_grad(gy, N)
+            g16 = _lib.empty_f16_padded(M, N, dev)
+            eg = torch.empty(M, dtype=torch.float32, device=dev)
+            gmax1 = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.rowscale_f16_max(g2d, g16, eg, gmax1)       # dY = g16 * eg[:,None], gmax1 = max eg
         gx = gw = gb = gA = gB = None
         need_x, need_w, need_b, need_A, need_B = ctx.needs_input_grad[:5]
         clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
@@ -181,7 +206,7 @@ class _CPTLinearFn(torch.autograd.Function):
                          clamp_abs=10.0 if ctx.weight_qtype == 'log' else 0.0)
         if ctx.has_bias and need_b:
             gb = g2d.float().sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None
+        return gx, gw, gb, gA, gB, None, None, None
 
 
 class CPTLinear(nn.Module):
@@ -287,6 +312,25 @@ class CPTLinear(nn.Module):
             with torch.no_grad():
                 base['WT_op'] = _quantized_operand(self.quantizer_weight, self.linear.weight, col_mul=base['inv_pk'], transposed=True)
         return dict(pk=base['pk'], WT_op=base['WT_op'], lora=None if lora is None else lora['bwd'])
+
+    def forward_with_cross_entropy(self, x: torch.Tensor, targets: torch.Tensor):
+        """(F.cross_entropy(self(x).view(-1, N), targets.view(-1), ignore_index=-100), self(x)) -- CPTModel's LM head with
+        labels (p2/cpt_model.py: lm_head + the shifted next-token loss).  At a calibrated quantised width with frozen base
+        weight / bias the loss kernel feeds this layer's backward directly (see _CPTLinearFn.forward); otherwise the two
+        steps are simply composed."""
+        qi, qw = self.quantizer_input, self.quantizer_weight
+        lora_on = not self.calibration_mode and self.shared_lora.rank > 0
+        lq = self.lora_weight_quantizers[f'{self.current_bits}bit'] if (lora_on and self.current_bits < 32) else None
+        frozen = not (torch.is_grad_enabled() and (self.linear.weight.requires_grad or
+                                                   (self.linear.bias is not None and self.linear.bias.requires_grad)))
+        if (self.current_bits < 32 and x.is_cuda and frozen and qi.ready() and qw.ready() and (lq is None or lq.ready())
+                and os.environ.get('SPQ_CPT_FUSED_CE', '1') != '0'):
+            tg = targets.reshape(-1).to(torch.int64).contiguous()
+            return _CPTLinearFn.apply(x, self.linear.weight, self.linear.bias,
+                                      self.shared_lora.lora_A if lora_on else None,
+                                      self.shared_lora.lora_B if lora_on else None, self, self.current_bits, tg)
+        logits = self.forward(x)
+        return F.cross_entropy(logits.reshape(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100), logits
 
     # ---------------------------------------------------------------- forward (p2/cpt_model.py:92-114)
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -446,12 +490,13 @@ class CPTModel(nn.Module):
             if use_cache:
                 presents.append(present)
         hidden_states = self.ln_f(hidden_states)
-        logits = self.lm_head(hidden_states)
         loss = None
         if labels is not None:
             targets = torch.full_like(labels, -100)
             targets[..., :-1] = labels[..., 1:]
-            loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.reshape(-1), ignore_index=-100)
+            loss, logits = self.lm_head.forward_with_cross_entropy(hidden_states, targets)
+        else:
+            logits = self.lm_head(hidden_states)
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=presents,
                                       hidden_states=hidden_states, attentions=None)
 

@@ -234,6 +234,48 @@ def test_cpt_calibration_manager_and_fused_gradient_quantizer():
     assert torch.allclose(codes, codes.round(), atol=1e-3) and float(codes.abs().max()) <= 127.001
 
 
+def test_cpt_lm_head_fused_cross_entropy(monkeypatch):
+    """CPTModel with labels: the quantised LM head hands its logits to the softmax-loss kernel, whose fp16 gradient
+    operand feeds the head's backward (CPTLinear.forward_with_cross_entropy).  Against the composition it replaces
+    (F.cross_entropy on the logits, SPQ_CPT_FUSED_CE=0): same loss, same logits, LoRA gradients of every layer and the
+    gradient reaching the embeddings within the fp16-operand tolerance; eval mode and the 32-bit width fall through."""
+    from llm_qat_on_gpt2_b200.cpt import CalibrationManager
+    g = torch.Generator().manual_seed(3)
+    loader = [{"input_ids": torch.randint(0, 211, (2, 32), generator=g)} for _ in range(2)]
+    ids = loader[0]["input_ids"].cuda()
+    labels = ids.clone(); labels[0, 5:9] = -100
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SPQ_CPT_FUSED_CE", fused)
+        model = _tiny_cpt()
+        mgr = CalibrationManager(model, loader, torch.device("cuda"))
+        for b in (4, 6, 8):
+            mgr.ensure_calibrated(b, num_batches=2)
+        model.train()
+        for p in model.parameters():
+            p.requires_grad_(False)
+        for m in model.modules():
+            if m.__class__.__name__ == "LoRAAdapter" and m.lora_A is not None:
+                m.lora_A.requires_grad_(True); m.lora_B.requires_grad_(True)
+        model.wte.weight.requires_grad_(True)
+        model.set_precision(6)
+        out = model(ids, labels=labels)
+        out.loss.backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        with torch.no_grad():
+            ev = model(ids, labels=labels).loss.item()
+            model.set_precision(32)
+            l32 = model(ids, labels=labels).loss.item()
+        res[fused] = (out.loss.item(), out.logits.detach().float().clone(), grads, ev, l32)
+    a, b = res["1"], res["0"]
+    assert abs(a[0] - b[0]) <= 1e-5 * abs(b[0]) and abs(a[3] - b[3]) <= 1e-5 * abs(b[3]) and a[4] == b[4]
+    assert torch.equal(a[1], b[1]) and a[1].shape == (2, 32, 211)
+    assert a[2].keys() == b[2].keys() and len(a[2]) >= 2 * 9 + 1
+    for n in a[2]:
+        ga, gb = a[2][n].double(), b[2][n].double()
+        assert float((ga - gb).norm() / gb.norm().clamp_min(1e-30)) <= 2e-3, n
+
+
 def test_cpt_trainer_graphs_match_eager_and_cycle():
     """CPTTrainer: per-width CUDA graphs (LoRA-level operand rebuild + forward + loss + backward) reproduce the eager
     steps while the width cycles per step along CyclicPrecisionScheduler; parameters move; losses agree."""
