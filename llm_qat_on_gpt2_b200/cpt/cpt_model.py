@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from ..lora import (_FpWeightCache, _act_config, _as_2d_f32, _as_2d_grad, _dequant, _grad_sink, _norm_pow2, _quantized_operand,
+from ..lora import (_FpWeightCache, _GradSide, _act_config, _as_2d_f32, _as_2d_grad, _dequant, _grad_sink, _norm_pow2, _quantized_operand,
                     _rowscaled_f16, _to_f16_operand, linear_fp)
 from ..quantization import pow2_ceil
 from .quantization import GradientQuantizer, LearnableFakeQuantize
@@ -162,6 +162,14 @@ class _CPTLinearFn(torch.autograd.Function):
             # GradientQuantizer (p2/quantization.py:14-26): calibrated -> fused into the gradient GEMM's fold pass in
             # front of the weight quantiser's STE clamp; collecting statistics -> the module call records them
             sl = mod.shared_lora
+            # gradients that accumulate straight into a driver-owned buffer may run on the driver's side stream (lora._GradSide)
+            fa = _grad_quantizer_scale(sl.grad_quantizer_A, K)[1] if need_A else True
+            fb = _grad_quantizer_scale(sl.grad_quantizer_B, N)[1] if need_B else True
+            on_side = ((not need_A or (fa and _grad_sink(sl.lora_A, (K, r)) is not None)) and
+                       (not need_B or (fb and _grad_sink(sl.lora_B, (N, r)) is not None)))
+            lane = _GradSide.fork(a_q, dt2, t2, g16, gmax1) if on_side else torch.cuda.current_stream()
+            side_ctx = torch.cuda.stream(lane)
+            side_ctx.__enter__()
             if need_A:
                 # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
                 gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_A, K)
@@ -190,6 +198,7 @@ class _CPTLinearFn(torch.autograd.Function):
                     gB = _grad_quantize(sl.grad_quantizer_B, gB)
                     if clamp_w:
                         gB = _lib.ste_backward(gB, _lib.LOG)
+            side_ctx.__exit__(None, None, None)
         if need_x:
             # both terms flow through q_in(x) here, so the STE clamp applies to their sum
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)

@@ -17,6 +17,7 @@ import math
 import torch
 
 from .. import _lib
+from ..lora import side_stream_grads
 
 
 class CPTTrainer:
@@ -65,13 +66,16 @@ class CPTTrainer:
         self.pool = None
         self.steps_done = 0
         self._frozen = None
+        import os
+        self.grad_stream = torch.cuda.Stream() if os.environ.get('SPQ_GRAD_SIDE', '1') != '0' else None
 
     # ------------------------------------------------------------------------------------------
     def _body(self, bits):
         m = self.model
         m.set_precision(bits)
         out = m(self.ids, labels=self.ids)
-        out.loss.backward()
+        with side_stream_grads(self.grad_stream):       # LoRA weight-gradient GEMMs beside the dX chain (lora._GradSide)
+            out.loss.backward()
         return out.loss.detach().reshape(1)
 
     def _signature(self, bits):

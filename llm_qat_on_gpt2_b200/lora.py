@@ -172,6 +172,50 @@ def _grad_sink(param, shape):
     return g
 
 
+class _GradSide:
+    """Optional side stream for the LoRA weight-gradient GEMMs (dA = x^T dT, dB = t^T dY): they hang off the backward
+    chain (nothing downstream reads them before the optimizer step), so a training driver that owns the step can let
+    them run beside the dX GEMMs of the layers that follow -- parallel branches once the micro-step is captured into a
+    CUDA graph.  OFF unless a driver enters `side_stream_grads()`; the driver joins with `.join()` before it reads the
+    gradients (training.SPTrainer, cpt.CPTTrainer).  Inputs are `record_stream`-ed: the caching allocator must not hand
+    their memory to a later main-stream allocation while the side kernel may still read it."""
+    stream = None
+
+    @classmethod
+    def fork(cls, *tensors):
+        """-> the stream to launch on (the current one when the feature is off)."""
+        side = cls.stream
+        cur = torch.cuda.current_stream()
+        if side is None:
+            return cur
+        side.wait_stream(cur)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(side)
+        return side
+
+    @classmethod
+    def join(cls):
+        if cls.stream is not None:
+            torch.cuda.current_stream().wait_stream(cls.stream)
+
+
+class side_stream_grads:
+    """with side_stream_grads(stream): ... backward ... -- see _GradSide."""
+
+    def __init__(self, stream):
+        self.stream, self.prev = stream, None
+
+    def __enter__(self):
+        self.prev, _GradSide.stream = _GradSide.stream, self.stream
+        return self
+
+    def __exit__(self, *exc):
+        _GradSide.join()
+        _GradSide.stream = self.prev
+        return False
+
+
 def _as_2d_grad(gy: torch.Tensor, last: int) -> torch.Tensor:
     """Incoming gradient as a contiguous 2-D matrix.  float16 gradients (the fp16 attention backward feeding c_attn)
     go to the row-scaling kernel as they are -- it widens them exactly -- instead of through a float32 copy."""
@@ -456,22 +500,26 @@ class _SPLinearFn(torch.autograd.Function):
             dt16, dt2, t2 = _lib.lora_bwd_prep(dtn, t16 if need_B else None, eg, gmax1, lb['dt_mul'],
                                                want_dt16=need_x, want_dt2=need_A, want_t2=need_B)
             adapter = ctx.mod.lora_adapters[f'{ctx.bits}bit']
-            if need_A:
-                # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; log STE clamp in the reduce pass
-                sink = _grad_sink(adapter.lora_A, (K, r))
-                gA = sink if sink is not None else torch.empty((K, r), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['inv_raw_mul'],
-                             clamp_abs=10.0 if lo['qtype_A'] == 'log' else 0.0, accumulate=sink is not None)
-                if sink is not None:
-                    gA = None
-            if need_B:
-                # dB[r,n] = scaling * sum_m t[m,r] dY[m,n],  t[m,r] = t16[m,r] / tau[r]
-                sink = _grad_sink(adapter.lora_B, (r, N))
-                gB = sink if sink is not None else torch.empty((r, N), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
-                             transposed_out=True, clamp_abs=10.0 if lo['qtype_B'] == 'log' else 0.0, accumulate=sink is not None)
-                if sink is not None:
-                    gB = None
+            sink_A = _grad_sink(adapter.lora_A, (K, r)) if need_A else None
+            sink_B = _grad_sink(adapter.lora_B, (r, N)) if need_B else None
+            # gradients that accumulate straight into a driver-owned buffer may run on the driver's side stream
+            on_side = (not need_A or sink_A is not None) and (not need_B or sink_B is not None)
+            lane = _GradSide.fork(a_raw, dt2, t2, g16, gmax1) if on_side else torch.cuda.current_stream()
+            with torch.cuda.stream(lane):
+                if need_A:
+                    # dA[k,r] = sum_m x[m,k] dt[m,r],  x[m,k] = a_raw[m,k] / raw_mul[k]; log STE clamp in the reduce pass
+                    gA = sink_A if sink_A is not None else torch.empty((K, r), dtype=torch.float32, device=dev)
+                    _lib.gemm_tn(a_raw, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['inv_raw_mul'],
+                                 clamp_abs=10.0 if lo['qtype_A'] == 'log' else 0.0, accumulate=sink_A is not None)
+                    if sink_A is not None:
+                        gA = None
+                if need_B:
+                    # dB[r,n] = scaling * sum_m t[m,r] dY[m,n],  t[m,r] = t16[m,r] / tau[r]
+                    gB = sink_B if sink_B is not None else torch.empty((r, N), dtype=torch.float32, device=dev)
+                    _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
+                                 transposed_out=True, clamp_abs=10.0 if lo['qtype_B'] == 'log' else 0.0, accumulate=sink_B is not None)
+                    if sink_B is not None:
+                        gB = None
 
         if need_x:
             # the fp16 attention output feeding c_proj takes its gradient in fp16 straight from the epilogue
