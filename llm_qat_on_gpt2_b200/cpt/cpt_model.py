@@ -168,37 +168,35 @@ class _CPTLinearFn(torch.autograd.Function):
             on_side = ((not need_A or (fa and _grad_sink(sl.lora_A, (K, r)) is not None)) and
                        (not need_B or (fb and _grad_sink(sl.lora_B, (N, r)) is not None)))
             lane = _GradSide.fork(a_q, dt2, t2, g16, gmax1) if on_side else torch.cuda.current_stream()
-            side_ctx = torch.cuda.stream(lane)
-            side_ctx.__enter__()
-            if need_A:
-                # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
-                gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_A, K)
-                sink = _grad_sink(sl.lora_A, (K, r)) if fused else None
-                gA = sink if sink is not None else torch.empty((K, r), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(a_q, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['absorb'],
-                             clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
-                             gq_bits=sl.grad_quantizer_A.num_bits if gqs is not None else 8, accumulate=sink is not None)
-                if sink is not None:
-                    gA = None
-                elif not fused:
-                    gA = _grad_quantize(sl.grad_quantizer_A, gA)
-                    if clamp_w:
-                        gA = _lib.ste_backward(gA, _lib.LOG)
-            if need_B:
-                # dB[n,j] = scaling * sum_m dY[m,n] t[m,j],  t[m,j] = t16[m,j] / tau
-                gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_B, N)
-                sink = _grad_sink(sl.lora_B, (N, r)) if fused else None
-                gB = sink if sink is not None else torch.empty((N, r), dtype=torch.float32, device=dev)
-                _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
-                             clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
-                             gq_bits=sl.grad_quantizer_B.num_bits if gqs is not None else 8, accumulate=sink is not None)
-                if sink is not None:
-                    gB = None
-                elif not fused:
-                    gB = _grad_quantize(sl.grad_quantizer_B, gB)
-                    if clamp_w:
-                        gB = _lib.ste_backward(gB, _lib.LOG)
-            side_ctx.__exit__(None, None, None)
+            with torch.cuda.stream(lane):
+                if need_A:
+                    # dA[k,j] = sum_m q(x)[m,k] dt[m,j],  q(x)[m,k] = a_q[m,k] * absorb[k]
+                    gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_A, K)
+                    sink = _grad_sink(sl.lora_A, (K, r)) if fused else None
+                    gA = sink if sink is not None else torch.empty((K, r), dtype=torch.float32, device=dev)
+                    _lib.gemm_tn(a_q, dt2, gA, alpha=1.0 / lb['dt_mul'], alpha_dev=gmax1, i_scale=act['absorb'],
+                                 clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
+                                 gq_bits=sl.grad_quantizer_A.num_bits if gqs is not None else 8, accumulate=sink is not None)
+                    if sink is not None:
+                        gA = None
+                    elif not fused:
+                        gA = _grad_quantize(sl.grad_quantizer_A, gA)
+                        if clamp_w:
+                            gA = _lib.ste_backward(gA, _lib.LOG)
+                if need_B:
+                    # dB[n,j] = scaling * sum_m dY[m,n] t[m,j],  t[m,j] = t16[m,j] / tau
+                    gqs, fused = _grad_quantizer_scale(sl.grad_quantizer_B, N)
+                    sink = _grad_sink(sl.lora_B, (N, r)) if fused else None
+                    gB = sink if sink is not None else torch.empty((N, r), dtype=torch.float32, device=dev)
+                    _lib.gemm_tn(g16, t2, gB, alpha=lo['scaling'], alpha_dev=gmax1, j_scale=lo['inv_tmul_vec'],
+                                 clamp_abs=clamp_w if fused else 0.0, gq_scale_i=gqs,
+                                 gq_bits=sl.grad_quantizer_B.num_bits if gqs is not None else 8, accumulate=sink is not None)
+                    if sink is not None:
+                        gB = None
+                    elif not fused:
+                        gB = _grad_quantize(sl.grad_quantizer_B, gB)
+                        if clamp_w:
+                            gB = _lib.ste_backward(gB, _lib.LOG)
         if need_x:
             # both terms flow through q_in(x) here, so the STE clamp applies to their sum
             gx = torch.empty((M, K), dtype=torch.float32, device=dev)

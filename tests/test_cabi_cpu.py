@@ -154,3 +154,23 @@ def test_disabled_lora_and_32bit_only_linear():
     on = LoRALayer(8, 12, 4, 8, 6, "log")
     assert on.enabled and on.scaling == 2.0 and torch.count_nonzero(on.lora_B) == 0
     assert on.quantize_A.channel_dim == 1 and on.quantize_B.quantizer_type == "log"
+
+
+def test_side_stream_gradients_are_opt_in():
+    """lora.side_stream_grads (the LoRA weight-gradient GEMMs on a side stream) is a training-driver feature: off by
+    default, scoped to the `with` block, restored on exit -- plain module users keep every kernel on their own stream."""
+    from llm_qat_on_gpt2_b200 import lora
+    assert lora._GradSide.stream is None
+    with lora.side_stream_grads(None):
+        assert lora._GradSide.stream is None
+    marker = object()
+    lora._GradSide.stream = None
+    try:
+        ctx = lora.side_stream_grads(None)
+        ctx.__enter__()
+        lora._GradSide.stream = None
+        ctx.__exit__(None, None, None)
+    finally:
+        assert lora._GradSide.stream is None
+    del marker
+
