@@ -163,14 +163,3 @@ def test_side_stream_gradients_are_opt_in():
     assert lora._GradSide.stream is None
     with lora.side_stream_grads(None):
         assert lora._GradSide.stream is None
-    marker = object()
-    lora._GradSide.stream = None
-    try:
-        ctx = lora.side_stream_grads(None)
-        ctx.__enter__()
-        lora._GradSide.stream = None
-        ctx.__exit__(None, None, None)
-    finally:
-        assert lora._GradSide.stream is None
-    del marker
-
