@@ -33,7 +33,7 @@ t_st = timed(lambda: lib.minmax_stats(y, lib.PER_COL, True, 1e-5, smin, smax, ac
 t_fr = timed(lambda: lib.ln_rowscale_stats(x, w, b, 1e-5, a_raw, rs, stats_mode=2, stat_eps=1e-5, stat_min=smin, stat_max=smax, accumulate=False, state=state))
 t_fr0 = timed(lambda: lib.ln_rowscale_stats(x, w, b, 1e-5, a_raw, rs))
 gb = M * K / 1e9
-print(f"M={M} K={K} RPI/cap env: {os.environ.get('SPQ_LN_CTAS_PER_SM', '-')}  lib: {os.environ.get('SPQ_LIB', 'default')}")
+print(f"M={M} K={K} CTAs-per-SM cap: {os.environ.get('SPQ_LN_CTAS_PER_SM', '-')}  lib: {os.environ.get('SPQ_LIB', 'default')}")
 print(f"layernorm_fwd {t_ln:.1f} us ({8 * gb / t_ln * 1e3:.2f} TB/s)   quantize_act {t_q:.1f} us ({8 * gb / t_q * 1e3:.2f} TB/s)   sum {t_ln + t_q:.1f}")
 print(f"ln_quantize_act {t_f:.1f} us ({8 * gb / t_f * 1e3:.2f} TB/s)")
 print(f"rowscale {t_rs:.1f} us   colstats {t_st:.1f} us   LN + rowscale + stats {t_ln + t_rs + t_st:.1f}")
