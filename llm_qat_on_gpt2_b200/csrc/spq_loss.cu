@@ -205,12 +205,12 @@ distill_kl_kernel(const float* __restrict__ s_logits, long long ld_s, const floa
 // max / sum-exp; loss + scaled store, the row scale from an analytic bound on |d|) only the first reads HBM.  Algorithmic bytes: 4 (8 for KIND 0) read +
 // 2 written per logit.
 template <int KIND, int NT>
-__global__ void __launch_bounds__(NT, 2048 / NT > 2 ? 2 : 2048 / NT)
+__global__ void __launch_bounds__(NT, 1024 / NT)            // 64 registers per thread at every CTA size
 softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, const float* __restrict__ t_logits, long long ld_t,
                            const long long* __restrict__ targets, long long ignore_index, long long M, long long V, float inv_T,
                            long long seq_len, float* __restrict__ row_loss, float* __restrict__ row_valid,
                            unsigned short* __restrict__ g16, long long ld_g, float* __restrict__ row_scale,
-                           float* __restrict__ max_scale) {
+                           float* __restrict__ max_scale, int prefetch_mode) {
     constexpr int NW = NT / 32;
     __shared__ float sm[4][32];
     __shared__ float s_b[4];
@@ -297,12 +297,12 @@ softmax_loss_grad16_kernel(const float* __restrict__ s_logits, long long ld_s, c
         // while passes 2 and 3 run out of L2, pull the NEXT row of this CTA towards L2 (its pass 1 then starts warm)
         {
             const long long nrow = row + gridDim.x;
-            if (nrow < M) {
+            if (nrow < M && prefetch_mode != 0) {
                 const char* ns = reinterpret_cast<const char*>(s_logits + nrow * ld_s);
                 const long long bytes = V * 4;
                 for (long long o = static_cast<long long>(tid) * 128; o < bytes; o += static_cast<long long>(NT) * 128) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(ns + o));
-                    if (KIND == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(t_logits + nrow * ld_t) + o));
+                    if (KIND == 0 && prefetch_mode == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(t_logits + nrow * ld_t) + o));
                 }
             }
         }
@@ -479,25 +479,36 @@ extern "C" int spq_softmax_loss_grad16(int kind, const float* s_logits, int64_t 
     SPQ_REQUIRE(kind == 0 || targets, "spq_softmax_loss_grad16: cross-entropy needs targets");
     cudaStream_t st = as_stream(stream);
     SPQ_CUDA_OK(cudaMemsetAsync(max_scale, 0, sizeof(float), st));
-    static int variant = -1;                    // SPQ_LOSS_THREADS=512: two 512-thread CTAs per SM (A/B switch)
-    if (variant < 0) { const char* e = getenv("SPQ_LOSS_THREADS"); variant = e ? atoi(e) : 1024; }
-    const int nt = variant == 512 ? 512 : 1024;
-    long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * (nt == 512 ? 2 : 1);
+    // CTA size / rows in flight / next-row L2 prefetch.  ncu of the first layout (one 1024-thread CTA per SM, prefetch of
+    // both matrices: profiles/r02c_softmax_loss_ncu_before.txt) showed DRAM at 5.3 TB/s for 2.4 TB/s of algorithmic
+    // traffic and an L2 hit rate of 16 %: 148 rows x 2 matrices x 201 KB plus the prefetched next rows do not fit the
+    // 126 MB L2, so pass 2 re-read everything from DRAM.  Measured at 8192 x 50257 (KL / CE, us): 1024 threads + prefetch
+    // 1722 / 921; 1024 threads, none 1433 / 919; 512 threads (2 CTAs per SM) + prefetch 1485 / 783; 512 threads, none
+    // 1085 / 671 <- default.  SPQ_LOSS_THREADS = 256 | 512 | 1024 and SPQ_LOSS_PREFETCH = 0 none | 1 every matrix |
+    // 2 student matrix only are the A/B switches.
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("SPQ_LOSS_THREADS"); variant = e ? atoi(e) : 512; }
+    const int nt = variant == 1024 ? 1024 : variant == 256 ? 256 : 512;
+    static int pf_env = -2;
+    if (pf_env == -2) { const char* e = getenv("SPQ_LOSS_PREFETCH"); pf_env = e ? atoi(e) : -1; }
+    const int pf = pf_env >= 0 ? pf_env : 0;
+    long long ctas = static_cast<long long>(sm_count() > 0 ? sm_count() : 148) * (1024 / nt);     // 1024 threads per SM
     if (ctas > M) ctas = M;
     const unsigned grid = static_cast<unsigned>(ctas);
     const long long* tg = reinterpret_cast<const long long*>(targets);
-    if (kind == 0 && nt == 1024)
-        loss::softmax_loss_grad16_kernel<0, 1024><<<grid, 1024, 0, st>>>(s_logits, ld_s, t_logits, ld_t, nullptr, ignore_index, M, V,
-            1.0f / temperature, seq_len, row_loss, row_valid, g16, ld_g, row_scale, max_scale);
-    else if (kind == 0)
-        loss::softmax_loss_grad16_kernel<0, 512><<<grid, 512, 0, st>>>(s_logits, ld_s, t_logits, ld_t, nullptr, ignore_index, M, V,
-            1.0f / temperature, seq_len, row_loss, row_valid, g16, ld_g, row_scale, max_scale);
-    else if (nt == 1024)
-        loss::softmax_loss_grad16_kernel<1, 1024><<<grid, 1024, 0, st>>>(s_logits, ld_s, nullptr, 0, tg, ignore_index, M, V, 1.0f, seq_len,
-            row_loss, row_valid, g16, ld_g, row_scale, max_scale);
-    else
-        loss::softmax_loss_grad16_kernel<1, 512><<<grid, 512, 0, st>>>(s_logits, ld_s, nullptr, 0, tg, ignore_index, M, V, 1.0f, seq_len,
-            row_loss, row_valid, g16, ld_g, row_scale, max_scale);
+#define SPQ_SOFTMAX_LAUNCH(KIND, NT, T_PTR, LD_T, TG, INV_T)                                                                  \
+    loss::softmax_loss_grad16_kernel<KIND, NT><<<grid, NT, 0, st>>>(s_logits, ld_s, T_PTR, LD_T, TG, ignore_index, M, V, INV_T, \
+                                                                     seq_len, row_loss, row_valid, g16, ld_g, row_scale, max_scale, pf)
+    if (kind == 0) {
+        if (nt == 1024) SPQ_SOFTMAX_LAUNCH(0, 1024, t_logits, ld_t, nullptr, 1.0f / temperature);
+        else if (nt == 512) SPQ_SOFTMAX_LAUNCH(0, 512, t_logits, ld_t, nullptr, 1.0f / temperature);
+        else SPQ_SOFTMAX_LAUNCH(0, 256, t_logits, ld_t, nullptr, 1.0f / temperature);
+    } else {
+        if (nt == 1024) SPQ_SOFTMAX_LAUNCH(1, 1024, nullptr, 0, tg, 1.0f);
+        else if (nt == 512) SPQ_SOFTMAX_LAUNCH(1, 512, nullptr, 0, tg, 1.0f);
+        else SPQ_SOFTMAX_LAUNCH(1, 256, nullptr, 0, tg, 1.0f);
+    }
+#undef SPQ_SOFTMAX_LAUNCH
     SPQ_LAUNCH_OK();
     return SPQ_OK;
 }
