@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPQ_ABI_VERSION 4
+#define SPQ_ABI_VERSION 5
 #define SPQ_API __attribute__((visibility("default")))
 
 typedef void* spq_stream_t;          /* cudaStream_t */
@@ -252,6 +252,12 @@ SPQ_API int spq_rowscale_f16(const void* g, int g_is_half, int64_t M, int64_t N,
 /* same, and max_scale[0] = max over rows of row_scale (what the token-reduction GEMMs fold the scales against) */
 SPQ_API int spq_rowscale_f16_max(const void* g, int g_is_half, int64_t M, int64_t N, spq_half_t* out, int64_t ld_out,
                          float* row_scale, float* max_scale, spq_stream_t stream);
+
+/* spq_rowscale_f16_max of g * gelu'(y): the gradient entering c_fc when its output went through nn.GELU() (p1/models_sp.py:
+ * 114-123 under autograd), taken from the gradient g of the GELU output and the pre-activation y -- replaces torch's
+ * gelu_backward pass and the float32 gradient it writes.  Dense float32 rows, N % 4 == 0, N <= 8192. */
+SPQ_API int spq_rowscale_dgelu_f16_max(const float* g, const float* y, int64_t M, int64_t N, spq_half_t* out, float* row_scale,
+                               float* max_scale, spq_stream_t stream);
 
 /* fp16 operands of the LoRA gradient GEMMs in one pass (STE backward of p1/lora.py:45-54):
  *   dt16 = fp16(dtn * dt_mul)                       (dX += dT q(A)^T; token scale applied in that GEMM's epilogue)

@@ -21,7 +21,7 @@ PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
 MINMAX, LOG = 0, 1
 OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW, OPERAND_CODE_E4M3 = 0, 1, 2, 3
 QTYPE = {"minmax": MINMAX, "log": LOG}
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); must list every SPQ_API symbol of include/spq_b200.h
 SIGNATURES = {
@@ -58,6 +58,7 @@ SIGNATURES = {
                             c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t,
                             c_void_p]),
     "spq_rowscale_f16_max": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "spq_rowscale_dgelu_f16_max": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "spq_lora_bwd_prep": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "spq_softmax_loss_grad16": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float,
@@ -497,6 +498,16 @@ def rowscale_f16_max(g2d, out, row_scale, max_scale):
     assert out.stride(-1) == 1 and g2d.is_contiguous() and g2d.dtype in (torch.float32, torch.float16)
     _check(load_library().spq_rowscale_f16_max(g2d.data_ptr(), int(g2d.dtype == torch.float16), M, N, out.data_ptr(), out.stride(0),
                                                row_scale.data_ptr(), max_scale.data_ptr(), _stream()), "spq_rowscale_f16_max")
+
+
+def rowscale_dgelu_f16_max(g2d, y2d, out, row_scale, max_scale):
+    """rowscale_f16_max of g2d * gelu'(y2d) (exact erf GELU): the gradient through nn.GELU() without torch's gelu_backward pass."""
+    _req_cuda(g2d, y2d, out, row_scale, max_scale)
+    M, N = g2d.shape
+    assert g2d.dtype == torch.float32 and y2d.dtype == torch.float32 and g2d.is_contiguous() and y2d.is_contiguous()
+    assert y2d.shape == g2d.shape and out.shape == (M, N) and out.stride(0) == N and out.dtype == torch.float16
+    _check(load_library().spq_rowscale_dgelu_f16_max(g2d.data_ptr(), y2d.data_ptr(), M, N, out.data_ptr(), row_scale.data_ptr(),
+                                                     max_scale.data_ptr(), _stream()), "spq_rowscale_dgelu_f16_max")
 
 
 def lora_bwd_prep(dtn, t16, row_scale, max_scale, dt_mul, want_dt16=True, want_dt2=True, want_t2=True):

@@ -318,12 +318,22 @@ struct ActArgs {
     float* raw_row_scale;       // row-scaled variant only
     const float* raw_col_mul;   // elementwise variant: per-column multiplier of the raw operand
     float* max_scale;           // row-scaled variant: optional device scalar, max over rows of the row scale
+    const float* dgelu_y;       // row-scaled DGELU variant: pre-activation y; the row that is scaled is x * gelu'(y)
 };
 
 // Row-scaled raw operand (no quantiser): one CTA of G threads owns a row at a time, the row stays in
 // registers (NV float4 per thread), its absmax gives the power-of-two scale.  Used where no calibrated
 // bound exists: calibration pass, 32-bit path, LM head, gradients.
-template <int NV, typename XT>
+// d/dy of the exact (erf) GELU, as torch's gelu_backward: Phi(y) + y phi(y)
+__device__ __forceinline__ float dgelu_erf(float y) {
+    const float cdf = 0.5f * (1.0f + erff(y * 0.70710678118654752f));
+    const float pdf = __expf(-0.5f * y * y) * 0.39894228040143268f;
+    return fmaf(y, pdf, cdf);
+}
+
+// DGELU: the row is x[m,:] * gelu'(y[m,:]) -- the gradient entering a linear whose output went through GELU, straight from
+// the gradient of the GELU output: torch's gelu_backward pass (12 B / element) and its float32 result never exist
+template <int NV, typename XT, bool DGELU = false>
 __global__ void __launch_bounds__(256)
 rowscale_kernel(ActArgs a) {
     const int G = blockDim.x;
@@ -338,6 +348,12 @@ rowscale_kernel(ActArgs a) {
         for (int i = 0; i < NV; ++i) {
             const long long c = (static_cast<long long>(i) * G + tid) * 4;
             v[i] = (c < a.K) ? ld_stream_x4<XT>(px + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (DGELU) {
+                if (c < a.K) {
+                    const float4 y = ld_stream_f4(a.dgelu_y + row * a.K + c);
+                    v[i].x *= dgelu_erf(y.x); v[i].y *= dgelu_erf(y.y); v[i].z *= dgelu_erf(y.z); v[i].w *= dgelu_erf(y.w);
+                }
+            }
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
         }
         amax = warp_fmax(amax);
@@ -540,7 +556,14 @@ static int launch_rowscale(const ActArgs& a, cudaStream_t st) {
     if (NV == 8) ctas = static_cast<long long>(sm_count()) * 4;
     if (ctas > a.M) ctas = a.M;
     const unsigned grid = static_cast<unsigned>(ctas);
-    if (a.x_half) {
+    if (a.dgelu_y) {
+        switch (NV) {
+            case 1: rowscale_kernel<1, float, true><<<grid, G, 0, st>>>(a); break;
+            case 2: rowscale_kernel<2, float, true><<<grid, G, 0, st>>>(a); break;
+            case 4: rowscale_kernel<4, float, true><<<grid, G, 0, st>>>(a); break;
+            default: rowscale_kernel<8, float, true><<<grid, G, 0, st>>>(a); break;
+        }
+    } else if (a.x_half) {
         switch (NV) {
             case 1: rowscale_kernel<1, __half><<<grid, G, 0, st>>>(a); break;
             case 2: rowscale_kernel<2, __half><<<grid, G, 0, st>>>(a); break;
@@ -957,6 +980,7 @@ extern "C" int spq_quantize_act(const void* x, int x_is_half, int64_t M, int64_t
     SPQ_REQUIRE(bcast == SPQ_PER_COL || bcast == SPQ_PER_TENSOR, "spq_quantize_act: per-row scales are not an activation layout");
     SPQ_REQUIRE(bits >= 1 && bits < 32, "spq_quantize_act: bits %d", bits);
     ActArgs a;
+    a.dgelu_y = nullptr;
     a.x = x; a.x_half = x_is_half ? 1 : 0; a.M = M; a.K = K; a.scale = scale; a.zp = zero_point; a.bcast = bcast;
     a.qp = make_qparams(bits, symmetric);
     a.operand_kind = operand_kind; a.col_mul = col_mul; a.mul = mul;
@@ -974,6 +998,7 @@ static int rowscale_impl(const void* g, int g_is_half, int64_t M, int64_t N, spq
     if (max_scale) SPQ_CUDA_OK(cudaMemsetAsync(max_scale, 0, sizeof(float), as_stream(stream)));
     if (ld_out == N && (N % 4) == 0 && N <= 8192 && aligned16(g)) {
         ActArgs a;
+    a.dgelu_y = nullptr;
         a.x = g; a.x_half = g_is_half ? 1 : 0; a.M = M; a.K = N; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
         a.qp = make_qparams(8, 1);
         a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
@@ -1148,3 +1173,19 @@ extern "C" int spq_ln_rowscale_stats(const float* x, int64_t M, int64_t K, const
                                              stat_min, stat_max, state, st);
     return SPQ_OK;
 }
+
+extern "C" int spq_rowscale_dgelu_f16_max(const float* g, const float* y, int64_t M, int64_t N, spq_half_t* out, float* row_scale,
+                                          float* max_scale, spq_stream_t stream) {
+    SPQ_REQUIRE(g && y && out && row_scale && max_scale && M > 0 && N > 0, "spq_rowscale_dgelu_f16_max: bad arguments");
+    SPQ_REQUIRE((N % 4) == 0 && N <= 8192 && aligned16(g) && aligned16(y) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+                "spq_rowscale_dgelu_f16_max: dense float32 rows, N %% 4 == 0, N <= 8192, 16-byte aligned inputs");
+    SPQ_CUDA_OK(cudaMemsetAsync(max_scale, 0, sizeof(float), as_stream(stream)));
+    ActArgs a;
+    a.dgelu_y = y;
+    a.x = g; a.x_half = 0; a.M = M; a.K = N; a.scale = nullptr; a.zp = nullptr; a.bcast = SPQ_PER_TENSOR;
+    a.qp = make_qparams(8, 1);
+    a.operand_kind = SPQ_OPERAND_RAW; a.col_mul = nullptr; a.mul = 1.0f;
+    a.a_q = nullptr; a.a_raw = out; a.raw_row_scale = row_scale; a.raw_col_mul = nullptr; a.max_scale = max_scale;
+    return launch_rowscale(a, as_stream(stream));
+}
+

@@ -105,6 +105,8 @@ def _rowscaled_f16(x2d: torch.Tensor):
 
 # LayerNorm fused into the consumer's activation-side kernel (SPQ_FUSE_LN=0: A/B switch, read at import)
 _FUSE_LN = os.environ.get("SPQ_FUSE_LN", "1") != "0"
+# gelu'(y) folded into the backward's row-scaling pass when GELU follows a linear under autograd (SPQ_FUSE_DGELU=0: A/B)
+_FUSE_DGELU = os.environ.get("SPQ_FUSE_DGELU", "1") != "0"
 
 
 def _ln_params(ln):
@@ -412,8 +414,11 @@ class _SPLinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, lora_A, lora_B, mod, bits, out_half=False, activation=0, residual=None,
-                grad_mode=True, ln=None):
+                grad_mode=True, ln=None, gelu_out=False):
         # ln: a SwitchableLayerNorm to apply to x first, inside the activation-side kernel (no_grad only)
+        # gelu_out (autograd on, frozen base weight / bias): the Function returns gelu(y) and keeps y; its backward takes
+        # the gradient of the GELU OUTPUT and folds gelu'(y) into the row-scaling pass that builds the fp16 gradient
+        # operand (spq_rowscale_dgelu_f16_max) -- torch's gelu_backward pass and its float32 result never exist
         # grad_mode: torch.is_grad_enabled() of the caller (always False inside Function.forward)
         use_lora = lora_A is not None
         base, lo = mod._operands_for(bits, use_lora)
@@ -464,13 +469,16 @@ class _SPLinearFn(torch.autograd.Function):
         ctx.mod, ctx.bits = mod, bits       # backward operands are built (and cached) when backward first runs
         ctx.weight_qtype = mod.quantizers_weight[f'{bits}bit'].quantizer_type
         keep_t = grad_mode and use_lora and need[4]
+        ctx.gelu_out = bool(gelu_out)
         ctx.save_for_backward(a_q if need[1] else None, a_raw if (grad_mode and use_lora and need[3]) else None,
-                              t16 if keep_t else None)
+                              t16 if keep_t else None, y if gelu_out else None)
+        if gelu_out:
+            return torch.nn.functional.gelu(y).view(*x.shape[:-1], N)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gy):
-        a_q, a_raw, t16 = ctx.saved_tensors
+        a_q, a_raw, t16, y_pre = ctx.saved_tensors
         base, lo = ctx.base, ctx.lo
         bw = ctx.mod._backward_operands_for(ctx.bits, ctx.use_lora)
         M, N, K = ctx.dims
@@ -482,7 +490,11 @@ class _SPLinearFn(torch.autograd.Function):
         g16 = _lib.empty_f16_padded(M, N, dev)
         eg = torch.empty(M, dtype=torch.float32, device=dev)
         gmax1 = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.rowscale_f16_max(g2d, g16, eg, gmax1)
+        if ctx.gelu_out:
+            # gy is the gradient of gelu(y): dY = gy * gelu'(y), formed inside the row-scaling pass
+            _lib.rowscale_dgelu_f16_max(g2d if g2d.dtype == torch.float32 else g2d.float(), y_pre, g16, eg, gmax1)
+        else:
+            _lib.rowscale_f16_max(g2d, g16, eg, gmax1)
         gx = gw = gb = gA = gB = None
         clamp_in = 10.0 if act['input_qtype'] == 'log' else 0.0
 
@@ -544,7 +556,7 @@ class _SPLinearFn(torch.autograd.Function):
                          clamp_abs=10.0 if ctx.weight_qtype == 'log' else 0.0)
         if ctx.has_bias and need_b:
             gb = g2d.float().sum(dim=0)
-        return gx, gw, gb, gA, gB, None, None, None, None, (gy if ctx.needs_input_grad[9] else None), None, None
+        return gx, gw, gb, gA, gB, None, None, None, None, (gy if ctx.needs_input_grad[9] else None), None, None, None
 
 
 class SPLinearWithLoRA(nn.Module):
@@ -824,11 +836,17 @@ class SPLinearWithLoRA(nn.Module):
 
         if input_quantizer.ready() and weight_quantizer.ready():
             lora_on = active_lora.enabled and active_lora.scaling != 0 and not self.calibration_mode
+            # GELU under autograd with frozen base weight / bias: inside the Function (gelu'(y) then rides in the backward's
+            # row-scaling pass); otherwise torch's GELU follows the call
+            N_ = self.linear.out_features
+            gelu_in_fn = (post_gelu and _FUSE_DGELU and not out_half and residual is None and N_ % 8 == 0 and N_ <= 8192
+                          and not self.linear.weight.requires_grad
+                          and (self.linear.bias is None or not self.linear.bias.requires_grad))
             y = _SPLinearFn.apply(x, self.linear.weight, self.linear.bias,
                                   active_lora.lora_A if lora_on else None,
                                   active_lora.lora_B if lora_on else None, self, self.current_bits, out_half, act,
-                                  residual, torch.is_grad_enabled(), pre_norm)
-            return torch.nn.functional.gelu(y) if post_gelu else y
+                                  residual, torch.is_grad_enabled(), pre_norm, gelu_in_fn)
+            return torch.nn.functional.gelu(y) if (post_gelu and not gelu_in_fn) else y
 
         # A quantiser is collecting statistics or is uncalibrated: compose the same steps as the
         # reference, module by module (this is the calibration pass; errors surface as upstream).

@@ -631,6 +631,28 @@ def test_qgemm_lse_and_cross_entropy_from_parts(M, V, K):
     assert lib.debug_status() == 0
 
 
+@pytest.mark.parametrize("M,N", [(257, 3072), (64, 96), (1000, 768), (33, 4096)])
+def test_rowscale_dgelu_fused(lib, M, N):
+    """spq_rowscale_dgelu_f16_max: the fp16 gradient operand of g * gelu'(y) (exact erf GELU) in one pass, against torch's
+    gelu_backward followed by spq_rowscale_f16_max: row scales identical (a row's absmax can only move across a power of
+    two by the last ulp of gelu'), values within fp16 rounding of the product."""
+    torch.manual_seed(M + N)
+    y = (torch.randn(M, N, device="cuda") * 2).requires_grad_(True)
+    g = torch.randn(M, N, device="cuda") * 1e-3
+    g[5].zero_()                                             # a row without gradient
+    (dy,) = torch.autograd.grad(torch.nn.functional.gelu(y), y, g)
+    want16 = torch.empty((M, N), dtype=torch.float16, device="cuda"); wrs = torch.empty(M, device="cuda"); wmx = torch.empty(1, device="cuda")
+    lib.rowscale_f16_max(dy.contiguous(), want16, wrs, wmx)
+    got16 = torch.empty_like(want16); rs = torch.empty_like(wrs); mx = torch.empty_like(wmx)
+    lib.rowscale_dgelu_f16_max(g, y.detach(), got16, rs, mx)
+    same = rs == wrs
+    assert float(same.float().mean()) >= 0.99 and torch.equal(mx, wmx) or float((mx / wmx).item()) in (0.5, 1.0, 2.0)
+    a = got16.float() * rs[:, None]; b = want16.float() * wrs[:, None]
+    assert float((a - b).norm() / b.norm()) <= 1e-3
+    assert float((a - dy).abs().max()) <= 2e-3 * float(dy.abs().max())
+    assert torch.equal(got16[5], torch.zeros_like(got16[5]))
+
+
 def test_mse_select_matches_torch(lib):
     """spq_mse_select (feature term of the distillation loss, p1/distillation_manager.py:82-116): the pair is chosen by an
     index read on the device; every index, an odd element count and out-of-range indices (clamped); run-to-run identical."""

@@ -766,6 +766,49 @@ def test_layernorm_fused_into_consumer_matches_unfused(bits, per_channel, monkey
         assert cos >= 0.999, (rel, cos)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [8, 4])
+def test_gelu_backward_fused_into_rowscale(bits, monkeypatch):
+    """Under autograd with frozen base weights, c_fc's autograd Function returns gelu(y) and its backward folds gelu'(y)
+    into the row-scaling pass of the incoming gradient (spq_rowscale_dgelu_f16_max).  Against torch's GELU after the call
+    (SPQ_FUSE_DGELU=0 semantics) on the same model: identical logits, LoRA / LayerNorm / input gradients within the
+    fp16-operand tolerance; with a trainable base weight the fusion stays off."""
+    from llm_qat_on_gpt2_b200 import SPLMHeadModel
+    import llm_qat_on_gpt2_b200.lora as lora_mod
+    res = {}
+    for fused in (True, False):
+        monkeypatch.setattr(lora_mod, "_FUSE_DGELU", fused)
+        torch.manual_seed(12)
+        model = SPLMHeadModel(_tiny_config()).cuda().train()
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith("lora_B"):
+                    p.normal_(0, 0.02)
+        ids = torch.randint(0, 211, (2, 32), device="cuda")
+        _calibrate_model(model, bits, [ids])
+        for n, p in model.named_parameters():
+            p.requires_grad_(("lora_" in n) or (".weights." in n) or (".biases." in n))
+        xe = model.transformer.wte(ids).detach().requires_grad_(True)
+        n0 = lora_mod._lib.launch_count()
+        out = model(inputs_embeds=xe, labels=ids)
+        out["loss"].backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        grads["inputs_embeds"] = xe.grad.clone()
+        res[fused] = (out["logits"].detach().float().clone(), grads, lora_mod._lib.launch_count() - n0)
+    a, b = res[True], res[False]
+    assert torch.equal(a[0], b[0])
+    assert a[1].keys() == b[1].keys() and len(a[1]) > 10
+    for n in a[1]:
+        ga, gb = a[1][n].double(), b[1][n].double()
+        assert float((ga - gb).norm() / gb.norm().clamp_min(1e-30)) <= 2e-3, n
+    # trainable base weight: the Function needs the plain gradient for dW -> torch's GELU stays outside
+    monkeypatch.setattr(lora_mod, "_FUSE_DGELU", True)
+    model.transformer.h[0].mlp.c_fc.linear.weight.requires_grad_(True)
+    model.zero_grad()
+    model(ids, labels=ids)["loss"].backward()
+    assert model.transformer.h[0].mlp.c_fc.linear.weight.grad is not None
+
+
 def test_sp_linear_fp8_path_per_tensor_4bit(monkeypatch):
     """The evaluation configuration (per_channel=False, 4-bit min-max: p1/deploy.py:210,238): SPLinearWithLoRA takes the
     e4m3 integer-code GEMM.  With the LoRA branch off the output is the exact product of the codes times s_x s_w (fp32
