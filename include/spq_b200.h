@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SPQ_ABI_VERSION 5
+#define SPQ_ABI_VERSION 6
 #define SPQ_API __attribute__((visibility("default")))
 
 typedef void* spq_stream_t;          /* cudaStream_t */
@@ -223,6 +223,11 @@ SPQ_API size_t spq_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cols);
 SPQ_API int spq_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean,
                       const float* rstd, int64_t rows, int64_t cols, float* dx, float* dweight,
                       float* dbias, int accumulate_params, void* workspace, size_t workspace_bytes, spq_stream_t stream);
+
+/* the column-sum fold of spq_layernorm_bwd as a call of its own: after spq_layernorm_bwd(..., dweight = dbias = NULL, ...)
+ * left the per-CTA sums in `workspace` (private to that call), this writes / accumulates dweight and dbias */
+SPQ_API int spq_layernorm_bwd_finalize(const void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols, float* dweight,
+                               float* dbias, int accumulate_params, spq_stream_t stream);
 
 /* ---- SwitchableLayerNorm fused into its consumer's activation-side kernel (no float32 round trip of the normalised
  * rows): ln_1 -> c_attn, ln_2 -> c_fc, ln_f -> LM head (p1/models_sp.py:139-147, 316-319; p1/lora.py:141-149).

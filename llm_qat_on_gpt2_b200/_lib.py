@@ -21,7 +21,7 @@ PER_TENSOR, PER_ROW, PER_COL = 0, 1, 2
 MINMAX, LOG = 0, 1
 OPERAND_CODE, OPERAND_DEQUANT, OPERAND_RAW, OPERAND_CODE_E4M3 = 0, 1, 2, 3
 QTYPE = {"minmax": MINMAX, "log": LOG}
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # name -> (restype, argtypes); must list every SPQ_API symbol of include/spq_b200.h
 SIGNATURES = {
@@ -73,6 +73,7 @@ SIGNATURES = {
     "spq_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "spq_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "spq_layernorm_bwd_finalize": (c_int, [c_void_p, c_size_t, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "spq_qgemm_lse_parts": (c_int64, [c_int64, c_int64]),
     "spq_qgemm_lse": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
@@ -378,6 +379,25 @@ def layernorm_bwd(dy2d, x2d, weight, mean, rstd, dx, dweight, dbias, accumulate_
     _check(lib.spq_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                  rows, cols, dx.data_ptr(), _ptr(dweight), _ptr(dbias), int(accumulate_params), ws.data_ptr(), ws.numel(),
                                  _stream()), "spq_layernorm_bwd")
+
+
+def layernorm_bwd_split(dy2d, x2d, weight, mean, rstd, dx):
+    """layernorm_bwd without the parameter-gradient fold: returns the private workspace holding the per-CTA column sums
+    (hand it to layernorm_bwd_finalize, possibly on another stream)."""
+    lib = load_library()
+    _req_cuda(dy2d, x2d, weight, mean, rstd, dx)
+    rows, cols = x2d.shape
+    ws = torch.empty(max(int(lib.spq_layernorm_bwd_workspace_bytes(rows, cols)), 16), dtype=torch.uint8, device=x2d.device)
+    _check(lib.spq_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                 rows, cols, dx.data_ptr(), None, None, 0, ws.data_ptr(), ws.numel(), _stream()),
+           "spq_layernorm_bwd")
+    return ws
+
+
+def layernorm_bwd_finalize(ws, rows, cols, dweight, dbias, accumulate_params=False):
+    _req_cuda(ws, dweight, dbias)
+    _check(load_library().spq_layernorm_bwd_finalize(ws.data_ptr(), ws.numel(), rows, cols, _ptr(dweight), _ptr(dbias),
+                                                     int(accumulate_params), _stream()), "spq_layernorm_bwd_finalize")
 
 
 def cross_entropy_fwd(logits2d, targets, ignore_index=-100):

@@ -259,3 +259,24 @@ extern "C" int spq_layernorm_bwd(const float* dy, const float* x, const float* w
     }
     return SPQ_OK;
 }
+
+// The second half of spq_layernorm_bwd on its own: fold the per-CTA column sums a call with dweight = dbias = null left
+// in `workspace` into dweight / dbias.  Lets a training driver run the fold (a latency-bound launch nothing downstream
+// waits for) on a side stream; the workspace must then be private to that backward call.
+extern "C" int spq_layernorm_bwd_finalize(const void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols, float* dweight,
+                                          float* dbias, int accumulate_params, spq_stream_t stream) {
+    SPQ_REQUIRE(workspace && rows > 0 && cols > 0 && (dweight || dbias), "spq_layernorm_bwd_finalize: bad arguments");
+    Cfg c;
+    if (!pick(rows, cols, &c, 8)) {
+        set_error("spq_layernorm_bwd_finalize: normalized dim %lld > 8192 unsupported", (long long)cols);
+        return SPQ_ERR_UNSUPPORTED;
+    }
+    SPQ_REQUIRE(workspace_bytes >= spq_layernorm_bwd_workspace_bytes(rows, cols), "spq_layernorm_bwd_finalize: workspace too small");
+    const float* pdw = reinterpret_cast<const float*>(workspace);
+    const float* pdb = pdw + static_cast<size_t>(c.grid) * cols;
+    colsum_finalize_kernel<<<static_cast<unsigned>((cols + 7) / 8), 256, 0, as_stream(stream)>>>(pdw, pdb, static_cast<int>(c.grid), cols, dweight,
+                                                                                               dbias, accumulate_params ? 1 : 0);
+    SPQ_LAUNCH_OK();
+    return SPQ_OK;
+}
+

@@ -53,8 +53,16 @@ class _LayerNormFn(torch.autograd.Function):
         sw = _grad_sink(wp, ctx.w_shape) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else None
         sb = _grad_sink(bp, ctx.w_shape) if sw is not None else None
         if sw is not None and sb is not None:
-            # the training driver owns the .grad buffers: the column sums are added straight into them
-            _lib.layernorm_bwd(g2d, x2d, w, mean, rstd, dx, sw.view(-1), sb.view(-1), accumulate_params=True)
+            # the training driver owns the .grad buffers: the column sums are added straight into them -- on the driver's
+            # side stream when it offers one (lora._GradSide: nothing downstream waits for the fold)
+            from .lora import _GradSide
+            if _GradSide.stream is not None:
+                ws = _lib.layernorm_bwd_split(g2d, x2d, w, mean, rstd, dx)
+                lane = _GradSide.fork(ws)
+                with torch.cuda.stream(lane):
+                    _lib.layernorm_bwd_finalize(ws, rows, cols, sw.view(-1), sb.view(-1), accumulate_params=True)
+            else:
+                _lib.layernorm_bwd(g2d, x2d, w, mean, rstd, dx, sw.view(-1), sb.view(-1), accumulate_params=True)
             return (dx.view(ctx.x_shape) if ctx.needs_input_grad[0] else None, None, None, None, None)
         dw = torch.empty(cols, dtype=torch.float32, device=gy.device) if need_p else None
         db = torch.empty(cols, dtype=torch.float32, device=gy.device) if need_p else None

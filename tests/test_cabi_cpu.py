@@ -30,7 +30,7 @@ def test_header_symbols_exported_and_bound(lib):
         assert hasattr(lib, s), f"{s} declared in spq_b200.h but not exported by libspq_b200.so"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in _lib.py"
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.spq_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.spq_abi_version() == _lib.ABI_VERSION == 6
     assert lib.spq_launch_count() == 0
 
 
